@@ -1,0 +1,156 @@
+/*
+ * mevi_b200.h — C ABI of libmevi_b200.so, the B200 (sm_100a) implementation of
+ * MEVI's index hot path.
+ *
+ * The reference (HugoZHL/MEVI) has no FFI of its own: the hot path is Python
+ * that calls torch / sklearn / faiss.  Each entry point below replaces one of
+ * those call sites; the citation after "replaces:" is the reference file:line
+ * whose arithmetic the entry point reproduces.  The Python mirror of the
+ * reference interface (mevi_b200/pq.py, faiss_search.py, document_encoder.py,
+ * rerank.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - Plain C types only.  All array arguments are DEVICE pointers unless the
+ *     name ends in `_host`.  Memory is caller-owned; the library keeps no
+ *     pointer past the call.  Scratch memory lives in the context and grows on
+ *     demand (never shrinks until mevi_ctx_destroy).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream).  Calls are asynchronous on that stream unless stated otherwise.
+ *   - Return value: 0 on success, negative MEVI_ERR_* otherwise;
+ *     mevi_last_error(ctx) then returns a message owned by the context.
+ *   - A context is bound to one device and is not re-entrant; different
+ *     contexts may be used from different threads.
+ *   - Row-major (C order) everywhere; `d` is the embedding width.
+ */
+#ifndef MEVI_B200_H
+#define MEVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEVI_ABI_VERSION 1
+
+#define MEVI_OK 0
+#define MEVI_ERR_INVALID (-1)     /* bad argument / unsupported shape */
+#define MEVI_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+#define MEVI_ERR_UNSUPPORTED (-3) /* requested mode not available for this shape */
+#define MEVI_ERR_NOMEM (-4)
+
+#define MEVI_METRIC_L2 0 /* pq.py:130  -sum((a-b)^2), argmax */
+#define MEVI_METRIC_IP 1 /* pq.py:126   sum(a*b),     argmax */
+
+#define MEVI_MODE_AUTO 0   /* tensor-core path when the shape allows it, else exact */
+#define MEVI_MODE_EXACT 1  /* fp32 direct-form on CUDA cores (also the arbiter of flagged rows) */
+#define MEVI_MODE_TENSOR 2 /* tcgen05 split-fp16 prefilter + exact fix-up; error if unsupported */
+
+typedef struct mevi_ctx mevi_ctx;
+
+/* ---- context ----------------------------------------------------------- */
+int mevi_abi_version(void);
+int mevi_ctx_create(int device, mevi_ctx** out);
+void mevi_ctx_destroy(mevi_ctx* ctx);
+const char* mevi_last_error(mevi_ctx* ctx);
+/* info[0]=SM count, [1]=cc major, [2]=cc minor, [3]=total global memory bytes,
+ * [4]=1 if the tcgen05 path is usable on this device (cc 10.x), [5]=L2 bytes */
+int mevi_device_info(mevi_ctx* ctx, int64_t info[8]);
+
+/* ---- RQ encode ---------------------------------------------------------- *
+ * replaces: MEVI/pq.py:281-305 get_rq_document_cluster (+124-131 compute_scores,
+ * 121-122 rq_minus_centroids); also the second copy at
+ * dataprocess/msmarco_passage/gen_sampled_to_full.py:65-86.
+ * Greedy residual quantisation of n rows against codebook[M][K][d]: per level
+ * nearest centroid (lowest index on exact fp32 ties), code written as int32,
+ * residual -= centroid after every level.
+ *   codes             [n, M] int32 out
+ *   residual_or_null  [n, d] fp32 out: the residual after the last level
+ *                     (pq.py:304-305 subtracts after every level), or NULL
+ *   stats_or_null     int64[8] DEVICE out: [0]=rows re-decided by the exact
+ *                     fix-up because their prefilter top-2 gap was inside the
+ *                     error bound (tensor mode), [1]=rows processed; rest 0   */
+int mevi_rq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K,
+                   int metric, int mode, int32_t* codes, float* residual_or_null, int64_t* stats_or_null,
+                   void* stream);
+
+/* Same operation on HOST buffers (the call a drop-in pq.get_document_cluster
+ * makes on an np.memmap, pq.py:283): rows are streamed to the device in
+ * `chunk_rows` pieces through pinned staging buffers, overlapped with the
+ * encode of the previous piece; codes are copied back.  Synchronous.
+ * stats_host_or_null: int64[8] host out, same meaning as above.              */
+int mevi_rq_encode_host(mevi_ctx* ctx, const float* X_host, int64_t n, int d, const float* codebook_host, int M,
+                        int K, int metric, int mode, int32_t* codes_host, int64_t chunk_rows,
+                        int64_t* stats_host_or_null);
+
+/* ---- k-means (full-batch Lloyd, shardable) ------------------------------ *
+ * replaces: MEVI/pq.py:551-598 (rq branch 582-594; sklearn MiniBatchKMeans on
+ * rank 0) with the data-parallel form BASELINE.json asks for; the sums/counts
+ * exchange mirrors pq.py:384-397.
+ * One pass over the shard R[n,d] (the residual of the level being trained):
+ *   assign_out_or_null [n] int32, stride `assign_stride` elements between rows
+ *                      (so it can write column j of a [n,M] code table)
+ *   sums_counts        [K*d + K] fp32 out (overwritten): per-centroid sums of
+ *                      the fp32 rows, then per-centroid counts — ONE buffer so
+ *                      a single all-reduce(SUM) combines shards
+ *   inertia_or_null    double DEVICE out: sum of squared distances to the
+ *                      assigned centroid over this shard                      */
+int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K, int mode,
+                     int32_t* assign_out_or_null, int64_t assign_stride, float* sums_counts,
+                     double* inertia_or_null, void* stream);
+/* centroids[k] = sums[k]/counts[k] where counts[k] > 0 (others unchanged);
+ * n_empty_or_null: int32 DEVICE out = number of empty clusters.              */
+int mevi_kmeans_update(mevi_ctx* ctx, const float* sums_counts, int K, int d, float* centroids,
+                       int32_t* n_empty_or_null, void* stream);
+/* R[i,:] -= centroids[assign[i*assign_stride], :]   replaces: pq.py:591-593  */
+int mevi_residual_update(mevi_ctx* ctx, float* R, int64_t n, int d, const float* centroids, int K,
+                         const int32_t* assign, int64_t assign_stride, void* stream);
+
+/* ---- inverted lists ------------------------------------------------------ *
+ * replaces: MEVI/pq.py:236-242 / 200-214 (python dict build) with a device
+ * sort by leaf key.  key(row) = sum_j codes[row,j] * K^(M-1-j)  (K^M < 2^62).
+ *   sorted_docids [n] int32 out: row indices ordered by (key, row) — ascending
+ *                 doc id inside a leaf, like the reference's append order
+ *   sorted_keys   [n] int64 out: the key of each entry of sorted_docids      */
+int mevi_build_inverted_lists(mevi_ctx* ctx, const int32_t* codes, int64_t n, int M, int K, int32_t* sorted_docids,
+                              int64_t* sorted_keys, void* stream);
+
+/* ---- cluster-restricted re-rank ----------------------------------------- *
+ * replaces: MEVI/main_models.py:3915-4014 (per query: leaves -> candidate rows
+ * -> q.P^T (document_encoder.py:128-132) -> descending sort) for all queries in
+ * one call, keeping the k best.
+ *   Q [nq,d], D [n,d] (row index == doc id - id_base)
+ *   leaf_offsets [n_leaves+1] int64 CSR into leaf_docids; leaf_docids int32 rows of D
+ *   query_leaves [nq,L] int32 CSR leaf index per beam-search leaf, -1 = leaf
+ *                holds no document (main_models.py:3928,3935)
+ *   scores [nq,k] fp32 out, descending, -inf padded; ids [nq,k] int64 out
+ *                (= id_base + row), -1 padded; n_candidates [nq] int32 out
+ * Ties between equal scores are ordered by ascending id.                      */
+int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d,
+                        const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                        const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
+                        int32_t* n_candidates, void* stream);
+
+/* ---- exact flat inner-product search ------------------------------------ *
+ * replaces: MEVI/faiss_search.py:13-21 with param='Flat' (faiss IndexFlatIP
+ * add + search): scores [nq,k] fp32 descending (-inf padded), ids [nq,k] int64
+ * (= id_base + row, -1 padded).                                               */
+int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int k,
+                      int64_t id_base, int mode, float* scores, int64_t* ids, void* stream);
+
+/* Merge S per-shard top-k lists (after an all-gather) into one.
+ * scores_in [S,nq,k], ids_in [S,nq,k] -> scores/ids [nq,k]; same ordering rule. */
+int mevi_topk_merge(mevi_ctx* ctx, const float* scores_in, const int64_t* ids_in, int S, int nq, int k,
+                    float* scores, int64_t* ids, void* stream);
+
+/* ---- dense scorer -------------------------------------------------------- *
+ * replaces: MEVI/document_encoder.py:128-132 compute_similarity(bmm=False):
+ * out[nq, n] = Q[nq,d] . P[n,d]^T in fp32 (exact FMA accumulation).            */
+int mevi_dense_scores(mevi_ctx* ctx, const float* Q, int nq, const float* P, int64_t n, int d, float* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEVI_B200_H */

@@ -1,0 +1,316 @@
+"""ctypes binding of libmevi_b200.so (include/mevi_b200.h).
+
+PyTorch is used only for device memory and streams: tensors are handed to the
+library as raw pointers + extents + the current cudaStream_t.  Nothing here
+computes; if the shared library is missing the import of any compute path fails
+loudly (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libmevi_b200.so"
+
+METRIC_L2, METRIC_IP = 0, 1
+MODE_AUTO, MODE_EXACT, MODE_TENSOR = 0, 1, 2
+_MODES = {"auto": MODE_AUTO, "exact": MODE_EXACT, "tensor": MODE_TENSOR}
+_METRICS = {"l2": METRIC_L2, "ip": METRIC_IP}
+
+# every symbol include/mevi_b200.h declares: (restype, argtypes)
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SYMBOLS = {
+    "mevi_abi_version": (_i, []),
+    "mevi_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "mevi_ctx_destroy": (None, [_vp]),
+    "mevi_last_error": (C.c_char_p, [_vp]),
+    "mevi_device_info": (_i, [_vp, C.POINTER(_i64)]),
+    "mevi_rq_encode": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "mevi_rq_encode_host": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "mevi_kmeans_step": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "mevi_kmeans_update": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "mevi_residual_update": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp]),
+    "mevi_build_inverted_lists": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
+    "mevi_flat_ip_topk": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
+    "mevi_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "mevi_dense_scores": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+}
+
+
+class MeviError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.environ.get("MEVI_B200_LIB", os.path.join(_HERE, _LIB_NAME))
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library():
+    """Load libmevi_b200.so and bind every declared symbol.  Raises MeviError if
+    the library has not been built (`python -c 'import __graft_entry__ as g; g.build()'`
+    or `make -C mevi_b200/csrc`)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.isfile(path):
+            raise MeviError(
+                f"{path} not found: the CUDA extension is not built. Run `make -C mevi_b200/csrc` "
+                "(needs nvcc; cross-compiles for sm_100a). There is no CPU fallback."
+            )
+        lib = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        if lib.mevi_abi_version() != 1:
+            raise MeviError(f"ABI version mismatch: library reports {lib.mevi_abi_version()}, binding expects 1")
+        _lib = lib
+        return lib
+
+
+def _ptr(t) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+class Context:
+    """One library context per CUDA device (owns scratch memory)."""
+
+    def __init__(self, device: int):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise MeviError("no CUDA device visible: mevi_b200 has no CPU path")
+        self.lib = load_library()
+        self.device = int(device)
+        h = _vp()
+        rc = self.lib.mevi_ctx_create(self.device, C.byref(h))
+        if rc != 0 or not h.value:
+            raise MeviError(f"mevi_ctx_create(device={device}) failed with {rc}")
+        self.handle = h
+        info = (C.c_int64 * 8)()
+        self._check(self.lib.mevi_device_info(self.handle, info))
+        self.sm_count, self.cc = int(info[0]), (int(info[1]), int(info[2]))
+        self.total_mem, self.tensor_path, self.l2_bytes = int(info[3]), bool(info[4]), int(info[5])
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.mevi_ctx_destroy(self.handle)
+            self.handle = _vp()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.mevi_last_error(self.handle)
+            raise MeviError(f"libmevi_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+    def _stream(self) -> int:
+        import torch
+
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- helpers ----------------------------------------------------------
+    def _dev(self, t, dtype, name):
+        import torch
+
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device.index != self.device:
+            raise MeviError(f"{name} must be a CUDA tensor on device {self.device}")
+        if t.dtype != dtype:
+            raise MeviError(f"{name} must have dtype {dtype}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise MeviError(f"{name} must be contiguous")
+        return t
+
+    # ---- RQ encode --------------------------------------------------------
+    def rq_encode(self, X, codebook, metric="l2", mode="auto", codes=None, residual=None, return_stats=False):
+        """X [n,d] fp32 cuda, codebook [M,K,d] fp32 cuda -> codes [n,M] int32 cuda."""
+        import torch
+
+        X = self._dev(X, torch.float32, "X")
+        cb = self._dev(codebook, torch.float32, "codebook")
+        n, d = X.shape
+        M, K, d2 = cb.shape
+        if d2 != d:
+            raise MeviError(f"codebook width {d2} != embedding width {d}")
+        if codes is None:
+            codes = torch.empty((n, M), dtype=torch.int32, device=X.device)
+        else:
+            self._dev(codes, torch.int32, "codes")
+        if residual is not None:
+            self._dev(residual, torch.float32, "residual")
+        stats = torch.zeros(8, dtype=torch.int64, device=X.device) if return_stats else None
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_rq_encode(self.handle, _ptr(X), n, d, _ptr(cb), M, K, _METRICS[metric], _MODES[mode],
+                                        _ptr(codes), _ptr(residual), _ptr(stats), self._stream())
+            )
+        return (codes, stats) if return_stats else codes
+
+    def rq_encode_host(self, X_host, codebook_host, codes_host, metric="l2", mode="auto", chunk_rows=0):
+        """numpy fp32 [n,d] (any host memory, pinned is faster) -> numpy int32 [n,M], streamed through the GPU."""
+        import numpy as np
+
+        assert X_host.dtype == np.float32 and X_host.flags.c_contiguous
+        assert codebook_host.dtype == np.float32 and codebook_host.flags.c_contiguous
+        assert codes_host.dtype == np.int32 and codes_host.flags.c_contiguous
+        n, d = X_host.shape
+        M, K, _ = codebook_host.shape
+        stats = np.zeros(8, dtype=np.int64)
+        self._check(
+            self.lib.mevi_rq_encode_host(self.handle, X_host.ctypes.data, n, d, codebook_host.ctypes.data, M, K,
+                                         _METRICS[metric], _MODES[mode], codes_host.ctypes.data, int(chunk_rows),
+                                         stats.ctypes.data)
+        )
+        return stats
+
+    def rq_encode_host_ptr(self, x_ptr, n, d, cb_ptr, M, K, codes_ptr, metric="l2", mode="auto", chunk_rows=0, stats_ptr=None):
+        self._check(
+            self.lib.mevi_rq_encode_host(self.handle, x_ptr, n, d, cb_ptr, M, K, _METRICS[metric], _MODES[mode],
+                                         codes_ptr, int(chunk_rows), stats_ptr)
+        )
+
+    # ---- k-means ----------------------------------------------------------
+    def kmeans_step(self, R, centroids, sums_counts, assign=None, assign_stride=1, inertia=None, mode="auto"):
+        import torch
+
+        R = self._dev(R, torch.float32, "R")
+        c = self._dev(centroids, torch.float32, "centroids")
+        self._dev(sums_counts, torch.float32, "sums_counts")
+        n, d = R.shape
+        K = c.shape[0]
+        assert sums_counts.numel() == K * d + K
+        if assign is not None:
+            assert assign.dtype == torch.int32 and assign.is_cuda
+        if inertia is not None:
+            assert inertia.dtype == torch.float64 and inertia.is_cuda
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_kmeans_step(self.handle, _ptr(R), n, d, _ptr(c), K, _MODES[mode], _ptr(assign),
+                                          int(assign_stride), _ptr(sums_counts), _ptr(inertia), self._stream())
+            )
+
+    def kmeans_update(self, sums_counts, centroids, n_empty=None):
+        import torch
+
+        K, d = centroids.shape
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_kmeans_update(self.handle, _ptr(sums_counts), K, d, _ptr(centroids), _ptr(n_empty),
+                                            self._stream())
+            )
+
+    def residual_update(self, R, centroids, assign, assign_stride=1):
+        import torch
+
+        n, d = R.shape
+        K = centroids.shape[0]
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_residual_update(self.handle, _ptr(R), n, d, _ptr(centroids), K, _ptr(assign),
+                                              int(assign_stride), self._stream())
+            )
+
+    # ---- inverted lists / re-rank ------------------------------------------
+    def build_inverted_lists(self, codes, K):
+        import torch
+
+        codes = self._dev(codes, torch.int32, "codes")
+        n, M = codes.shape
+        docids = torch.empty(n, dtype=torch.int32, device=codes.device)
+        keys = torch.empty(n, dtype=torch.int64, device=codes.device)
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_build_inverted_lists(self.handle, _ptr(codes), n, M, int(K), _ptr(docids), _ptr(keys),
+                                                   self._stream())
+            )
+        return docids, keys
+
+    def cluster_rerank(self, Q, D, leaf_offsets, leaf_docids, query_leaves, k, id_base=0):
+        import torch
+
+        Q = self._dev(Q, torch.float32, "Q")
+        D = self._dev(D, torch.float32, "D")
+        lo = self._dev(leaf_offsets, torch.int64, "leaf_offsets")
+        ld = self._dev(leaf_docids, torch.int32, "leaf_docids")
+        ql = self._dev(query_leaves, torch.int32, "query_leaves")
+        nq, d = Q.shape
+        n = D.shape[0]
+        L = ql.shape[1]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
+        ncand = torch.empty((nq,), dtype=torch.int32, device=Q.device)
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_cluster_rerank(self.handle, _ptr(Q), nq, _ptr(D), n, d, _ptr(lo), lo.numel() - 1, _ptr(ld),
+                                             _ptr(ql), L, int(k), int(id_base), _ptr(scores), _ptr(ids), _ptr(ncand),
+                                             self._stream())
+            )
+        return scores, ids, ncand
+
+    def flat_ip_topk(self, Q, D, k, id_base=0, mode="auto"):
+        import torch
+
+        Q = self._dev(Q, torch.float32, "Q")
+        D = self._dev(D, torch.float32, "D")
+        nq, d = Q.shape
+        n = D.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_flat_ip_topk(self.handle, _ptr(Q), nq, _ptr(D), n, d, int(k), int(id_base), _MODES[mode],
+                                           _ptr(scores), _ptr(ids), self._stream())
+            )
+        return scores, ids
+
+    def topk_merge(self, scores_in, ids_in):
+        """[S,nq,k] lists -> merged [nq,k] (score desc, id asc; -1 padded)."""
+        import torch
+
+        s = self._dev(scores_in, torch.float32, "scores_in")
+        i = self._dev(ids_in, torch.int64, "ids_in")
+        S, nq, k = s.shape
+        scores = torch.empty((nq, k), dtype=torch.float32, device=s.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=s.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_topk_merge(self.handle, _ptr(s), _ptr(i), S, nq, k, _ptr(scores), _ptr(ids), self._stream()))
+        return scores, ids
+
+    def dense_scores(self, Q, P):
+        import torch
+
+        Q = self._dev(Q, torch.float32, "q_reps")
+        P = self._dev(P, torch.float32, "p_reps")
+        nq, d = Q.shape
+        n = P.shape[0]
+        out = torch.empty((nq, n), dtype=torch.float32, device=Q.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_dense_scores(self.handle, _ptr(Q), nq, _ptr(P), n, d, _ptr(out), self._stream()))
+        return out
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def get_context(device: Optional[int] = None) -> Context:
+    import torch
+
+    if not torch.cuda.is_available():
+        raise MeviError("no CUDA device visible: mevi_b200 has no CPU path")
+    if device is None:
+        device = torch.cuda.current_device()
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]

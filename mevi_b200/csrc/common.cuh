@@ -1,0 +1,126 @@
+// common.cuh — context, error plumbing and warp helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mevi_b200.h"
+
+#define MEVI_WARP 32
+#define MEVI_FULL_MASK 0xffffffffu
+
+enum WsSlot {
+  WS_RQ_PREP = 0,   // tensor path: packed fp16 codebook image, norms, gram
+  WS_RQ_WORK,       // tensor path: flagged-row worklist
+  WS_KM_PARTIAL,    // k-means: per-CTA partial sums
+  WS_KM_ASSIGN,     // k-means: assignment scratch when the caller passes none
+  WS_TOPK_PART,     // re-rank / flat: per-split partial top-k lists
+  WS_TOPK_AUX,      // flat: thresholds, counters, candidate buffers
+  WS_SORT_TMP,      // inverted lists: radix sort temp
+  WS_SORT_KEYS,     // inverted lists: unsorted keys / ids
+  WS_HOST_STAGE_A,  // device staging for the host-buffer encode (double buffered)
+  WS_HOST_STAGE_B,
+  WS_HOST_CODES_A,
+  WS_HOST_CODES_B,
+  WS_MISC,
+  WS_NUM
+};
+
+struct mevi_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  size_t l2_bytes = 0;
+  std::string err;
+  void* ws[WS_NUM] = {nullptr};
+  size_t ws_bytes[WS_NUM] = {0};
+  void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t pinned_bytes[4] = {0, 0, 0, 0};
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* tmap_encode_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
+};
+
+int mevi_set_error(mevi_ctx* ctx, int code, const char* fmt, ...);
+// grow-on-demand scratch; returns nullptr (and sets the error) on failure
+void* mevi_ws(mevi_ctx* ctx, int slot, size_t bytes);
+void* mevi_pinned(mevi_ctx* ctx, int slot, size_t bytes);
+
+#define MEVI_CHECK_CTX(ctx) \
+  do {                      \
+    if (!(ctx)) return MEVI_ERR_INVALID; \
+  } while (0)
+
+#define MEVI_CUDA(ctx, expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return mevi_set_error((ctx), MEVI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define MEVI_REQUIRE(ctx, cond, ...)                                        \
+  do {                                                                      \
+    if (!(cond)) return mevi_set_error((ctx), MEVI_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// streaming 128-bit load that does not allocate in L1 (row data read exactly once)
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(MEVI_FULL_MASK, v, o);
+  return v;
+}
+
+// (score desc, id asc) ordering used by every top-k in the library
+__device__ __forceinline__ bool topk_before(float sa, int64_t ia, float sb, int64_t ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+// shared-memory bitonic sort of n (power of two) (score,id) pairs into topk_before order
+template <typename IdT>
+__device__ __forceinline__ void block_bitonic_sort(float* s, IdT* id, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          bool up = ((i & k) == 0);
+          float a = s[i], b = s[ixj];
+          IdT ia = id[i], ib = id[ixj];
+          bool a_first = topk_before(a, (int64_t)ia, b, (int64_t)ib);
+          if (a_first != up) {
+            s[i] = b; s[ixj] = a;
+            id[i] = ib; id[ixj] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}

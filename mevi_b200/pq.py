@@ -1,0 +1,384 @@
+"""Drop-in `ProductQuantization` for the RQ path of MEVI/pq.py, backed by libmevi_b200.
+
+Same constructor, method names, argument meaning, side effects (`self.codebook`,
+`self.last_preds`, `self.get_preds`) and on-disk formats as the reference
+(MEVI/pq.py:15-741) for the shipped configuration: `pq_type='rq'`,
+`dist_mode in ('l2','ip')`, `pq_init_method in ('none','kmeans')`.  The hot
+arithmetic runs in hand-written CUDA kernels through the C ABI
+(include/mevi_b200.h); PyTorch only owns memory, streams and the process
+group.  Out-of-scope branches of the reference (pq/opq quantisers, 'iptol2',
+faiss index import/export, EMA codebook update, tied NCI centroids) raise
+NotImplementedError instead of silently doing something else.
+
+Differences that are deliberate:
+  * codebook training is full-batch Lloyd, data-parallel over the row blocks of
+    pq.py:218-225, with ONE all-reduce of the fused [K*d+K] sums|counts buffer
+    per iteration, instead of sklearn MiniBatchKMeans on rank 0
+    (pq.py:449,557-563).  Codebooks therefore differ from sklearn's; encode
+    parity is always defined given a codebook.
+  * every rank takes part in `initialize` when torch.distributed is initialised
+    (the reference parks ranks 1.. behind the broadcast at pq.py:483-484).
+"""
+from __future__ import annotations
+
+import os.path as osp
+from collections import defaultdict
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+from .dist_utils import shard_bounds
+
+
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+class ProductQuantization(nn.Module):
+    # MEVI/pq.py:16-80
+    def __init__(
+        self,
+        pq_type: str = "pq",
+        subvector_num: int = 32,
+        subvector_bits: int = 8,
+        dist_mode: str = "ip",
+        emb_size: int = 768,
+        pq_init_method: str = "faiss",
+        pq_update_method: str = "grad",
+        tie_nci_pq_centroid: int = 0,
+        lm_head: nn.Parameter = None,
+        centroid_update_loss: str = "none",
+        rq_topk_score: str = "prod",
+    ):
+        super().__init__()
+        assert pq_type in ("pq", "opq", "rq")
+        assert dist_mode in ("ip", "l2", "iptol2")
+        if pq_type != "rq":
+            raise NotImplementedError(
+                f"mevi_b200 implements the RQ branch of MEVI/pq.py only (pq_type={pq_type!r} is out of scope, SURVEY §8f.4)"
+            )
+        if dist_mode == "iptol2":
+            raise NotImplementedError("dist_mode='iptol2' is out of scope (SURVEY §8f.4)")
+        if tie_nci_pq_centroid:
+            raise NotImplementedError("tie_nci_pq_centroid couples the codebook to the T5 lm_head: out of scope")
+        if pq_update_method == "ema":
+            raise NotImplementedError("EMA codebook update (pq.py:371-433) is out of scope (SURVEY §8f.4)")
+        self.pq_type = pq_type
+        self.subvector_num = subvector_num
+        self.subvector_bits = subvector_bits
+        self.subvector_cents = 2 ** subvector_bits
+        self.dist_mode = dist_mode
+        self.emb_size = emb_size
+        self.pq_init_method = pq_init_method
+        self.pq_update_method = pq_update_method
+        self.tie_nci_pq_centroid = tie_nci_pq_centroid
+        self.centroid_update_loss = centroid_update_loss
+        self.rq_topk_score = rq_topk_score
+        self.get_preds = False
+        self.last_dim = emb_size  # pq.py:50-54 (rq: full width)
+        # pq.py:67-68 — a CPU float Parameter [M, K, d]
+        self.codebook = nn.Parameter(
+            torch.empty(subvector_num, self.subvector_cents, emb_size), requires_grad=(pq_update_method == "grad")
+        ).type(torch.FloatTensor)
+        # knobs of the B200 trainer / encoder (not in the reference signature)
+        self.kernel_mode = "auto"  # 'auto' | 'exact' | 'tensor'
+        self.lloyd_iters = 25
+        self.lloyd_tol = 1e-7
+        self.init_sample = 16384
+        self.device_index: Optional[int] = None
+
+    # ------------------------------------------------------------------ #
+    def _ctx(self) -> "_lib.Context":
+        return _lib.get_context(self.device_index)
+
+    def rq_minus_centroids(self, embeddings, centroids):  # pq.py:121-122
+        return embeddings - centroids[..., : self.last_dim]
+
+    def compute_scores(self, a, b):  # pq.py:124-131 (API compatibility; the kernels do this on the device)
+        if self.dist_mode == "ip":
+            result = a * b
+        else:
+            result = -((a - b) ** 2)
+        return torch.sum(result, dim=-1)
+
+    def get_codebook(self):  # pq.py:133-141
+        return self.codebook
+
+    def fix(self):  # pq.py:435-438
+        self.codebook.requires_grad_(False)
+
+    # ------------------------------------------------------------------ #
+    # encode                                                             #
+    # ------------------------------------------------------------------ #
+    @torch.no_grad()
+    def get_rq_document_cluster(self, doc_embeddings, cluster: torch.Tensor, start: int, ending: int, rank: int,
+                                batch_size: int = 1024):
+        """pq.py:281-305.  Fills `cluster` (int32 [ending-start, M]) in place.
+        `doc_embeddings` may be an np.ndarray / np.memmap (streamed host->device
+        in pinned chunks, pq.py:283's shard copy never materialises on the host)
+        or a CUDA tensor (encoded in place on the device).  `batch_size` is
+        accepted for signature compatibility; batching is the kernel's business."""
+        ctx = self._ctx()
+        cb = self.get_codebook().detach()
+        if isinstance(doc_embeddings, torch.Tensor) and doc_embeddings.is_cuda:
+            x = doc_embeddings[start:ending].contiguous().float()
+            codes = ctx.rq_encode(x, cb.to(x.device).contiguous(), metric=self.dist_mode, mode=self.kernel_mode)
+            cluster.copy_(codes.to(cluster.device))
+            return
+        part = np.asarray(doc_embeddings[start:ending]) if not isinstance(doc_embeddings, np.memmap) else doc_embeddings[start:ending]
+        if part.dtype != np.float32 or not part.flags.c_contiguous:
+            part = np.ascontiguousarray(part, dtype=np.float32)
+        assert cluster.dtype == torch.int32 and cluster.is_contiguous() and not cluster.is_cuda
+        cb_host = np.ascontiguousarray(cb.cpu().numpy(), dtype=np.float32)
+        self.last_encode_stats = ctx.rq_encode_host(part, cb_host, cluster.numpy(), metric=self.dist_mode,
+                                                    mode=self.kernel_mode)
+
+    @torch.no_grad()
+    def get_document_cluster(self, doc_embeddings, rank: int, nrank: int, batch_size: int = 1024,
+                             return_mapping: bool = False):
+        """pq.py:216-247: row block of this rank, encode, then the
+        {code tuple -> [doc ids]} / {doc id -> code tuple} dictionaries."""
+        num_docs = doc_embeddings.shape[0]
+        start, ending = shard_bounds(num_docs, rank, nrank)
+        cluster = torch.empty((ending - start, self.subvector_num), dtype=torch.int32)
+        self.get_rq_document_cluster(doc_embeddings, cluster, start, ending, rank, batch_size)
+        doc_cluster, new_mapping = codes_to_dicts(cluster.numpy(), start, return_mapping)
+        print("Number of document clusters:", len(doc_cluster))
+        if return_mapping:
+            return doc_cluster, new_mapping
+        return doc_cluster
+
+    @torch.no_grad()
+    def get_document_cluster_simple(self, return_mapping: bool = False):
+        """pq.py:200-214: dictionaries from the codes the trainer kept in `last_preds`."""
+        assert self.get_preds
+        cluster, mapping = codes_to_dicts(np.asarray(self.last_preds), 0, True)
+        del self.last_preds
+        self.get_preds = False
+        if return_mapping:
+            return cluster, mapping
+        return cluster
+
+    # ------------------------------------------------------------------ #
+    # build                                                              #
+    # ------------------------------------------------------------------ #
+    @torch.no_grad()
+    def initialize(self, index_file, doc_emb, rank, seed, pq_cluster_path, encode_batch_size):
+        """pq.py:440-486."""
+        if self.pq_init_method == "none":
+            return
+        if self.pq_init_method == "faiss":
+            raise NotImplementedError("pq_init_method='faiss' (faiss ResidualQuantizer import) is out of scope")
+        if self.pq_init_method == "avg":
+            raise NotImplementedError("pq_init_method='avg' is out of scope")
+        assert self.pq_init_method.endswith("kmeans")
+        use_file = index_file is not None and osp.isfile(index_file)
+        if not use_file:
+            self.get_preds = True
+        if use_file:
+            if rank == 0:
+                print("Intializing codebook with torch file...")
+                tensor = torch.load(index_file, map_location="cpu")
+                self.codebook.copy_(tensor)
+                del tensor
+            if _dist_on():
+                self._broadcast_codebook()
+        else:
+            print("Intializing codebook by kmeans clustering...")
+            self.unsupervised_update_codebook_manually(doc_emb, seed, self.pq_init_method)
+            if rank == 0 and index_file is not None:
+                torch.save(self.codebook, index_file)  # pq.py:469-470: the Parameter itself
+
+    def _broadcast_codebook(self):
+        # pq.py:483-484; NCCL needs a device buffer
+        if dist.get_backend() == "nccl":
+            buf = self.codebook.data.cuda()
+            dist.broadcast(buf, 0)
+            self.codebook.data.copy_(buf.cpu())
+        else:
+            dist.broadcast(self.codebook.data, 0)
+
+    @torch.no_grad()
+    def unsupervised_update_codebook(self, doc_emb, rank, seed, align=False):
+        """pq.py:526-542."""
+        if align:
+            raise NotImplementedError("align_codebook (pq.py:600-611) is out of scope")
+        if self.pq_update_method == "faiss":
+            raise NotImplementedError("pq_update_method='faiss' is out of scope")
+        if self.pq_update_method.endswith("kmeans"):
+            self.get_preds = True
+            self.unsupervised_update_codebook_manually(doc_emb, seed, self.pq_update_method)
+
+    @torch.no_grad()
+    def unsupervised_update_codebook_manually(self, doc_emb, seed, kmeans_method):
+        """pq.py:550-598, rq branch: per level k-means on the current residual,
+        then residual -= centers[pred] (skipped after the last level, 591-593);
+        sets `self.codebook` and `self.last_preds` (codes of every row, on rank 0).
+
+        Full-batch Lloyd on the device, sharded over ranks (see module docstring)."""
+        print("Updating codebook using KMeans...")
+        if kmeans_method != "kmeans":
+            raise NotImplementedError(f"kmeans_method={kmeans_method!r} (pq.py:564-565 raises too)")
+        from .trainer import train_rq_lloyd
+
+        codebook, codes_all = train_rq_lloyd(
+            doc_emb,
+            M=self.subvector_num,
+            K=self.subvector_cents,
+            seed=int(seed),
+            iters=self.lloyd_iters,
+            tol=self.lloyd_tol,
+            init_sample=self.init_sample,
+            mode=self.kernel_mode,
+            device_index=self.device_index,
+            metric=self.dist_mode,
+        )
+        self.last_preds = codes_all  # np.int32 [N, M] on rank 0 (None elsewhere)
+        self.last_train_info = getattr(train_rq_lloyd, "last_info", None)
+        with torch.no_grad():
+            self.codebook.copy_(codebook.cpu())
+
+    # ------------------------------------------------------------------ #
+    # leaf producer                                                      #
+    # ------------------------------------------------------------------ #
+    @torch.no_grad()
+    def beam_search(self, doc_emb: torch.Tensor, num_return_sequences, num_beams=None, do_sample=False,
+                    return_proba=False):
+        """pq.py:613-713, rq branch.  Runs on whatever device `doc_emb` lives on
+        (tensor ops only — the leaf producer is not on the timed path, SURVEY
+        §2.4 C6).  Returns labels int64 [bs, beams, M] (+ beam scores)."""
+        if num_beams is None:
+            num_beams = num_return_sequences
+        if do_sample:
+            raise NotImplementedError("do_sample=True (torch.multinomial branch, pq.py:686-688) is out of scope")
+        codebook = self.get_codebook().detach().to(doc_emb.device)
+        K = self.subvector_cents
+        bs = doc_emb.size(0)
+        beam_scores = doc_emb.new_ones(bs, 1)
+        temp_embed = doc_emb.unsqueeze(1).clone()
+        temp_index = torch.zeros((bs, 1, 1), device=doc_emb.device, dtype=torch.int32)
+        for i in range(self.subvector_num):
+            cur_codebook = codebook[i : i + 1].expand(bs, -1, -1).unsqueeze(1)
+            proba = self.compute_scores(temp_embed.unsqueeze(-2), cur_codebook)
+            proba = F.softmax(proba, dim=-1)
+            if self.rq_topk_score == "prod":
+                proba = beam_scores.unsqueeze(-1) * proba
+            proba = proba.view(bs, -1)
+            prev = beam_scores.size(1)
+            beam_of = torch.div(torch.arange(prev * K, device=doc_emb.device), K, rounding_mode="floor")
+            code_of = torch.arange(K, device=doc_emb.device).repeat(prev)
+            if num_beams < proba.size(1):
+                _, top = proba.topk(num_beams, dim=-1)
+                prev_beams = beam_of[top].unsqueeze(-1)
+                cur_code = code_of[top]
+                beam_scores = proba.gather(1, top)
+                temp_index = torch.cat(
+                    [temp_index.gather(1, prev_beams.expand(-1, -1, temp_index.size(-1))), cur_code.unsqueeze(-1)], dim=-1)
+                if i != self.subvector_num - 1:
+                    temp_embed = temp_embed.gather(1, prev_beams.expand(-1, -1, temp_embed.size(-1))) \
+                        - codebook[i][cur_code][..., : self.last_dim]
+            else:
+                beam_scores = proba
+                temp_index = torch.cat(
+                    [temp_index.repeat_interleave(K, dim=1), code_of.unsqueeze(-1).unsqueeze(0).expand(bs, -1, -1)], dim=-1)
+                if i != self.subvector_num - 1:
+                    temp_embed = temp_embed.repeat_interleave(K, dim=1) - codebook[i][code_of][..., : self.last_dim]
+        assert beam_scores.size(1) == num_beams
+        topk_label = temp_index[:, :, 1:]
+        if return_proba:
+            return topk_label, beam_scores
+        return topk_label
+
+    @torch.no_grad()
+    def get_topk_document_mapping(self, doc_embeddings, rank: int, nrank: int, num_return_sequences: int,
+                                  batch_size: int = 1024):
+        """pq.py:715-741."""
+        num_docs = doc_embeddings.shape[0]
+        start, ending = shard_bounds(num_docs, rank, nrank)
+        out = torch.empty((ending - start, num_return_sequences, self.subvector_num), dtype=torch.int32, device="cpu")
+        dev = torch.device("cuda", self.device_index if self.device_index is not None else torch.cuda.current_device())
+        for i in range(start, ending, batch_size):
+            e = min(i + batch_size, ending)
+            cur = torch.tensor(np.asarray(doc_embeddings[i:e]), device=dev)
+            out[i - start : e - start] = self.beam_search(cur, num_return_sequences).to("cpu", torch.int32)
+        return out
+
+    # ------------------------------------------------------------------ #
+    # training-time forward (tensor ops; not on the index hot path)       #
+    # ------------------------------------------------------------------ #
+    def forward(self, vecs, return_loss=True):
+        """pq.py:307-369 (`forward_rq`): (proba [B,M,K], index [B,M], loss)."""
+        allproba, index = [], []
+        codebook = self.get_codebook()
+        use_rec = self.centroid_update_loss == "reconstruct"
+        errors = []
+        for i in range(self.subvector_num):
+            cur_codebook = codebook[i : i + 1].expand(vecs.size(0), -1, -1)
+            proba = self.compute_scores(vecs.unsqueeze(-2), cur_codebook)
+            part_index = proba.max(dim=-1)[1]
+            allproba.append(proba)
+            index.append(part_index)
+            cur_centroid = codebook[i][part_index]
+            if use_rec:
+                errors.append(vecs.detach() - cur_centroid)
+            if i != self.subvector_num - 1:
+                vecs = vecs - cur_centroid.detach()
+        proba = torch.stack(allproba, dim=1)
+        index = torch.stack(index, dim=1)
+        loss = (torch.stack(errors) ** 2).mean() if (return_loss and use_rec) else None
+        return proba, index, loss
+
+    def get_reconstruct_vector(self, index, codebook=None):
+        """pq.py:768-784, rq: sum of the selected centroids."""
+        if codebook is None:
+            codebook = self.get_codebook()[..., : self.last_dim]
+        assert index.dim() in (1, 2)
+        M = self.subvector_num
+        parts = [codebook[j][index[..., j]] for j in range(M)]
+        return torch.stack(parts, dim=-2).sum(dim=-2)
+
+
+def codes_to_dicts(codes: np.ndarray, start: int = 0, return_mapping: bool = True):
+    """The dictionaries of pq.py:236-242 from an int code table: python-int tuples,
+    doc ids ascending inside a leaf, leaves in order of first appearance (the
+    insertion order of the reference's defaultdict)."""
+    codes = np.asarray(codes)
+    n = codes.shape[0]
+    tuples = list(map(tuple, codes.tolist()))
+    doc_cluster = defaultdict(list)
+    for k, t in enumerate(tuples):
+        doc_cluster[t].append(k + start)
+    mapping = dict(zip(range(start, start + n), tuples)) if return_mapping else None
+    return dict(doc_cluster), mapping
+
+
+def _cli():
+    # MEVI/pq.py:802-827 keeps these flags; the reference's own __main__ reads an undefined
+    # `args.emb_size` (pq.py:825) and dies with AttributeError before doing anything.  Here the same
+    # flags build the RQ codebook on the device and save it (torch.save of the Parameter).
+    import argparse
+
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--embedding_path", type=str, required=True)
+    parser.add_argument("--save_path", type=str, required=True)
+    parser.add_argument("--dist_mode", type=str, default="l2")
+    parser.add_argument("--pq_type", type=str, default="rq")
+    parser.add_argument("--subvector_num", type=int, default=4)
+    parser.add_argument("--subvector_bits", type=int, default=4)
+    parser.add_argument("--dim", type=int, default=768)
+    parser.add_argument("--seed", type=int, default=41)
+    args = parser.parse_args()
+    assert args.dist_mode in ("l2", "ip", "iptol2")
+    assert args.pq_type in ("pq", "opq", "rq")
+    doc_embeddings = np.memmap(args.embedding_path, dtype=np.float32, mode="r").reshape(-1, args.dim)
+    pq = ProductQuantization(args.pq_type, args.subvector_num, args.subvector_bits, args.dist_mode, args.dim, "kmeans")
+    pq.initialize(args.save_path, doc_embeddings, 0, args.seed, None, 1024)
+
+
+if __name__ == "__main__":
+    _cli()

@@ -1,0 +1,123 @@
+"""Data-parallel full-batch Lloyd trainer for the RQ codebook.
+
+Replaces the rq branch of MEVI/pq.py:550-598 (sklearn MiniBatchKMeans on rank 0,
+residual subtraction in numpy) with the sharded form BASELINE.json's north star
+describes: every rank owns the row block of pq.py:218-225, runs the assignment
++ per-centroid sum/count kernels on it, and ONE all-reduce(SUM) of the fused
+[K*d + K] fp32 buffer per iteration (precedent: pq.py:396-397) gives all ranks
+identical new centroids — no broadcast needed afterwards.
+
+The compute backend is `mevi_b200._lib.Context` (CUDA kernels via the C ABI);
+the trainer itself only sequences kernels and collectives.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .dist_utils import dist_on, gather_rows_to_rank0, rank_world, shard_bounds
+
+
+def kmeanspp_init(sample: np.ndarray, K: int, rs: np.random.RandomState) -> np.ndarray:
+    """k-means++ seeding (D^2 sampling) on a small host sample, float64 arithmetic.
+    The reference seeds with sklearn's init='k-means++' (pq.py:559); this is the
+    textbook algorithm, seeded by `random_state=seed` like the reference."""
+    x = np.asarray(sample, dtype=np.float64)
+    n = x.shape[0]
+    centers = np.empty((K, x.shape[1]), dtype=np.float64)
+    first = int(rs.randint(n))
+    centers[0] = x[first]
+    d2 = ((x - centers[0]) ** 2).sum(1)
+    for k in range(1, K):
+        tot = d2.sum()
+        if not np.isfinite(tot) or tot <= 0:
+            idx = int(rs.randint(n))
+        else:
+            idx = int(np.searchsorted(np.cumsum(d2), rs.random_sample() * tot))
+            idx = min(idx, n - 1)
+        centers[k] = x[idx]
+        d2 = np.minimum(d2, ((x - centers[k]) ** 2).sum(1))
+    return centers.astype(np.float32)
+
+
+def _upload_rows(doc_emb, start: int, end: int, device: torch.device, chunk: int = 1 << 19) -> torch.Tensor:
+    if isinstance(doc_emb, torch.Tensor):
+        return doc_emb[start:end].to(device=device, dtype=torch.float32).clone()
+    n, d = end - start, doc_emb.shape[1]
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    for a in range(0, n, chunk):
+        b = min(a + chunk, n)
+        host = torch.from_numpy(np.ascontiguousarray(doc_emb[start + a : start + b], dtype=np.float32))
+        out[a:b].copy_(host, non_blocking=False)
+    return out
+
+
+@torch.no_grad()
+def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: float = 1e-7, init_sample: int = 16384,
+                   mode: str = "auto", device_index: Optional[int] = None, backend=None, metric: str = "l2",
+                   gather_codes: bool = True):
+    """Returns (codebook [M,K,d] fp32 tensor on the compute device, codes np.int32 [N,M] on rank 0 or None).
+    k-means is always L2 (as sklearn's in the reference), whatever `metric` the encoder uses later."""
+    be = backend if backend is not None else _lib.get_context(device_index)
+    dev = be.torch_device if backend is not None else torch.device("cuda", be.device)
+    rank, world = rank_world()
+    N, d = doc_emb.shape
+    start, end = shard_bounds(N, rank, world)
+    n = end - start
+    R = _upload_rows(doc_emb, start, end, dev)
+    codes = torch.zeros((n, M), dtype=torch.int32, device=dev)
+    codebook = torch.empty((M, K, d), dtype=torch.float32, device=dev)
+    buf = torch.empty(K * d + K, dtype=torch.float32, device=dev)
+    inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+    n_empty = torch.zeros(1, dtype=torch.int32, device=dev)
+    rs = np.random.RandomState(seed)
+    info = {"levels": [], "world": world, "rows_local": n}
+    for j in range(M):
+        t0 = time.time()
+        # ---- seeding on rank 0's shard, shared by broadcast -------------------
+        C = torch.empty((K, d), dtype=torch.float32, device=dev)
+        if rank == 0:
+            s = min(init_sample, n)
+            idx = np.sort(rs.choice(n, size=s, replace=False)) if s < n else np.arange(n)
+            sample = R[torch.from_numpy(idx).to(dev)].cpu().numpy()
+            C.copy_(torch.from_numpy(kmeanspp_init(sample, K, rs)).to(dev))
+        if dist_on():
+            dist.broadcast(C, 0)
+        prev = math.inf
+        n_it = 0
+        col = codes[:, j]
+        for it in range(iters):
+            be.kmeans_step(R, C, buf, assign=col, assign_stride=M, inertia=inertia, mode=mode)
+            if dist_on():
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+                dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+            be.kmeans_update(buf, C, n_empty)
+            n_it = it + 1
+            cur = float(inertia.item())
+            if prev - cur <= tol * max(cur, 1e-30):
+                prev = cur
+                break
+            prev = cur
+        # ---- labels from the FINAL centroids (sklearn's fit_predict does the same) ----
+        be.kmeans_step(R, C, buf, assign=col, assign_stride=M, inertia=inertia, mode=mode)
+        if dist_on():
+            dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+        codebook[j].copy_(C)
+        if j != M - 1:  # pq.py:591-593
+            be.residual_update(R, C, col, assign_stride=M)
+        info["levels"].append({"level": j, "iters": n_it, "inertia": float(inertia.item()),
+                               "mse": float(inertia.item()) / max(N, 1) / d, "seconds": time.time() - t0})
+    train_rq_lloyd.last_info = info
+    codes_all = None
+    if gather_codes:
+        counts = [shard_bounds(N, r, world)[1] - shard_bounds(N, r, world)[0] for r in range(world)]
+        g = gather_rows_to_rank0(codes, counts)
+        if g is not None:
+            codes_all = g.cpu().numpy()
+    return codebook, codes_all

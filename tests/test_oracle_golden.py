@@ -1,0 +1,117 @@
+"""The oracle (CPU restatement) against golden vectors minted by the UNMODIFIED reference
+(tests/golden/make_golden.py ran MEVI/pq.py in the authoring container)."""
+import numpy as np
+import torch
+
+from oracle import oracle
+
+
+def test_encode_matches_reference_codes(case):
+    codes = oracle.rq_encode(case.X, case.codebook, batch_size=128)
+    assert codes.dtype == np.int32 and codes.shape == (case.n, case.M)
+    assert (codes == case.codes).all()
+
+
+def test_encode_batch_size_and_shard_invariance(case):
+    a = oracle.rq_encode(case.X, case.codebook, batch_size=1024)
+    assert (a == case.codes).all()
+    half = case.n // 2
+    b0 = oracle.rq_encode(case.X, case.codebook, 0, half)
+    b1 = oracle.rq_encode(case.X, case.codebook, half, case.n)
+    assert (np.concatenate([b0, b1]) == case.codes).all()
+
+
+def test_second_reference_statement_agrees(case):
+    # gen_sampled_to_full.py:65-86 / forward_rq restated
+    assert (oracle.rq_encode_forward(case.X, case.codebook) == case.codes).all()
+
+
+def test_kmeans_fit_predict_codes_vs_reencode(case):
+    # sklearn's fit_predict labels (pq.py:587,595) equal a re-encode with the final codebook except at
+    # fp32 near-ties (GEMM-form vs direct-form distances); the generator recorded the mismatch count.
+    rep = oracle.classify_code_mismatches(case.X, case.codebook, case.last_preds, case.codes)
+    assert rep["n_mismatch"] == case.meta["preds_vs_codes_mismatch_rows"]
+    assert rep["n_hard"] == 0
+
+
+def test_ip_metric_codes(case):
+    codes = oracle.rq_encode(case.X, case.codebook, dist_mode="ip")
+    assert (codes == case.codes_ip).all()
+
+
+def test_cluster_and_mapping_dicts(case):
+    clus, mapping = oracle.document_cluster(case.codes)
+    ref_clus, ref_map = case.pickle("rqclus.pkl"), case.pickle("rqmapping.pkl")
+    assert clus == ref_clus and mapping == ref_map
+    assert list(clus.keys()) == list(ref_clus.keys())  # same insertion order -> same pickle bytes
+    assert len(clus) == case.meta["n_leaves"]
+    c2, m2 = oracle.document_cluster(case.last_preds)
+    assert c2 == case.pickle("rqclus_simple.pkl") and m2 == case.pickle("rqmapping_simple.pkl")
+    k0 = next(iter(ref_clus))
+    assert all(type(v) is int for v in k0) and type(ref_clus[k0][0]) is int
+
+
+def test_beam_search(case):
+    for nb in (10, 100):
+        lab_ref = case.load(f"beam{nb}_labels.npy")
+        sc_ref = case.load(f"beam{nb}_scores.npy")
+        lab, sc = oracle.beam_search(torch.tensor(case.codebook), torch.tensor(case.Q), nb)
+        assert lab.dtype == torch.int64 and tuple(lab.shape) == lab_ref.shape
+        assert (lab.numpy() == lab_ref).all()
+        np.testing.assert_allclose(sc.numpy(), sc_ref, rtol=1e-6, atol=0)
+
+
+def test_codebook_file_is_a_parameter(case):
+    assert isinstance(case.codebook_param, torch.nn.Parameter)
+    assert tuple(case.codebook_param.shape) == (case.M, case.K, case.d)
+    assert case.codebook_param.dtype == torch.float32
+
+
+def test_tie_rule_on_synthetic_duplicates():
+    # duplicated centroids: argmax returns the lowest index (SURVEY §7 "Hard parts")
+    rs = np.random.RandomState(0)
+    X = rs.standard_normal((64, 32)).astype(np.float32)
+    cb = rs.standard_normal((2, 8, 32)).astype(np.float32)
+    cb[0, 7] = cb[0, 3]
+    codes = oracle.rq_encode(X, cb)
+    assert not (codes[:, 0] == 7).any()
+    flipped = codes.copy()
+    rows = np.nonzero(codes[:, 0] == 3)[0]
+    flipped[rows, 0] = 7
+    rep = oracle.classify_code_mismatches(X, cb, codes, flipped)
+    assert rep["n_mismatch"] == len(rows) and rep["n_hard"] == 0
+    wrong = codes.copy()
+    wrong[:, 0] = (wrong[:, 0] + 1) % 8
+    rep = oracle.classify_code_mismatches(X, cb, codes, wrong)
+    assert rep["n_hard"] > 0
+
+
+def test_flat_ip_oracle_properties():
+    rs = np.random.RandomState(3)
+    Q = rs.standard_normal((7, 48)).astype(np.float32)
+    D = rs.standard_normal((500, 48)).astype(np.float32)
+    s, i = oracle.flat_ip_topk(Q, D, 20, block=128)
+    full = Q @ D.T
+    for q in range(7):
+        order = np.lexsort((np.arange(500), -full[q]))[:20]
+        assert (i[q] == order).all()
+        np.testing.assert_allclose(s[q], full[q][order], rtol=1e-6)
+    s, i = oracle.flat_ip_topk(Q, D[:5], 8)
+    assert (i[:, 5:] == -1).all() and np.isneginf(s[:, 5:]).all() and i.dtype == np.int64 and s.dtype == np.float32
+
+
+def test_rerank_oracle_against_bruteforce(gauss):
+    clus, _ = oracle.document_cluster(gauss.codes)
+    dec = gauss.load("beam10_labels.npy")[:8]
+    res = oracle.cluster_rerank(gauss.Q[:8], gauss.X, clus, dec, batch_size=64)
+    for qi, (docs, scores, ndoc) in enumerate(res):
+        cand = [d for leaf in dec[qi] for d in clus.get(tuple(int(v) for v in leaf), [])]
+        assert ndoc == len(cand) and len(docs) == len(cand)
+        assert sorted(docs.tolist()) == sorted(cand)
+        assert (np.diff(scores) <= 0).all()
+        np.testing.assert_allclose(scores, (gauss.X[docs] @ gauss.Q[qi]), rtol=1e-4, atol=1e-4)
+
+
+def test_text_formats():
+    assert oracle.faiss_result_line("q", [3, 1], [np.float32(0.1), np.float32(2.0)]) == "q\t\t3,1\t0.10000000149011612,2.0"
+    assert oracle.hn_result_line("q", "", [5], [np.float32(1.5)]) == "q\t\t5\t1.5"
