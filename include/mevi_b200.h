@@ -55,7 +55,8 @@ int mevi_ctx_create(int device, mevi_ctx** out);
 void mevi_ctx_destroy(mevi_ctx* ctx);
 const char* mevi_last_error(mevi_ctx* ctx);
 /* info[0]=SM count, [1]=cc major, [2]=cc minor, [3]=total global memory bytes,
- * [4]=1 if the tcgen05 path is usable on this device (cc 10.x), [5]=L2 bytes */
+ * [4]=1 if the tcgen05 path is usable on this device (cc 10.x), [5]=L2 bytes,
+ * [6]=kernels this context has launched so far (its own kernels; library sorts excluded) */
 int mevi_device_info(mevi_ctx* ctx, int64_t info[8]);
 
 /* ---- RQ encode ---------------------------------------------------------- *

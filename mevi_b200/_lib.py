@@ -104,6 +104,13 @@ class Context:
         self.sm_count, self.cc = int(info[0]), (int(info[1]), int(info[2]))
         self.total_mem, self.tensor_path, self.l2_bytes = int(info[3]), bool(info[4]), int(info[5])
 
+    @property
+    def launches(self) -> int:
+        """Kernels this context has launched so far (mevi_device_info info[6])."""
+        info = (C.c_int64 * 8)()
+        self._check(self.lib.mevi_device_info(self.handle, info))
+        return int(info[6])
+
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             self.lib.mevi_ctx_destroy(self.handle)

@@ -118,7 +118,7 @@ int mevi_device_info(mevi_ctx* ctx, int64_t info[8]) {
   info[3] = (int64_t)ctx->total_mem;
   info[4] = (ctx->cc_major == 10) ? 1 : 0;
   info[5] = (int64_t)ctx->l2_bytes;
-  info[6] = 0;
+  info[6] = ctx->launches;
   info[7] = 0;
   return MEVI_OK;
 }

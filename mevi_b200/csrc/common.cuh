@@ -42,12 +42,15 @@ struct mevi_ctx {
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   void* tmap_encode_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
+  int64_t launches = 0;            // kernels launched by this context (reported by mevi_device_info)
 };
 
 int mevi_set_error(mevi_ctx* ctx, int code, const char* fmt, ...);
 // grow-on-demand scratch; returns nullptr (and sets the error) on failure
 void* mevi_ws(mevi_ctx* ctx, int slot, size_t bytes);
 void* mevi_pinned(mevi_ctx* ctx, int slot, size_t bytes);
+
+#define MEVI_COUNT_LAUNCH(ctx, n) ((ctx)->launches += (n))
 
 #define MEVI_CHECK_CTX(ctx) \
   do {                      \

@@ -58,5 +58,6 @@ extern "C" int mevi_dense_scores(mevi_ctx* ctx, const float* Q, int nq, const fl
   else if (d <= 768) dense_scores_kernel<6><<<grid, 256, 0, st>>>(Q, nq, P, n, d, out);
   else dense_scores_kernel<8><<<grid, 256, 0, st>>>(Q, nq, P, n, d, out);
   MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
   return MEVI_OK;
 }

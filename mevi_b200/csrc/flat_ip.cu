@@ -210,6 +210,7 @@ extern "C" int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const fl
   for (int attempt = 0; attempt < 2; ++attempt) {
     const bool safe = attempt == 1;
     flat_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(stt, nq);
+    MEVI_COUNT_LAUNCH(ctx, 1);
     MEVI_CUDA(ctx, cudaGetLastError());
     const int64_t first = ((capg - k) / FT_BN) * FT_BN;  // a chunk this small can never overflow
     int64_t chunk = first;
@@ -223,9 +224,11 @@ extern "C" int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const fl
       } else {
         dim3 grid((unsigned)((end - pos + FT_BN - 1) / FT_BN), (unsigned)((nq + FT_BM - 1) / FT_BM));
         flat_tile_kernel<<<grid, FT_THREADS, 0, st>>>(Q, nq, D, pos, end, d, stt);
+        MEVI_COUNT_LAUNCH(ctx, 1);
         MEVI_CUDA(ctx, cudaGetLastError());
       }
       flat_compact_kernel<<<nq, 256, smem_compact, st>>>(stt, k, capg);
+      MEVI_COUNT_LAUNCH(ctx, 1);
       MEVI_CUDA(ctx, cudaGetLastError());
       pos = end;
       if (!safe) {
@@ -243,6 +246,7 @@ extern "C" int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const fl
     if (safe) return mevi_set_error(ctx, MEVI_ERR_CUDA, "flat search candidate buffer overflowed in safe mode");
   }
   flat_emit_kernel<<<nq, 128, 0, st>>>(stt, nq, k, id_base, scores, ids);
+  MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   return MEVI_OK;
 }

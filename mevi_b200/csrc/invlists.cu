@@ -44,6 +44,7 @@ extern "C" int mevi_build_inverted_lists(mevi_ctx* ctx, const int32_t* codes, in
   }
   int grid = ctx->sm_count * 8;
   leaf_key_kernel<<<grid, 256, 0, st>>>(codes, n, M, K, keys_in, rows_in);
+  MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   size_t tmp_bytes = 0;
   MEVI_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, sorted_keys, rows_in, sorted_docids,

@@ -285,11 +285,13 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
     int threads = 256;
     int blocks = (int)((kd + K + threads - 1) / threads);
     kmeans_reduce_partials_kernel<<<blocks, threads, 0, st>>>(ps, pc, G, K, d, sums_counts);
+    MEVI_COUNT_LAUNCH(ctx, 2);
     MEVI_CUDA(ctx, cudaGetLastError());
   } else {
     MEVI_CUDA(ctx, cudaMemsetAsync(sums_counts, 0, (size_t)(kd + K) * sizeof(float), st));
     int grid = ctx->sm_count * 8;
     kmeans_accumulate_atomic_kernel<<<grid, 256, 0, st>>>(R, n, d, assign, stride, K, sums_counts, sums_counts + kd);
+    MEVI_COUNT_LAUNCH(ctx, 1);
     MEVI_CUDA(ctx, cudaGetLastError());
   }
   return MEVI_OK;
@@ -306,6 +308,7 @@ int mevi_kmeans_update(mevi_ctx* ctx, const float* sums_counts, int K, int d, fl
   int threads = 256;
   int blocks = (int)((kd + threads - 1) / threads);
   kmeans_update_kernel<<<blocks, threads, 0, st>>>(sums_counts, K, d, centroids, n_empty_or_null);
+  MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   return MEVI_OK;
 }
@@ -319,6 +322,7 @@ int mevi_residual_update(mevi_ctx* ctx, float* R, int64_t n, int d, const float*
   if (n <= 0) return MEVI_OK;
   int grid = ctx->sm_count * 16;
   residual_update_kernel<<<grid, 256, 0, st>>>(R, n, d / 4, centroids, K, assign, assign_stride);
+  MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   return MEVI_OK;
 }

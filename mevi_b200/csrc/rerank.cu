@@ -242,6 +242,7 @@ int mevi_topk_merge_launch(mevi_ctx* ctx, const float* in_s, const int64_t* in_i
   const size_t smem = (size_t)cap * (sizeof(int64_t) + sizeof(float));
   MEVI_CUDA(ctx, cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<nq, 256, smem, st>>>(in_s, in_i, S, nq, k, cap, list_stride, shard_stride, out_s, out_i);
+  MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   return MEVI_OK;
 }
@@ -290,6 +291,7 @@ int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, i
   else if (d <= 768) e = launch_rerank<6>(p, smem, st);
   else e = launch_rerank<8>(p, smem, st);
   if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "rerank launch: %s", cudaGetErrorString(e));
+  MEVI_COUNT_LAUNCH(ctx, 1);
   if (S > 1) {
     // lists of one query are contiguous: [q][s][k]  -> shard_stride = k, list_stride = S*k
     return mevi_topk_merge_launch(ctx, p.out_scores, p.out_ids, S, nq, k, (int64_t)S * k, (int64_t)k, scores, ids, st);

@@ -37,6 +37,7 @@ int encode_dispatch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float
   if (rc != MEVI_OK) return rc;
   if (stats_accum) {
     stats_add_kernel<<<1, 32, 0, st>>>(stats_accum, 0, n);
+    MEVI_COUNT_LAUNCH(ctx, 1);
     MEVI_CUDA(ctx, cudaGetLastError());
   }
   return MEVI_OK;

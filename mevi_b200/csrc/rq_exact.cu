@@ -226,5 +226,6 @@ int mevi_rq_exact_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const 
   else if (d <= 768) e = launch_exact<6, 4>(p, ctx->sm_count, st);
   else e = launch_exact<8, 2>(p, ctx->sm_count, st);
   if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "rq_encode_exact launch: %s", cudaGetErrorString(e));
+  MEVI_COUNT_LAUNCH(ctx, 1);
   return MEVI_OK;
 }

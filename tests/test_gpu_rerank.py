@@ -1,0 +1,96 @@
+"""Inverted lists, cluster-restricted re-rank, top-k merge and dense scorer parity."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from gpu_util import assert_topk_equivalent, ctx, dev
+
+pytestmark = pytest.mark.gpu
+
+
+def test_inverted_lists_equal_reference_dicts(case):
+    from mevi_b200.rerank import ClusterIndex
+
+    idx = ClusterIndex.from_codes(case.codes, case.K)
+    clus, mapping = idx.to_dicts()
+    ref_clus, ref_map = case.pickle("rqclus.pkl"), case.pickle("rqmapping.pkl")
+    assert clus == ref_clus and mapping == ref_map  # same content (dict order differs: sorted by key here)
+    idx2 = ClusterIndex.from_cluster_dict(ref_clus, case.K)
+    assert torch.equal(idx2.leaf_keys, idx.leaf_keys) and torch.equal(idx2.leaf_offsets, idx.leaf_offsets)
+    assert torch.equal(idx2.leaf_docids, idx.leaf_docids)
+
+
+@pytest.mark.parametrize("nb,k", [(10, 100), (100, 100), (10, 1000), (100, 7)])
+def test_rerank_matches_oracle(case, nb, k):
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    dec = case.load(f"beam{nb}_labels.npy")
+    clus = case.pickle("rqclus.pkl")
+    rr = ClusterReranker(dev(case.X), ClusterIndex.from_codes(case.codes, case.K))
+    scores, ids, ncand = rr.rerank(case.Q, dec, topk=k)
+    scores, ids, ncand = scores.cpu().numpy(), ids.cpu().numpy(), ncand.cpu().numpy()
+    ref = oracle.cluster_rerank(case.Q, case.X, clus, dec, topk=k)
+    s_ref = np.full((len(ref), k), -np.inf, np.float32)
+    i_ref = np.full((len(ref), k), -1, np.int64)
+    for q, (d_, s_, nd) in enumerate(ref):
+        s_ref[q, : len(s_)] = s_
+        i_ref[q, : len(d_)] = d_
+        assert ncand[q] == nd
+    X64, Q64 = case.X.astype(np.float64), case.Q.astype(np.float64)
+    assert_topk_equivalent(scores, ids, s_ref, i_ref, rtol=1e-5, atol=1e-4,
+                           pool_scores=lambda q, doc: float(X64[doc] @ Q64[q]))
+    assert (np.diff(np.where(np.isfinite(scores), scores, -1e30), axis=1) <= 0).all()
+
+
+def test_rerank_split_path_and_empty_leaves(gauss):
+    """Few queries -> several CTAs per query + merge; leaves that hold no document are legal."""
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    dec = gauss.load("beam100_labels.npy")[:2].copy()
+    dec[0, :50] = 31  # (31,31,31,31) almost surely empty
+    clus = gauss.pickle("rqclus.pkl")
+    rr = ClusterReranker(dev(gauss.X), ClusterIndex.from_codes(gauss.codes, gauss.K))
+    scores, ids, ncand = rr.rerank(gauss.Q[:2], dec, topk=50)
+    ref = oracle.cluster_rerank(gauss.Q[:2], gauss.X, clus, dec, topk=50)
+    for q, (d_, s_, nd) in enumerate(ref):
+        assert int(ncand[q]) == nd
+        kk = len(d_)
+        np.testing.assert_allclose(scores[q, :kk].cpu().numpy(), s_, rtol=1e-5, atol=1e-4)
+        assert (ids[q, kk:] == -1).all()
+    # a query whose leaves are all empty
+    dec2 = np.full((1, 10, gauss.M), 31, dtype=np.int64)
+    s2, i2, n2 = rr.rerank(gauss.Q[:1], dec2, topk=10)
+    assert int(n2[0]) == 0 and (i2 == -1).all() and torch.isinf(s2).all()
+
+
+def test_topk_merge_matches_numpy():
+    rs = np.random.RandomState(2)
+    S, nq, k = 8, 37, 100
+    s = rs.standard_normal((S, nq, k)).astype(np.float32)
+    s[:, :, 10:12] = 0.5  # exact score ties across shards -> id order decides
+    i = rs.permutation(S * nq * k).reshape(S, nq, k).astype(np.int64)
+    s[3, :, 90:] = -np.inf
+    i[3, :, 90:] = -1
+    ms, mi = ctx().topk_merge(dev(s), dev(i))
+    for q in range(nq):
+        fs, fi = s[:, q].ravel(), i[:, q].ravel()
+        keep = fi >= 0
+        order = np.lexsort((fi[keep], -fs[keep]))[:k]
+        assert np.array_equal(mi[q].cpu().numpy(), fi[keep][order])
+        assert np.array_equal(ms[q].cpu().numpy(), fs[keep][order])
+
+
+def test_dense_scorer_matches_torch_matmul(gauss):
+    from mevi_b200.document_encoder import DocumentEncoder
+
+    enc = DocumentEncoder()
+    P = dev(gauss.X[:1024])
+    q = dev(gauss.Q[0])
+    out = enc.generate(q, p_reps=P).scores
+    assert tuple(out.shape) == (1024,)
+    ref = torch.matmul(torch.tensor(gauss.Q[0]), torch.tensor(gauss.X[:1024]).transpose(0, 1))  # document_encoder.py:132
+    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
+    out2 = enc.compute_similarity(dev(gauss.Q[:5]), P)
+    np.testing.assert_allclose(out2.cpu().numpy(), gauss.Q[:5] @ gauss.X[:1024].T, rtol=1e-5, atol=1e-4)
+    assert torch.equal(enc.compute_similarity(dev(gauss.Q[:3]), P[:3], bmm=True), torch.sum(dev(gauss.Q[:3]) * P[:3], -1))

@@ -1,0 +1,109 @@
+"""Host-side logic that needs no GPU: sharding rule, dictionaries, text formats, constructor surface."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+
+def test_shard_bounds_is_the_reference_rule():
+    from mevi_b200.dist_utils import shard_bounds
+
+    for n in (0, 1, 7, 8841823, 21015324):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            per = n // world  # pq.py:219-224
+            for r, (s, e) in enumerate(spans):
+                assert s == per * r and e == (n if r + 1 == world else s + per)
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_codes_to_dicts_matches_reference_pickles(case):
+    from mevi_b200.pq import codes_to_dicts
+
+    clus, mapping = codes_to_dicts(case.codes, 0, True)
+    ref_clus, ref_map = case.pickle("rqclus.pkl"), case.pickle("rqmapping.pkl")
+    assert clus == ref_clus and mapping == ref_map
+    assert list(clus) == list(ref_clus) and list(mapping) == list(ref_map)
+    import pickle
+
+    assert pickle.dumps(clus) == pickle.dumps(ref_clus) and pickle.dumps(mapping) == pickle.dumps(ref_map)
+    # offset start (sharded ranks)
+    c2, m2 = codes_to_dicts(case.codes[100:200], 100, True)
+    assert all(m2[i] == ref_map[i] for i in range(100, 200))
+
+
+def test_constructor_surface_and_out_of_scope_branches():
+    from mevi_b200.pq import ProductQuantization
+
+    pq = ProductQuantization("rq", 4, 5, "l2", 768, "kmeans", "grad")
+    assert tuple(pq.codebook.shape) == (4, 32, 768) and pq.codebook.dtype == torch.float32
+    assert pq.subvector_cents == 32 and pq.last_dim == 768 and pq.get_preds is False
+    assert "codebook" in pq.state_dict()
+    for bad in (dict(pq_type="pq"), dict(pq_type="opq"), dict(pq_type="rq", dist_mode="iptol2"),
+                dict(pq_type="rq", pq_update_method="ema"), dict(pq_type="rq", tie_nci_pq_centroid=1)):
+        with pytest.raises(NotImplementedError):
+            ProductQuantization(**bad)
+
+
+def test_beam_search_mirror_matches_reference_golden(case):
+    from mevi_b200.pq import ProductQuantization
+
+    pq = ProductQuantization("rq", case.M, case.meta["bits"], "l2", case.d, "kmeans", "grad")
+    with torch.no_grad():
+        pq.codebook.copy_(torch.tensor(case.codebook))
+    for nb in (10, 100):
+        lab, sc = pq.beam_search(torch.tensor(case.Q), nb, return_proba=True)
+        assert lab.dtype == torch.int64
+        assert (lab.numpy() == case.load(f"beam{nb}_labels.npy")).all()
+        np.testing.assert_allclose(sc.numpy(), case.load(f"beam{nb}_scores.npy"), rtol=1e-6)
+
+
+def test_forward_mirror_matches_oracle(gauss):
+    from mevi_b200.pq import ProductQuantization
+
+    pq = ProductQuantization("rq", gauss.M, 5, "l2", gauss.d, "kmeans", "grad")
+    with torch.no_grad():
+        pq.codebook.copy_(torch.tensor(gauss.codebook))
+    proba, index, loss = pq.forward(torch.tensor(gauss.X[:256]))
+    assert tuple(proba.shape) == (256, gauss.M, gauss.K) and loss is None
+    assert (index.numpy() == gauss.codes[:256]).all()
+    rec = pq.get_reconstruct_vector(index)
+    ref = sum(torch.tensor(gauss.codebook[j])[index[:, j]] for j in range(gauss.M))
+    assert torch.allclose(rec, ref)
+
+
+def test_kmeanspp_seeding_is_seeded_and_spread():
+    from mevi_b200.trainer import kmeanspp_init
+
+    rs = np.random.RandomState(0)
+    centers = rs.standard_normal((8, 16)) * 10
+    x = (centers[rs.randint(0, 8, 2000)] + rs.standard_normal((2000, 16)) * 0.1).astype(np.float32)
+    a = kmeanspp_init(x, 8, np.random.RandomState(41))
+    b = kmeanspp_init(x, 8, np.random.RandomState(41))
+    assert np.array_equal(a, b) and a.dtype == np.float32
+    # one seed per well-separated blob
+    owner = ((a[:, None, :] - centers[None]) ** 2).sum(-1).argmin(1)
+    assert len(set(owner.tolist())) == 8
+
+
+def test_text_formats_match_reference_writers(tmp_path):
+    from mevi_b200 import faiss_search, rerank
+
+    dists = np.array([[1.5, 0.1], [2.25, -3.0]], dtype=np.float32)
+    ids = np.array([[7, 3], [1, -1]], dtype=np.int64)
+    qf = tmp_path / "q.tsv"
+    qf.write_text("what is x\t12\nwho is y\t13\n")
+    out = tmp_path / "o.txt"
+    faiss_search.to_file(str(qf), str(out), dists, ids)
+    lines = out.read_text().splitlines()
+    assert lines[0] == "what is x\t\t7,3\t1.5,0.10000000149011612"
+    assert lines[0] == oracle.faiss_result_line("what is x", ids[0], dists[0])
+    hn = rerank.hn_lines(["what is x", "who is y"], dists, ids)
+    assert hn[0] == oracle.hn_result_line("what is x", "", ids[0], dists[0])
+    assert hn[1] == "who is y\t\t1\t2.25"  # padding (-1) is not printed
+    arr = np.arange(12, dtype=np.float32).reshape(3, 4)
+    p = tmp_path / "emb.bin"
+    arr.tofile(p)
+    assert np.array_equal(faiss_search.read(str(p), 4), arr)
