@@ -308,24 +308,52 @@ def our_arm(args, rank, local_rank, world):
 
 def cpu_baseline_leg(X, cb_cpu):
     """Reference CPU arithmetic (oracle port of pq.py:281-305, batch 128) on a bounded sample of the
-    same corpus: ~10-30 s of CPU work."""
+    same corpus (~10-30 s of CPU work).  Runs in a CHILD process that never initialises CUDA: inside a
+    CUDA process every munmap of the 12.6 MB torch temporaries goes through the UVM notifier and the
+    CPU path runs ~10x slower than the reference would on its own."""
+    import tempfile
+
+    import numpy as np
+
+    S = int(min(1 << 18, X.shape[0]))
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(shm, f"mevi_bench_sample_{os.getpid()}.npy")
+    np.save(path, X[:S].cpu().numpy())
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-baseline-child", "--sample-file", path],
+                             capture_output=True, text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+
+
+def cpu_baseline_child(args):
+    import numpy as np
     import torch
 
     from oracle import oracle
 
-    probe = X[:16384].cpu().numpy()
-    oracle.rq_encode(probe[:4096], cb_cpu, batch_size=128)
+    sample = np.load(args.sample_file)
+    cb_cpu = load_codebook()
+    oracle.rq_encode(sample[:8192], cb_cpu, batch_size=128)  # warm-up (allocator, threads)
     t0 = time.perf_counter()
-    oracle.rq_encode(probe, cb_cpu, batch_size=128)
-    rate = 16384 / (time.perf_counter() - t0)
-    S = int(min(max(rate * 15.0, 32768), 1 << 20, X.shape[0]))
-    sample = X[:S].cpu().numpy()
+    oracle.rq_encode(sample[:32768], cb_cpu, batch_size=128)
+    rate = 32768 / (time.perf_counter() - t0)
+    reps = int(max(1, min(64, round(rate * 15.0 / len(sample)))))
     t0 = time.perf_counter()
-    oracle.rq_encode(sample, cb_cpu, batch_size=128)
+    for _ in range(reps):
+        oracle.rq_encode(sample, cb_cpu, batch_size=128)
     dt = time.perf_counter() - t0
-    return {"value": S / dt, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"first {S} rows of the bench corpus, torch CPU restatement of pq.py:281-305 (batch 128), {dt:.1f} s",
-            "host_cpus": os.cpu_count()}
+    print(json.dumps({"value": len(sample) * reps / dt, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": "port",
+                      "sample": f"first {len(sample)} rows of the bench corpus x {reps} passes, torch CPU restatement of "
+                                f"pq.py:281-305 (batch 128) in a CUDA-free child process, {dt:.1f} s",
+                      "host_cpus": os.cpu_count()}), flush=True)
 
 
 def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
@@ -443,7 +471,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "cpu-baseline-child"])
+    ap.add_argument("--sample-file", type=str, default=None)
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--docs", type=int, default=N_MARCO, help="rows per GPU (default: MSMARCO 8,841,823)")
     ap.add_argument("--flat-docs", type=int, default=1 << 20)
@@ -457,6 +486,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.impl == "cpu-baseline-child":
+        cpu_baseline_child(args)
         return
     if world != args.gpus:
         log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")

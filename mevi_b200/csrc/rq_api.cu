@@ -51,8 +51,8 @@ int mevi_rq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float*
   MEVI_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
-  MEVI_REQUIRE(ctx, codebook && codes && (X || n == 0), "NULL argument");
   MEVI_REQUIRE(ctx, n >= 0 && n < (int64_t)2147483647, "n out of range");
+  MEVI_REQUIRE(ctx, codebook && ((codes && X) || n == 0), "NULL argument");
   MEVI_REQUIRE(ctx, metric == MEVI_METRIC_L2 || metric == MEVI_METRIC_IP, "unknown metric %d", metric);
   if (stats_or_null) MEVI_CUDA(ctx, cudaMemsetAsync(stats_or_null, 0, 8 * sizeof(int64_t), st));
   if (n == 0) return MEVI_OK;
