@@ -34,8 +34,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must never hang the GPU (a hang costs the whole box).  Returns false
 // after ~2^28 polls (seconds); callers then set the kernel's error flag and bail out.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 28); ++i)
     if (mbar_try_wait(bar, parity)) return true;
+  return false;
+}
+
+// Same, with a back-off between polls: for roles that are not on the critical path (they would
+// otherwise steal issue slots from the converter warps sharing their scheduler).
+__device__ __forceinline__ bool mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return true;
+  for (uint32_t i = 0; i < (1u << 24); ++i) {
+    __nanosleep(ns);
+    if (mbar_try_wait(bar, parity)) return true;
+  }
   return false;
 }
 

@@ -220,7 +220,14 @@ int mevi_rq_exact_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const 
   p.work_rows = work_rows; p.work_levels = work_levels; p.n_work_dev = n_work_dev; p.n_items = n_items;
   p.inertia = inertia;
   cudaError_t e;
-  if (d <= 128) e = launch_exact<1, 4>(p, ctx->sm_count, st);
+  if (work_rows) {
+    // sparse re-decision of flagged rows: one row per warp, light on registers -> many warps per SM
+    if (d <= 128) e = launch_exact<1, 1>(p, ctx->sm_count * 2, st);
+    else if (d <= 256) e = launch_exact<2, 1>(p, ctx->sm_count * 2, st);
+    else if (d <= 512) e = launch_exact<4, 1>(p, ctx->sm_count * 2, st);
+    else if (d <= 768) e = launch_exact<6, 1>(p, ctx->sm_count * 2, st);
+    else e = launch_exact<8, 1>(p, ctx->sm_count * 2, st);
+  } else if (d <= 128) e = launch_exact<1, 4>(p, ctx->sm_count, st);
   else if (d <= 256) e = launch_exact<2, 4>(p, ctx->sm_count, st);
   else if (d <= 512) e = launch_exact<4, 4>(p, ctx->sm_count, st);
   else if (d <= 768) e = launch_exact<6, 4>(p, ctx->sm_count, st);

@@ -57,7 +57,7 @@ enum { C_SC = 0, C_SX, C_INV, C_INV_SX2, C_FX, C_FC, C_NUM = 8 };
 struct Params {
   const float* X; int64_t n; int d; int nchunks;
   int M, K, NT, N1, metric;
-  const __half* Bimg; const float* cn2; const float* cnorm; const float* gram; const float* consts;
+  const __half* Bimg; const float* cn2; const float* e1; const float* lvl; const float* gram; const float* consts;
   int gram_floats;
   int32_t* codes; int64_t codes_stride;
   int32_t* work_rows; int32_t* work_levels; unsigned long long* work_count;
@@ -66,7 +66,7 @@ struct Params {
 };
 
 struct SmemLayout {
-  int a_off, b_off, gram_off, cn2_off, cnorm_off, stats_off, bar_off, holder_off, total;
+  int a_off, b_off, gram_off, cn2_off, cnorm_off, lvl_off, stats_off, bar_off, holder_off, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int M, int K, int NT, int N1) {
   SmemLayout L;
@@ -77,22 +77,145 @@ __host__ __device__ inline SmemLayout smem_layout(int M, int K, int NT, int N1) 
   for (int j = 1; j < M; ++j) gram_pad += j * K * (K + 1);
   L.cn2_off = L.gram_off + gram_pad * 4;
   L.cnorm_off = L.cn2_off + NT * 4;
-  L.stats_off = L.cnorm_off + NT * 4;
+  L.lvl_off = L.cnorm_off + NT * 4;
+  L.stats_off = L.lvl_off + 4 * 4 * 4;
   L.bar_off = (L.stats_off + 2 * TM * 4 + 7) & ~7;
   L.holder_off = L.bar_off + (2 * NSA + 2 * NSB + 6) * 8;
   L.total = L.holder_off + 16;
   return L;
 }
 
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// register budgets per warpgroup after setmaxnreg (launch allocates 128 x 512 = 65536):
+//   control warps 0-3: 56, converter warps 4-11: 168, epilogue warps 12-15: 112  -> 64,512 registers
+constexpr int REGS_CTRL = 56, REGS_CONV = 168, REGS_EPI = 112;
+
+
+// Converter warp: streams this CTA's tiles chunk by chunk.  Lane (half, l16) of warp cw owns rows
+// 2*(cw+8q)+half (q = 0..7) and the 16 bytes at float column 4*l16 of every 64-wide chunk: one
+// LDG.128 per q covers two full 256-byte row pieces per warp.  Three register buffers rotate so two
+// chunks (64 KB per SM) are always in flight while the third is being converted.
+template <bool SCALE>
+__device__ __forceinline__ void converter_loop(const Params& p, uint8_t* sA, float* sStats, uint64_t* a_full,
+                                               uint64_t* a_empty, uint64_t* acc_empty, uint64_t* st_full, int cw, int lane) {
+  const int half = lane >> 4, l16 = lane & 15;
+  const int rl0 = 2 * cw + half;  // row of q = 0; q adds 16 rows (same row & 7 -> same swizzle phase)
+  const float sx = p.consts[C_SX], inv_sx2 = p.consts[C_INV_SX2];
+  const int nchunks = p.nchunks;
+  const int64_t tile_stride = gridDim.x;
+  const int64_t qstride = (int64_t)16 * p.d;
+  // shared-memory byte offset of this lane's 8 bytes inside an operand tile (q = 0)
+  const uint32_t soff = (uint32_t)rl0 * 128u + ((uint32_t)((l16 >> 1) ^ (rl0 & 7)) << 4) + ((uint32_t)(l16 & 1) << 3);
+  const uint32_t sA_u32 = ptx::smem_u32(sA);
+
+  // load cursor
+  int64_t l_tile = blockIdx.x;
+  int l_c = 0;
+  const float* l_ptr = p.X + (l_tile * TM + rl0) * p.d + l16 * 4;
+  int l_valid = 0;  // number of q with a row inside the matrix for the cursor's tile
+  auto set_valid = [&]() {
+    const int64_t left = p.n - (l_tile * TM + rl0);  // rows from this lane's first row to the end
+    l_valid = l_tile < p.n_tiles ? (left <= 0 ? 0 : (left >= 128 ? 8 : (int)((left + 15) >> 4))) : -1;
+  };
+  set_valid();
+  auto load_chunk = [&](float4 (&v)[8]) {
+    if (l_valid < 0) return;  // past the last tile
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < l_valid) v[q] = ld_stream_f4(l_ptr + q * qstride);
+    }
+    if (++l_c == nchunks) {
+      l_c = 0;
+      l_tile += tile_stride;
+      l_ptr = p.X + (l_tile * TM + rl0) * p.d + l16 * 4;
+      set_valid();
+    } else {
+      l_ptr += KC;
+    }
+  };
+
+  // process cursor
+  int64_t p_tile = blockIdx.x;
+  int p_c = 0;
+  uint32_t p_stage = 0, p_phase = 0, p_it = 0;
+  float norm[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) norm[q] = 0.f;
+  bool ok = true;
+  auto process_chunk = [&](const float4 (&v)[8]) {
+    if (p_tile >= p.n_tiles || !ok) return;
+    if (!ptx::mbar_wait(&a_empty[p_stage], p_phase ^ 1)) { atomicExch(p.err_flag, 4); ok = false; return; }
+    const uint32_t st_hi = sA_u32 + p_stage * A_STAGE_BYTES + soff;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float t0 = v[q].x, t1 = v[q].y, t2 = v[q].z, t3 = v[q].w;
+      if (SCALE) { t0 *= sx; t1 *= sx; t2 *= sx; t3 *= sx; }
+      norm[q] = fmaf(t0, t0, norm[q]);
+      norm[q] = fmaf(t1, t1, norm[q]);
+      norm[q] = fmaf(t2, t2, norm[q]);
+      norm[q] = fmaf(t3, t3, norm[q]);
+      const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+      const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+      const __half2 l01 = __floats2half2_rn(t0 - b01.x, t1 - b01.y), l23 = __floats2half2_rn(t2 - b23.x, t3 - b23.y);
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_hi + q * 2048), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                   "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(st_hi + A_TILE_BYTES + q * 2048),
+                   "r"(*reinterpret_cast<const uint32_t*>(&l01)), "r"(*reinterpret_cast<const uint32_t*>(&l23)) : "memory");
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&a_full[p_stage]);
+    if (++p_stage == NSA) { p_stage = 0; p_phase ^= 1; }
+    if (++p_c == nchunks) {
+      // tile finished: publish squared row norms for the epilogue
+      const uint32_t buf = p_it & 1, ph = (p_it >> 1) & 1;
+      if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 5); ok = false; return; }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float s = norm[q];
+        s += __shfl_xor_sync(MEVI_FULL_MASK, s, 8);
+        s += __shfl_xor_sync(MEVI_FULL_MASK, s, 4);
+        s += __shfl_xor_sync(MEVI_FULL_MASK, s, 2);
+        s += __shfl_xor_sync(MEVI_FULL_MASK, s, 1);
+        if (l16 == 0) sStats[buf * TM + rl0 + 16 * q] = SCALE ? s * inv_sx2 : s;
+        norm[q] = 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&st_full[buf]);
+      p_c = 0;
+      p_tile += tile_stride;
+      ++p_it;
+    }
+  };
+  float4 b0[8], b1[8], b2[8];
+  load_chunk(b0);
+  load_chunk(b1);
+  while (p_tile < p.n_tiles && ok) {
+    load_chunk(b2);
+    process_chunk(b0);
+    load_chunk(b0);
+    process_chunk(b1);
+    load_chunk(b1);
+    process_chunk(b2);
+  }
+}
+
+template <int M>
 __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemLayout L = smem_layout(p.M, p.K, p.NT, p.N1);
+  const SmemLayout L = smem_layout(M, p.K, p.NT, p.N1);
   uint8_t* sA = smem + L.a_off;
   uint8_t* sB = smem + L.b_off;
   float* sGram = reinterpret_cast<float*>(smem + L.gram_off);
   float* sCn2 = reinterpret_cast<float*>(smem + L.cn2_off);
-  float* sCnorm = reinterpret_cast<float*>(smem + L.cnorm_off);
-  float* sStats = reinterpret_cast<float*>(smem + L.stats_off);  // [2][TM] squared row norms
+  float* sE1 = reinterpret_cast<float*>(smem + L.cnorm_off);      // [NT] per-candidate error coefficient (x |x|)
+  float* sLvl = reinterpret_cast<float*>(smem + L.lvl_off);       // [M][4] per-level margin constants
+  float* sStats = reinterpret_cast<float*>(smem + L.stats_off);   // [2][TM] squared row norms
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NSA;
@@ -108,18 +231,16 @@ __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
   const uint32_t b_stage_bytes = (uint32_t)N1 * 128u;
 
   // ---- one-time setup ---------------------------------------------------------------------
-  {  // Gram table: global rows of K floats -> shared rows padded to K+1 (bank-conflict-free per-thread rows)
-    const int rows = p.gram_floats / K;
-    for (int i = tid; i < p.gram_floats; i += THREADS) {
-      const int r = i / K, c = i - r * K;
-      sGram[r * (K + 1) + c] = p.gram[i];
-    }
-    (void)rows;
-    for (int i = tid; i < NT; i += THREADS) {
-      sCn2[i] = p.cn2[i];
-      sCnorm[i] = p.cnorm[i];
-    }
+  // Gram table: global rows of K floats -> shared rows padded to K+1 (conflict-free per-thread rows)
+  for (int i = tid; i < p.gram_floats; i += THREADS) {
+    const int r = i / K, c = i - r * K;
+    sGram[r * (K + 1) + c] = p.gram[i];
   }
+  for (int i = tid; i < NT; i += THREADS) {
+    sCn2[i] = p.cn2[i];
+    sE1[i] = p.e1[i];
+  }
+  for (int i = tid; i < M * 4; i += THREADS) sLvl[i] = p.lvl[i];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSA; ++s) { ptx::mbar_init(&a_full[s], CONV_WARPS); ptx::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < NSB; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
@@ -136,23 +257,22 @@ __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
   const int64_t tile_stride = gridDim.x;
   const int nchunks = p.nchunks;
 
-  if (warp == 0) {
-    // ===== B producer =========================================================================
-    if (lane == 0) {
+  if (warp < 4) {
+    reg_dec<REGS_CTRL>();
+    if (warp == 0 && lane == 0) {
+      // ===== B producer: one bulk copy per K chunk of the pre-swizzled [C_hi|C_lo] image ==========
       uint32_t g = 0;
       bool ok = true;
       for (int64_t tile = first_tile; tile < p.n_tiles && ok; tile += tile_stride) {
         for (int c = 0; c < nchunks; ++c, ++g) {
           const uint32_t s = g % NSB, ph = (g / NSB) & 1;
-          if (!ptx::mbar_wait(&b_empty[s], ph ^ 1)) { atomicExch(p.err_flag, 1); ok = false; break; }
+          if (!ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 64)) { atomicExch(p.err_flag, 1); ok = false; break; }
           ptx::mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
           ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * N1 * KC, b_stage_bytes, &b_full[s]);
         }
       }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer ===========================================================================
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
+      // ===== MMA issuer ===========================================================================
       const uint32_t idesc_n1 = ptx::umma_idesc_f16_m128((uint32_t)N1);
       const uint32_t idesc_nt = ptx::umma_idesc_f16_m128((uint32_t)NT);
       uint32_t g = 0, it = 0;
@@ -182,143 +302,90 @@ __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
         if (ok) ptx::umma_commit(&acc_full[buf]);
       }
     }
-  } else if (warp >= CONV_WARP0 && warp < CONV_WARP0 + CONV_WARPS) {
+  } else if (warp < EPI_WARP0) {
     // ===== converters ===========================================================================
-    const int cw = warp - CONV_WARP0;
-    const int half = lane >> 4, l16 = lane & 15;
-    const float sx = p.consts[C_SX], inv_sx2 = p.consts[C_INV_SX2];
-    int64_t my_tiles = 0;
-    if (first_tile < p.n_tiles) my_tiles = (p.n_tiles - first_tile + tile_stride - 1) / tile_stride;
-    const int64_t total_chunks = my_tiles * nchunks;
-    float4 cur[8], nxt[8];
-    float norm[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) norm[q] = 0.f;
-
-    auto load_chunk = [&](int64_t gg, float4 (&v)[8]) {
-      const int64_t it = gg / nchunks;
-      const int c = (int)(gg - it * nchunks);
-      const int64_t row0 = (first_tile + it * tile_stride) * TM;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int64_t row = row0 + 2 * (cw + 8 * q) + half;
-        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < p.n) v[q] = ld_stream_f4(p.X + row * p.d + c * KC + l16 * 4);
-      }
-    };
-    bool ok = true;
-    if (total_chunks > 0) load_chunk(0, cur);
-    for (int64_t gg = 0; gg < total_chunks && ok; ++gg) {
-      if (gg + 1 < total_chunks) load_chunk(gg + 1, nxt);
-      const uint32_t sa = (uint32_t)(gg % NSA), pa = (uint32_t)((gg / NSA) & 1);
-      if (!ptx::mbar_wait(&a_empty[sa], pa ^ 1)) { atomicExch(p.err_flag, 4); ok = false; break; }
-      uint8_t* stage = sA + (size_t)sa * A_STAGE_BYTES;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int rl = 2 * (cw + 8 * q) + half;
-        const float t0 = cur[q].x * sx, t1 = cur[q].y * sx, t2 = cur[q].z * sx, t3 = cur[q].w * sx;
-        norm[q] = fmaf(t0, t0, norm[q]);
-        norm[q] = fmaf(t1, t1, norm[q]);
-        norm[q] = fmaf(t2, t2, norm[q]);
-        norm[q] = fmaf(t3, t3, norm[q]);
-        const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
-        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn(t0 - b01.x, t1 - b01.y), l23 = __floats2half2_rn(t2 - b23.x, t3 - b23.y);
-        const uint32_t off = (uint32_t)rl * 128u + ((uint32_t)((l16 >> 1) ^ (rl & 7)) << 4) + ((uint32_t)(l16 & 1) << 3);
-        uint2 hv, lv;
-        hv.x = *reinterpret_cast<const uint32_t*>(&h01);
-        hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-        lv.x = *reinterpret_cast<const uint32_t*>(&l01);
-        lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(stage + off) = hv;
-        *reinterpret_cast<uint2*>(stage + A_TILE_BYTES + off) = lv;
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&a_full[sa]);
-      const int64_t it = gg / nchunks;
-      if (gg - it * nchunks == nchunks - 1) {
-        // tile finished: publish squared row norms for the epilogue
-        const uint32_t buf = (uint32_t)(it & 1), ph = (uint32_t)((it >> 1) & 1);
-        if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 5); ok = false; break; }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float v = norm[q];
-          v += __shfl_xor_sync(MEVI_FULL_MASK, v, 8);
-          v += __shfl_xor_sync(MEVI_FULL_MASK, v, 4);
-          v += __shfl_xor_sync(MEVI_FULL_MASK, v, 2);
-          v += __shfl_xor_sync(MEVI_FULL_MASK, v, 1);
-          if (l16 == 0) sStats[buf * TM + 2 * (cw + 8 * q) + half] = v * inv_sx2;
-          norm[q] = 0.f;
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&st_full[buf]);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
-    }
-  } else if (warp >= EPI_WARP0) {
+    reg_inc<REGS_CONV>();
+    if (p.consts[C_SX] == 1.f)
+      converter_loop<false>(p, sA, sStats, a_full, a_empty, acc_empty, st_full, warp - CONV_WARP0, lane);
+    else
+      converter_loop<true>(p, sA, sStats, a_full, a_empty, acc_empty, st_full, warp - CONV_WARP0, lane);
+  } else {
     // ===== epilogue ===============================================================================
+    reg_dec<REGS_EPI>();
     const int ew = warp - EPI_WARP0;  // == warp % 4: TMEM lanes 32*ew .. 32*ew+31
     const int rl = ew * 32 + lane;
-    const float inv = p.consts[C_INV], fx = p.consts[C_FX], fc = p.consts[C_FC];
+    const float m2inv = (p.metric == MEVI_METRIC_L2 ? -2.f : -1.f) * p.consts[C_INV];
     const bool l2 = p.metric == MEVI_METRIC_L2;
     double inertia_acc = 0.0;
     uint32_t it = 0;
     bool ok = true;
     for (int64_t tile = first_tile; tile < p.n_tiles && ok; tile += tile_stride, ++it) {
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      if (!ptx::mbar_wait(&acc_full[buf], ph) || !ptx::mbar_wait(&st_full[buf], ph)) { atomicExch(p.err_flag, 6); ok = false; break; }
+      if (!ptx::mbar_wait_backoff(&acc_full[buf], ph, 96) || !ptx::mbar_wait_backoff(&st_full[buf], ph, 32)) { atomicExch(p.err_flag, 6); ok = false; break; }
       ptx::tc_fence_after_sync();
       const float xn2 = sStats[buf * TM + rl];
-      const float xn = sqrtf(xn2);
+      const float xn = sqrtf(xn2), nxn = -xn;
       const uint32_t taddr = tmem_base + buf * TMEM_BUF_COLS + ((uint32_t)(ew * 32) << 16);
       const int64_t row = tile * TM + rl;
-      int code[8];
+      int code[M];
       int flag_level = -1;
       float last_best = 0.f;
-      int goff = 0;  // offset of level j's Gram block inside sGram
-      for (int j = 0; j < p.M; ++j) {
-        float best = CUDART_INF_F, second = CUDART_INF_F, best_err = 0.f, second_err = 0.f;
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        // Gram block of level j starts after the blocks of levels 1..j-1: sum_{t<j} t*K rows
+        const float* gj = sGram + (j * (j - 1) / 2) * K * (K + 1);
+        const float* grow[M > 1 ? M - 1 : 1];
+#pragma unroll
+        for (int m = 0; m < j; ++m) grow[m] = gj + (m * K + code[m]) * (K + 1);
+        // best by distance; (u1,u2) = two smallest LOWER bounds u_k = d_k - |x| E1_k over all candidates
+        float m1 = CUDART_INF_F, ub = CUDART_INF_F, eb = 0.f, u1 = CUDART_INF_F, u2 = CUDART_INF_F;
         int besti = 0;
         for (int k0 = 0; k0 < K; k0 += 32) {
           uint32_t rm[32], rc[32];
           ptx::tmem_ld32(taddr + j * K + k0, rm);
           ptx::tmem_ld32(taddr + NT + j * K + k0, rc);
           ptx::tmem_ld_wait();
+          float dk[32];
+          float c1 = CUDART_INF_F;
 #pragma unroll
           for (int kk = 0; kk < 32; ++kk) {
-            const int k = k0 + kk;
-            const float a = (__uint_as_float(rm[kk]) + __uint_as_float(rc[kk])) * inv;
+            float base = l2 ? sCn2[j * K + k0 + kk] : 0.f;
             float g = 0.f;
-            for (int m = 0; m < j; ++m) g += sGram[goff + (m * K + code[m]) * (K + 1) + k];
-            const float cnk = sCnorm[j * K + k];
-            const float dot = a - g;
-            const float dist = l2 ? fmaf(-2.f, dot, sCn2[j * K + k]) : -dot;
-            // bound on |dot - exact|: contraction + representation floors + fp32 epilogue arithmetic
-            const float err = U_REL * xn * cnk + fx * cnk + fc * xn + 2.4e-7f * (fabsf(a) + fabsf(g) + (l2 ? sCn2[j * K + k] : 0.f));
-            if (dist < best) {
-              second = best; second_err = best_err;
-              best = dist; best_err = err; besti = k;
-            } else if (dist < second) {
-              second = dist; second_err = err;
-            }
+#pragma unroll
+            for (int m = 0; m < j; ++m) g += grow[m][k0 + kk];
+            base = l2 ? fmaf(2.f, g, base) : g;
+            // dist = |c|^2 - 2 (x.c - g)  (L2)   or   -(x.c - g)  (IP)
+            dk[kk] = fmaf(__uint_as_float(rm[kk]) + __uint_as_float(rc[kk]), m2inv, base);
+            c1 = fminf(c1, dk[kk]);
+            const float u = fmaf(nxn, sE1[j * K + k0 + kk], dk[kk]);
+            u2 = fminf(u2, fmaxf(u1, u));
+            u1 = fminf(u1, u);
+          }
+          int ci = 0;
+#pragma unroll
+          for (int kk = 31; kk >= 0; --kk)
+            if (dk[kk] == c1) ci = kk;  // lowest index among equals
+          if (c1 < m1) {
+            m1 = c1;
+            besti = k0 + ci;
+            eb = xn * sE1[j * K + besti];
+            ub = fmaf(nxn, sE1[j * K + besti], c1);
           }
         }
         code[j] = besti;
-        const float margin = (l2 ? 2.f : 1.f) * (best_err + second_err);
-        const bool clear = (second - best) > margin;  // NaN/inf -> not clear -> exact path decides
+        // the best candidate's own lower bound is u1 unless another candidate undercuts it
+        const float other_lo = (ub == u1) ? u2 : u1;
+        const bool clear = other_lo > m1 + eb + sLvl[j * 4 + 1];  // inf/NaN -> not clear -> exact kernel decides
         if (!clear && flag_level < 0) flag_level = j;
-        last_best = best;
-        goff += j > 0 ? j * K * (K + 1) : 0;
-        if (j == 0) goff = 0;
+        last_best = m1;
       }
       if (row < p.n) {
         int32_t* dst = p.codes + row * p.codes_stride;
-        if (p.M == 4 && p.codes_stride == 4) {
-          *reinterpret_cast<int4*>(dst) = make_int4(code[0], code[1], code[2], code[3]);
+        if (M == 4 && p.codes_stride == 4) {
+          *reinterpret_cast<int4*>(dst) = make_int4(code[0], code[M > 1 ? 1 : 0], code[M > 2 ? 2 : 0], code[M > 3 ? 3 : 0]);
         } else {
-          for (int j = 0; j < p.M; ++j) dst[j] = code[j];
+#pragma unroll
+          for (int j = 0; j < M; ++j) dst[j] = code[j];
         }
         if (flag_level >= 0) {
           const unsigned long long slot = atomicAdd(p.work_count, 1ull);
@@ -437,6 +504,43 @@ __global__ void gram_kernel(const float* __restrict__ cb, int M, int K, int d, f
   if ((threadIdx.x & 31) == 0) gram[e] = (float)s;
 }
 
+
+// Error model of the prefilter (all in distance units; f = 2 for L2 where dist = |c|^2 - 2 dot, 1 for IP):
+//   |dist_k - exact| <= |x| * E1_k + B_j/2,
+//   E1_k = f (U_REL + EPS_A) |c_k| + f Fc      contraction error + fp16 floor of the codebook + fp32 epilogue
+//   B_j  = 2 [ f Fx cmax_j + EPS_A (c2max_j + f j gmax_j) ]   fp16 floor of x + roundings of |c|^2 and Gram terms
+// A (row, level) is decided by the prefilter only if  d_other - |x| E1_other > d_best + |x| E1_best + B_j
+// for every other candidate; otherwise the exact kernel re-decides it.  One block per level.
+__global__ void level_consts_kernel(const float* __restrict__ cnorm, const float* __restrict__ cn2,
+                                    const float* __restrict__ gram, int M, int K, int metric,
+                                    const float* __restrict__ consts, float* __restrict__ e1, float* __restrict__ lvl) {
+  const int j = blockIdx.x, lane = threadIdx.x;
+  const float f = metric == MEVI_METRIC_L2 ? 2.f : 1.f;
+  const float EPS_A = 4.8e-7f;  // 2^-21
+  float cmax = 0.f, c2max = 0.f, gmax = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float cn = cnorm[j * K + k];
+    cmax = fmaxf(cmax, cn);
+    c2max = fmaxf(c2max, cn2[j * K + k]);
+    e1[j * K + k] = f * (U_REL + EPS_A) * cn + f * consts[C_FC];
+  }
+  if (j > 0) {
+    const float* gj = gram + (size_t)(j * (j - 1) / 2) * K * K;
+    for (int i = lane; i < j * K * K; i += 32) gmax = fmaxf(gmax, fabsf(gj[i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    cmax = fmaxf(cmax, __shfl_xor_sync(MEVI_FULL_MASK, cmax, o));
+    c2max = fmaxf(c2max, __shfl_xor_sync(MEVI_FULL_MASK, c2max, o));
+    gmax = fmaxf(gmax, __shfl_xor_sync(MEVI_FULL_MASK, gmax, o));
+  }
+  if (lane == 0) {
+    lvl[j * 4 + 0] = 0.f;
+    lvl[j * 4 + 1] = 2.f * (f * consts[C_FX] * cmax + EPS_A * (c2max + f * (float)j * gmax));
+    lvl[j * 4 + 2] = cmax;
+    lvl[j * 4 + 3] = gmax;
+  }
+}
+
 __global__ void finish_stats_kernel(const unsigned long long* work_count, int64_t rows, int64_t* stats) {
   if (threadIdx.x == 0 && blockIdx.x == 0 && stats) {
     atomicAdd((unsigned long long*)&stats[0], *work_count);
@@ -467,7 +571,7 @@ __global__ void residual_from_codes_kernel(const float* __restrict__ X, int64_t 
 bool mevi_rq_tensor_supported(mevi_ctx* ctx, int d, int M, int K, int metric) {
   if (!ctx || ctx->cc_major != 10) return false;
   if (d < KC || d % KC != 0 || d > 8192) return false;
-  if (M < 1 || M > 8 || K < 32 || K % 32 != 0) return false;
+  if (M < 1 || M > 4 || K < 32 || K % 32 != 0) return false;
   const int NT = M * K;
   if (NT > 128 || NT % 16 != 0) return false;
   if (metric != MEVI_METRIC_L2 && metric != MEVI_METRIC_IP) return false;
@@ -496,7 +600,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t o_consts = take(C_NUM * 4), o_abs = take(8), o_err = take(4), o_cnt = take(8), o_cn2 = take(NT * 4),
-               o_cnorm = take(NT * 4), o_gram = take((size_t)(gram_floats ? gram_floats : 1) * 4),
+               o_cnorm = take(NT * 4), o_e1 = take(NT * 4), o_lvl = take(8 * 4 * 4), o_gram = take((size_t)(gram_floats ? gram_floats : 1) * 4),
                o_bimg = take((size_t)nchunks * N1 * KC * 2);
   char* ws = (char*)mevi_ws(ctx, WS_RQ_PREP, off);
   if (!ws) return MEVI_ERR_NOMEM;
@@ -506,6 +610,8 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   unsigned long long* work_count = (unsigned long long*)(ws + o_cnt);
   float* cn2 = (float*)(ws + o_cn2);
   float* cnorm = (float*)(ws + o_cnorm);
+  float* lvl = (float*)(ws + o_lvl);
+  float* e1 = (float*)(ws + o_e1);
   float* gram = (float*)(ws + o_gram);
   __half* Bimg = (__half*)(ws + o_bimg);
   int32_t* work = (int32_t*)mevi_ws(ctx, WS_RQ_WORK, (size_t)n * 8);
@@ -515,28 +621,39 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
 
   MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, o_cn2 - o_abs, st));  // absmax2, err flag, work count
   absmax_kernel<<<32, 256, 0, st>>>(cb, (int64_t)M * K, d, 1, absmax2);
-  const int64_t sample_rows = 8192;
+  const int64_t sample_rows = 2048;
   const int64_t row_step = n > sample_rows ? n / sample_rows : 1;
   absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(X, n, d, row_step, absmax2 + 1);
   consts_kernel<<<1, 32, 0, st>>>(absmax2, d, consts);
   bimg_kernel<<<(NT * (d / 8) + 255) / 256, 256, 0, st>>>(cb, M * K, d, NT, consts, Bimg);
   cnorm_kernel<<<(NT + 7) / 8, 256, 0, st>>>(cb, M * K, d, NT, cn2, cnorm);
   if (gram_floats) gram_kernel<<<(gram_floats + 7) / 8, 256, 0, st>>>(cb, M, K, d, gram, gram_floats);
+  level_consts_kernel<<<M, 32, 0, st>>>(cnorm, cn2, gram, M, K, metric, consts, e1, lvl);
   MEVI_CUDA(ctx, cudaGetLastError());
-  MEVI_COUNT_LAUNCH(ctx, gram_floats ? 6 : 5);
+  MEVI_COUNT_LAUNCH(ctx, gram_floats ? 7 : 6);
 
   Params p;
   p.X = X; p.n = n; p.d = d; p.nchunks = nchunks; p.M = M; p.K = K; p.NT = NT; p.N1 = N1; p.metric = metric;
-  p.Bimg = Bimg; p.cn2 = cn2; p.cnorm = cnorm; p.gram = gram; p.consts = consts; p.gram_floats = gram_floats;
+  p.Bimg = Bimg; p.cn2 = cn2; p.e1 = e1; p.lvl = lvl; p.gram = gram; p.consts = consts; p.gram_floats = gram_floats;
   p.codes = codes; p.codes_stride = codes_stride;
   p.work_rows = work; p.work_levels = work + n; p.work_count = work_count;
   p.inertia = inertia; p.err_flag = err_flag;
   p.n_tiles = (n + TM - 1) / TM;
   const SmemLayout L = smem_layout(M, K, NT, N1);
   const size_t smem_bytes = (size_t)L.total + 1024;  // slack for the 1024-byte alignment of the dynamic base
-  MEVI_CUDA(ctx, cudaFuncSetAttribute(rq_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   const int grid = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
-  rq_tensor_kernel<<<grid, THREADS, smem_bytes, st>>>(p);
+#define MEVI_LAUNCH_RQ_TENSOR(MM)                                                                                         \
+  do {                                                                                                                    \
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(rq_tensor_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+    rq_tensor_kernel<MM><<<grid, THREADS, smem_bytes, st>>>(p);                                                           \
+  } while (0)
+  switch (M) {
+    case 1: MEVI_LAUNCH_RQ_TENSOR(1); break;
+    case 2: MEVI_LAUNCH_RQ_TENSOR(2); break;
+    case 3: MEVI_LAUNCH_RQ_TENSOR(3); break;
+    default: MEVI_LAUNCH_RQ_TENSOR(4); break;
+  }
+#undef MEVI_LAUNCH_RQ_TENSOR
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaMemcpyAsync(host_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
