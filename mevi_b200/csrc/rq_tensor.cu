@@ -30,6 +30,7 @@
 //               corrections, error-bound test, code store, work-list append, TMEM buffer release
 // Roofline: HBM (4*d B/row); tensor work is 72 cycles/row/SM, shared-memory traffic ~13.5 KB/row.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -63,6 +64,7 @@ struct Params {
   int32_t* work_rows; int32_t* work_levels; unsigned long long* work_count;
   double* inertia; int* err_flag;
   int64_t n_tiles;
+  int debug;  // MEVI_RQ_DEBUG bit mask for pipeline ablations (timing experiments only; results are wrong)
 };
 
 struct SmemLayout {
@@ -91,14 +93,14 @@ template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // register budgets per warpgroup after setmaxnreg (launch allocates 128 x 512 = 65536):
-//   control warps 0-3: 56, converter warps 4-11: 168, epilogue warps 12-15: 112  -> 64,512 registers
-constexpr int REGS_CTRL = 56, REGS_CONV = 168, REGS_EPI = 112;
+//   control warps 0-3: 32, converter warps 4-11: 184, epilogue warps 12-15: 112  -> 65,536 registers
+constexpr int REGS_CTRL = 32, REGS_CONV = 184, REGS_EPI = 112;
 
 
 // Converter warp: streams this CTA's tiles chunk by chunk.  Lane (half, l16) of warp cw owns rows
 // 2*(cw+8q)+half (q = 0..7) and the 16 bytes at float column 4*l16 of every 64-wide chunk: one
-// LDG.128 per q covers two full 256-byte row pieces per warp.  Three register buffers rotate so two
-// chunks (64 KB per SM) are always in flight while the third is being converted.
+// LDG.128 per q covers two full 256-byte row pieces per warp.  Four register buffers rotate so three
+// chunks (96 KB per SM) are always in flight while the fourth is being converted.
 template <bool SCALE>
 __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* sA, float* sStats, uint64_t* a_full,
                                                uint64_t* a_empty, uint64_t* acc_empty, uint64_t* st_full, int cw, int lane) {
@@ -124,10 +126,15 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* sA, flo
   set_valid();
   auto load_chunk = [&](float4 (&v)[8]) {
     if (l_valid < 0) return;  // past the last tile
+    if (l_valid == 8) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (q < l_valid) v[q] = ld_stream_f4(l_ptr + q * qstride);
+      for (int q = 0; q < 8; ++q) v[q] = ld_stream_f4(l_ptr + q * qstride);
+    } else {  // ragged last tile: rows past the end read as zero
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < l_valid) v[q] = ld_stream_f4(l_ptr + q * qstride);
+      }
     }
     if (++l_c == nchunks) {
       l_c = 0;
@@ -154,6 +161,7 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* sA, flo
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float t0 = v[q].x, t1 = v[q].y, t2 = v[q].z, t3 = v[q].w;
+      if (p.debug & 8) { norm[q] += t0 + t1 + t2 + t3; continue; }
       if (SCALE) { t0 *= sx; t1 *= sx; t2 *= sx; t3 *= sx; }
       norm[q] = fmaf(t0, t0, norm[q]);
       norm[q] = fmaf(t1, t1, norm[q]);
@@ -192,16 +200,20 @@ __device__ __forceinline__ void converter_loop(const Params& p, uint8_t* sA, flo
       ++p_it;
     }
   };
-  float4 b0[8], b1[8], b2[8];
+  // four register buffers in rotation: three chunks (96 KB per SM) stay in flight while one is converted
+  float4 b0[8], b1[8], b2[8], b3[8];
   load_chunk(b0);
   load_chunk(b1);
+  load_chunk(b2);
   while (p_tile < p.n_tiles && ok) {
-    load_chunk(b2);
+    load_chunk(b3);
     process_chunk(b0);
     load_chunk(b0);
     process_chunk(b1);
     load_chunk(b1);
     process_chunk(b2);
+    load_chunk(b2);
+    process_chunk(b3);
   }
 }
 
@@ -267,6 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
         for (int c = 0; c < nchunks; ++c, ++g) {
           const uint32_t s = g % NSB, ph = (g / NSB) & 1;
           if (!ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 64)) { atomicExch(p.err_flag, 1); ok = false; break; }
+          if ((p.debug & 1) && g >= NSB) { ptx::mbar_arrive(&b_full[s]); continue; }
           ptx::mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
           ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * N1 * KC, b_stage_bytes, &b_full[s]);
         }
@@ -289,13 +302,15 @@ __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
           const uint32_t a_hi = ptx::smem_u32(sA + (size_t)sa * A_STAGE_BYTES);
           const uint32_t a_lo = a_hi + A_TILE_BYTES;
           const uint32_t b_ad = ptx::smem_u32(sB + (size_t)sb * b_stage_bytes);
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks)
-            ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_hi + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc_n1,
-                          (c | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < KC / 16; ++ks)
+              ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_hi + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc_n1,
+                            (c | ks) != 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks)
-            ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_lo + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc_nt, 1u);
+            for (int ks = 0; ks < KC / 16; ++ks)
+              ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_lo + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc_nt, 1u);
+          }
           ptx::umma_commit(&a_empty[sa]);
           ptx::umma_commit(&b_empty[sb]);
         }
@@ -331,7 +346,10 @@ __global__ void __launch_bounds__(THREADS, 1) rq_tensor_kernel(Params p) {
       int flag_level = -1;
       float last_best = 0.f;
 #pragma unroll
+      for (int j = 0; j < M; ++j) code[j] = 0;
+#pragma unroll
       for (int j = 0; j < M; ++j) {
+        if (p.debug & 4) break;
         // Gram block of level j starts after the blocks of levels 1..j-1: sum_{t<j} t*K rows
         const float* gj = sGram + (j * (j - 1) / 2) * K * (K + 1);
         const float* grow[M > 1 ? M - 1 : 1];
@@ -639,6 +657,10 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   p.work_rows = work; p.work_levels = work + n; p.work_count = work_count;
   p.inertia = inertia; p.err_flag = err_flag;
   p.n_tiles = (n + TM - 1) / TM;
+  {
+    const char* dbg = getenv("MEVI_RQ_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const SmemLayout L = smem_layout(M, K, NT, N1);
   const size_t smem_bytes = (size_t)L.total + 1024;  // slack for the 1024-byte alignment of the dynamic base
   const int grid = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);

@@ -34,7 +34,7 @@ print("M=1 K=32: mismatches", int((a1 != a2).sum()))
 # timing at 2M rows
 n = 2_000_000
 Xd = torch.randn((n, 768), device="cuda")
-for mode in ("tensor",):
+for mode in ("tensor", "exact"):
     for _ in range(2): ctx.rq_encode(Xd, cbd, mode=mode)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
