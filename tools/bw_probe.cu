@@ -50,22 +50,29 @@ __global__ void __launch_bounds__(T) tile_read(const float* __restrict__ X, int6
 }
 
 template <int W, int T, int D>
-int run(const float* X, int64_t n, float* out, const char* name, int ctas_per_sm = 1) {
+int run(const float* X, int64_t n, float* out, const char* name, int ctas_per_sm = 1, int smem = 0) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   int grid = 148 * ctas_per_sm;
-  tile_read<W, T, D><<<grid, T>>>(X, n, out);
+  CK(cudaFuncSetAttribute(tile_read<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tile_read<W, T, D><<<grid, T, smem>>>(X, n, out);
   CK(cudaDeviceSynchronize());
   cudaEventRecord(a);
-  for (int i = 0; i < 3; ++i) tile_read<W, T, D><<<grid, T>>>(X, n, out);
+  for (int i = 0; i < 3; ++i) tile_read<W, T, D><<<grid, T, smem>>>(X, n, out);
   cudaEventRecord(b); CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, a, b); ms /= 3;
-  printf("%-34s W=%4d T=%3d D=%d ctas/SM=%d : %7.3f ms  %7.1f GB/s\n", name, W, T, D, ctas_per_sm, ms, n * 3072.0 / ms / 1e6);
+  printf("%-34s W=%4d T=%3d D=%d ctas/SM=%d smem=%6d : %7.3f ms  %7.1f GB/s\n", name, W, T, D, ctas_per_sm, smem, ms, n * 3072.0 / ms / 1e6);
   return 0;
 }
 
 int main() {
   const int64_t n = 4000000 / 128 * 128;
   float *X, *out; CK(cudaMalloc(&X, n * 3072)); CK(cudaMalloc(&out, 16)); CK(cudaMemset(X, 0, n * 3072));
+  run<256, 256, 4>(X, n, out, "smem sweep", 1, 0);
+  run<256, 256, 4>(X, n, out, "smem sweep", 1, 64 * 1024);
+  run<256, 256, 4>(X, n, out, "smem sweep", 1, 150 * 1024);
+  run<256, 256, 4>(X, n, out, "smem sweep", 1, 200 * 1024);
+  run<256, 256, 4>(X, n, out, "smem sweep", 1, 221 * 1024);
+  run<256, 512, 4>(X, n, out, "smem sweep T=512", 1, 221 * 1024);
   run<256, 256, 2>(X, n, out, "tile pieces (current kernel)");
   run<256, 256, 3>(X, n, out, "tile pieces");
   run<256, 256, 4>(X, n, out, "tile pieces");
