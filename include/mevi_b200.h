@@ -121,17 +121,27 @@ int mevi_build_inverted_lists(mevi_ctx* ctx, const int32_t* codes, int64_t n, in
  * replaces: MEVI/main_models.py:3915-4014 (per query: leaves -> candidate rows
  * -> q.P^T (document_encoder.py:128-132) -> descending sort) for all queries in
  * one call, keeping the k best.
- *   Q [nq,d], D [n,d] (row index == doc id - id_base)
- *   leaf_offsets [n_leaves+1] int64 CSR into leaf_docids; leaf_docids int32 rows of D
+ *   Q [nq,d], D [n,d]
+ *   d_layout     0: row i of D is document row i (candidates are gathered row by row)
+ *                1: D is stored in CSR order, row j of D is document leaf_docids[j] (see
+ *                   mevi_gather_rows) — every leaf is one contiguous byte range, streamed with bulk
+ *                   async copies; this is the fast path
+ *   leaf_offsets [n_leaves+1] int64 CSR into leaf_docids; leaf_docids int32 document rows
  *   query_leaves [nq,L] int32 CSR leaf index per beam-search leaf, -1 = leaf
  *                holds no document (main_models.py:3928,3935)
  *   scores [nq,k] fp32 out, descending, -inf padded; ids [nq,k] int64 out
  *                (= id_base + row), -1 padded; n_candidates [nq] int32 out
  * Ties between equal scores are ordered by ascending id.                      */
-int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d,
+int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int d_layout,
                         const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
                         const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
                         int32_t* n_candidates, void* stream);
+
+/* out[i,:] = D[rows[i],:] for i < m: builds the leaf-ordered copy of the document matrix
+ * (rows = the CSR's leaf_docids).  Replaces the per-leaf memmap fancy-index gather of
+ * MEVI/main_models.py:3944 (IndexedData.__getitem__, 1011-1017) with a one-time permutation.  */
+int mevi_gather_rows(mevi_ctx* ctx, const float* D, int64_t n, int d, const int32_t* rows, int64_t m, float* out,
+                     void* stream);
 
 /* ---- exact flat inner-product search ------------------------------------ *
  * replaces: MEVI/faiss_search.py:13-21 with param='Flat' (faiss IndexFlatIP

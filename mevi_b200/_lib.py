@@ -34,7 +34,8 @@ SYMBOLS = {
     "mevi_kmeans_update": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "mevi_residual_update": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp]),
     "mevi_build_inverted_lists": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
-    "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
+    "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
+    "mevi_gather_rows": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "mevi_flat_ip_topk": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "mevi_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "mevi_dense_scores": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
@@ -242,7 +243,20 @@ class Context:
             )
         return docids, keys
 
-    def cluster_rerank(self, Q, D, leaf_offsets, leaf_docids, query_leaves, k, id_base=0):
+    def gather_rows(self, D, rows):
+        """out[i] = D[rows[i]] (rows int32 on the device)."""
+        import torch
+
+        D = self._dev(D, torch.float32, "D")
+        rows = self._dev(rows, torch.int32, "rows")
+        out = torch.empty((rows.numel(), D.shape[1]), dtype=torch.float32, device=D.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_gather_rows(self.handle, _ptr(D), D.shape[0], D.shape[1], _ptr(rows), rows.numel(),
+                                                  _ptr(out), self._stream()))
+        return out
+
+    def cluster_rerank(self, Q, D, leaf_offsets, leaf_docids, query_leaves, k, id_base=0, leaf_ordered=False):
+        """`leaf_ordered=True`: D is the CSR-ordered copy (`gather_rows(D, leaf_docids)`) — the fast path."""
         import torch
 
         Q = self._dev(Q, torch.float32, "Q")
@@ -258,7 +272,8 @@ class Context:
         ncand = torch.empty((nq,), dtype=torch.int32, device=Q.device)
         with torch.cuda.device(self.device):
             self._check(
-                self.lib.mevi_cluster_rerank(self.handle, _ptr(Q), nq, _ptr(D), n, d, _ptr(lo), lo.numel() - 1, _ptr(ld),
+                self.lib.mevi_cluster_rerank(self.handle, _ptr(Q), nq, _ptr(D), n, d, 1 if leaf_ordered else 0, _ptr(lo),
+                                             lo.numel() - 1, _ptr(ld),
                                              _ptr(ql), L, int(k), int(id_base), _ptr(scores), _ptr(ids), _ptr(ncand),
                                              self._stream())
             )

@@ -105,6 +105,30 @@ __device__ __forceinline__ bool topk_before(float sa, int64_t ia, float sb, int6
   return (sa > sb) || (sa == sb && ia < ib);
 }
 
+// bitonic sort by a SUBSET of the CTA's warps: threads pass their rank in the group (gtid) and the
+// group size; synchronisation uses named barrier `bar_id` (count = nthreads) instead of __syncthreads
+template <typename IdT>
+__device__ __forceinline__ void group_bitonic_sort(float* s, IdT* id, int n, int gtid, int nthreads, int bar_id) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = gtid; i < n; i += nthreads) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          bool up = ((i & k) == 0);
+          float a = s[i], b = s[ixj];
+          IdT ia = id[i], ib = id[ixj];
+          bool a_first = topk_before(a, (int64_t)ia, b, (int64_t)ib);
+          if (a_first != up) {
+            s[i] = b; s[ixj] = a;
+            id[i] = ib; id[ixj] = ia;
+          }
+        }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    }
+  }
+}
+
 // shared-memory bitonic sort of n (power of two) (score,id) pairs into topk_before order
 template <typename IdT>
 __device__ __forceinline__ void block_bitonic_sort(float* s, IdT* id, int n) {

@@ -10,10 +10,10 @@
 //
 // Accumulation is DETERMINISTIC: a CTA walks a contiguous range of rows in
 // tiles; inside a tile rows are bucketed by centroid with a stable counting
-// sort, and warp w owns centroids w, w+8, ... — it adds that centroid's rows,
-// in ascending row order, into register accumulators that live for the whole
-// CTA.  Per-CTA partials are then reduced in a fixed order.  No float atomics,
-// so sums are bit-reproducible for a given (n, grid) and ranks stay in lockstep.
+// sort, and every (centroid, column) accumulator is a register owned by one
+// thread that adds the bucket's rows in ascending row order.  Per-CTA partials
+// are then reduced in a fixed order.  No float atomics, so sums are
+// bit-reproducible for a given (n, grid) and ranks stay in lockstep.
 // Roofline: HBM (one more read of the shard: 4*d bytes per row + 4 B assignment).
 #include "common.cuh"
 
@@ -32,115 +32,97 @@ constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_TILE = 256;
 
-// CPW = centroids owned per warp (K <= 8*CPW); NCH float4 chunks per lane.
-template <int NCH, int CPW>
-__global__ void __launch_bounds__(KM_THREADS) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
-                                                                       const int32_t* __restrict__ assign,
-                                                                       int64_t assign_stride, int K,
-                                                                       float* __restrict__ partial_sums,   // [grid][K][d]
-                                                                       int32_t* __restrict__ partial_counts)  // [grid][K]
+// Column-owner accumulation (skew-proof and deterministic).  Thread t owns columns 2t, 2t+1 of
+// every centroid: KMAX x 2 fp32 accumulators in registers for the CTA's whole row range.  A tile of
+// 256 rows is bucketed by centroid with a stable counting sort; then for each centroid (unrolled, so
+// the accumulator is a fixed register) every thread walks the bucket's rows in ascending order and
+// adds its two columns (8-byte loads, 256..3072 contiguous bytes per row across the CTA).  All threads
+// work on every row, so one dominant cluster (the reference-trained codebooks put >80 % of N(0,1)
+// rows into two centroids) costs nothing extra.
+template <int KMAX, int NT>
+__global__ void __launch_bounds__(NT, (KMAX <= 32 && NT <= 384 ? 2 : 1)) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
+                                                                const int32_t* __restrict__ assign,
+                                                                int64_t assign_stride, int K,
+                                                                float* __restrict__ partial_sums,     // [grid][K][d]
+                                                                int32_t* __restrict__ partial_counts)  // [grid][K]
 {
   __shared__ int s_assign[KM_TILE];
-  __shared__ int s_hist[KM_WARPS * CPW + 1];
-  __shared__ int s_start[KM_WARPS * CPW + 1];
+  __shared__ int s_hist[KMAX + 1];
+  __shared__ int s_start[KMAX + 1];
   __shared__ int s_order[KM_TILE];
-  __shared__ int s_count_total[KM_WARPS * CPW];
+  __shared__ int s_count_total[KMAX];
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int KP = KM_WARPS * CPW;
+  const int tid = threadIdx.x;
+  const bool owner = 2 * tid < d;  // this thread owns columns 2*tid, 2*tid+1
   const int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_end = row_begin + rows_per_cta < n ? row_begin + rows_per_cta : n;
 
-  float4 acc[CPW][NCH];
+  float2 acc[KMAX];
 #pragma unroll
-  for (int c = 0; c < CPW; ++c)
-#pragma unroll
-    for (int t = 0; t < NCH; ++t) acc[c][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = threadIdx.x; i < KP; i += KM_THREADS) s_count_total[i] = 0;
+  for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
+  for (int i = tid; i < KMAX; i += blockDim.x) s_count_total[i] = 0;
   __syncthreads();
 
   for (int64_t tile = row_begin; tile < row_end; tile += KM_TILE) {
     const int rows = (int)((row_end - tile) < KM_TILE ? (row_end - tile) : KM_TILE);
-    for (int i = threadIdx.x; i <= KP; i += KM_THREADS) s_hist[i] = 0;
+    for (int i = tid; i <= KMAX; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    if (threadIdx.x < rows) {
-      int a = assign[(tile + threadIdx.x) * assign_stride];
+    if (tid < rows) {
+      int a = assign[(tile + tid) * assign_stride];
       a = a < 0 ? 0 : (a >= K ? K - 1 : a);
-      s_assign[threadIdx.x] = a;
+      s_assign[tid] = a;
       atomicAdd(&s_hist[a], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       int run = 0;
-      for (int k = 0; k < KP; ++k) {
+      for (int k = 0; k < KMAX; ++k) {
         s_start[k] = run;
         run += s_hist[k];
       }
-      s_start[KP] = run;
+      s_start[KMAX] = run;
     }
     __syncthreads();
-    // stable placement: a row's slot = bucket start + number of earlier rows with the same assignment
-    if (threadIdx.x < rows) {
-      const int a = s_assign[threadIdx.x];
+    // stable placement: slot = bucket start + number of earlier rows with the same assignment
+    if (tid < rows) {
+      const int a = s_assign[tid];
       int rank = 0;
-      for (int j = 0; j < threadIdx.x; ++j) rank += (s_assign[j] == a);
-      s_order[s_start[a] + rank] = threadIdx.x;
+      for (int j = 0; j < tid; ++j) rank += (s_assign[j] == a);
+      s_order[s_start[a] + rank] = tid;
     }
-    if (threadIdx.x < KP) s_count_total[threadIdx.x] += s_hist[threadIdx.x];
+    if (tid < KMAX) s_count_total[tid] += s_hist[tid];
     __syncthreads();
+    if (owner) {
+      const float* base = R + tile * d + 2 * tid;
 #pragma unroll
-    for (int c = 0; c < CPW; ++c) {
-      const int k = warp + KM_WARPS * c;
-      const int b = s_start[k], e = s_start[k + 1];
-      int j = b;
-      for (; j + 1 < e; j += 2) {  // two rows in flight per warp
-        const float* r0 = R + (tile + s_order[j]) * d;
-        const float* r1 = R + (tile + s_order[j + 1]) * d;
-        float4 v0[NCH], v1[NCH];
+      for (int k = 0; k < KMAX; ++k) {
+        const int b = s_start[k], e = s_start[k + 1];
+        int j = b;
+        for (; j + 7 < e; j += 8) {  // eight rows in flight per thread
+          float2 v[8];
 #pragma unroll
-        for (int t = 0; t < NCH; ++t) {
-          int c4 = (lane + 32 * t) * 4;
-          v0[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          v1[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c4 < d) {
-            v0[t] = ld_stream_f4(r0 + c4);
-            v1[t] = ld_stream_f4(r1 + c4);
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float2*>(base + (int64_t)s_order[j + u] * d));
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {  // ascending row order: the sum is reproducible
+            acc[k].x += v[u].x;
+            acc[k].y += v[u].y;
           }
         }
-#pragma unroll
-        for (int t = 0; t < NCH; ++t) {
-          acc[c][t].x += v0[t].x; acc[c][t].y += v0[t].y; acc[c][t].z += v0[t].z; acc[c][t].w += v0[t].w;
-          acc[c][t].x += v1[t].x; acc[c][t].y += v1[t].y; acc[c][t].z += v1[t].z; acc[c][t].w += v1[t].w;
-        }
-      }
-      if (j < e) {
-        const float* r0 = R + (tile + s_order[j]) * d;
-#pragma unroll
-        for (int t = 0; t < NCH; ++t) {
-          int c4 = (lane + 32 * t) * 4;
-          if (c4 < d) {
-            float4 v = ld_stream_f4(r0 + c4);
-            acc[c][t].x += v.x; acc[c][t].y += v.y; acc[c][t].z += v.z; acc[c][t].w += v.w;
-          }
+        for (; j < e; ++j) {
+          const float2 v0 = __ldcs(reinterpret_cast<const float2*>(base + (int64_t)s_order[j] * d));
+          acc[k].x += v0.x; acc[k].y += v0.y;
         }
       }
     }
     __syncthreads();
   }
+  if (owner) {
 #pragma unroll
-  for (int c = 0; c < CPW; ++c) {
-    const int k = warp + KM_WARPS * c;
-    if (k < K) {
-      float* out = partial_sums + ((int64_t)blockIdx.x * K + k) * d;
-#pragma unroll
-      for (int t = 0; t < NCH; ++t) {
-        int c4 = (lane + 32 * t) * 4;
-        if (c4 < d) *reinterpret_cast<float4*>(out + c4) = acc[c][t];
-      }
-      if (lane == 0) partial_counts[(int64_t)blockIdx.x * K + k] = s_count_total[k];
-    }
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) *reinterpret_cast<float2*>(partial_sums + ((int64_t)blockIdx.x * K + k) * d + 2 * tid) = acc[k];
   }
+  if (tid < K) partial_counts[(int64_t)blockIdx.x * K + tid] = s_count_total[tid];
 }
 
 // generic fallback (any K, d % 4 == 0): warp per row, float atomics into sums
@@ -204,10 +186,13 @@ __global__ void residual_update_kernel(float* __restrict__ R, int64_t n, int d4,
   }
 }
 
-template <int NCH, int CPW>
+template <int KMAX>
 cudaError_t launch_accumulate(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
                               float* ps, int32_t* pc, cudaStream_t st) {
-  kmeans_accumulate_kernel<NCH, CPW><<<G, KM_THREADS, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
+  // one thread per column pair; at least 256 threads because they also run the counting sort
+  if (d <= 512) kmeans_accumulate_kernel<KMAX, 256><<<G, 256, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
+  else if (d <= 768) kmeans_accumulate_kernel<KMAX, 384><<<G, 384, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
+  else kmeans_accumulate_kernel<KMAX, 512><<<G, 512, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
   return cudaGetLastError();
 }
 
@@ -258,7 +243,7 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
   if (rc != MEVI_OK) return rc;
 
   // 2. accumulation
-  const bool fast = (K <= 32 && d <= 768) || (K <= 64 && d <= 384);
+  const bool fast = K <= 64 && d <= 1024 && d % 2 == 0;
   if (fast) {
     int G = ctx->sm_count * 2;
     int64_t max_g = (n + KM_TILE - 1) / KM_TILE;
@@ -271,16 +256,9 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
     float* ps = (float*)ws;
     int32_t* pc = (int32_t*)(ws + ps_bytes);
     cudaError_t e;
-    if (K <= 32) {
-      if (d <= 128) e = launch_accumulate<1, 4>(R, n, d, assign, stride, K, G, ps, pc, st);
-      else if (d <= 256) e = launch_accumulate<2, 4>(R, n, d, assign, stride, K, G, ps, pc, st);
-      else if (d <= 512) e = launch_accumulate<4, 4>(R, n, d, assign, stride, K, G, ps, pc, st);
-      else e = launch_accumulate<6, 4>(R, n, d, assign, stride, K, G, ps, pc, st);
-    } else {
-      if (d <= 128) e = launch_accumulate<1, 8>(R, n, d, assign, stride, K, G, ps, pc, st);
-      else if (d <= 256) e = launch_accumulate<2, 8>(R, n, d, assign, stride, K, G, ps, pc, st);
-      else e = launch_accumulate<3, 8>(R, n, d, assign, stride, K, G, ps, pc, st);
-    }
+    if (K <= 16) e = launch_accumulate<16>(R, n, d, assign, stride, K, G, ps, pc, st);
+    else if (K <= 32) e = launch_accumulate<32>(R, n, d, assign, stride, K, G, ps, pc, st);
+    else e = launch_accumulate<64>(R, n, d, assign, stride, K, G, ps, pc, st);
     if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "kmeans_accumulate launch: %s", cudaGetErrorString(e));
     int threads = 256;
     int blocks = (int)((kd + K + threads - 1) / threads);

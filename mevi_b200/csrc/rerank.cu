@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace {
 
@@ -181,6 +182,211 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankParams p) {
   }
 }
 
+
+// ---- leaf-ordered streaming variant ---------------------------------------------------------------
+// D is stored in CSR (leaf) order, so a leaf is one contiguous byte range: candidates are streamed with
+// bulk async copies (TMA engine) into a shared-memory ring by a producer warp — no registers tied up in
+// flight, six 8-row stages (144 KB at d=768) of loads outstanding per SM, one TLB page per leaf instead
+// of one per candidate.  Eight consumer warps take one row each per stage (conflict-free 16 B shared
+// loads), reduce with shuffles and feed the same threshold + bitonic-compaction top-k as above.
+constexpr int RS_ROWS = 8;      // rows per stage (one per consumer warp)
+constexpr int RS_STAGES = 6;
+constexpr int RS_CONSUMERS = 8; // warps 1..8; warp 0 is the producer
+constexpr int RS_THREADS = 32 * (1 + RS_CONSUMERS);
+constexpr int RS_CHECK = 16;    // stages between compaction checks (<= 128 appends)
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * RS_CONSUMERS) : "memory"); }
+
+template <int NCH>
+__global__ void __launch_bounds__(RS_THREADS) rerank_stream_kernel(RerankParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int d = p.d;
+  const uint32_t row_bytes = (uint32_t)d * 4u;
+  const uint32_t stage_bytes = RS_ROWS * row_bytes;
+  unsigned char* s_ring = smem_raw;                                                  // [RS_STAGES][RS_ROWS][d] fp32
+  float* s_score = reinterpret_cast<float*>(s_ring + (size_t)RS_STAGES * stage_bytes);
+  int32_t* s_id = reinterpret_cast<int32_t*>(s_score + p.cap);
+  int64_t* s_prefix = reinterpret_cast<int64_t*>(s_id + p.cap);                      // [L+1]
+  int64_t* s_leafbeg = s_prefix + (p.L + 1);                                         // [L]
+  __shared__ __align__(8) uint64_t full_bar[RS_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[RS_STAGES];
+  __shared__ int s_meta_row[RS_STAGES];
+  __shared__ int s_meta_n[RS_STAGES];
+  __shared__ int s_count;
+  __shared__ float s_tau;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t cta = blockIdx.x;
+  const int q = (int)(cta / p.S);
+  const int s = (int)(cta - (int64_t)q * p.S);
+
+  for (int t = tid; t < p.L; t += RS_THREADS) {
+    const int leaf = p.query_leaves[(int64_t)q * p.L + t];
+    int64_t b = 0, sz = 0;
+    if (leaf >= 0 && leaf < p.n_leaves) {
+      b = p.leaf_offsets[leaf];
+      sz = p.leaf_offsets[leaf + 1] - b;
+    }
+    s_leafbeg[t] = b;
+    s_prefix[t + 1] = sz;
+  }
+  if (tid == 0) {
+    s_prefix[0] = 0;
+    s_count = 0;
+    s_tau = -CUDART_INF_F;
+    for (int i = 0; i < RS_STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], RS_CONSUMERS);
+    }
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int64_t run = 0;
+    for (int t = 1; t <= p.L; ++t) {
+      run += s_prefix[t];
+      s_prefix[t] = run;
+    }
+  }
+  __syncthreads();
+  const int64_t C = s_prefix[p.L];
+  if (s == 0 && tid == 0 && p.n_candidates) p.n_candidates[q] = (int32_t)(C > 0x7fffffff ? 0x7fffffff : C);
+  const int64_t lo = C * s / p.S, hi = C * (s + 1) / p.S;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      uint32_t g = 0;
+      bool ok = true;
+      for (int t = 0; t < p.L && ok; ++t) {
+        int64_t a = s_prefix[t] > lo ? s_prefix[t] : lo;
+        const int64_t b = s_prefix[t + 1] < hi ? s_prefix[t + 1] : hi;
+        for (; a < b && ok; a += RS_ROWS, ++g) {
+          const int nrows = (int)((b - a) < RS_ROWS ? (b - a) : RS_ROWS);
+          const int64_t row = s_leafbeg[t] + (a - s_prefix[t]);
+          const uint32_t st = g % RS_STAGES, ph = (g / RS_STAGES) & 1;
+          if (!ptx::mbar_wait(&empty_bar[st], ph ^ 1)) { ok = false; break; }
+          s_meta_row[st] = (int)row;
+          s_meta_n[st] = nrows;
+          const uint32_t bytes = (uint32_t)nrows * row_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[st], bytes);
+          ptx::bulk_g2s(s_ring + (size_t)st * stage_bytes, p.D + row * d, bytes, &full_bar[st]);
+        }
+      }
+      // sentinel: tells the consumers the stream has ended
+      const uint32_t st = g % RS_STAGES, ph = (g / RS_STAGES) & 1;
+      if (ok && ptx::mbar_wait(&empty_bar[st], ph ^ 1)) {
+        s_meta_n[st] = 0;
+        ptx::mbar_arrive(&full_bar[st]);
+      }
+    }
+  } else {
+    // ===== consumers =====
+    const int cw = warp - 1;
+    const int gtid = tid - 32;
+    float4 qreg[NCH];
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) {
+      const int c4 = (lane + 32 * t) * 4;
+      qreg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < d) qreg[t] = ldg_f4(p.Q + (int64_t)q * d + c4);
+    }
+    uint32_t g = 0;
+    for (;; ++g) {
+      const uint32_t st = g % RS_STAGES, ph = (g / RS_STAGES) & 1;
+      if (!ptx::mbar_wait(&full_bar[st], ph)) break;
+      const int nrows = s_meta_n[st];
+      if (nrows == 0) break;
+      if (cw < nrows) {
+        const float* src = reinterpret_cast<const float*>(s_ring + (size_t)st * stage_bytes + (size_t)cw * row_bytes);
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+          const int c4 = (lane + 32 * t) * 4;
+          if (c4 < d) {
+            const float4 v = *reinterpret_cast<const float4*>(src + c4);
+            acc = fmaf(qreg[t].x, v.x, acc);
+            acc = fmaf(qreg[t].y, v.y, acc);
+            acc = fmaf(qreg[t].z, v.z, acc);
+            acc = fmaf(qreg[t].w, v.w, acc);
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const float tau = *reinterpret_cast<volatile float*>(&s_tau);
+          if (!(acc < tau)) {
+            const int slot = atomicAdd(&s_count, 1);
+            s_score[slot] = acc;
+            s_id[slot] = p.leaf_docids[s_meta_row[st] + cw];  // CSR position -> document row
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[st]);
+      if ((g % RS_CHECK) == RS_CHECK - 1) {
+        consumer_bar();
+        const int cnt = s_count;
+        if (cnt > p.cap - RS_CHECK * RS_ROWS) {
+          for (int i = cnt + gtid; i < p.cap; i += 32 * RS_CONSUMERS) {
+            s_score[i] = -CUDART_INF_F;
+            s_id[i] = 0x7fffffff;
+          }
+          consumer_bar();
+          group_bitonic_sort<int32_t>(s_score, s_id, p.cap, gtid, 32 * RS_CONSUMERS, 1);
+          if (gtid == 0) {
+            const int kept = cnt < p.k ? cnt : p.k;
+            s_count = kept;
+            s_tau = (kept >= p.k) ? s_score[p.k - 1] : -CUDART_INF_F;
+          }
+        }
+        consumer_bar();
+      }
+    }
+    // final compaction + output
+    consumer_bar();
+    const int cnt = s_count;
+    for (int i = cnt + gtid; i < p.cap; i += 32 * RS_CONSUMERS) {
+      s_score[i] = -CUDART_INF_F;
+      s_id[i] = 0x7fffffff;
+    }
+    consumer_bar();
+    group_bitonic_sort<int32_t>(s_score, s_id, p.cap, gtid, 32 * RS_CONSUMERS, 1);
+    const int kept = cnt < p.k ? cnt : p.k;
+    float* os = p.out_scores + cta * p.k;
+    int64_t* oi = p.out_ids + cta * p.k;
+    for (int i = gtid; i < p.k; i += 32 * RS_CONSUMERS) {
+      if (i < kept) {
+        os[i] = s_score[i];
+        oi[i] = p.id_base + (int64_t)s_id[i];
+      } else {
+        os[i] = -CUDART_INF_F;
+        oi[i] = -1;
+      }
+    }
+  }
+}
+
+template <int NCH>
+cudaError_t launch_rerank_stream(const RerankParams& p, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rerank_stream_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t grid = (int64_t)p.nq * p.S;
+  rerank_stream_kernel<NCH><<<(unsigned)grid, RS_THREADS, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ D, int d4, const int32_t* __restrict__ rows, int64_t m,
+                                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t i = warp_global; i < m; i += n_warps) {
+    const float4* src = reinterpret_cast<const float4*>(D) + (int64_t)rows[i] * d4;
+    float4* dst = reinterpret_cast<float4*>(out) + i * d4;
+    for (int c = lane; c < d4; c += 32) dst[c] = __ldg(src + c);
+  }
+}
+
 // One CTA per query: merge S lists of k (score,id) into the k best. cap = pow2 >= S*k.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ in_s, const int64_t* __restrict__ in_i,
                                                          int S, int nq, int k, int cap, int64_t list_stride,
@@ -249,7 +455,7 @@ int mevi_topk_merge_launch(mevi_ctx* ctx, const float* in_s, const int64_t* in_i
 
 extern "C" {
 
-int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d,
+int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int d_layout,
                         const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
                         const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
                         int32_t* n_candidates, void* stream) {
@@ -262,6 +468,7 @@ int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, i
   MEVI_REQUIRE(ctx, L >= 1 && L <= 4096, "L must be in [1, 4096] (got %d)", L);
   MEVI_REQUIRE(ctx, n < (int64_t)2147483647, "shard too large for int32 row ids");
   if (nq <= 0) return MEVI_OK;
+  MEVI_REQUIRE(ctx, d_layout == 0 || d_layout == 1, "d_layout must be 0 (document order) or 1 (CSR / leaf order)");
   const int cap = next_pow2(k + 2 * RR_SUPER);
   int S = (4 * ctx->sm_count + nq - 1) / nq;
   const int smax = 8192 / next_pow2(k) < 64 ? 8192 / next_pow2(k) : 64;
@@ -283,9 +490,19 @@ int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, i
     p.out_ids = (int64_t*)ws;
     p.out_scores = (float*)(ws + (size_t)nq * S * k * sizeof(int64_t));
   }
-  const size_t smem = (size_t)cap * 8 + (size_t)(2 * L + 1) * sizeof(int64_t);
+  size_t smem = (size_t)cap * 8 + (size_t)(2 * L + 1) * sizeof(int64_t);
   cudaError_t e;
-  if (d <= 128) e = launch_rerank<1>(p, smem, st);
+  const size_t ring = (size_t)RS_STAGES * RS_ROWS * d * 4;
+  if (d_layout == 1 && smem + ring + 256 <= 220 * 1024) {
+    smem += ring + 128;
+    if (d <= 128) e = launch_rerank_stream<1>(p, smem, st);
+    else if (d <= 256) e = launch_rerank_stream<2>(p, smem, st);
+    else if (d <= 512) e = launch_rerank_stream<4>(p, smem, st);
+    else if (d <= 768) e = launch_rerank_stream<6>(p, smem, st);
+    else e = launch_rerank_stream<8>(p, smem, st);
+  } else if (d_layout == 1) {
+    return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "leaf-ordered re-rank: ring + top-k buffers exceed shared memory (d=%d k=%d L=%d)", d, k, L);
+  } else if (d <= 128) e = launch_rerank<1>(p, smem, st);
   else if (d <= 256) e = launch_rerank<2>(p, smem, st);
   else if (d <= 512) e = launch_rerank<4>(p, smem, st);
   else if (d <= 768) e = launch_rerank<6>(p, smem, st);
@@ -296,6 +513,18 @@ int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, i
     // lists of one query are contiguous: [q][s][k]  -> shard_stride = k, list_stride = S*k
     return mevi_topk_merge_launch(ctx, p.out_scores, p.out_ids, S, nq, k, (int64_t)S * k, (int64_t)k, scores, ids, st);
   }
+  return MEVI_OK;
+}
+
+int mevi_gather_rows(mevi_ctx* ctx, const float* D, int64_t n, int d, const int32_t* rows, int64_t m, float* out,
+                     void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  MEVI_REQUIRE(ctx, D && rows && out && d > 0 && d % 4 == 0 && n >= 0 && m >= 0, "bad argument");
+  if (m == 0) return MEVI_OK;
+  gather_rows_kernel<<<ctx->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(D, d / 4, rows, m, out);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
   return MEVI_OK;
 }
 

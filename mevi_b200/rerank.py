@@ -129,16 +129,22 @@ class ClusterIndex:
 class ClusterReranker:
     """Holds a (shard of the) doc-embedding matrix on the device plus its inverted lists."""
 
-    def __init__(self, all_embeddings, index: ClusterIndex, device_index: Optional[int] = None):
+    def __init__(self, all_embeddings, index: ClusterIndex, device_index: Optional[int] = None,
+                 leaf_ordered: bool = True):
+        """`leaf_ordered=True` (default) keeps a copy of the matrix permuted into CSR order so that each
+        leaf is one contiguous byte range (streamed with bulk async copies); False gathers candidate
+        rows one by one from the document-ordered matrix."""
         self.ctx = _lib.get_context(device_index if device_index is not None else index.device.index)
         dev = torch.device("cuda", self.ctx.device)
         if isinstance(all_embeddings, torch.Tensor):
-            self.D = all_embeddings.to(device=dev, dtype=torch.float32).contiguous()
+            D = all_embeddings.to(device=dev, dtype=torch.float32).contiguous()
         else:
             from .trainer import _upload_rows
 
-            self.D = _upload_rows(all_embeddings, 0, all_embeddings.shape[0], dev)
+            D = _upload_rows(all_embeddings, 0, all_embeddings.shape[0], dev)
         self.index = index
+        self.leaf_ordered = bool(leaf_ordered)
+        self.D = self.ctx.gather_rows(D, index.leaf_docids) if self.leaf_ordered else D
 
     @torch.no_grad()
     def rerank(self, query_embedding, dec, topk: int = 100):
@@ -151,7 +157,7 @@ class ClusterReranker:
         Q = query_embedding.to(device=dev, dtype=torch.float32).contiguous()
         ql = self.index.lookup(dec)
         scores, ids, ncand = self.ctx.cluster_rerank(Q, self.D, self.index.leaf_offsets, self.index.leaf_docids, ql, topk,
-                                                     id_base=self.index.id_base)
+                                                     id_base=self.index.id_base, leaf_ordered=self.leaf_ordered)
         if dist_on():
             s_all = all_gather_stack(scores)
             i_all = all_gather_stack(ids)

@@ -21,13 +21,14 @@ def test_inverted_lists_equal_reference_dicts(case):
     assert torch.equal(idx2.leaf_docids, idx.leaf_docids)
 
 
+@pytest.mark.parametrize("leaf_ordered", [True, False])
 @pytest.mark.parametrize("nb,k", [(10, 100), (100, 100), (10, 1000), (100, 7)])
-def test_rerank_matches_oracle(case, nb, k):
+def test_rerank_matches_oracle(case, nb, k, leaf_ordered):
     from mevi_b200.rerank import ClusterIndex, ClusterReranker
 
     dec = case.load(f"beam{nb}_labels.npy")
     clus = case.pickle("rqclus.pkl")
-    rr = ClusterReranker(dev(case.X), ClusterIndex.from_codes(case.codes, case.K))
+    rr = ClusterReranker(dev(case.X), ClusterIndex.from_codes(case.codes, case.K), leaf_ordered=leaf_ordered)
     scores, ids, ncand = rr.rerank(case.Q, dec, topk=k)
     scores, ids, ncand = scores.cpu().numpy(), ids.cpu().numpy(), ncand.cpu().numpy()
     ref = oracle.cluster_rerank(case.Q, case.X, clus, dec, topk=k)
@@ -43,14 +44,15 @@ def test_rerank_matches_oracle(case, nb, k):
     assert (np.diff(np.where(np.isfinite(scores), scores, -1e30), axis=1) <= 0).all()
 
 
-def test_rerank_split_path_and_empty_leaves(gauss):
+@pytest.mark.parametrize("leaf_ordered", [True, False])
+def test_rerank_split_path_and_empty_leaves(gauss, leaf_ordered):
     """Few queries -> several CTAs per query + merge; leaves that hold no document are legal."""
     from mevi_b200.rerank import ClusterIndex, ClusterReranker
 
     dec = gauss.load("beam100_labels.npy")[:2].copy()
     dec[0, :50] = 31  # (31,31,31,31) almost surely empty
     clus = gauss.pickle("rqclus.pkl")
-    rr = ClusterReranker(dev(gauss.X), ClusterIndex.from_codes(gauss.codes, gauss.K))
+    rr = ClusterReranker(dev(gauss.X), ClusterIndex.from_codes(gauss.codes, gauss.K), leaf_ordered=leaf_ordered)
     scores, ids, ncand = rr.rerank(gauss.Q[:2], dec, topk=50)
     ref = oracle.cluster_rerank(gauss.Q[:2], gauss.X, clus, dec, topk=50)
     for q, (d_, s_, nd) in enumerate(ref):
