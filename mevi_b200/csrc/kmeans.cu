@@ -16,6 +16,7 @@
 // bit-reproducible for a given (n, grid) and ranks stay in lockstep.
 // Roofline: HBM (one more read of the shard: 4*d bytes per row + 4 B assignment).
 #include "common.cuh"
+#include "ptx.cuh"
 
 int mevi_rq_exact_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* cb, int M, int K, int metric,
                          int32_t* codes, int64_t codes_stride, float* residual, const int32_t* work_rows,
@@ -33,85 +34,130 @@ constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_TILE = 256;
 
 // Column-owner accumulation (skew-proof and deterministic).  Thread t owns columns 2t, 2t+1 of
-// every centroid: KMAX x 2 fp32 accumulators in registers for the CTA's whole row range.  A tile of
-// 256 rows is bucketed by centroid with a stable counting sort; then for each centroid (unrolled, so
-// the accumulator is a fixed register) every thread walks the bucket's rows in ascending order and
-// adds its two columns (8-byte loads, 256..3072 contiguous bytes per row across the CTA).  All threads
-// work on every row, so one dominant cluster (the reference-trained codebooks put >80 % of N(0,1)
-// rows into two centroids) costs nothing extra.
+// every centroid: KMAX x 2 fp32 accumulators in registers for the CTA's whole (contiguous) row range.
+// Rows arrive in sub-tiles of up to 32 rows — one contiguous byte range, fetched with a single bulk
+// async copy (TMA engine) into a double-buffered shared-memory stage, so ~100-190 KB per SM are in
+// flight without holding registers.  Warp 0 buckets the sub-tile's rows by centroid (match_any +
+// popc = stable counting sort); then for each centroid (unrolled, so the accumulator is a fixed
+// register) every thread walks the bucket's rows in ascending order and adds its two columns from
+// shared memory.  All threads work on every row, so one dominant cluster (the reference-trained
+// codebooks put >80 % of N(0,1) rows into two centroids) costs nothing extra.
 template <int KMAX, int NT>
-__global__ void __launch_bounds__(NT, (KMAX <= 32 && NT <= 384 ? 2 : 1)) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
-                                                                const int32_t* __restrict__ assign,
-                                                                int64_t assign_stride, int K,
-                                                                float* __restrict__ partial_sums,     // [grid][K][d]
-                                                                int32_t* __restrict__ partial_counts)  // [grid][K]
+__global__ void __launch_bounds__(NT, 1) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
+                                                                  const int32_t* __restrict__ assign,
+                                                                  int64_t assign_stride, int K, int sub_rows,
+                                                                  float* __restrict__ partial_sums,     // [grid][K][d]
+                                                                  int32_t* __restrict__ partial_counts)  // [grid][K]
 {
-  __shared__ int s_assign[KM_TILE];
-  __shared__ int s_hist[KMAX + 1];
+  extern __shared__ __align__(128) unsigned char km_smem[];  // [2][sub_rows][d] fp32
+  __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ int s_start[KMAX + 1];
-  __shared__ int s_order[KM_TILE];
+  __shared__ int s_order[32];
   __shared__ int s_count_total[KMAX];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool owner = 2 * tid < d;  // this thread owns columns 2*tid, 2*tid+1
   const int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
   const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t row_end = row_begin + rows_per_cta < n ? row_begin + rows_per_cta : n;
+  const int64_t my_rows = row_end > row_begin ? row_end - row_begin : 0;
+  const int64_t nsub = (my_rows + sub_rows - 1) / sub_rows;
+  const size_t stage_bytes = (size_t)sub_rows * d * sizeof(float);
 
   float2 acc[KMAX];
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
-  for (int i = tid; i < KMAX; i += blockDim.x) s_count_total[i] = 0;
+  for (int i = tid; i < KMAX; i += NT) s_count_total[i] = 0;
+  if (tid == 0) {
+    ptx::mbar_init(&full_bar[0], 1);
+    ptx::mbar_init(&full_bar[1], 1);
+    ptx::mbar_fence_init();
+  }
   __syncthreads();
+  auto issue = [&](int64_t i) {  // thread 0: bulk copy of sub-tile i into stage i & 1
+    const int64_t r0 = row_begin + i * sub_rows;
+    const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
+    const uint32_t bytes = (uint32_t)rows * (uint32_t)d * 4u;
+    ptx::mbar_arrive_expect_tx(&full_bar[i & 1], bytes);
+    ptx::bulk_g2s(km_smem + (size_t)(i & 1) * stage_bytes, R + r0 * d, bytes, &full_bar[i & 1]);
+  };
+  if (tid == 0 && nsub > 0) issue(0);
+  // warp 0 prefetches the assignments of the next sub-tile one iteration ahead
+  int next_a = KMAX;
+  if (warp == 0 && nsub > 0) {
+    const int64_t r = row_begin + lane;
+    if (lane < sub_rows && r < row_end) {
+      int a = assign[r * assign_stride];
+      next_a = a < 0 ? 0 : (a >= K ? K - 1 : a);
+    }
+  }
 
-  for (int64_t tile = row_begin; tile < row_end; tile += KM_TILE) {
-    const int rows = (int)((row_end - tile) < KM_TILE ? (row_end - tile) : KM_TILE);
-    for (int i = tid; i <= KMAX; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
-    if (tid < rows) {
-      int a = assign[(tile + tid) * assign_stride];
-      a = a < 0 ? 0 : (a >= K ? K - 1 : a);
-      s_assign[tid] = a;
-      atomicAdd(&s_hist[a], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int run = 0;
-      for (int k = 0; k < KMAX; ++k) {
-        s_start[k] = run;
-        run += s_hist[k];
+  for (int64_t i = 0; i < nsub; ++i) {
+    const int64_t r0 = row_begin + i * sub_rows;
+    const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
+    if (tid == 0 && i + 1 < nsub) issue(i + 1);  // stage (i+1)&1 was released by the barrier that ended iteration i-1
+    if (warp == 0) {
+      // stable counting sort of <= 32 rows by centroid
+      const int a = next_a;  // KMAX for lanes past the sub-tile
+      next_a = KMAX;
+      if (i + 1 < nsub) {
+        const int64_t r = r0 + sub_rows + lane;
+        if (lane < sub_rows && r < row_end) {
+          int an = assign[r * assign_stride];
+          next_a = an < 0 ? 0 : (an >= K ? K - 1 : an);
+        }
       }
-      s_start[KMAX] = run;
+      const unsigned same = __match_any_sync(MEVI_FULL_MASK, a);
+      const int rank = __popc(same & ((1u << lane) - 1u));
+      // bucket starts: lane k (and k+32) counts the rows assigned to centroid k, then an exclusive scan
+      int start_lo = 0, start_hi = 0;
+      {
+        int c_lo = 0, c_hi = 0;
+#pragma unroll
+        for (int src = 0; src < 32; ++src) {
+          const int av = __shfl_sync(MEVI_FULL_MASK, a, src);
+          c_lo += (av == lane);
+          c_hi += (av == lane + 32);
+        }
+        if (lane < KMAX) s_count_total[lane] += c_lo;
+        if (KMAX > 32 && lane + 32 < KMAX) s_count_total[lane + 32] += c_hi;
+        int inc = c_lo;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(MEVI_FULL_MASK, inc, o);
+          if (lane >= o) inc += v;
+        }
+        start_lo = inc - c_lo;
+        const int total_lo = __shfl_sync(MEVI_FULL_MASK, inc, 31);
+        int inc2 = c_hi;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(MEVI_FULL_MASK, inc2, o);
+          if (lane >= o) inc2 += v;
+        }
+        start_hi = total_lo + inc2 - c_hi;
+        if (lane < KMAX) s_start[lane] = start_lo;
+        if (KMAX > 32 && lane + 32 < KMAX) s_start[lane + 32] = start_hi;
+        if (lane == 0) s_start[KMAX] = rows;
+      }
+      {  // every lane takes part in the broadcast (the source lane = centroid id need not share `a`)
+        const int src = a & 31;
+        const int from_lo = __shfl_sync(MEVI_FULL_MASK, start_lo, src);
+        const int from_hi = __shfl_sync(MEVI_FULL_MASK, start_hi, src);
+        if (a < KMAX) s_order[(a < 32 ? from_lo : from_hi) + rank] = lane;
+      }
     }
-    __syncthreads();
-    // stable placement: slot = bucket start + number of earlier rows with the same assignment
-    if (tid < rows) {
-      const int a = s_assign[tid];
-      int rank = 0;
-      for (int j = 0; j < tid; ++j) rank += (s_assign[j] == a);
-      s_order[s_start[a] + rank] = tid;
-    }
-    if (tid < KMAX) s_count_total[tid] += s_hist[tid];
+    ptx::mbar_wait(&full_bar[i & 1], (uint32_t)((i >> 1) & 1));
     __syncthreads();
     if (owner) {
-      const float* base = R + tile * d + 2 * tid;
+      const float* base = reinterpret_cast<const float*>(km_smem + (size_t)(i & 1) * stage_bytes) + 2 * tid;
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
         const int b = s_start[k], e = s_start[k + 1];
-        int j = b;
-        for (; j + 7 < e; j += 8) {  // eight rows in flight per thread
-          float2 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __ldcs(reinterpret_cast<const float2*>(base + (int64_t)s_order[j + u] * d));
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {  // ascending row order: the sum is reproducible
-            acc[k].x += v[u].x;
-            acc[k].y += v[u].y;
-          }
-        }
-        for (; j < e; ++j) {
-          const float2 v0 = __ldcs(reinterpret_cast<const float2*>(base + (int64_t)s_order[j] * d));
-          acc[k].x += v0.x; acc[k].y += v0.y;
+        for (int j = b; j < e; ++j) {  // ascending row order inside the bucket: reproducible sums
+          const float2 v = *reinterpret_cast<const float2*>(base + (size_t)s_order[j] * d);
+          acc[k].x += v.x;
+          acc[k].y += v.y;
         }
       }
     }
@@ -186,14 +232,27 @@ __global__ void residual_update_kernel(float* __restrict__ R, int64_t n, int d4,
   }
 }
 
+template <int KMAX, int NT>
+cudaError_t launch_accumulate_nt(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
+                                 float* ps, int32_t* pc, cudaStream_t st) {
+  int sub_rows = (int)(96 * 1024 / ((size_t)d * 4));
+  if (sub_rows > 32) sub_rows = 32;
+  if (sub_rows < 1) sub_rows = 1;
+  const size_t smem = 2 * (size_t)sub_rows * d * 4 + 128;
+  cudaError_t e = cudaFuncSetAttribute(kmeans_accumulate_kernel<KMAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kmeans_accumulate_kernel<KMAX, NT><<<G, NT, smem, st>>>(R, n, d, assign, stride, K, sub_rows, ps, pc);
+  return cudaGetLastError();
+}
+
 template <int KMAX>
 cudaError_t launch_accumulate(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
                               float* ps, int32_t* pc, cudaStream_t st) {
-  // one thread per column pair; at least 256 threads because they also run the counting sort
-  if (d <= 512) kmeans_accumulate_kernel<KMAX, 256><<<G, 256, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
-  else if (d <= 768) kmeans_accumulate_kernel<KMAX, 384><<<G, 384, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
-  else kmeans_accumulate_kernel<KMAX, 512><<<G, 512, 0, st>>>(R, n, d, assign, stride, K, ps, pc);
-  return cudaGetLastError();
+  // one thread per column pair
+  if (d <= 256) return launch_accumulate_nt<KMAX, 128>(R, n, d, assign, stride, K, G, ps, pc, st);
+  if (d <= 512) return launch_accumulate_nt<KMAX, 256>(R, n, d, assign, stride, K, G, ps, pc, st);
+  if (d <= 768) return launch_accumulate_nt<KMAX, 384>(R, n, d, assign, stride, K, G, ps, pc, st);
+  return launch_accumulate_nt<KMAX, 512>(R, n, d, assign, stride, K, G, ps, pc, st);
 }
 
 }  // namespace
@@ -243,9 +302,9 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
   if (rc != MEVI_OK) return rc;
 
   // 2. accumulation
-  const bool fast = K <= 64 && d <= 1024 && d % 2 == 0;
+  const bool fast = K <= 64 && d <= 1024 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
   if (fast) {
-    int G = ctx->sm_count * 2;
+    int G = ctx->sm_count;  // one CTA per SM (shared-memory stages), persistent over its row range
     int64_t max_g = (n + KM_TILE - 1) / KM_TILE;
     if (G > max_g) G = (int)max_g;
     if (G < 1) G = 1;
