@@ -464,7 +464,9 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
                           "queries_per_sec_at_this_shard": NQ_MARCO / (ms / 1e3),
                           "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": tf32_peak,
                                        "unit": "TFLOP/s", "frac": flops / (ms / 1e3) / 1e12 / tf32_peak,
-                                       "note": "peak = measured bf16 cuBLAS / 2 (TF32-equivalent dense rate)"}}
+                                       "note": "FLOPs = 2*nq*N*d (algorithmic); peak = measured bf16 cuBLAS / 2 (TF32-equivalent dense "
+                                               "rate for fp32 data); the kernel is a single-pass fp16 tcgen05 prefilter + exact fp32 "
+                                               "re-score, time includes the fp32->fp16 image pass, compactions and the re-score"}}
     except Exception as e:
         out["flat_ip"] = {"error": repr(e)[:300]}
     return out
@@ -479,7 +481,7 @@ def main():
     ap.add_argument("--sample-file", type=str, default=None)
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--docs", type=int, default=N_MARCO, help="rows per GPU (default: MSMARCO 8,841,823)")
-    ap.add_argument("--flat-docs", type=int, default=1 << 20)
+    ap.add_argument("--flat-docs", type=int, default=1 << 22)
     ap.add_argument("--ref-sample", type=int, default=65536)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

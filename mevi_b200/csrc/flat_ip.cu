@@ -3,9 +3,9 @@
 // Replaces MEVI/faiss_search.py:13-21 with param='Flat' (faiss IndexFlatIP
 // add + search: Q[nq,d].D[N,d]^T, k best per query, descending).
 //
-// Structure (shared by the CUDA-core tile kernel below and the tcgen05 tile
-// kernel in flat_tensor.cu): documents are visited in chunks whose size grows
-// geometrically.  A tile kernel scores a [128 queries x 128 docs] block and
+// This file holds the fp32 CUDA-core path (MODE_EXACT, small inputs, and the
+// fallback of the tcgen05 prefilter in flat_tensor.cu).  Structure shared by
+// both: documents are visited in chunks whose size grows geometrically.  A tile kernel scores a [128 queries x 128 docs] block and
 // appends (score,id) to the query's candidate buffer only when the score is not
 // below the query's running k-th best (tau, fixed during a chunk).  After each
 // chunk a per-query compaction kernel sorts the buffer, keeps the k best and
@@ -165,9 +165,8 @@ int pow2_at_least(int v) {
 }  // namespace
 
 bool mevi_flat_tensor_supported(mevi_ctx* ctx, int d, int k);
-int mevi_flat_tensor_tiles(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n_begin, int64_t n_end, int d,
-                           float* tau, int* count, float* cand_score, int32_t* cand_id, int* overflow, int capg,
-                           cudaStream_t st);
+int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int k,
+                            int64_t id_base, float* scores, int64_t* ids, int* fell_back, cudaStream_t st);
 
 extern "C" int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int k,
                                  int64_t id_base, int mode, float* scores, int64_t* ids, void* stream) {
@@ -186,6 +185,14 @@ extern "C" int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const fl
     use_tensor = true;
   } else if (mode == MEVI_MODE_AUTO) {
     use_tensor = mevi_flat_tensor_supported(ctx, d, k) && n >= 8192;
+  }
+
+  if (use_tensor) {
+    int fell_back = 1;
+    int rc = mevi_flat_tensor_search(ctx, Q, nq, D, n, d, k, id_base, scores, ids, &fell_back, st);
+    if (rc != MEVI_OK) return rc;
+    if (!fell_back) return MEVI_OK;
+    // margin window overflowed or fp16 range exceeded: the fp32 path below computes the answer instead
   }
 
   const int capg = pow2_at_least(k) < 2048 ? 4096 : 8192;  // >= 2k, power of two for the sorter
@@ -217,11 +224,7 @@ extern "C" int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const fl
     int64_t pos = 0;
     while (pos < n) {
       int64_t end = pos + chunk < n ? pos + chunk : n;
-      if (use_tensor) {
-        int rc = mevi_flat_tensor_tiles(ctx, Q, nq, D, pos, end, d, stt.tau, stt.count, stt.cand_score, stt.cand_id,
-                                        stt.overflow, capg, st);
-        if (rc != MEVI_OK) return rc;
-      } else {
+      {
         dim3 grid((unsigned)((end - pos + FT_BN - 1) / FT_BN), (unsigned)((nq + FT_BM - 1) / FT_BM));
         flat_tile_kernel<<<grid, FT_THREADS, 0, st>>>(Q, nq, D, pos, end, d, stt);
         MEVI_COUNT_LAUNCH(ctx, 1);

@@ -1,10 +1,427 @@
-// flat_tensor.cu — tcgen05 tile kernel for the flat search (placeholder until the kernel lands).
+// flat_tensor.cu — K2: exact flat inner-product top-k with a tcgen05 fp16 prefilter.
+//
+// Replaces MEVI/faiss_search.py:13-21 with param='Flat' (faiss IndexFlatIP add + search) for large
+// inputs.  The dense contraction Q[nq,d].D[N,d]^T runs on the 5th-generation tensor cores in fp16
+// (one pass, fp32 accumulation in TMEM); because fp16 rounding perturbs a score by at most
+//     E(q,d) = 1.01 * 2^-10 * |q| * |d|            (two RN roundings to 11 bits per product)
+// the tensor result is only a PREFILTER: a document is kept for a query if its approximate score is
+// within 2*E_max of the query's running k-th best approximate score, which provably includes every
+// member of the exact top-k; the survivors (k plus a few dozen) are re-scored in exact fp32 and sorted.
+// If more survivors than the buffer holds fall inside the margin, the call falls back to the fp32
+// CUDA-core search of flat_ip.cu, so the answer is always the exact one.
+//
+// Data path.  One streaming pass converts D (and Q) to fp16 "images": [tile][K chunk][rows][64 halfs]
+// with the 128-byte XOR swizzle UMMA expects, so every pipeline stage is ONE contiguous block fetched
+// by a single bulk async copy (no tensor maps).  GEMM CTA (persistent, 192 threads): warp 0 = bulk-copy
+// producer (A: 128 docs x 64, 16 KB; B: 256 queries x 64, 32 KB; 4 stages), warp 1 = one thread issuing
+// tcgen05.mma M=128 N=256 K=16, accumulators double-buffered in TMEM (2 x 256 columns), warps 2-5 =
+// epilogue: tcgen05.ld, compare with the per-query threshold, rare atomic append.  Work items are
+// (doc tile, query block) pairs in doc-tile-major order so a doc tile is reused from L2 by all query
+// blocks.  Roofline: tensor pipe (2*nq*N*d FLOP); L2->SM operand traffic is the practical limiter.
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
 #include "common.cuh"
+#include "ptx.cuh"
 
-bool mevi_flat_tensor_supported(mevi_ctx* ctx, int d, int k) { return false; }
+namespace {
 
-int mevi_flat_tensor_tiles(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n_begin, int64_t n_end, int d,
-                           float* tau, int* count, float* cand_score, int32_t* cand_id, int* overflow, int capg,
-                           cudaStream_t st) {
-  return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "tensor flat path not built");
+constexpr int FT_TM = 128;       // docs per tile (UMMA M)
+constexpr int FT_TN = 256;       // queries per block (UMMA N)
+constexpr int FT_KC = 64;        // K elements per chunk (128-byte rows)
+constexpr int FT_STAGES = 4;
+constexpr int FT_A_BYTES = FT_TM * 128, FT_B_BYTES = FT_TN * 128;
+constexpr int FT_STAGE_BYTES = FT_A_BYTES + FT_B_BYTES;  // 48 KB
+constexpr int FT_THREADS2 = 192;
+constexpr int FT_KEEP = 512;     // approximate candidates kept per query between chunks
+
+enum { FC_SD = 0, FC_SQ, FC_INV, FC_DMAX, FC_CLAMPED, FC_NUM = 8 };
+
+// ---- fp32 -> swizzled fp16 image, one warp per row; also row norms and the maximum norm -----------
+__global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, int d, int rows_per_tile,
+                                     const float* __restrict__ consts, int scale_slot, __half* __restrict__ img,
+                                     float* __restrict__ norms, unsigned* __restrict__ max_norm_bits,
+                                     int* __restrict__ clamped, int64_t padded_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float s = consts[scale_slot];
+  const int units = d / 8;  // 16-byte units per row
+  const int nchunks = d / FT_KC;
+  for (int64_t row = warp_global; row < padded_rows; row += n_warps) {
+    const int64_t tile = row / rows_per_tile;
+    const int r = (int)(row - tile * rows_per_tile);
+    float nrm = 0.f;
+    bool clamp = false;
+    for (int u = lane; u < units; u += 32) {
+      float v[8];
+      if (row < rows) {
+        const float4 a = ld_stream_f4(X + row * d + u * 8), b = ld_stream_f4(X + row * d + u * 8 + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+      __half h[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        nrm = fmaf(v[e], v[e], nrm);
+        float t = v[e] * s;
+        if (fabsf(t) > 65000.f) { t = copysignf(65000.f, t); clamp = true; }
+        h[e] = __float2half_rn(t);
+      }
+      const int chunk = u / 8, uu = u & 7;
+      __half* dst = img + (((size_t)tile * nchunks + chunk) * rows_per_tile + r) * FT_KC + ((uu ^ (r & 7)) * 8);
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+    }
+    nrm = warp_sum(nrm);
+    if (lane == 0 && row < rows) {
+      const float nn = sqrtf(nrm);
+      if (norms) norms[row] = nn;
+      if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nn));
+    }
+    if (clamp) atomicExch(clamped, 1);
+  }
+}
+
+__global__ void flat_absmax_kernel(const float* __restrict__ p, int64_t rows, int d, int64_t row_step, unsigned* out) {
+  unsigned m = 0;
+  const int64_t nsel = (rows + row_step - 1) / row_step;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nsel * d; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = (i / d) * row_step;
+    const float v = fabsf(p[r * d + (i % d)]);
+    if (v == v && v < CUDART_INF_F) m = max(m, __float_as_uint(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(MEVI_FULL_MASK, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+__global__ void flat_consts_kernel(const unsigned* absmax2, float* consts) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // 2^s with absmax * 2^s in [2^11, 2^12): 16x headroom below the fp16 maximum (D is only sampled)
+    const float ad = __uint_as_float(absmax2[0]), aq = __uint_as_float(absmax2[1]);
+    const float sd = ad > 0.f ? ldexpf(1.f, 11 - ilogbf(ad)) : 1.f;
+    const float sq = aq > 0.f ? ldexpf(1.f, 11 - ilogbf(aq)) : 1.f;
+    consts[FC_SD] = sd;
+    consts[FC_SQ] = sq;
+    consts[FC_INV] = 1.f / (sd * sq);
+  }
+}
+
+// per-query slack: a true top-k member's approximate score is at least (k-th approximate) - 2 E_max
+__global__ void flat_margin_kernel(const float* __restrict__ qnorm, int nq, const unsigned* __restrict__ dmax_bits,
+                                   float* __restrict__ margin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) margin[i] = 2.f * 1.01f * 9.765625e-4f * qnorm[i] * __uint_as_float(*dmax_bits);
+}
+
+struct GemmParams {
+  const __half* Aimg; const __half* Bimg;
+  int64_t tile_begin, tile_end;   // doc tiles of this chunk
+  int64_t n_end;                  // first invalid doc row
+  int nq, n_qblocks, nchunks;
+  const float* consts; const float* tau; const float* margin;
+  int* count; float* cand_score; int32_t* cand_id; int* overflow; int capg;
+  int* err_flag;
+};
+
+__global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;  // [FT_STAGES][A 16 KB | B 32 KB]
+  float* s_thr = reinterpret_cast<float*>(smem + (size_t)FT_STAGES * FT_STAGE_BYTES);  // [2][FT_TN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_thr + 2 * FT_TN);
+  uint64_t* full = bars;
+  uint64_t* empty = full + FT_STAGES;
+  uint64_t* acc_full = empty + FT_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < FT_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_holder, 512);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int64_t n_items = (p.tile_end - p.tile_begin) * p.n_qblocks;
+  const int nchunks = p.nchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      bool ok = true;
+      for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x) {
+        const int64_t tile = p.tile_begin + w / p.n_qblocks;
+        const int qb = (int)(w % p.n_qblocks);
+        const __half* a_src = p.Aimg + (size_t)tile * nchunks * FT_TM * FT_KC;
+        const __half* b_src = p.Bimg + (size_t)qb * nchunks * FT_TN * FT_KC;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t s = g % FT_STAGES, ph = (g / FT_STAGES) & 1;
+          if (!ptx::mbar_wait_backoff(&empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); ok = false; break; }
+          ptx::mbar_arrive_expect_tx(&full[s], FT_STAGE_BYTES);
+          ptx::bulk_g2s(ring + (size_t)s * FT_STAGE_BYTES, a_src + (size_t)c * FT_TM * FT_KC, FT_A_BYTES, &full[s]);
+          ptx::bulk_g2s(ring + (size_t)s * FT_STAGE_BYTES + FT_A_BYTES, b_src + (size_t)c * FT_TN * FT_KC, FT_B_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16_m128(FT_TN);
+      uint32_t g = 0, it = 0;
+      bool ok = true;
+      for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 2); ok = false; break; }
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * FT_TN;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t s = g % FT_STAGES, ph2 = (g / FT_STAGES) & 1;
+          if (!ptx::mbar_wait(&full[s], ph2)) { atomicExch(p.err_flag, 3); ok = false; break; }
+          ptx::tc_fence_after_sync();
+          const uint32_t a_ad = ptx::smem_u32(ring + (size_t)s * FT_STAGE_BYTES);
+          const uint32_t b_ad = a_ad + FT_A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < FT_KC / 16; ++ks)
+            ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_ad + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc,
+                          (c | ks) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty[s]);
+        }
+        if (ok) ptx::umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..5; TMEM lane group = warp % 4) =====
+    const int lg = warp & 3;
+    const int etid = tid - 64;  // 0..127
+    const float inv = p.consts[FC_INV];
+    uint32_t it = 0;
+    bool ok = true;
+    for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x, ++it) {
+      const int64_t tile = p.tile_begin + w / p.n_qblocks;
+      const int qb = (int)(w % p.n_qblocks);
+      const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+      // thresholds of this query block (tau is fixed during a chunk; stale values only admit more)
+      float* thr = s_thr + buf * FT_TN;
+      for (int j = etid; j < FT_TN; j += 128) {
+        const int q = qb * FT_TN + j;
+        thr[j] = q < p.nq ? p.tau[q] - p.margin[q] : CUDART_INF_F;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!ptx::mbar_wait_backoff(&acc_full[buf], ph, 64)) { atomicExch(p.err_flag, 4); ok = false; break; }
+      ptx::tc_fence_after_sync();
+      const int64_t doc = tile * FT_TM + lg * 32 + lane;
+      const bool doc_ok = doc < p.n_end;
+      const uint32_t taddr = tmem_base + buf * FT_TN + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < FT_TN; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float sc = __uint_as_float(r[j]) * inv;
+          if (doc_ok && !(sc < thr[c0 + j])) {
+            const int q = qb * FT_TN + c0 + j;
+            const int slot = atomicAdd(&p.count[q], 1);
+            if (slot < p.capg) {
+              p.cand_score[(int64_t)q * p.capg + slot] = sc;
+              p.cand_id[(int64_t)q * p.capg + slot] = (int32_t)doc;
+            } else {
+              *p.overflow = 1;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// one CTA per query: sort approximate candidates, keep FT_KEEP, tau = k-th approximate score;
+// a dropped candidate inside the margin window breaks the guarantee -> overflow flag
+__global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, const float* margin, int* count, float* cand_score,
+                                                                  int32_t* cand_id, int* overflow, int capg, int k, int keep) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_score = reinterpret_cast<float*>(smem_raw);
+  int32_t* s_id = reinterpret_cast<int32_t*>(s_score + capg);
+  const int q = blockIdx.x;
+  int cnt = count[q];
+  if (cnt > capg) cnt = capg;
+  if (cnt == 0) return;
+  for (int i = threadIdx.x; i < capg; i += blockDim.x) {
+    if (i < cnt) {
+      s_score[i] = cand_score[(int64_t)q * capg + i];
+      s_id[i] = cand_id[(int64_t)q * capg + i];
+    } else {
+      s_score[i] = -CUDART_INF_F;
+      s_id[i] = 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  block_bitonic_sort<int32_t>(s_score, s_id, capg);
+  const int kept = cnt < keep ? cnt : keep;
+  for (int i = threadIdx.x; i < kept; i += blockDim.x) {
+    cand_score[(int64_t)q * capg + i] = s_score[i];
+    cand_id[(int64_t)q * capg + i] = s_id[i];
+  }
+  if (threadIdx.x == 0) {
+    count[q] = kept;
+    const float t = (cnt >= k) ? s_score[k - 1] : -CUDART_INF_F;
+    tau[q] = t;
+    if (cnt > keep && !(s_score[keep] < t - margin[q])) *overflow = 1;
+  }
+}
+
+// one CTA per query: exact fp32 re-score of the surviving candidates, sort, emit the k best
+__global__ void __launch_bounds__(256) flat_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ D, int d,
+                                                           const int* __restrict__ count, const int32_t* __restrict__ cand_id,
+                                                           int capg, int k, int keep_pow2, int64_t id_base,
+                                                           float* __restrict__ scores, int64_t* __restrict__ ids) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_score = reinterpret_cast<float*>(smem_raw);
+  int32_t* s_id = reinterpret_cast<int32_t*>(s_score + keep_pow2);
+  const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int cnt = count[q];
+  if (cnt > keep_pow2) cnt = keep_pow2;
+  for (int i = threadIdx.x; i < keep_pow2; i += blockDim.x) {
+    s_score[i] = -CUDART_INF_F;
+    s_id[i] = 0x7fffffff;
+  }
+  __syncthreads();
+  for (int i = warp; i < cnt; i += 8) {
+    const int32_t row = cand_id[(int64_t)q * capg + i];
+    float acc = 0.f;
+    for (int c4 = lane * 4; c4 < d; c4 += 128) {  // same summation pattern as the dense scorer
+      const float4 a = ldg_f4(Q + (int64_t)q * d + c4);
+      const float4 b = ld_stream_f4(D + (int64_t)row * d + c4);
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      s_score[i] = acc;
+      s_id[i] = row;
+    }
+  }
+  __syncthreads();
+  block_bitonic_sort<int32_t>(s_score, s_id, keep_pow2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const bool ok = i < cnt;
+    scores[(int64_t)q * k + i] = ok ? s_score[i] : -CUDART_INF_F;
+    ids[(int64_t)q * k + i] = ok ? id_base + (int64_t)s_id[i] : -1;
+  }
+}
+
+__global__ void flat_tensor_init_kernel(float* tau, int* count, int* overflow, int* err, int nq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) {
+    tau[i] = -CUDART_INF_F;
+    count[i] = 0;
+  }
+  if (i == 0) {
+    *overflow = 0;
+    *err = 0;
+  }
+}
+
+}  // namespace
+
+bool mevi_flat_tensor_supported(mevi_ctx* ctx, int d, int k) {
+  return ctx && ctx->cc_major == 10 && d >= FT_KC && d % FT_KC == 0 && d <= 4096 && k >= 1 && k <= FT_KEEP / 2;
+}
+
+// Returns MEVI_OK with *fell_back = 0 when scores/ids hold the exact answer; *fell_back = 1 when the
+// guarantee could not be established (margin overflow, fp16 clamp, pipeline time-out): the caller then
+// runs the fp32 search.
+int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int k,
+                            int64_t id_base, float* scores, int64_t* ids, int* fell_back, cudaStream_t st) {
+  *fell_back = 1;
+  const int nchunks = d / FT_KC;
+  const int64_t n_tiles = (n + FT_TM - 1) / FT_TM;
+  const int n_qblocks = (nq + FT_TN - 1) / FT_TN;
+  const int capg = 4096;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t o_consts = take(FC_NUM * 4), o_abs = take(16), o_flags = take(16), o_tau = take((size_t)nq * 4),
+               o_margin = take((size_t)nq * 4), o_qnorm = take((size_t)nq * 4), o_cnt = take((size_t)nq * 4),
+               o_cs = take((size_t)nq * capg * 4), o_ci = take((size_t)nq * capg * 4),
+               o_bimg = take((size_t)n_qblocks * FT_TN * d * 2), o_aimg = take((size_t)n_tiles * FT_TM * d * 2);
+  char* ws = (char*)mevi_ws(ctx, WS_TOPK_PART, off);
+  if (!ws) return MEVI_ERR_NOMEM;
+  float* consts = (float*)(ws + o_consts);
+  unsigned* absmax2 = (unsigned*)(ws + o_abs);        // [0] D sample absmax, [1] Q absmax, [2] max doc norm
+  int* flags = (int*)(ws + o_flags);                   // [0] overflow, [1] pipeline error, [2] clamped
+  float* tau = (float*)(ws + o_tau);
+  float* margin = (float*)(ws + o_margin);
+  float* qnorm = (float*)(ws + o_qnorm);
+  int* count = (int*)(ws + o_cnt);
+  float* cand_score = (float*)(ws + o_cs);
+  int32_t* cand_id = (int32_t*)(ws + o_ci);
+  __half* Bimg = (__half*)(ws + o_bimg);
+  __half* Aimg = (__half*)(ws + o_aimg);
+
+  MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, 32 + 256, st));  // absmax2 + flags
+  flat_tensor_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(tau, count, flags, flags + 1, nq);
+  const int64_t sample_rows = 4096;
+  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(D, n, d, n > sample_rows ? n / sample_rows : 1, absmax2);
+  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(Q, nq, d, 1, absmax2 + 1);
+  flat_consts_kernel<<<1, 32, 0, st>>>(absmax2, consts);
+  to_fp16_image_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(D, n, d, FT_TM, consts, FC_SD, Aimg, nullptr, absmax2 + 2, flags + 2,
+                                                          n_tiles * FT_TM);
+  to_fp16_image_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(Q, nq, d, FT_TN, consts, FC_SQ, Bimg, qnorm, nullptr, flags + 2,
+                                                          (int64_t)n_qblocks * FT_TN);
+  flat_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(qnorm, nq, absmax2 + 2, margin);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 7);
+
+  GemmParams p;
+  p.Aimg = Aimg; p.Bimg = Bimg; p.nq = nq; p.n_qblocks = n_qblocks; p.nchunks = nchunks; p.n_end = n;
+  p.consts = consts; p.tau = tau; p.margin = margin; p.count = count; p.cand_score = cand_score; p.cand_id = cand_id;
+  p.overflow = flags; p.capg = capg; p.err_flag = flags + 1;
+  const size_t smem_gemm = (size_t)FT_STAGES * FT_STAGE_BYTES + 2 * FT_TN * 4 + (2 * FT_STAGES + 4) * 8 + 16 + 1024;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
+  const size_t smem_compact = (size_t)capg * 8;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
+
+  // chunks of document tiles growing geometrically: the first can never overflow the candidate buffers
+  int64_t chunk_tiles = (capg - FT_KEEP) / FT_TM;
+  int64_t pos = 0;
+  while (pos < n_tiles) {
+    const int64_t end = pos + chunk_tiles < n_tiles ? pos + chunk_tiles : n_tiles;
+    p.tile_begin = pos;
+    p.tile_end = end;
+    const int64_t items = (end - pos) * n_qblocks;
+    const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
+    flat_gemm_kernel<<<grid, FT_THREADS2, smem_gemm, st>>>(p);
+    flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(tau, margin, count, cand_score, cand_id, flags, capg, k, FT_KEEP);
+    MEVI_CUDA(ctx, cudaGetLastError());
+    MEVI_COUNT_LAUNCH(ctx, 2);
+    pos = end;
+    int64_t next = pos * 3;
+    const int64_t cap_chunk = ((int64_t)1 << 22) / FT_TM;
+    chunk_tiles = next > cap_chunk ? cap_chunk : next;
+  }
+  int h_flags[4] = {0, 0, 0, 0};
+  MEVI_CUDA(ctx, cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+  if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "flat tensor kernel pipeline time-out (code %d)", h_flags[1]);
+  if (h_flags[0] || h_flags[2]) return MEVI_OK;  // guarantee not established: caller falls back to fp32
+  const size_t smem_rescore = (size_t)FT_KEEP * 8;
+  flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D, d, count, cand_id, capg, k, FT_KEEP, id_base, scores, ids);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  *fell_back = 0;
+  return MEVI_OK;
 }

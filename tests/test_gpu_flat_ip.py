@@ -9,10 +9,11 @@ from gpu_util import assert_topk_equivalent, ctx, dev
 pytestmark = pytest.mark.gpu
 
 
-def _modes(c):
+def _modes(c, d=768, k=100):
+    """exact always; tensor when the library supports this (d, k) on this device."""
     modes = ["exact"]
     try:
-        c.flat_ip_topk(torch.zeros((1, 768), device="cuda:0"), torch.zeros((8, 768), device="cuda:0"), 1, mode="tensor")
+        c.flat_ip_topk(torch.zeros((1, d), device="cuda:0"), torch.zeros((8, d), device="cuda:0"), k, mode="tensor")
         modes.append("tensor")
     except Exception as e:
         if "unsupported" not in str(e).lower() and "not built" not in str(e).lower():
@@ -20,7 +21,8 @@ def _modes(c):
     return modes
 
 
-@pytest.mark.parametrize("n,nq,d,k", [(3000, 32, 768, 100), (20000, 130, 768, 100), (5000, 7, 64, 1000), (50, 5, 768, 100)])
+@pytest.mark.parametrize("n,nq,d,k", [(3000, 32, 768, 100), (20000, 130, 768, 100), (5000, 7, 64, 1000), (50, 5, 768, 100),
+                                      (70000, 300, 128, 10), (9000, 257, 768, 256)])
 def test_flat_matches_oracle(n, nq, d, k):
     rs = np.random.RandomState(n + k)
     D = rs.standard_normal((n, d)).astype(np.float32)
@@ -28,7 +30,7 @@ def test_flat_matches_oracle(n, nq, d, k):
     s_ref, i_ref = oracle.flat_ip_topk(Q, D, k)
     c = ctx()
     D64, Q64 = D.astype(np.float64), Q.astype(np.float64)
-    for mode in _modes(c):
+    for mode in _modes(c, d, k) + ["auto"]:
         s, i = c.flat_ip_topk(dev(Q), dev(D), k, mode=mode)
         assert s.dtype == torch.float32 and i.dtype == torch.int64
         assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref, rtol=1e-5, atol=2e-4,
@@ -46,6 +48,21 @@ def test_sorted_documents_trigger_safe_mode():
     s_ref, i_ref = oracle.flat_ip_topk(q, D, 100)
     s, i = ctx().flat_ip_topk(dev(q), dev(D), 100, mode="exact")
     assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref, rtol=1e-5, atol=1e-4)
+
+
+def test_near_duplicate_documents_defeat_the_fp16_margin_and_fall_back():
+    """Thousands of near-duplicate documents put more candidates inside the fp16 error window than the
+    prefilter may keep; the tensor path must notice and hand over to the fp32 search (still exact)."""
+    rs = np.random.RandomState(4)
+    d, n = 128, 20000
+    base = rs.standard_normal((1, d)).astype(np.float32)
+    D = (base + 1e-4 * rs.standard_normal((n, d))).astype(np.float32)
+    Q = rs.standard_normal((3, d)).astype(np.float32)
+    s_ref, i_ref = oracle.flat_ip_topk(Q, D, 50)
+    D64, Q64 = D.astype(np.float64), Q.astype(np.float64)
+    s, i = ctx().flat_ip_topk(dev(Q), dev(D), 50, mode="auto")
+    assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref, rtol=1e-5, atol=2e-4,
+                           pool_scores=lambda q, doc: float(D64[doc] @ Q64[q]))
 
 
 def test_search_dropin_pieces_id_base_and_file(tmp_path, gauss):
