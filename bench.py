@@ -134,6 +134,7 @@ def reference_arm(args, rank, world):
 
     from oracle import oracle
 
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference uses every core
     torch.manual_seed(1234)
     S = args.ref_sample
     X = torch.randn(S, D).numpy()
@@ -339,6 +340,7 @@ def cpu_baseline_child(args):
 
     from oracle import oracle
 
+    torch.set_num_threads(os.cpu_count() or 1)
     sample = np.load(args.sample_file)
     cb_cpu = load_codebook()
     oracle.rq_encode(sample[:8192], cb_cpu, batch_size=128)  # warm-up (allocator, threads)
