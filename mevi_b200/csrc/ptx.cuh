@@ -64,6 +64,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// ---- TMA 2-D tiled load global -> shared (UTMALDG); coordinates are {inner element, row} -----------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* holder_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(holder_smem)), "r"(cols) : "memory");
@@ -92,6 +103,11 @@ constexpr uint32_t SW128_SBO = 1024 >> 4;
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)SW128_SBO << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
+}
+// K-major operand tile, 64-byte rows, 64B swizzle: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
 }
 // instruction descriptor: D=f32, A=B=f16 (kind::f16), both K-major, M=128
 __host__ __device__ constexpr uint32_t umma_idesc_f16_m128(uint32_t n) {

@@ -596,6 +596,8 @@ __global__ void residual_from_codes_kernel(const float* __restrict__ X, int64_t 
   }
 }
 
+#include "rq_tensor3.cuh"
+
 }  // namespace
 
 bool mevi_rq_tensor_supported(mevi_ctx* ctx, int d, int M, int K, int metric) {
@@ -631,7 +633,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t o_consts = take(C_NUM * 4), o_abs = take(8), o_err = take(4), o_cnt = take(8), o_cn2 = take(NT * 4),
                o_cnorm = take(NT * 4), o_e1 = take(NT * 4), o_lvl = take(8 * 4 * 4), o_gram = take((size_t)(gram_floats ? gram_floats : 1) * 4),
-               o_bimg = take((size_t)nchunks * N1 * KC * 2);
+               o_bimg = take((size_t)nchunks * N1 * KC * 2 + 1024);
   char* ws = (char*)mevi_ws(ctx, WS_RQ_PREP, off);
   if (!ws) return MEVI_ERR_NOMEM;
   float* consts = (float*)(ws + o_consts);
@@ -673,6 +675,32 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     const char* dbg = getenv("MEVI_RQ_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  const char* ver = getenv("MEVI_RQ_KERNEL");
+  const bool use_v3 = !(ver && atoi(ver) == 2);
+  if (use_v3) {
+    // third-generation kernel: TMA-fed fp32 ring, 256-row tiles, 64B-swizzle operands (rq_tensor3.cuh)
+    CUtensorMap tmap;
+    int trc = v3::make_x_tensormap(ctx, X, n, d, &tmap);
+    if (trc != MEVI_OK) return trc;
+    v3::bimg32_kernel<<<(NT * (d / 8) + 255) / 256, 256, 0, st>>>(cb, M * K, d, NT, consts, Bimg);
+    MEVI_COUNT_LAUNCH(ctx, 1);
+    p.n_tiles = (n + v3::TM3 - 1) / v3::TM3;
+    const v3::Smem3 L3 = v3::smem3_layout(M, K, NT);
+    const size_t smem3 = (size_t)L3.total + 1024;
+    const int grid3 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+#define MEVI_LAUNCH_RQ_TENSOR3(MM)                                                                                          \
+  do {                                                                                                                      \
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(v3::rq_tensor3_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3)); \
+    v3::rq_tensor3_kernel<MM><<<grid3, v3::THREADS3, smem3, st>>>(p, tmap);                                                 \
+  } while (0)
+    switch (M) {
+      case 1: MEVI_LAUNCH_RQ_TENSOR3(1); break;
+      case 2: MEVI_LAUNCH_RQ_TENSOR3(2); break;
+      case 3: MEVI_LAUNCH_RQ_TENSOR3(3); break;
+      default: MEVI_LAUNCH_RQ_TENSOR3(4); break;
+    }
+#undef MEVI_LAUNCH_RQ_TENSOR3
+  } else {
   const SmemLayout L = smem_layout(M, K, NT, N1);
   const size_t smem_bytes = (size_t)L.total + 1024;  // slack for the 1024-byte alignment of the dynamic base
   const int grid = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
@@ -688,6 +716,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     default: MEVI_LAUNCH_RQ_TENSOR(4); break;
   }
 #undef MEVI_LAUNCH_RQ_TENSOR
+  }
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaMemcpyAsync(host_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
