@@ -32,142 +32,89 @@ namespace {
 constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_TILE = 256;
+#ifndef MEVI_KA_STAGES
+#define MEVI_KA_STAGES 2
+#endif
+constexpr int KA_STAGES = MEVI_KA_STAGES;  // shared-memory stages of the accumulate kernel (KA_STAGES-1 bulk copies in flight)
 
-// Column-owner accumulation (skew-proof and deterministic).  Thread t owns columns 2t, 2t+1 of
-// every centroid: KMAX x 2 fp32 accumulators in registers for the CTA's whole (contiguous) row range.
-// Rows arrive in sub-tiles of up to 32 rows — one contiguous byte range, fetched with a single bulk
-// async copy (TMA engine) into a double-buffered shared-memory stage, so ~100-190 KB per SM are in
-// flight without holding registers.  Warp 0 buckets the sub-tile's rows by centroid (match_any +
-// popc = stable counting sort); then for each centroid (unrolled, so the accumulator is a fixed
-// register) every thread walks the bucket's rows in ascending order and adds its two columns from
-// shared memory.  All threads work on every row, so one dominant cluster (the reference-trained
-// codebooks put >80 % of N(0,1) rows into two centroids) costs nothing extra.
-template <int KMAX, int NT>
+// Column-owner accumulation (skew-proof and deterministic).  The CTA keeps the running [K][d] fp32
+// sums in shared memory; thread t owns column t of every centroid.  Rows arrive in sub-tiles — one
+// contiguous byte range, fetched with a single bulk async copy (TMA engine) into a double-buffered
+// shared-memory stage.  Every thread then walks the sub-tile's rows in order and adds its column to
+// the accumulator row of the row's centroid (a CTA-uniform index, so the access stays conflict-free).
+// All threads work on every row, so one dominant cluster (the reference-trained codebooks put >80 %
+// of N(0,1) rows into two centroids) costs nothing extra; the summation order is the row order.
+template <int NT>
 __global__ void __launch_bounds__(NT, 1) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
                                                                   const int32_t* __restrict__ assign,
                                                                   int64_t assign_stride, int K, int sub_rows,
                                                                   float* __restrict__ partial_sums,     // [grid][K][d]
                                                                   int32_t* __restrict__ partial_counts)  // [grid][K]
 {
-  extern __shared__ __align__(128) unsigned char km_smem[];  // [2][sub_rows][d] fp32
-  __shared__ __align__(8) uint64_t full_bar[2];
-  __shared__ int s_start[KMAX + 1];
-  __shared__ int s_order[32];
-  __shared__ int s_count_total[KMAX];
+  extern __shared__ __align__(128) unsigned char km_smem[];  // [KA_STAGES][sub_rows][d] fp32, then acc [K][d]
+  __shared__ __align__(8) uint64_t full_bar[KA_STAGES];
+  __shared__ int s_assign[KA_STAGES][32];
+  __shared__ int s_count_total[64];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool owner = 2 * tid < d;  // this thread owns columns 2*tid, 2*tid+1
-  const int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
-  const int64_t row_begin = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t row_end = row_begin + rows_per_cta < n ? row_begin + rows_per_cta : n;
-  const int64_t my_rows = row_end > row_begin ? row_end - row_begin : 0;
-  const int64_t nsub = (my_rows + sub_rows - 1) / sub_rows;
+  const int tid = threadIdx.x;
+  const bool owner = tid < d;  // this thread owns column tid of every centroid's running sum
+  // sub-tiles are dealt round-robin (CTA b takes sub-tiles b, b+G, ...): neighbouring SMs stream
+  // neighbouring memory, like the encode kernel; the per-CTA order is still fixed -> reproducible
+  const int64_t total_sub = (n + sub_rows - 1) / sub_rows;
+  const int64_t nsub = total_sub > blockIdx.x ? (total_sub - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t row_end = n;
   const size_t stage_bytes = (size_t)sub_rows * d * sizeof(float);
+  float* s_acc = reinterpret_cast<float*>(km_smem + KA_STAGES * stage_bytes);
 
-  float2 acc[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) acc[k] = make_float2(0.f, 0.f);
-  for (int i = tid; i < KMAX; i += NT) s_count_total[i] = 0;
+  for (int i = tid; i < K * d; i += NT) s_acc[i] = 0.f;
+  for (int i = tid; i < 64; i += NT) s_count_total[i] = 0;
   if (tid == 0) {
-    ptx::mbar_init(&full_bar[0], 1);
-    ptx::mbar_init(&full_bar[1], 1);
+    for (int s = 0; s < KA_STAGES; ++s) ptx::mbar_init(&full_bar[s], 1);
     ptx::mbar_fence_init();
   }
   __syncthreads();
-  auto issue = [&](int64_t i) {  // thread 0: bulk copy of sub-tile i into stage i & 1
-    const int64_t r0 = row_begin + i * sub_rows;
+  auto issue = [&](int64_t i) {  // thread 0: bulk copy of sub-tile i into stage i % KA_STAGES
+    const int64_t r0 = (blockIdx.x + i * gridDim.x) * sub_rows;
     const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
     const uint32_t bytes = (uint32_t)rows * (uint32_t)d * 4u;
-    ptx::mbar_arrive_expect_tx(&full_bar[i & 1], bytes);
-    ptx::bulk_g2s(km_smem + (size_t)(i & 1) * stage_bytes, R + r0 * d, bytes, &full_bar[i & 1]);
+    const int s = (int)(i % KA_STAGES);
+    ptx::mbar_arrive_expect_tx(&full_bar[s], bytes);
+    ptx::bulk_g2s(km_smem + (size_t)s * stage_bytes, R + r0 * d, bytes, &full_bar[s]);
   };
-  if (tid == 0 && nsub > 0) issue(0);
-  // warp 0 prefetches the assignments of the next sub-tile one iteration ahead
-  int next_a = KMAX;
-  if (warp == 0 && nsub > 0) {
-    const int64_t r = row_begin + lane;
-    if (lane < sub_rows && r < row_end) {
+  auto load_assign = [&](int64_t i) {  // threads 0..sub_rows-1: assignments of sub-tile i -> s_assign[i % KA_STAGES]
+    const int64_t r = (blockIdx.x + i * gridDim.x) * sub_rows + tid;
+    if (tid < sub_rows && r < row_end) {
       int a = assign[r * assign_stride];
-      next_a = a < 0 ? 0 : (a >= K ? K - 1 : a);
+      a = a < 0 ? 0 : (a >= K ? K - 1 : a);
+      s_assign[i % KA_STAGES][tid] = a;
+      atomicAdd(&s_count_total[a], 1);
     }
+  };
+  for (int64_t i = 0; i < KA_STAGES - 1 && i < nsub; ++i) {
+    if (tid == 0) issue(i);
+    load_assign(i);
   }
-
   for (int64_t i = 0; i < nsub; ++i) {
-    const int64_t r0 = row_begin + i * sub_rows;
+    const int64_t r0 = (blockIdx.x + i * gridDim.x) * sub_rows;
     const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
-    if (tid == 0 && i + 1 < nsub) issue(i + 1);  // stage (i+1)&1 was released by the barrier that ended iteration i-1
-    if (warp == 0) {
-      // stable counting sort of <= 32 rows by centroid
-      const int a = next_a;  // KMAX for lanes past the sub-tile
-      next_a = KMAX;
-      if (i + 1 < nsub) {
-        const int64_t r = r0 + sub_rows + lane;
-        if (lane < sub_rows && r < row_end) {
-          int an = assign[r * assign_stride];
-          next_a = an < 0 ? 0 : (an >= K ? K - 1 : an);
-        }
-      }
-      const unsigned same = __match_any_sync(MEVI_FULL_MASK, a);
-      const int rank = __popc(same & ((1u << lane) - 1u));
-      // bucket starts: lane k (and k+32) counts the rows assigned to centroid k, then an exclusive scan
-      int start_lo = 0, start_hi = 0;
-      {
-        int c_lo = 0, c_hi = 0;
-#pragma unroll
-        for (int src = 0; src < 32; ++src) {
-          const int av = __shfl_sync(MEVI_FULL_MASK, a, src);
-          c_lo += (av == lane);
-          c_hi += (av == lane + 32);
-        }
-        if (lane < KMAX) s_count_total[lane] += c_lo;
-        if (KMAX > 32 && lane + 32 < KMAX) s_count_total[lane + 32] += c_hi;
-        int inc = c_lo;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(MEVI_FULL_MASK, inc, o);
-          if (lane >= o) inc += v;
-        }
-        start_lo = inc - c_lo;
-        const int total_lo = __shfl_sync(MEVI_FULL_MASK, inc, 31);
-        int inc2 = c_hi;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(MEVI_FULL_MASK, inc2, o);
-          if (lane >= o) inc2 += v;
-        }
-        start_hi = total_lo + inc2 - c_hi;
-        if (lane < KMAX) s_start[lane] = start_lo;
-        if (KMAX > 32 && lane + 32 < KMAX) s_start[lane + 32] = start_hi;
-        if (lane == 0) s_start[KMAX] = rows;
-      }
-      {  // every lane takes part in the broadcast (the source lane = centroid id need not share `a`)
-        const int src = a & 31;
-        const int from_lo = __shfl_sync(MEVI_FULL_MASK, start_lo, src);
-        const int from_hi = __shfl_sync(MEVI_FULL_MASK, start_hi, src);
-        if (a < KMAX) s_order[(a < 32 ? from_lo : from_hi) + rank] = lane;
-      }
+    if (i + KA_STAGES - 1 < nsub) {  // that stage was released by the barrier that ended iteration i-1
+      if (tid == 0) issue(i + KA_STAGES - 1);
+      load_assign(i + KA_STAGES - 1);
     }
-    ptx::mbar_wait(&full_bar[i & 1], (uint32_t)((i >> 1) & 1));
-    __syncthreads();
+    const int stg = (int)(i % KA_STAGES);
+    ptx::mbar_wait(&full_bar[stg], (uint32_t)((i / KA_STAGES) & 1));
+    __syncthreads();  // s_assign[stg] (written at least one iteration ago) is visible
     if (owner) {
-      const float* base = reinterpret_cast<const float*>(km_smem + (size_t)(i & 1) * stage_bytes) + 2 * tid;
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        const int b = s_start[k], e = s_start[k + 1];
-        for (int j = b; j < e; ++j) {  // ascending row order inside the bucket: reproducible sums
-          const float2 v = *reinterpret_cast<const float2*>(base + (size_t)s_order[j] * d);
-          acc[k].x += v.x;
-          acc[k].y += v.y;
-        }
-      }
+      const float* base = reinterpret_cast<const float*>(km_smem + (size_t)stg * stage_bytes) + tid;
+      const int* as = s_assign[stg];
+      float* my_acc = s_acc + tid;
+      // the row's centroid is a CTA-uniform value, so the dynamically indexed accumulator row costs
+      // nothing in shared memory; rows are added in order -> the sum is reproducible
+      for (int r = 0; r < rows; ++r) my_acc[(size_t)as[r] * d] += base[(size_t)r * d];
     }
     __syncthreads();
   }
-  if (owner) {
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) *reinterpret_cast<float2*>(partial_sums + ((int64_t)blockIdx.x * K + k) * d + 2 * tid) = acc[k];
-  }
+  for (int i = tid; i < K * d; i += NT) partial_sums[(int64_t)blockIdx.x * K * d + i] = s_acc[i];
   if (tid < K) partial_counts[(int64_t)blockIdx.x * K + tid] = s_count_total[tid];
 }
 
@@ -232,27 +179,23 @@ __global__ void residual_update_kernel(float* __restrict__ R, int64_t n, int d4,
   }
 }
 
-template <int KMAX, int NT>
+template <int NT>
 cudaError_t launch_accumulate_nt(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
-                                 float* ps, int32_t* pc, cudaStream_t st) {
-  int sub_rows = (int)(96 * 1024 / ((size_t)d * 4));
-  if (sub_rows > 32) sub_rows = 32;
-  if (sub_rows < 1) sub_rows = 1;
-  const size_t smem = 2 * (size_t)sub_rows * d * 4 + 128;
-  cudaError_t e = cudaFuncSetAttribute(kmeans_accumulate_kernel<KMAX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                 float* ps, int32_t* pc, int sub_rows, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kmeans_accumulate_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kmeans_accumulate_kernel<KMAX, NT><<<G, NT, smem, st>>>(R, n, d, assign, stride, K, sub_rows, ps, pc);
+  kmeans_accumulate_kernel<NT><<<G, NT, smem, st>>>(R, n, d, assign, stride, K, sub_rows, ps, pc);
   return cudaGetLastError();
 }
 
-template <int KMAX>
 cudaError_t launch_accumulate(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
-                              float* ps, int32_t* pc, cudaStream_t st) {
-  // one thread per column pair
-  if (d <= 256) return launch_accumulate_nt<KMAX, 128>(R, n, d, assign, stride, K, G, ps, pc, st);
-  if (d <= 512) return launch_accumulate_nt<KMAX, 256>(R, n, d, assign, stride, K, G, ps, pc, st);
-  if (d <= 768) return launch_accumulate_nt<KMAX, 384>(R, n, d, assign, stride, K, G, ps, pc, st);
-  return launch_accumulate_nt<KMAX, 512>(R, n, d, assign, stride, K, G, ps, pc, st);
+                              float* ps, int32_t* pc, int sub_rows, size_t smem, cudaStream_t st) {
+  // one thread per column
+  if (d <= 128) return launch_accumulate_nt<128>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+  if (d <= 256) return launch_accumulate_nt<256>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+  if (d <= 512) return launch_accumulate_nt<512>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+  if (d <= 768) return launch_accumulate_nt<768>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+  return launch_accumulate_nt<1024>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
 }
 
 }  // namespace
@@ -302,10 +245,14 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
   if (rc != MEVI_OK) return rc;
 
   // 2. accumulation
-  const bool fast = K <= 64 && d <= 1024 && d % 4 == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
+  // shared-memory budget: [K][d] accumulators + KA_STAGES stages of sub_rows rows
+  const size_t acc_bytes = (size_t)kd * sizeof(float);
+  int sub_rows = acc_bytes + 4096 < 220 * 1024 ? (int)((220 * 1024 - acc_bytes) / ((size_t)KA_STAGES * d * 4)) : 0;
+  if (sub_rows > 32) sub_rows = 32;
+  const bool fast = K <= 64 && d <= 1024 && d % 4 == 0 && sub_rows >= 4 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
   if (fast) {
-    int G = ctx->sm_count;  // one CTA per SM (shared-memory stages), persistent over its row range
-    int64_t max_g = (n + KM_TILE - 1) / KM_TILE;
+    int G = ctx->sm_count;  // one CTA per SM (shared-memory stages), persistent
+    int64_t max_g = (n + sub_rows - 1) / sub_rows;
     if (G > max_g) G = (int)max_g;
     if (G < 1) G = 1;
     size_t ps_bytes = (size_t)G * kd * sizeof(float);
@@ -314,10 +261,8 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
     if (!ws) return MEVI_ERR_NOMEM;
     float* ps = (float*)ws;
     int32_t* pc = (int32_t*)(ws + ps_bytes);
-    cudaError_t e;
-    if (K <= 16) e = launch_accumulate<16>(R, n, d, assign, stride, K, G, ps, pc, st);
-    else if (K <= 32) e = launch_accumulate<32>(R, n, d, assign, stride, K, G, ps, pc, st);
-    else e = launch_accumulate<64>(R, n, d, assign, stride, K, G, ps, pc, st);
+    const size_t smem = (size_t)KA_STAGES * sub_rows * d * 4 + acc_bytes + 128;
+    cudaError_t e = launch_accumulate(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
     if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "kmeans_accumulate launch: %s", cudaGetErrorString(e));
     int threads = 256;
     int blocks = (int)((kd + K + threads - 1) / threads);

@@ -23,5 +23,5 @@ for r in rows[h+1:]:
     if 'distribution' in n: continue
     print(f"{v:>14s} {u}  {n}")
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_tensor_kernel -s 2 -c 1 -o gpurun_out/prof_tensor python /tmp/prof_driver.py 2000000 > gpurun_out/prof_tensor.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_tensor3_kernel -s 2 -c 1 -o gpurun_out/prof_tensor python /tmp/prof_driver.py 2000000 > gpurun_out/prof_tensor.log 2>&1
 echo "ncu rc=$?"; tail -2 gpurun_out/prof_tensor.log
