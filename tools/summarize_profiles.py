@@ -1,0 +1,68 @@
+"""Turn the ncu reports brought back in gpurun_out/ into the small tracked summaries under profiles/."""
+import collections, csv, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+G = os.path.join(ROOT, "gpurun_out")
+
+def ncu_csv(rep, page):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(txt.splitlines()))
+
+def launches(path, out):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    h = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+    H = rows[h]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[h + 1:]:
+        v = float(r[H.index("Metric Value")].replace(",", "")); u = r[H.index("Metric Unit")]
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1e-6)
+        name = r[H.index("Kernel Name")]
+        bare = name.replace("void ", "")
+        mine = bare.startswith("<unnamed>::") and not bare.startswith("<unnamed>::elementwise")
+        key = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")[:70]
+        agg[("mevi_b200" if mine else "torch/cub") + "  " + key][0] += 1
+        agg[("mevi_b200" if mine else "torch/cub") + "  " + key][1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as fw:
+        fw.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (cold-cache, serialised launches: compare SHARES)\n")
+        fw.write("# command: python bench.py --steps 2 --warmup 3 --no-cpu-baseline   (5 encode passes, e2e passes, extras)\n")
+        fw.write(f"# total device time {tot:.1f} ms over {sum(v[0] for v in agg.values())} launches\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            fw.write(f"{v[1]:12.3f} ms {v[0]:6d}x {100 * v[1] / tot:6.2f}%  {k}\n")
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
+        "smsp__inst_executed.sum"]
+
+def kernels(rep, fw, seen):
+    rows = ncu_csv(rep, "raw")
+    H, U = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[H.index("Kernel Name")]
+        short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")
+        if short in seen: continue
+        seen.add(short)
+        fw.write(f"\n## {short}\n")
+        for k in KEYS:
+            if k in H: fw.write(f"  {k:78s} {r[H.index(k)]:>18s} {U[H.index(k)]}\n")
+    return rows
+
+os.makedirs(OUT, exist_ok=True)
+launches(os.path.join(G, "launches_bench.csv"), os.path.join(OUT, "r01_launches_bench.txt"))
+seen = set()
+with open(os.path.join(OUT, "r01_ncu_kernels.md"), "w") as fw:
+    fw.write("# ncu --set full --clock-control none  (one launch per kernel; B200, round 1)\n")
+    fw.write("rq_tensor3_kernel<4> captured inside `bench.py` at the bench size (8,841,823 x 768); the others on 2,000,000 x 768.\n")
+    rows = kernels(os.path.join(G, "prof_rq_encode.ncu-rep"), fw, seen)
+    H = rows[0]; r = rows[2]
+    rd = float(r[H.index("dram__bytes_read.sum")]); wr = float(r[H.index("dram__bytes_write.sum")])
+    ur, uw = rows[1][H.index("dram__bytes_read.sum")], rows[1][H.index("dram__bytes_write.sum")]
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    traffic = rd * mult[ur] + wr * mult[uw]
+    kernels(os.path.join(G, "prof_others.ncu-rep"), fw, seen)
+json.dump({"rq_encode_dram_bytes_per_launch": traffic, "source": "profiles/r01_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of rq_tensor3_kernel<4>, one launch at the bench size)"},
+          open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+print("traffic", traffic)
