@@ -1,0 +1,24 @@
+"""CLI with the flags of MEVI/ensemble_marco.py:243-259."""
+from argparse import ArgumentParser
+
+from .ensemble import combine_main_marco as combine_main
+
+
+def main(argv=None):
+    parser = ArgumentParser()
+    parser.add_argument("--dir_path", type=str, default=None)
+    parser.add_argument("--gt_file", type=str, required=True)
+    parser.add_argument("--ance_file", type=str, required=True)
+    parser.add_argument("--fine_file", type=str, default=None)
+    parser.add_argument("--coarse_file", type=str, default=None)
+    parser.add_argument("--mapping_file", type=str, default=None)
+    parser.add_argument("--alphas", type=str, default="0.6")
+    parser.add_argument("--betas", type=str, default="0.03")
+    parser.add_argument("--gammas", type=str, default="0.02")
+    parser.add_argument("--recall_num", type=str, default="10,50,1000")
+    parser.add_argument("--ofile", type=str, default=None)
+    combine_main(parser.parse_args(argv))
+
+
+if __name__ == "__main__":
+    main()
