@@ -597,6 +597,7 @@ __global__ void residual_from_codes_kernel(const float* __restrict__ X, int64_t 
 }
 
 #include "rq_tensor3.cuh"
+#include "rq_tensor4.cuh"
 
 }  // namespace
 
@@ -676,8 +677,34 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     p.debug = dbg ? atoi(dbg) : 0;
   }
   const char* ver = getenv("MEVI_RQ_KERNEL");
-  const bool use_v3 = !(ver && atoi(ver) == 2);
-  if (use_v3) {
+  // default: third generation.  MEVI_RQ_KERNEL=4 selects the tensor-memory-operand variant (correct, but
+  // measured 5 % slower: its single accumulator buffer exposes the epilogue), =2 the register-staged one.
+  const int kver = ver ? atoi(ver) : 3;
+  const bool use_v3 = kver == 3;
+  if (kver >= 4) {
+    // fourth-generation kernel: document operand through tensor memory (rq_tensor4.cuh)
+    CUtensorMap tmap;
+    int trc = v4::make_x_tensormap4(ctx, X, n, d, &tmap);
+    if (trc != MEVI_OK) return trc;
+    v3::bimg32_kernel<<<(NT * (d / 8) + 255) / 256, 256, 0, st>>>(cb, M * K, d, NT, consts, Bimg);
+    MEVI_COUNT_LAUNCH(ctx, 1);
+    p.n_tiles = (n + v4::TM4 - 1) / v4::TM4;
+    const v4::Smem4 L4 = v4::smem4_layout(M, K, NT);
+    const size_t smem4 = (size_t)L4.total + 1024;
+    const int grid4 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+#define MEVI_LAUNCH_RQ_TENSOR4(MM)                                                                                          \
+  do {                                                                                                                      \
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+    v4::rq_tensor4_kernel<MM><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                                 \
+  } while (0)
+    switch (M) {
+      case 1: MEVI_LAUNCH_RQ_TENSOR4(1); break;
+      case 2: MEVI_LAUNCH_RQ_TENSOR4(2); break;
+      case 3: MEVI_LAUNCH_RQ_TENSOR4(3); break;
+      default: MEVI_LAUNCH_RQ_TENSOR4(4); break;
+    }
+#undef MEVI_LAUNCH_RQ_TENSOR4
+  } else if (use_v3) {
     // third-generation kernel: TMA-fed fp32 ring, 256-row tiles, 64B-swizzle operands (rq_tensor3.cuh)
     CUtensorMap tmap;
     int trc = v3::make_x_tensormap(ctx, X, n, d, &tmap);

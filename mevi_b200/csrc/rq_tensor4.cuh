@@ -1,0 +1,352 @@
+// rq_tensor4.cuh — K1, fourth generation: the document operand goes through TENSOR MEMORY.
+//
+// Same algorithm / error model / work-list protocol as the earlier generations (rq_tensor.cu).  v3 is bound
+// by shared-memory bandwidth (70 % of the LSU data pipe: TMA writes + converter loads + converter stores +
+// UMMA operand fetches = 19.5 KB per document).  Here the converters write the fp16 hi|lo operand tiles
+// straight into TMEM with tcgen05.st and tcgen05.mma reads A from TMEM, which removes the converter stores
+// and the A-operand fetches from shared memory (12 KB per document) and frees 64 KB of it for a deeper
+// TMA ring:
+//   warp 0      TMA producer: [256 rows x 32 fp32] boxes, 128B-swizzled, into a 5-stage ring (160 KB in flight)
+//   warp 3      codebook producer: 16 KB bulk copies of the pre-swizzled [C_hi|C_lo] chunk image (2 stages)
+//   warps 4-11  converters, ONE THREAD PER ROW (thread = TMEM lane): 8 conflict-free 16-byte loads of the row's
+//               chunk, scale/split, 2 x tcgen05.st.x16 into one of 4 TMEM operand stages; the row norm is a
+//               plain per-thread accumulator (no shuffles)
+//   warp 1      tcgen05.mma with A in TMEM: per 128-row half and K step A_hi.C_hi + A_hi.C_lo + A_lo.C_hi into
+//               one 128-column accumulator per half
+//   warps 12-15 epilogue (single accumulator buffer; the 4 TMEM operand stages absorb its ~2.5 us)
+// TMEM map (512 columns): [0,256) accumulators (half h at 128h), [256,512) 4 operand stages x (2 halves x (16 hi + 16 lo)).
+#pragma once
+
+namespace v4 {
+
+constexpr int TM4 = 256;
+constexpr int KC4 = 32;
+constexpr int NSX4 = 5, NSB4 = 2, NSA4 = 4;
+constexpr int X_STAGE4 = TM4 * KC4 * 4;  // 32 KB
+constexpr int THREADS4 = 512;
+constexpr uint32_t A_COL0 = 256;         // first TMEM column of the operand stages
+
+struct Smem4 {
+  int x_off, b_off, gram_off, cn2_off, e1_off, lvl_off, stats_off, bar_off, holder_off, total;
+};
+__host__ __device__ inline Smem4 smem4_layout(int M, int K, int NT) {
+  Smem4 L;
+  L.x_off = 0;
+  L.b_off = L.x_off + NSX4 * X_STAGE4;
+  L.gram_off = L.b_off + NSB4 * (2 * NT) * 64;
+  int gram_pad = 0;
+  for (int j = 1; j < M; ++j) gram_pad += j * K * (K + 1);
+  L.cn2_off = L.gram_off + gram_pad * 4;
+  L.e1_off = L.cn2_off + NT * 4;
+  L.lvl_off = L.e1_off + NT * 4;
+  L.stats_off = L.lvl_off + 64;
+  L.bar_off = (L.stats_off + 2 * TM4 * 4 + 7) & ~7;
+  L.holder_off = L.bar_off + 32 * 8;
+  L.total = L.holder_off + 16;
+  return L;
+}
+
+template <bool SCALE>
+__device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, float* sStats, uint32_t tmem_base, uint64_t* x_full,
+                                                uint64_t* x_empty, uint64_t* a_full, uint64_t* a_empty, uint64_t* st_full,
+                                                int cw, int lane) {
+  const int half = cw >> 2;                       // warps 4-7 -> rows 0..127, warps 8-11 -> rows 128..255
+  const int rl = (cw & 3) * 32 + lane;            // row inside the half == TMEM lane
+  const int row = half * 128 + rl;                // row inside the tile == row of the TMA box
+  const float sx = p.consts[C_SX], inv_sx2 = p.consts[C_INV_SX2];
+  const int nchunks = p.d / KC4;
+  const uint32_t src_row = ptx::smem_u32(sX) + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);        // 128B swizzle: 16-byte chunk j of this row sits at j ^ (row & 7)
+  const uint32_t t_lane = tmem_base + ((uint32_t)((cw & 3) * 32) << 16) + A_COL0 + (uint32_t)half * 32u;
+  float norm = 0.f;
+  uint32_t xs = 0, xph = 0, as = 0, aph = 0, it = 0, pend_stage = 0;
+  bool pending = false;
+  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (int c = 0; c < nchunks; ++c) {
+      if (!ptx::mbar_wait(&x_full[xs], xph) || !ptx::mbar_wait(&a_empty[as], aph ^ 1)) { atomicExch(p.err_flag, 4); return; }
+      ptx::tc_fence_after_sync();
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t0, t1, t2, t3;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3)
+                     : "r"(src_row + xs * X_STAGE4 + (((uint32_t)j ^ sw) << 4)));
+        if (SCALE) { t0 *= sx; t1 *= sx; t2 *= sx; t3 *= sx; }
+        norm = fmaf(t0, t0, norm);
+        norm = fmaf(t1, t1, norm);
+        norm = fmaf(t2, t2, norm);
+        norm = fmaf(t3, t3, norm);
+        const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(t0 - b01.x, t1 - b01.y), l23 = __floats2half2_rn(t2 - b23.x, t3 - b23.y);
+        hi[2 * j] = *reinterpret_cast<const uint32_t*>(&h01);       // K elements 4j, 4j+1
+        hi[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h23);   // K elements 4j+2, 4j+3
+        lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l01);
+        lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+      }
+      // publish the PREVIOUS chunk's operand stage: its tcgen05.st had this chunk's conversion time to land
+      if (pending) {
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&a_full[pend_stage]);
+      }
+      ptx::tmem_st16(t_lane + as * 64, hi);
+      ptx::tmem_st16(t_lane + as * 64 + 16, lo);
+      // the stores consumed every value loaded from the X stage: hand it back to the TMA producer
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&x_empty[xs]);
+      pending = true;
+      pend_stage = as;
+      if (++xs == NSX4) { xs = 0; xph ^= 1; }
+      if (++as == NSA4) { as = 0; aph ^= 1; }
+    }
+    // end of tile: publish its last operand stage right away (the MMA needs it to finish the tile)
+    if (pending) {
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&a_full[pend_stage]);
+      pending = false;
+    }
+    sStats[(it & 1) * TM4 + row] = SCALE ? norm * inv_sx2 : norm;
+    norm = 0.f;
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&st_full[it & 1]);
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int K = p.K, NT = p.NT;
+  const Smem4 L = smem4_layout(M, K, NT);
+  uint8_t* sX = smem + L.x_off;
+  uint8_t* sB = smem + L.b_off;
+  float* sGram = reinterpret_cast<float*>(smem + L.gram_off);
+  float* sCn2 = reinterpret_cast<float*>(smem + L.cn2_off);
+  float* sE1 = reinterpret_cast<float*>(smem + L.e1_off);
+  float* sLvl = reinterpret_cast<float*>(smem + L.lvl_off);
+  float* sStats = reinterpret_cast<float*>(smem + L.stats_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + NSX4;
+  uint64_t* a_full = x_empty + NSX4;
+  uint64_t* a_empty = a_full + NSA4;
+  uint64_t* b_full = a_empty + NSA4;
+  uint64_t* b_empty = b_full + NSB4;
+  uint64_t* acc_full = b_empty + NSB4;
+  uint64_t* acc_empty = acc_full + 1;
+  uint64_t* st_full = acc_empty + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L.holder_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t b_stage_bytes = (uint32_t)(2 * NT) * 64u;
+  const int nchunks = p.d / KC4;
+
+  for (int i = tid; i < p.gram_floats; i += THREADS4) {
+    const int r = i / K, c = i - r * K;
+    sGram[r * (K + 1) + c] = p.gram[i];
+  }
+  for (int i = tid; i < NT; i += THREADS4) {
+    sCn2[i] = p.cn2[i];
+    sE1[i] = p.e1[i];
+  }
+  for (int i = tid; i < M * 4; i += THREADS4) sLvl[i] = p.lvl[i];
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSX4; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], CONV_WARPS); }
+    for (int s = 0; s < NSA4; ++s) { ptx::mbar_init(&a_full[s], CONV_WARPS); ptx::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NSB4; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, 4);
+    ptx::mbar_init(&st_full[0], CONV_WARPS);
+    ptx::mbar_init(&st_full[1], CONV_WARPS);
+    ptx::mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) ptx::tma_prefetch_desc(&tmap);
+  if (warp == 2) ptx::tmem_alloc(tmem_holder, TMEM_COLS);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+          if (!ptx::mbar_wait_backoff(&x_empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); return; }
+          ptx::mbar_arrive_expect_tx(&x_full[s], X_STAGE4);
+          ptx::tma_load_2d(sX + (size_t)s * X_STAGE4, &tmap, c * KC4, (int)(tile * TM4), &x_full[s]);
+          if (++s == NSX4) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+          if (!ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 7); return; }
+          ptx::mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
+          ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * (2 * NT) * KC4, b_stage_bytes, &b_full[s]);
+          if (++s == NSB4) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16_m128((uint32_t)NT);
+      uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        // single accumulator buffer: the previous tile's epilogue must have drained it
+        if (!ptx::mbar_wait(acc_empty, (it & 1) ^ 1)) { atomicExch(p.err_flag, 2); return; }
+        ptx::tc_fence_after_sync();
+        for (int c = 0; c < nchunks; ++c) {
+          if (!ptx::mbar_wait(&a_full[as], aph) || !ptx::mbar_wait(&b_full[bs], bph)) { atomicExch(p.err_flag, 3); return; }
+          ptx::tc_fence_after_sync();
+          const uint32_t b_hi = ptx::smem_u32(sB + (size_t)bs * b_stage_bytes);
+          const uint32_t b_lo = b_hi + (uint32_t)NT * 64u;
+          if (!(p.debug & 2)) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d_tmem = tmem_base + h * 128;
+              const uint32_t a_hi = tmem_base + A_COL0 + as * 64 + h * 32, a_lo = a_hi + 16;
+#pragma unroll
+              for (int ks = 0; ks < KC4 / 16; ++ks) {
+                ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, (c | ks) != 0 ? 1u : 0u);
+                ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_lo + ks * 32), idesc, 1u);
+                ptx::umma_f16_ts(d_tmem, a_lo + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, 1u);
+              }
+            }
+          }
+          ptx::umma_commit(&a_empty[as]);
+          ptx::umma_commit(&b_empty[bs]);
+          if (++as == NSA4) { as = 0; aph ^= 1; }
+          if (++bs == NSB4) { bs = 0; bph ^= 1; }
+        }
+        ptx::umma_commit(acc_full);
+      }
+    }
+  } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+    if (p.consts[C_SX] == 1.f)
+      converter_loop4<false>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
+    else
+      converter_loop4<true>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
+  } else if (warp >= EPI_WARP0) {
+    const int ew = warp - EPI_WARP0;
+    const float m2inv = (p.metric == MEVI_METRIC_L2 ? -2.f : -1.f) * p.consts[C_INV];
+    const bool l2 = p.metric == MEVI_METRIC_L2;
+    double inertia_acc = 0.0;
+    uint32_t it = 0;
+    bool ok = true;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, ++it) {
+      if (!ptx::mbar_wait_backoff(acc_full, it & 1, 64) || !ptx::mbar_wait_backoff(&st_full[it & 1], (it >> 1) & 1, 32)) { atomicExch(p.err_flag, 6); ok = false; break; }
+      ptx::tc_fence_after_sync();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int rl = h * 128 + ew * 32 + lane;
+        const float xn2 = sStats[(it & 1) * TM4 + rl];
+        const float xn = sqrtf(xn2), nxn = -xn;
+        const uint32_t taddr = tmem_base + h * 128 + ((uint32_t)(ew * 32) << 16);
+        const int64_t row = tile * TM4 + rl;
+        int code[M];
+        int flag_level = -1;
+        float last_best = 0.f;
+#pragma unroll
+        for (int j = 0; j < M; ++j) code[j] = 0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          if (p.debug & 4) break;
+          const float* gj = sGram + (j * (j - 1) / 2) * K * (K + 1);
+          const float* grow[M > 1 ? M - 1 : 1];
+#pragma unroll
+          for (int m = 0; m < j; ++m) grow[m] = gj + (m * K + code[m]) * (K + 1);
+          float m1 = CUDART_INF_F, ub = CUDART_INF_F, eb = 0.f, u1 = CUDART_INF_F, u2 = CUDART_INF_F;
+          int besti = 0;
+          for (int k0 = 0; k0 < K; k0 += 32) {
+            uint32_t ra[32];
+            ptx::tmem_ld32(taddr + j * K + k0, ra);
+            ptx::tmem_ld_wait();
+            float dk[32];
+            float c1 = CUDART_INF_F;
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) {
+              float base = l2 ? sCn2[j * K + k0 + kk] : 0.f;
+              float g = 0.f;
+#pragma unroll
+              for (int m = 0; m < j; ++m) g += grow[m][k0 + kk];
+              base = l2 ? fmaf(2.f, g, base) : g;
+              dk[kk] = fmaf(__uint_as_float(ra[kk]), m2inv, base);
+              c1 = fminf(c1, dk[kk]);
+              const float u = fmaf(nxn, sE1[j * K + k0 + kk], dk[kk]);
+              u2 = fminf(u2, fmaxf(u1, u));
+              u1 = fminf(u1, u);
+            }
+            int ci = 0;
+#pragma unroll
+            for (int kk = 31; kk >= 0; --kk)
+              if (dk[kk] == c1) ci = kk;
+            if (c1 < m1) {
+              m1 = c1;
+              besti = k0 + ci;
+              eb = xn * sE1[j * K + besti];
+              ub = fmaf(nxn, sE1[j * K + besti], c1);
+            }
+          }
+          code[j] = besti;
+          const float other_lo = (ub == u1) ? u2 : u1;
+          const bool clear = other_lo > m1 + eb + sLvl[j * 4 + 1];
+          if (!clear && flag_level < 0) flag_level = j;
+          last_best = m1;
+        }
+        if (row < p.n) {
+          int32_t* dst = p.codes + row * p.codes_stride;
+          if (M == 4 && p.codes_stride == 4) {
+            *reinterpret_cast<int4*>(dst) = make_int4(code[0], code[M > 1 ? 1 : 0], code[M > 2 ? 2 : 0], code[M > 3 ? 3 : 0]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < M; ++j) dst[j] = code[j];
+          }
+          if (flag_level >= 0) {
+            const unsigned long long slot = atomicAdd(p.work_count, 1ull);
+            p.work_rows[slot] = (int32_t)row;
+            p.work_levels[slot] = flag_level;
+          }
+          if (p.inertia) inertia_acc += (double)(l2 ? fmaxf(last_best + xn2, 0.f) : -last_best);
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
+    }
+    if (p.inertia) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) inertia_acc += __shfl_xor_sync(MEVI_FULL_MASK, inertia_acc, o);
+      if (lane == 0 && inertia_acc != 0.0) atomicAdd(p.inertia, inertia_acc);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+inline int make_x_tensormap4(mevi_ctx* ctx, const float* X, int64_t n, int d, CUtensorMap* out) {
+  if (!ctx->tmap_encode_fn) {
+    CUtensorMap dummy;
+    int rc = v3::make_x_tensormap(ctx, X, n, d, &dummy);  // resolves the driver entry point
+    if (rc != MEVI_OK) return rc;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n};
+  const cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)KC4, (cuuint32_t)TM4};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((v3::EncodeTiledFn)ctx->tmap_encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estr,
+                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return mevi_set_error(ctx, MEVI_ERR_CUDA, "cuTensorMapEncodeTiled (128B swizzle) failed with %d", (int)r);
+  return MEVI_OK;
+}
+
+}  // namespace v4

@@ -176,6 +176,118 @@ __global__ void bulk_copy_probe(const float* __restrict__ src, float* __restrict
     for (int i = threadIdx.x; i < n_floats; i += blockDim.x) dst[i] = reinterpret_cast<float*>(smem)[i];
 }
 
+
+// ---- A operand from tensor memory: each thread writes its row of A (fp16, K-major) into TMEM with
+// tcgen05.st, two consecutive K elements per 32-bit column; B stays in shared memory (SW128). -------------
+template <int PACK>
+__global__ void __launch_bounds__(128) probe_ts_kernel(const __half* __restrict__ Ag, const __half* __restrict__ Bg,
+                                                      float* __restrict__ Dg, int N, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_base_holder;
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = 64;
+  // B tile [N][64 halfs] SW128
+  for (int i = tid; i < N * 8; i += blockDim.x) {
+    const int row = i / 8, u = i % 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(Bg + (size_t)row * K + u * 8);
+    *reinterpret_cast<uint4*>(smem + (size_t)row * 128 + ((u ^ (row & 7)) * 16)) = v;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_holder)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_holder;
+  const uint32_t a_col = 256;
+  {  // row tid of A -> 32 columns starting at a_col, lane = tid
+    uint32_t r[32];
+    const __half* arow = Ag + (size_t)tid * K;
+    for (int c = 0; c < 32; ++c) {
+      const uint32_t lo = __half_as_ushort(arow[2 * c]), hi = __half_as_ushort(arow[2 * c + 1]);
+      r[c] = PACK == 0 ? (lo | (hi << 16)) : (hi | (lo << 16));
+    }
+    const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + a_col;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+                    "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+                    "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t db = make_desc(smem_u32(smem) + ks * 32, 1, 64, 2);
+      const uint32_t a_addr = tmem + a_col + ks * 8;
+      const uint32_t acc = ks > 0;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem), "r"(a_addr), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+  }
+  __syncwarp();
+  const bool done = mbar_wait_capped(smem_u32(&mbar), 0, 1 << 22);
+  if (!done && tid == 0) *status = -1;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (done) {
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                     "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                     "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                     "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                   : "r"(addr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int j = 0; j < 32; ++j) Dg[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+template <int PACK>
+static int run_ts(const char* name) {
+  const int N = 128, K = 64;
+  std::vector<__half> A((size_t)128 * K), B((size_t)N * K);
+  std::vector<double> Ar(A.size()), Br(B.size());
+  srand(7);
+  for (size_t i = 0; i < A.size(); ++i) { float v = (float)((rand() % 2001) - 1000) / 1000.f; A[i] = __float2half_rn(v); Ar[i] = __half2float(A[i]); }
+  for (size_t i = 0; i < B.size(); ++i) { float v = (float)((rand() % 2001) - 1000) / 1000.f; B[i] = __float2half_rn(v); Br[i] = __half2float(B[i]); }
+  __half *dA, *dB; float* dD; int* dS;
+  CK(cudaMalloc(&dA, A.size() * 2)); CK(cudaMalloc(&dB, B.size() * 2)); CK(cudaMalloc(&dD, 128 * N * 4)); CK(cudaMalloc(&dS, 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xFF, 128 * N * 4)); CK(cudaMemset(dS, 0, 4));
+  const size_t smem = (size_t)N * 128 + 1024;
+  CK(cudaFuncSetAttribute(probe_ts_kernel<PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_ts_kernel<PACK><<<1, 128, smem>>>(dA, dB, dD, N, dS);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-44s : CUDA ERROR %s\n", name, cudaGetErrorString(e)); return 2; }
+  std::vector<float> D((size_t)128 * N); int st;
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, dS, 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0; int bad = 0;
+  for (int i = 0; i < 128; ++i) for (int j = 0; j < N; ++j) {
+    double ref = 0; for (int k = 0; k < K; ++k) ref += Ar[(size_t)i * K + k] * Br[(size_t)j * K + k];
+    double err = fabs(D[(size_t)i * N + j] - ref); if (!(err <= 1e30)) err = 1e30;
+    if (err > maxerr) maxerr = err; if (err > 1e-2 * (1 + fabs(ref))) ++bad;
+  }
+  printf("%-44s : %s  status=%d max_abs_err=%.3e bad=%d\n", name, (bad == 0 && st == 0) ? "PASS" : "FAIL", st, maxerr, bad);
+  return 0;
+}
+
 static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 static float tf32_rn(float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x00000FFFu + ((u >> 13) & 1); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
@@ -237,6 +349,8 @@ int main() {
   for (auto& v : A) v = rnd();
   for (auto& v : B) v = rnd();
 
+  run_ts<0>("A in TMEM (tcgen05.st, k even in low half)");
+  run_ts<1>("A in TMEM (tcgen05.st, k even in high half)");
   // ---- 1. descriptor encodings, fp16
   run_cfg<0>("f16 SW128 N=128 lbo=1 sbo=64 lt=2", Cfg{0, 128, K, 3, 2, 1, 64}, A, B);
   run_cfg<0>("f16 SW128 N=256 lbo=1 sbo=64 lt=2", Cfg{0, 256, K, 3, 2, 1, 64}, A, B);
