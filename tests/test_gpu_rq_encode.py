@@ -119,3 +119,41 @@ def test_pq_dropin_get_document_cluster(gauss, tmp_path):
         for k, v in cdict.items():
             merged.setdefault(k, []).extend(v)
     assert merged == clus
+
+
+@pytest.mark.parametrize("n,d,M,K,metric", [(5000, 128, 2, 64, "l2"), (4099, 1024, 3, 32, "l2"), (6000, 64, 4, 32, "l2"),
+                                            (5000, 256, 1, 128, "l2"), (5000, 768, 4, 32, "ip"), (3000, 320, 2, 32, "l2"),
+                                            (3000, 100, 2, 8, "l2")])
+def test_shape_family_tensor_and_exact(n, d, M, K, metric):
+    """Other members of the shape family (levels, codebook sizes, widths, metric): whichever modes the
+    library supports for the shape must agree with the oracle; 'auto' must always work."""
+    c = ctx()
+    rs = np.random.RandomState(d + M + K)
+    centers = rs.standard_normal((K, d)).astype(np.float32)
+    X = (centers[rs.randint(0, K, n)] + 0.7 * rs.standard_normal((n, d))).astype(np.float32)
+    cb = np.empty((M, K, d), dtype=np.float32)
+    res = X.copy()
+    for j in range(M):
+        cb[j] = res[rs.choice(n, K, replace=False)] * (0.9 if j == 0 else 0.5)
+        res = res - cb[j][oracle.rq_encode(res, cb[j : j + 1], dist_mode=metric)[:, 0]]
+    ref = oracle.rq_encode(X, cb, dist_mode=metric)
+    modes = tensor_modes(c, d, M, K, metric) + ["auto"]
+    for mode in modes:
+        codes, stats = c.rq_encode(dev(X), dev(cb), metric=metric, mode=mode, return_stats=True)
+        rep = _check(X, cb, codes.cpu().numpy(), ref, metric=metric)
+        print(f"d={d} M={M} K={K} {metric} {mode}: ties {rep['n_ties']} flagged {int(stats[0])}")
+
+
+def test_badly_scaled_and_outlier_rows_still_exact(gauss):
+    """Rows far outside the sampled range (fp16 overflow after scaling) and all-zero rows must come out
+    right: the tensor path sends them to the exact kernel instead of trusting the prefilter."""
+    c = ctx()
+    X = gauss.X[:8192].copy()
+    X[7] *= 1e6
+    X[100] = 0.0
+    X[200] *= 1e-6
+    X[4000:4010] *= 3e4
+    ref = oracle.rq_encode(X, gauss.codebook)
+    for mode in tensor_modes(c, gauss.d, gauss.M, gauss.K):
+        codes = c.rq_encode(dev(X), dev(gauss.codebook), mode=mode).cpu().numpy()
+        _check(X, gauss.codebook, codes, ref)
