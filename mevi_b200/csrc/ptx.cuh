@@ -53,6 +53,33 @@ __device__ __forceinline__ bool mbar_wait_backoff(uint64_t* bar, uint32_t parity
 
 // ---- proxies / fences ---------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (UMMA operand fetch, bulk copies)
+// One lane of a CONVERGED warp.  Code under `if (elect_one())` runs with a single active lane and ptxas knows it,
+// so tcgen05.mma / TMA operands move to uniform registers with one R2UR instead of a per-instruction
+// ELECT + BRA.U.ANY waterfall loop (which is what `if (lane == 0)` produces: ~10 extra dependent
+// instructions per MMA, enough to make the issuing thread the bottleneck of a small-tile pipeline).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// packed fp32 pairs (sm_100: FMUL2 / FFMA2 / FADD2 — one issue slot for two lanes of fp32 work)
+__device__ __forceinline__ unsigned long long f2_bits(float2 a) { return *reinterpret_cast<unsigned long long*>(&a); }
+__device__ __forceinline__ float2 f2_from(unsigned long long r) { return *reinterpret_cast<float2*>(&r); }
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(r);
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return f2_from(r);
+}
+__device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
+  unsigned long long r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(r);
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

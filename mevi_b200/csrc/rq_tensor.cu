@@ -31,6 +31,8 @@
 // Roofline: HBM (4*d B/row); tensor work is 72 cycles/row/SM, shared-memory traffic ~13.5 KB/row.
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <cstdio>
+#include <vector>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -71,7 +73,27 @@ struct Params {
   double* inertia; int* err_flag;
   int64_t n_tiles;
   int debug;  // MEVI_RQ_DEBUG bit mask for pipeline ablations (timing experiments only; results are wrong)
+  unsigned long long* trace;  // MEVI_RQ_TRACE=<file>: per-warp event timestamps of CTA 0 (pipeline debugging), else null
 };
+
+// Pipeline trace (debug aid): lane 0 of every warp of CTA 0 appends (clock << 16 | event << 12 | tile_it << 8 | chunk)
+// for tile iterations [TRACE_IT0, TRACE_IT1).  tools/rq_trace.py turns the dump into a per-role timeline.
+constexpr int TRACE_SLOTS = 512, TRACE_WARPS = 20, TRACE_IT0 = 6, TRACE_IT1 = 9;
+// (SM clock, global nanosecond timer) at the start (which = 0) and end (which = 1) of CTA 0: the SM clock the kernel really ran at
+__device__ __forceinline__ void trace_clock(const Params& p, int which) {
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.trace[TRACE_SLOTS * TRACE_WARPS + 2 * which] = (unsigned long long)clock64();
+    p.trace[TRACE_SLOTS * TRACE_WARPS + 2 * which + 1] = ns;
+  }
+}
+__device__ __forceinline__ void trace_ev(const Params& p, int warp, int lane, uint32_t& idx, uint32_t it, uint32_t c, uint32_t ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && it >= TRACE_IT0 && it < TRACE_IT1 && idx < TRACE_SLOTS) {
+    p.trace[warp * TRACE_SLOTS + idx] = ((unsigned long long)clock64() << 16) | (ev << 12) | ((it & 15u) << 8) | (c & 255u);
+    ++idx;
+  }
+}
 
 struct SmemLayout {
   int a_off, b_off, gram_off, cn2_off, cnorm_off, lvl_off, stats_off, bar_off, holder_off, total;
@@ -598,6 +620,7 @@ __global__ void residual_from_codes_kernel(const float* __restrict__ X, int64_t 
 
 #include "rq_tensor3.cuh"
 #include "rq_tensor4.cuh"
+#include "rq_tensor5.cuh"
 
 }  // namespace
 
@@ -676,12 +699,42 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     const char* dbg = getenv("MEVI_RQ_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  p.trace = nullptr;
+  const char* trace_path = getenv("MEVI_RQ_TRACE");
+  if (trace_path && *trace_path) {
+    MEVI_CUDA(ctx, cudaMalloc(&p.trace, sizeof(unsigned long long) * (TRACE_SLOTS * TRACE_WARPS + 4)));
+    MEVI_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(unsigned long long) * (TRACE_SLOTS * TRACE_WARPS + 4), st));
+  }
   const char* ver = getenv("MEVI_RQ_KERNEL");
-  // default: third generation.  MEVI_RQ_KERNEL=4 selects the tensor-memory-operand variant (correct, but
-  // measured 5 % slower: its single accumulator buffer exposes the epilogue), =2 the register-staged one.
-  const int kver = ver ? atoi(ver) : 3;
+  // default: fourth generation (document operand through tensor memory, rq_tensor4.cuh).  MEVI_RQ_KERNEL selects the
+  // others for comparison: 5 = 128-row tiles with double-buffered accumulators, 3 = shared-memory operands with a
+  // TMA-fed ring, 2 = register-staged loads.  All produce identical codes; DESIGN.md has the measurements.
+  const int kver = ver ? atoi(ver) : 4;
   const bool use_v3 = kver == 3;
-  if (kver >= 4) {
+  if (kver >= 5) {
+    // fifth-generation kernel: 128-row tiles, operand through tensor memory, double-buffered accumulators (rq_tensor5.cuh)
+    CUtensorMap tmap;
+    int trc = v5::make_x_tensormap5(ctx, X, n, d, &tmap);
+    if (trc != MEVI_OK) return trc;
+    v3::bimg32_kernel<<<(NT * (d / 8) + 255) / 256, 256, 0, st>>>(cb, M * K, d, NT, consts, Bimg);
+    MEVI_COUNT_LAUNCH(ctx, 1);
+    p.n_tiles = (n + v5::TM5 - 1) / v5::TM5;
+    const v5::Smem5 L5 = v5::smem5_layout(M, K, NT);
+    const size_t smem5 = (size_t)L5.total + 1024;
+    const int grid5 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+#define MEVI_LAUNCH_RQ_TENSOR5(MM)                                                                                          \
+  do {                                                                                                                      \
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(v5::rq_tensor5_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5)); \
+    v5::rq_tensor5_kernel<MM><<<grid5, v5::THREADS5, smem5, st>>>(p, tmap);                                                 \
+  } while (0)
+    switch (M) {
+      case 1: MEVI_LAUNCH_RQ_TENSOR5(1); break;
+      case 2: MEVI_LAUNCH_RQ_TENSOR5(2); break;
+      case 3: MEVI_LAUNCH_RQ_TENSOR5(3); break;
+      default: MEVI_LAUNCH_RQ_TENSOR5(4); break;
+    }
+#undef MEVI_LAUNCH_RQ_TENSOR5
+  } else if (kver >= 4) {
     // fourth-generation kernel: document operand through tensor memory (rq_tensor4.cuh)
     CUtensorMap tmap;
     int trc = v4::make_x_tensormap4(ctx, X, n, d, &tmap);
@@ -745,6 +798,16 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
 #undef MEVI_LAUNCH_RQ_TENSOR
   }
   MEVI_CUDA(ctx, cudaGetLastError());
+  if (p.trace) {
+    std::vector<unsigned long long> host((size_t)TRACE_SLOTS * TRACE_WARPS + 4);
+    MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+    MEVI_CUDA(ctx, cudaMemcpy(host.data(), p.trace, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(host.data(), sizeof(unsigned long long), host.size(), f);
+      fclose(f);
+    }
+  }
   MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaMemcpyAsync(host_err, err_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
 

@@ -20,6 +20,7 @@ namespace v3 {
 constexpr int TM3 = 256;
 constexpr int KC3 = 32;
 constexpr int NSX = 3, NSA3 = 2, NSB3 = 2;
+static_assert(NSA3 == NSB3, "the A and B rings share their 'empty' barriers");
 constexpr int X_STAGE = TM3 * KC3 * 4;  // 32 KB
 constexpr int A_HALF = 128 * 64;        // one fp16 operand tile: 128 rows x 64 B
 constexpr int A_STAGE3 = 4 * A_HALF;    // [half0 hi][half0 lo][half1 hi][half1 lo]
@@ -88,27 +89,31 @@ __device__ __forceinline__ void converter_loop3(const Params& p, uint8_t* sX, ui
     st_off[i] = (uint32_t)half * (2 * A_HALF) + (uint32_t)rl * 64u + ((uint32_t)((c4 >> 1) ^ ((rl >> 1) & 3)) << 4) +
                 ((uint32_t)(c4 & 1) << 3);
   }
-  float norm[8];
+  float2 norm[8];  // (even, odd) partial sums: packed fp32 FMAs
 #pragma unroll
-  for (int i = 0; i < 8; ++i) norm[i] = 0.f;
+  for (int i = 0; i < 8; ++i) norm[i] = make_float2(0.f, 0.f);
+  const float2 sx2 = make_float2(sx, sx);
   uint32_t xs = 0, xph = 0, as = 0, aph = 0, it = 0;
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
     for (int c = 0; c < nchunks; ++c) {
       if (!ptx::mbar_wait(&x_full[xs], xph) || !ptx::mbar_wait(&a_empty[as], aph ^ 1)) { atomicExch(p.err_flag, 4); return; }
       const uint32_t src = sX_u32 + xs * X_STAGE + ld_off;
       const uint32_t dst = sA_u32 + as * A_STAGE3;
+      // all eight 16-byte loads first (the volatile loads/stores keep program order, so interleaving
+      // them with the stores would expose the shared-memory latency eight times per chunk)
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + i * 32 * 128));
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float t0, t1, t2, t3;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3) : "r"(src + i * 32 * 128));
-        if (SCALE) { t0 *= sx; t1 *= sx; t2 *= sx; t3 *= sx; }
-        norm[i] = fmaf(t0, t0, norm[i]);
-        norm[i] = fmaf(t1, t1, norm[i]);
-        norm[i] = fmaf(t2, t2, norm[i]);
-        norm[i] = fmaf(t3, t3, norm[i]);
-        const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
-        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn(t0 - b01.x, t1 - b01.y), l23 = __floats2half2_rn(t2 - b23.x, t3 - b23.y);
+        float2 p01 = make_float2(v[i].x, v[i].y), p23 = make_float2(v[i].z, v[i].w);
+        if (SCALE) { p01 = ptx::f2_mul(p01, sx2); p23 = ptx::f2_mul(p23, sx2); }
+        norm[i] = ptx::f2_fma(p01, p01, norm[i]);
+        norm[i] = ptx::f2_fma(p23, p23, norm[i]);
+        const __half2 h01 = __float22half2_rn(p01), h23 = __float22half2_rn(p23);
+        const __half2 l01 = __float22half2_rn(ptx::f2_sub(p01, __half22float2(h01)));
+        const __half2 l23 = __float22half2_rn(ptx::f2_sub(p23, __half22float2(h23)));
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + st_off[i]), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
                      "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
         asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst + st_off[i] + A_HALF),
@@ -128,12 +133,12 @@ __device__ __forceinline__ void converter_loop3(const Params& p, uint8_t* sX, ui
     if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 5); return; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float s = norm[i];
+      float s = norm[i].x + norm[i].y;
       s += __shfl_xor_sync(MEVI_FULL_MASK, s, 4);
       s += __shfl_xor_sync(MEVI_FULL_MASK, s, 2);
       s += __shfl_xor_sync(MEVI_FULL_MASK, s, 1);
       if (c4 == 0) sStats[buf * TM3 + row0 + 32 * i] = SCALE ? s * inv_sx2 : s;
-      norm[i] = 0.f;
+      norm[i] = make_float2(0.f, 0.f);
     }
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&st_full[buf]);
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(THREADS3, 1) rq_tensor3_kernel(Params p, const
       uint32_t s = 0, ph = 0;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
-          if (!ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 7); return; }
+          if (!ptx::mbar_wait_backoff(&a_empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 7); return; }
           ptx::mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
           ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * (2 * NT) * KC3, b_stage_bytes, &b_full[s]);
           if (++s == NSB3) { s = 0; ph ^= 1; }
@@ -219,20 +224,26 @@ __global__ void __launch_bounds__(THREADS3, 1) rq_tensor3_kernel(Params p, const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      const uint32_t idesc = ptx::umma_idesc_f16_m128((uint32_t)NT);
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 2); return; }
+    // ===== MMA issuer: the whole warp walks the loop (all operands warp-uniform), one elected lane issues =====
+    const uint32_t idesc = ptx::umma_idesc_f16_m128((uint32_t)NT);
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+      if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&acc_empty[buf], ph ^ 1))) {
+        if (lane == 0) atomicExch(p.err_flag, 2);
+        return;
+      }
+      ptx::tc_fence_after_sync();
+      for (int c = 0; c < nchunks; ++c) {
+        if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&a_full[as], aph) && ptx::mbar_wait(&b_full[bs], bph))) {
+          if (lane == 0) atomicExch(p.err_flag, 3);
+          return;
+        }
         ptx::tc_fence_after_sync();
-        for (int c = 0; c < nchunks; ++c) {
-          if (!ptx::mbar_wait(&a_full[as], aph) || !ptx::mbar_wait(&b_full[bs], bph)) { atomicExch(p.err_flag, 3); return; }
-          ptx::tc_fence_after_sync();
-          const uint32_t a_base = ptx::smem_u32(sA + (size_t)as * A_STAGE3);
-          const uint32_t b_hi = ptx::smem_u32(sB + (size_t)bs * b_stage_bytes);
-          const uint32_t b_lo = b_hi + (uint32_t)NT * 64u;
+        const uint32_t a_base = ptx::smem_u32(sA + (size_t)as * A_STAGE3);
+        const uint32_t b_hi = ptx::smem_u32(sB + (size_t)bs * b_stage_bytes);
+        const uint32_t b_lo = b_hi + (uint32_t)NT * 64u;
+        if (ptx::elect_one()) {
           if (!(p.debug & 2)) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -246,12 +257,15 @@ __global__ void __launch_bounds__(THREADS3, 1) rq_tensor3_kernel(Params p, const
               }
             }
           }
+          // ONE commit per chunk: a tcgen05.commit stalls the MMA stream for ~600 cycles (tools/umma_rate.cu), a
+          // second one back to back another ~245.  The A and B rings advance in lockstep, so the converters and
+          // the codebook producer both wait on a_empty[as].
           ptx::umma_commit(&a_empty[as]);
-          ptx::umma_commit(&b_empty[bs]);
-          if (++as == NSA3) { as = 0; aph ^= 1; }
-          if (++bs == NSB3) { bs = 0; bph ^= 1; }
+          if (c == nchunks - 1) ptx::umma_commit(&acc_full[buf]);
         }
-        ptx::umma_commit(&acc_full[buf]);
+        __syncwarp();
+        if (++as == NSA3) { as = 0; aph ^= 1; }
+        if (++bs == NSB3) { bs = 0; bph ^= 1; }
       }
     }
   } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {

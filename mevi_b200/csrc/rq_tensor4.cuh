@@ -6,14 +6,15 @@
 // straight into TMEM with tcgen05.st and tcgen05.mma reads A from TMEM, which removes the converter stores
 // and the A-operand fetches from shared memory (12 KB per document) and frees 64 KB of it for a deeper
 // TMA ring:
-//   warp 0      TMA producer: [256 rows x 32 fp32] boxes, 128B-swizzled, into a 5-stage ring (160 KB in flight)
-//   warp 3      codebook producer: 16 KB bulk copies of the pre-swizzled [C_hi|C_lo] chunk image (2 stages)
+//   warp 0      TMA producer: [256 rows x 32 fp32] boxes, 128B-swizzled, into a 4-stage ring (128 KB in flight)
+//   warp 3      codebook producer: 16 KB bulk copies of the pre-swizzled [C_hi|C_lo] chunk image (4 stages, in lockstep with the operand stages)
 //   warps 4-11  converters, ONE THREAD PER ROW (thread = TMEM lane): 8 conflict-free 16-byte loads of the row's
 //               chunk, scale/split, 2 x tcgen05.st.x16 into one of 4 TMEM operand stages; the row norm is a
 //               plain per-thread accumulator (no shuffles)
-//   warp 1      tcgen05.mma with A in TMEM: per 128-row half and K step A_hi.C_hi + A_hi.C_lo + A_lo.C_hi into
-//               one 128-column accumulator per half
-//   warps 12-15 epilogue (single accumulator buffer; the 4 TMEM operand stages absorb its ~2.5 us)
+//   warps 1-2   tcgen05.mma with A in TMEM, one warp per 128-row half: per K step A_hi.C_hi + A_hi.C_lo + A_lo.C_hi
+//               into the half's 128-column accumulator; ONE commit per warp and chunk releases operand + codebook stage
+//   warps 12-19 epilogue, one row per thread (single accumulator buffer; the 4 TMEM operand stages keep the
+//               converters busy while it drains)
 // TMEM map (512 columns): [0,256) accumulators (half h at 128h), [256,512) 4 operand stages x (2 halves x (16 hi + 16 lo)).
 #pragma once
 
@@ -21,9 +22,11 @@ namespace v4 {
 
 constexpr int TM4 = 256;
 constexpr int KC4 = 32;
-constexpr int NSX4 = 5, NSB4 = 2, NSA4 = 4;
+constexpr int NSX4 = 4, NSB4 = 4, NSA4 = 4;
+static_assert(NSA4 == NSB4, "the A (TMEM) and B (smem) rings share their 'empty' barriers");
 constexpr int X_STAGE4 = TM4 * KC4 * 4;  // 32 KB
-constexpr int THREADS4 = 512;
+constexpr int THREADS4 = 640;
+constexpr int EPI_WARPS4 = 8;
 constexpr uint32_t A_COL0 = 256;         // first TMEM column of the operand stages
 
 struct Smem4 {
@@ -58,27 +61,31 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
   const uint32_t src_row = ptx::smem_u32(sX) + (uint32_t)row * 128u;
   const uint32_t sw = (uint32_t)(row & 7);        // 128B swizzle: 16-byte chunk j of this row sits at j ^ (row & 7)
   const uint32_t t_lane = tmem_base + ((uint32_t)((cw & 3) * 32) << 16) + A_COL0 + (uint32_t)half * 32u;
-  float norm = 0.f;
-  uint32_t xs = 0, xph = 0, as = 0, aph = 0, it = 0, pend_stage = 0;
+  float2 norm2 = make_float2(0.f, 0.f);  // (even, odd) partial sums of the squared row norm
+  const float2 sx2 = make_float2(sx, sx);
+  uint32_t xs = 0, xph = 0, as = 0, aph = 0, it = 0, pend_stage = 0, tix = 0;
+  const int warp = cw + CONV_WARP0;
   bool pending = false;
   for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
     for (int c = 0; c < nchunks; ++c) {
-      if (!ptx::mbar_wait(&x_full[xs], xph) || !ptx::mbar_wait(&a_empty[as], aph ^ 1)) { atomicExch(p.err_flag, 4); return; }
+      if (!ptx::mbar_wait(&x_full[xs], xph)) { atomicExch(p.err_flag, 4); return; }
+      trace_ev(p, warp, lane, tix, it, c, 0);  // X stage landed
+      if (!ptx::mbar_wait_backoff(&a_empty[as], aph ^ 1, 32)) { atomicExch(p.err_flag, 4); return; }
+      trace_ev(p, warp, lane, tix, it, c, 1);  // operand stage free
       ptx::tc_fence_after_sync();
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float t0, t1, t2, t3;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3)
+        float2 p01, p23;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(p01.x), "=f"(p01.y), "=f"(p23.x), "=f"(p23.y)
                      : "r"(src_row + xs * X_STAGE4 + (((uint32_t)j ^ sw) << 4)));
-        if (SCALE) { t0 *= sx; t1 *= sx; t2 *= sx; t3 *= sx; }
-        norm = fmaf(t0, t0, norm);
-        norm = fmaf(t1, t1, norm);
-        norm = fmaf(t2, t2, norm);
-        norm = fmaf(t3, t3, norm);
-        const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
-        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-        const __half2 l01 = __floats2half2_rn(t0 - b01.x, t1 - b01.y), l23 = __floats2half2_rn(t2 - b23.x, t3 - b23.y);
+        // packed fp32 pairs (FMUL2 / FFMA2 / FADD2): a quarter fewer issue slots -- and joules -- per converted float
+        if (SCALE) { p01 = ptx::f2_mul(p01, sx2); p23 = ptx::f2_mul(p23, sx2); }
+        norm2 = ptx::f2_fma(p01, p01, norm2);
+        norm2 = ptx::f2_fma(p23, p23, norm2);
+        const __half2 h01 = __float22half2_rn(p01), h23 = __float22half2_rn(p23);
+        const __half2 l01 = __float22half2_rn(ptx::f2_sub(p01, __half22float2(h01)));
+        const __half2 l23 = __float22half2_rn(ptx::f2_sub(p23, __half22float2(h23)));
         hi[2 * j] = *reinterpret_cast<const uint32_t*>(&h01);       // K elements 4j, 4j+1
         hi[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h23);   // K elements 4j+2, 4j+3
         lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l01);
@@ -96,6 +103,7 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
       // the stores consumed every value loaded from the X stage: hand it back to the TMA producer
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&x_empty[xs]);
+      trace_ev(p, warp, lane, tix, it, c, 2);  // converted, stores issued
       pending = true;
       pend_stage = as;
       if (++xs == NSX4) { xs = 0; xph ^= 1; }
@@ -109,8 +117,8 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
       if (lane == 0) ptx::mbar_arrive(&a_full[pend_stage]);
       pending = false;
     }
-    sStats[(it & 1) * TM4 + row] = SCALE ? norm * inv_sx2 : norm;
-    norm = 0.f;
+    sStats[(it & 1) * TM4 + row] = SCALE ? (norm2.x + norm2.y) * inv_sx2 : norm2.x + norm2.y;
+    norm2 = make_float2(0.f, 0.f);
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&st_full[it & 1]);
   }
@@ -155,10 +163,10 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
   for (int i = tid; i < M * 4; i += THREADS4) sLvl[i] = p.lvl[i];
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSX4; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], CONV_WARPS); }
-    for (int s = 0; s < NSA4; ++s) { ptx::mbar_init(&a_full[s], CONV_WARPS); ptx::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NSA4; ++s) { ptx::mbar_init(&a_full[s], CONV_WARPS); ptx::mbar_init(&a_empty[s], 2); }  // one commit per MMA warp
     for (int s = 0; s < NSB4; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
-    ptx::mbar_init(acc_full, 1);
-    ptx::mbar_init(acc_empty, 4);
+    ptx::mbar_init(acc_full, 2);
+    ptx::mbar_init(acc_empty, EPI_WARPS4);
     ptx::mbar_init(&st_full[0], CONV_WARPS);
     ptx::mbar_init(&st_full[1], CONV_WARPS);
     ptx::mbar_fence_init();
@@ -169,63 +177,94 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  trace_clock(p, 0);
 
+  // The three control warps walk their loops with all 32 lanes (operands stay warp-uniform) and issue from one
+  // elected lane: `if (lane == 0)` would wrap every TMA / tcgen05 instruction in an R2UR waterfall loop.
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < nchunks; ++c) {
-          if (!ptx::mbar_wait_backoff(&x_empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); return; }
+    uint32_t s = 0, ph = 0, tix = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      for (int c = 0; c < nchunks; ++c) {
+        if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(&x_empty[s], ph ^ 1, 32))) {
+          if (lane == 0) atomicExch(p.err_flag, 1);
+          return;
+        }
+        trace_ev(p, warp, lane, tix, it, c, 0);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&x_full[s], X_STAGE4);
           ptx::tma_load_2d(sX + (size_t)s * X_STAGE4, &tmap, c * KC4, (int)(tile * TM4), &x_full[s]);
-          if (++s == NSX4) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == NSX4) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 3) {
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int c = 0; c < nchunks; ++c) {
-          if (!ptx::mbar_wait_backoff(&b_empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 7); return; }
-          ptx::mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
-          ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * (2 * NT) * KC4, b_stage_bytes, &b_full[s]);
-          if (++s == NSB4) { s = 0; ph ^= 1; }
+    uint32_t s = 0, ph = 0, tix = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      for (int c = 0; c < nchunks; ++c) {
+        if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(&a_empty[s], ph ^ 1, 32))) {
+          if (lane == 0) atomicExch(p.err_flag, 7);
+          return;
         }
+        trace_ev(p, warp, lane, tix, it, c, 0);
+        if (ptx::elect_one()) {
+          const bool twice = (p.debug & 16) != 0;  // experiment: what would twice the codebook traffic cost?
+          ptx::mbar_arrive_expect_tx(&b_full[s], twice ? 2 * b_stage_bytes : b_stage_bytes);
+          ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * (2 * NT) * KC4, b_stage_bytes, &b_full[s]);
+          if (twice) ptx::bulk_g2s(sB + (size_t)s * b_stage_bytes, p.Bimg + (size_t)c * (2 * NT) * KC4, b_stage_bytes, &b_full[s]);
+        }
+        __syncwarp();
+        if (++s == NSB4) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16_m128((uint32_t)NT);
-      uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0;
-      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-        // single accumulator buffer: the previous tile's epilogue must have drained it
-        if (!ptx::mbar_wait(acc_empty, (it & 1) ^ 1)) { atomicExch(p.err_flag, 2); return; }
+  } else if (warp == 1 || warp == 2) {
+    // TWO MMA warps, one per 128-row half (own accumulator, own commits): a single issuing thread leaves a
+    // bubble in the tensor pipe after every tcgen05.commit; two independent streams fill each other's bubbles
+    // (tools/umma_rate.cu: 12 TS MMAs + 2 commits per chunk in ~850 cycles instead of ~1630).
+    const int h = warp - 1;
+    const uint32_t idesc = ptx::umma_idesc_f16_m128((uint32_t)NT);
+    const uint32_t d_tmem = tmem_base + h * 128;
+    uint32_t as = 0, aph = 0, it = 0, tix = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      // single accumulator buffer: the previous tile's epilogue must have drained it
+      if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(acc_empty, (it & 1) ^ 1))) {
+        if (lane == 0) atomicExch(p.err_flag, 2);
+        return;
+      }
+      ptx::tc_fence_after_sync();
+      trace_ev(p, warp, lane, tix, it, 255, 3);  // accumulator free
+      for (int c = 0; c < nchunks; ++c) {
+        if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&a_full[as], aph))) {
+          if (lane == 0) atomicExch(p.err_flag, 3);
+          return;
+        }
+        trace_ev(p, warp, lane, tix, it, c, 0);  // operand stage full
+        if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&b_full[as], aph))) {
+          if (lane == 0) atomicExch(p.err_flag, 3);
+          return;
+        }
+        trace_ev(p, warp, lane, tix, it, c, 1);  // codebook stage full
         ptx::tc_fence_after_sync();
-        for (int c = 0; c < nchunks; ++c) {
-          if (!ptx::mbar_wait(&a_full[as], aph) || !ptx::mbar_wait(&b_full[bs], bph)) { atomicExch(p.err_flag, 3); return; }
-          ptx::tc_fence_after_sync();
-          const uint32_t b_hi = ptx::smem_u32(sB + (size_t)bs * b_stage_bytes);
-          const uint32_t b_lo = b_hi + (uint32_t)NT * 64u;
+        const uint32_t b_hi = ptx::smem_u32(sB + (size_t)as * b_stage_bytes);
+        const uint32_t b_lo = b_hi + (uint32_t)NT * 64u;
+        if (ptx::elect_one()) {
           if (!(p.debug & 2)) {
+            const uint32_t a_hi = tmem_base + A_COL0 + as * 64 + h * 32, a_lo = a_hi + 16;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_base + h * 128;
-              const uint32_t a_hi = tmem_base + A_COL0 + as * 64 + h * 32, a_lo = a_hi + 16;
-#pragma unroll
-              for (int ks = 0; ks < KC4 / 16; ++ks) {
-                ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, (c | ks) != 0 ? 1u : 0u);
-                ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_lo + ks * 32), idesc, 1u);
-                ptx::umma_f16_ts(d_tmem, a_lo + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, 1u);
-              }
+            for (int ks = 0; ks < KC4 / 16; ++ks) {
+              ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, (c | ks) != 0 ? 1u : 0u);
+              ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_lo + ks * 32), idesc, 1u);
+              ptx::umma_f16_ts(d_tmem, a_lo + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, 1u);
             }
           }
+          // the operand (TMEM) and codebook (smem) rings advance in lockstep: converters and the codebook producer
+          // both wait on a_empty[as], which completes when BOTH MMA warps have committed
           ptx::umma_commit(&a_empty[as]);
-          ptx::umma_commit(&b_empty[bs]);
-          if (++as == NSA4) { as = 0; aph ^= 1; }
-          if (++bs == NSB4) { bs = 0; bph ^= 1; }
+          if (c == nchunks - 1) ptx::umma_commit(acc_full);
         }
-        ptx::umma_commit(acc_full);
+        __syncwarp();
+        trace_ev(p, warp, lane, tix, it, c, 2);  // issued + committed
+        if (++as == NSA4) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
@@ -238,17 +277,18 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
     const float m2inv = (p.metric == MEVI_METRIC_L2 ? -2.f : -1.f) * p.consts[C_INV];
     const bool l2 = p.metric == MEVI_METRIC_L2;
     double inertia_acc = 0.0;
-    uint32_t it = 0;
+    uint32_t it = 0, tix = 0;
     bool ok = true;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x, ++it) {
       if (!ptx::mbar_wait_backoff(acc_full, it & 1, 64) || !ptx::mbar_wait_backoff(&st_full[it & 1], (it >> 1) & 1, 32)) { atomicExch(p.err_flag, 6); ok = false; break; }
       ptx::tc_fence_after_sync();
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int rl = h * 128 + ew * 32 + lane;
+      trace_ev(p, warp, lane, tix, it, 255, 0);  // accumulators ready
+      {
+        const int h = ew >> 2, q = ew & 3;  // half of the tile, 32-lane quarter of TMEM (== warp % 4)
+        const int rl = h * 128 + q * 32 + lane;
         const float xn2 = sStats[(it & 1) * TM4 + rl];
         const float xn = sqrtf(xn2), nxn = -xn;
-        const uint32_t taddr = tmem_base + h * 128 + ((uint32_t)(ew * 32) << 16);
+        const uint32_t taddr = tmem_base + h * 128 + ((uint32_t)(q * 32) << 16);
         const int64_t row = tile * TM4 + rl;
         int code[M];
         int flag_level = -1;
@@ -318,6 +358,7 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
+      trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
       if (lane == 0) ptx::mbar_arrive(acc_empty);
     }
     if (p.inertia) {
@@ -329,6 +370,7 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  trace_clock(p, 1);
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
