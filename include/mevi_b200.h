@@ -108,6 +108,31 @@ int mevi_kmeans_update(mevi_ctx* ctx, const float* sums_counts, int K, int d, fl
 int mevi_residual_update(mevi_ctx* ctx, float* R, int64_t n, int d, const float* centroids, int K,
                          const int32_t* assign, int64_t assign_stride, void* stream);
 
+/* sums_counts [K*d + K] fp32 out (overwritten): per-centroid sums of the rows of X under a GIVEN assignment,
+ * then the per-centroid counts — the same fused buffer mevi_kmeans_step produces, so one all-reduce combines
+ * shards.  replaces: MEVI/pq.py:380-393 (ema_update's one-hot scatter + bmm(one_hot^T, vectors) and
+ * one_hot.sum(0)) for one level; assign[i*assign_stride] is row i's code at that level.                    */
+int mevi_accumulate_by_code(mevi_ctx* ctx, const float* X, int64_t n, int d, const int32_t* assign,
+                            int64_t assign_stride, int K, float* sums_counts, void* stream);
+
+/* ---- product-quantiser encode ------------------------------------------- *
+ * replaces: MEVI/pq.py:249-279 get_pq_document_cluster ('pq'; 'opq' after the caller applied the rotation of
+ * pq.py:259-261).  codebook [M, K, d/M]; codes [n, M] int32 out: per sub-vector j the argmax over k of
+ * compute_scores(X[:, j*dsub:(j+1)*dsub], codebook[j,k]) (pq.py:124-131), lowest index on exact fp32 ties. */
+int mevi_pq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K, int metric,
+                   int32_t* codes, void* stream);
+
+/* ---- RQ beam search (leaf producer) -------------------------------------- *
+ * replaces: MEVI/pq.py:613-713 beam_search, rq branch, do_sample=False: per level
+ * softmax_k(compute_scores(residual_b, codebook[i,k])), multiplied by the running beam score when `prod`
+ * (rq_topk_score == 'prod'), top-num_beams over beam x K (all candidates kept, in (beam, k) order, while there
+ * are at most num_beams of them), then the winners' prefixes and residuals.
+ *   X [bs,d]; labels [bs, num_beams, M] int32 out; scores [bs, num_beams] fp32 out (descending wherever a
+ *   top-k was taken).  Candidates with equal fp32 score are ordered by ascending (beam, k) index
+ *   (torch.topk leaves that order unspecified).                                                            */
+int mevi_rq_beam_search(mevi_ctx* ctx, const float* X, int64_t bs, int d, const float* codebook, int M, int K,
+                        int metric, int num_beams, int prod, int32_t* labels, float* scores, void* stream);
+
 /* ---- inverted lists ------------------------------------------------------ *
  * replaces: MEVI/pq.py:236-242 / 200-214 (python dict build) with a device
  * sort by leaf key.  key(row) = sum_j codes[row,j] * K^(M-1-j)  (K^M < 2^62).

@@ -33,6 +33,9 @@ SYMBOLS = {
     "mevi_kmeans_step": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "mevi_kmeans_update": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "mevi_residual_update": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp]),
+    "mevi_accumulate_by_code": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp]),
+    "mevi_pq_encode": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "mevi_rq_beam_search": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mevi_build_inverted_lists": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "mevi_gather_rows": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
@@ -227,6 +230,67 @@ class Context:
                 self.lib.mevi_residual_update(self.handle, _ptr(R), n, d, _ptr(centroids), K, _ptr(assign),
                                               int(assign_stride), self._stream())
             )
+
+    def accumulate_by_code(self, X, assign, K, sums_counts=None, assign_stride=1):
+        """Per-centroid sums|counts [K*d+K] of the rows of X under a given assignment (int32, strided)."""
+        import torch
+
+        X = self._dev(X, torch.float32, "X")
+        n, d = X.shape
+        assert assign.dtype == torch.int32 and assign.is_cuda
+        if sums_counts is None:
+            sums_counts = torch.empty(K * d + K, dtype=torch.float32, device=X.device)
+        else:
+            self._dev(sums_counts, torch.float32, "sums_counts")
+            assert sums_counts.numel() == K * d + K
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_accumulate_by_code(self.handle, _ptr(X), n, d, _ptr(assign), int(assign_stride), int(K),
+                                                 _ptr(sums_counts), self._stream())
+            )
+        return sums_counts
+
+    # ---- product quantiser / beam search -------------------------------------
+    def pq_encode(self, X, codebook, metric="l2", codes=None):
+        """X [n,d] fp32 cuda, codebook [M,K,d/M] fp32 cuda -> codes [n,M] int32 cuda (pq.py:249-279)."""
+        import torch
+
+        X = self._dev(X, torch.float32, "X")
+        cb = self._dev(codebook, torch.float32, "codebook")
+        n, d = X.shape
+        M, K, dsub = cb.shape
+        if dsub * M != d:
+            raise MeviError(f"codebook [{M},{K},{dsub}] does not tile embedding width {d}")
+        if codes is None:
+            codes = torch.empty((n, M), dtype=torch.int32, device=X.device)
+        else:
+            self._dev(codes, torch.int32, "codes")
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_pq_encode(self.handle, _ptr(X), n, d, _ptr(cb), M, K, _METRICS[metric], _ptr(codes),
+                                        self._stream())
+            )
+        return codes
+
+    def rq_beam_search(self, X, codebook, num_beams, metric="l2", prod=True):
+        """X [bs,d], codebook [M,K,d] -> (labels int32 [bs,num_beams,M], scores fp32 [bs,num_beams]) (pq.py:613-713)."""
+        import torch
+
+        X = self._dev(X, torch.float32, "X")
+        cb = self._dev(codebook, torch.float32, "codebook")
+        bs, d = X.shape
+        M, K, d2 = cb.shape
+        if d2 != d:
+            raise MeviError(f"codebook width {d2} != embedding width {d}")
+        labels = torch.empty((bs, num_beams, M), dtype=torch.int32, device=X.device)
+        scores = torch.empty((bs, num_beams), dtype=torch.float32, device=X.device)
+        with torch.cuda.device(self.device):
+            self._check(
+                self.lib.mevi_rq_beam_search(self.handle, _ptr(X), bs, d, _ptr(cb), M, K, _METRICS[metric],
+                                             int(num_beams), 1 if prod else 0, _ptr(labels), _ptr(scores),
+                                             self._stream())
+            )
+        return labels, scores
 
     # ---- inverted lists / re-rank ------------------------------------------
     def build_inverted_lists(self, codes, K):

@@ -198,6 +198,44 @@ cudaError_t launch_accumulate(const float* R, int64_t n, int d, const int32_t* a
   return launch_accumulate_nt<1024>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
 }
 
+// per-centroid sums|counts of the rows of R under a given assignment -> sums_counts [K*d + K]
+int accumulate_by_code(mevi_ctx* ctx, const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K,
+                       float* sums_counts, cudaStream_t st) {
+  const int64_t kd = (int64_t)K * d;
+  // shared-memory budget: [K][d] accumulators + KA_STAGES stages of sub_rows rows
+  const size_t acc_bytes = (size_t)kd * sizeof(float);
+  int sub_rows = acc_bytes + 4096 < 220 * 1024 ? (int)((220 * 1024 - acc_bytes) / ((size_t)KA_STAGES * d * 4)) : 0;
+  if (sub_rows > 32) sub_rows = 32;
+  const bool fast = K <= 64 && d <= 1024 && d % 4 == 0 && sub_rows >= 4 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
+  if (fast) {
+    int G = ctx->sm_count;  // one CTA per SM (shared-memory stages), persistent
+    int64_t max_g = (n + sub_rows - 1) / sub_rows;
+    if (G > max_g) G = (int)max_g;
+    if (G < 1) G = 1;
+    size_t ps_bytes = (size_t)G * kd * sizeof(float);
+    size_t pc_bytes = (size_t)G * K * sizeof(int32_t);
+    char* ws = (char*)mevi_ws(ctx, WS_KM_PARTIAL, ps_bytes + pc_bytes);
+    if (!ws) return MEVI_ERR_NOMEM;
+    float* ps = (float*)ws;
+    int32_t* pc = (int32_t*)(ws + ps_bytes);
+    const size_t smem = (size_t)KA_STAGES * sub_rows * d * 4 + acc_bytes + 128;
+    cudaError_t e = launch_accumulate(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+    if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "kmeans_accumulate launch: %s", cudaGetErrorString(e));
+    int threads = 256;
+    int blocks = (int)((kd + K + threads - 1) / threads);
+    kmeans_reduce_partials_kernel<<<blocks, threads, 0, st>>>(ps, pc, G, K, d, sums_counts);
+    MEVI_COUNT_LAUNCH(ctx, 2);
+    MEVI_CUDA(ctx, cudaGetLastError());
+  } else {
+    MEVI_CUDA(ctx, cudaMemsetAsync(sums_counts, 0, (size_t)(kd + K) * sizeof(float), st));
+    int grid = ctx->sm_count * 8;
+    kmeans_accumulate_atomic_kernel<<<grid, 256, 0, st>>>(R, n, d, assign, stride, K, sums_counts, sums_counts + kd);
+    MEVI_COUNT_LAUNCH(ctx, 1);
+    MEVI_CUDA(ctx, cudaGetLastError());
+  }
+  return MEVI_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -245,38 +283,24 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
   if (rc != MEVI_OK) return rc;
 
   // 2. accumulation
-  // shared-memory budget: [K][d] accumulators + KA_STAGES stages of sub_rows rows
-  const size_t acc_bytes = (size_t)kd * sizeof(float);
-  int sub_rows = acc_bytes + 4096 < 220 * 1024 ? (int)((220 * 1024 - acc_bytes) / ((size_t)KA_STAGES * d * 4)) : 0;
-  if (sub_rows > 32) sub_rows = 32;
-  const bool fast = K <= 64 && d <= 1024 && d % 4 == 0 && sub_rows >= 4 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
-  if (fast) {
-    int G = ctx->sm_count;  // one CTA per SM (shared-memory stages), persistent
-    int64_t max_g = (n + sub_rows - 1) / sub_rows;
-    if (G > max_g) G = (int)max_g;
-    if (G < 1) G = 1;
-    size_t ps_bytes = (size_t)G * kd * sizeof(float);
-    size_t pc_bytes = (size_t)G * K * sizeof(int32_t);
-    char* ws = (char*)mevi_ws(ctx, WS_KM_PARTIAL, ps_bytes + pc_bytes);
-    if (!ws) return MEVI_ERR_NOMEM;
-    float* ps = (float*)ws;
-    int32_t* pc = (int32_t*)(ws + ps_bytes);
-    const size_t smem = (size_t)KA_STAGES * sub_rows * d * 4 + acc_bytes + 128;
-    cudaError_t e = launch_accumulate(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
-    if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "kmeans_accumulate launch: %s", cudaGetErrorString(e));
-    int threads = 256;
-    int blocks = (int)((kd + K + threads - 1) / threads);
-    kmeans_reduce_partials_kernel<<<blocks, threads, 0, st>>>(ps, pc, G, K, d, sums_counts);
-    MEVI_COUNT_LAUNCH(ctx, 2);
-    MEVI_CUDA(ctx, cudaGetLastError());
-  } else {
-    MEVI_CUDA(ctx, cudaMemsetAsync(sums_counts, 0, (size_t)(kd + K) * sizeof(float), st));
-    int grid = ctx->sm_count * 8;
-    kmeans_accumulate_atomic_kernel<<<grid, 256, 0, st>>>(R, n, d, assign, stride, K, sums_counts, sums_counts + kd);
-    MEVI_COUNT_LAUNCH(ctx, 1);
-    MEVI_CUDA(ctx, cudaGetLastError());
-  }
+  rc = accumulate_by_code(ctx, R, n, d, assign, stride, K, sums_counts, st);
+  if (rc != MEVI_OK) return rc;
   return MEVI_OK;
+}
+
+int mevi_accumulate_by_code(mevi_ctx* ctx, const float* X, int64_t n, int d, const int32_t* assign, int64_t assign_stride,
+                            int K, float* sums_counts, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, X && assign && sums_counts, "NULL argument");
+  MEVI_REQUIRE(ctx, n >= 0 && d > 0 && d % 4 == 0 && d <= 1024 && K >= 1 && assign_stride >= 1,
+               "unsupported shape n=%lld d=%d K=%d", (long long)n, d, K);
+  if (n == 0) {
+    MEVI_CUDA(ctx, cudaMemsetAsync(sums_counts, 0, (size_t)((int64_t)K * d + K) * sizeof(float), st));
+    return MEVI_OK;
+  }
+  return accumulate_by_code(ctx, X, n, d, assign, assign_stride, K, sums_counts, st);
 }
 
 int mevi_kmeans_update(mevi_ctx* ctx, const float* sums_counts, int K, int d, float* centroids, int32_t* n_empty_or_null,

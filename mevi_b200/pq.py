@@ -2,13 +2,18 @@
 
 Same constructor, method names, argument meaning, side effects (`self.codebook`,
 `self.last_preds`, `self.get_preds`) and on-disk formats as the reference
-(MEVI/pq.py:15-741) for the shipped configuration: `pq_type='rq'`,
-`dist_mode in ('l2','ip')`, `pq_init_method in ('none','kmeans')`.  The hot
-arithmetic runs in hand-written CUDA kernels through the C ABI
-(include/mevi_b200.h); PyTorch only owns memory, streams and the process
-group.  Out-of-scope branches of the reference (pq/opq quantisers, 'iptol2',
-faiss index import/export, EMA codebook update, tied NCI centroids) raise
-NotImplementedError instead of silently doing something else.
+(MEVI/pq.py:15-741): `pq_type in ('rq','pq','opq')` (the shipped scripts use
+'rq'), `dist_mode in ('l2','ip')`, `pq_init_method in ('none','kmeans')`,
+`pq_update_method in ('grad','kmeans','ema','fixpq',...)`.  The hot arithmetic
+runs in hand-written CUDA kernels through the C ABI (include/mevi_b200.h);
+PyTorch only owns memory, streams and the process group.  Branches that need
+packages or state the reference itself does not have here raise
+NotImplementedError instead of silently doing something else: faiss index
+import/export (`pq_init_method='faiss'`, and with it the only way the reference
+obtains an OPQ rotation), tied NCI centroids (T5 lm_head), and
+`dist_mode='iptol2'`, which the reference cannot run either — it writes to
+`self.extracol`, an attribute that is never created (pq.py:113-117), so every
+iptol2 path dies with AttributeError.
 
 Differences that are deliberate:
   * codebook training is full-batch Lloyd, data-parallel over the row blocks of
@@ -58,16 +63,12 @@ class ProductQuantization(nn.Module):
         super().__init__()
         assert pq_type in ("pq", "opq", "rq")
         assert dist_mode in ("ip", "l2", "iptol2")
-        if pq_type != "rq":
-            raise NotImplementedError(
-                f"mevi_b200 implements the RQ branch of MEVI/pq.py only (pq_type={pq_type!r} is out of scope, SURVEY §8f.4)"
-            )
         if dist_mode == "iptol2":
-            raise NotImplementedError("dist_mode='iptol2' is out of scope (SURVEY §8f.4)")
+            raise NotImplementedError(
+                "dist_mode='iptol2': the reference writes to self.extracol, which it never creates (pq.py:113-117), "
+                "so this mode raises AttributeError there as well")
         if tie_nci_pq_centroid:
             raise NotImplementedError("tie_nci_pq_centroid couples the codebook to the T5 lm_head: out of scope")
-        if pq_update_method == "ema":
-            raise NotImplementedError("EMA codebook update (pq.py:371-433) is out of scope (SURVEY §8f.4)")
         self.pq_type = pq_type
         self.subvector_num = subvector_num
         self.subvector_bits = subvector_bits
@@ -80,11 +81,19 @@ class ProductQuantization(nn.Module):
         self.centroid_update_loss = centroid_update_loss
         self.rq_topk_score = rq_topk_score
         self.get_preds = False
-        self.last_dim = emb_size  # pq.py:50-54 (rq: full width)
-        # pq.py:67-68 — a CPU float Parameter [M, K, d]
+        self.last_dim = emb_size if pq_type == "rq" else emb_size // subvector_num  # pq.py:50-54
+        # pq.py:67-68 — a CPU float Parameter [M, K, last_dim]
         self.codebook = nn.Parameter(
-            torch.empty(subvector_num, self.subvector_cents, emb_size), requires_grad=(pq_update_method == "grad")
+            torch.empty(subvector_num, self.subvector_cents, self.last_dim), requires_grad=(pq_update_method == "grad")
         ).type(torch.FloatTensor)
+        if pq_type == "opq":  # pq.py:69-71
+            self.rotate = nn.Parameter(torch.empty(emb_size, emb_size), requires_grad=False).type(torch.FloatTensor)
+        if pq_update_method == "ema":  # pq.py:72-80
+            self.decay = 0.99
+            self.eps = 1e-5
+            self.restart_unused_codes = True
+            self.register_buffer("cluster_size_ema", torch.zeros(subvector_num, self.subvector_cents))
+            self.register_buffer("embed_ema", self.codebook.detach().clone())
         # knobs of the B200 trainer / encoder (not in the reference signature)
         self.kernel_mode = "auto"  # 'auto' | 'exact' | 'tensor'
         self.lloyd_iters = 25
@@ -111,6 +120,8 @@ class ProductQuantization(nn.Module):
 
     def fix(self):  # pq.py:435-438
         self.codebook.requires_grad_(False)
+        if self.pq_type == "opq":
+            self.rotate.requires_grad_(False)
 
     # ------------------------------------------------------------------ #
     # encode                                                             #
@@ -139,6 +150,28 @@ class ProductQuantization(nn.Module):
                                                     mode=self.kernel_mode)
 
     @torch.no_grad()
+    def get_pq_document_cluster(self, doc_embeddings, cluster: torch.Tensor, start: int, ending: int, rank: int,
+                                batch_size: int = 1024):
+        """pq.py:249-279: per sub-vector nearest centroid ('opq': after x @ rotate.T, 259-261).  Host rows are
+        streamed to the device in 256k-row pieces; the encode is `mevi_pq_encode`, the rotation a plain fp32
+        library GEMM.  Fills `cluster` (int32 [ending-start, M]) in place."""
+        ctx = self._ctx()
+        dev = torch.device("cuda", ctx.device)
+        cb = self.get_codebook().detach().to(dev).contiguous()
+        rot_t = self.rotate.detach().to(dev).T.contiguous() if self.pq_type == "opq" else None
+        step = 1 << 18
+        for a in range(start, ending, step):
+            b = min(a + step, ending)
+            if isinstance(doc_embeddings, torch.Tensor):
+                x = doc_embeddings[a:b].to(device=dev, dtype=torch.float32).contiguous()
+            else:
+                x = torch.from_numpy(np.ascontiguousarray(doc_embeddings[a:b], dtype=np.float32)).to(dev)
+            if rot_t is not None:
+                x = _matmul_fp32(x, rot_t)
+            codes = ctx.pq_encode(x, cb, metric=self.dist_mode)
+            cluster[a - start : b - start].copy_(codes.to(cluster.device))
+
+    @torch.no_grad()
     def get_document_cluster(self, doc_embeddings, rank: int, nrank: int, batch_size: int = 1024,
                              return_mapping: bool = False):
         """pq.py:216-247: row block of this rank, encode, then the
@@ -146,7 +179,8 @@ class ProductQuantization(nn.Module):
         num_docs = doc_embeddings.shape[0]
         start, ending = shard_bounds(num_docs, rank, nrank)
         cluster = torch.empty((ending - start, self.subvector_num), dtype=torch.int32)
-        self.get_rq_document_cluster(doc_embeddings, cluster, start, ending, rank, batch_size)
+        func = self.get_rq_document_cluster if self.pq_type == "rq" else self.get_pq_document_cluster  # pq.py:228-231
+        func(doc_embeddings, cluster, start, ending, rank, batch_size)
         doc_cluster, new_mapping = codes_to_dicts(cluster.numpy(), start, return_mapping)
         print("Number of document clusters:", len(doc_cluster))
         if return_mapping:
@@ -222,10 +256,20 @@ class ProductQuantization(nn.Module):
 
         Full-batch Lloyd on the device, sharded over ranks (see module docstring)."""
         print("Updating codebook using KMeans...")
+        assert self.pq_type != "opq"  # pq.py:553
         if kmeans_method != "kmeans":
             raise NotImplementedError(f"kmeans_method={kmeans_method!r} (pq.py:564-565 raises too)")
-        from .trainer import train_rq_lloyd
+        from .trainer import train_pq_lloyd, train_rq_lloyd
 
+        if self.pq_type == "pq":  # pq.py:568-581
+            codebook, codes_all = train_pq_lloyd(
+                doc_emb, M=self.subvector_num, K=self.subvector_cents, seed=int(seed), iters=self.lloyd_iters,
+                tol=self.lloyd_tol, init_sample=self.init_sample, mode=self.kernel_mode, device_index=self.device_index)
+            self.last_preds = codes_all
+            self.last_train_info = getattr(train_pq_lloyd, "last_info", None)
+            with torch.no_grad():
+                self.codebook.copy_(codebook.cpu())
+            return
         codebook, codes_all = train_rq_lloyd(
             doc_emb,
             M=self.subvector_num,
@@ -249,24 +293,47 @@ class ProductQuantization(nn.Module):
     @torch.no_grad()
     def beam_search(self, doc_emb: torch.Tensor, num_return_sequences, num_beams=None, do_sample=False,
                     return_proba=False):
-        """pq.py:613-713, rq branch.  Runs on whatever device `doc_emb` lives on
-        (tensor ops only — the leaf producer is not on the timed path, SURVEY
-        §2.4 C6).  Returns labels int64 [bs, beams, M] (+ beam scores)."""
+        """pq.py:613-713.  CUDA input, rq: `mevi_rq_beam_search` (one pass for the x.c table, then table
+        arithmetic per level — csrc/beam.cu).  CPU input (the reference runs on `codebook.device`, the CPU by
+        default) and the pq/opq branch: the reference's own tensor operations, restated below.
+        Returns labels int64 [bs, beams, M] (+ beam scores)."""
         if num_beams is None:
             num_beams = num_return_sequences
         if do_sample:
             raise NotImplementedError("do_sample=True (torch.multinomial branch, pq.py:686-688) is out of scope")
+        if self.pq_type == "rq" and doc_emb.is_cuda:
+            ctx = _lib.get_context(doc_emb.device)
+            cb = self.get_codebook().detach().to(doc_emb.device).contiguous()
+            labels, scores = ctx.rq_beam_search(doc_emb.contiguous().float(), cb, int(num_beams), metric=self.dist_mode,
+                                                prod=(self.rq_topk_score == "prod"))
+            labels = labels.long()  # pq.py: the int32 seed column is promoted by cat with int64 codes
+            return (labels, scores) if return_proba else labels
+        return self._beam_search_tensor_ops(doc_emb, num_beams, return_proba)
+
+    def _beam_search_tensor_ops(self, doc_emb, num_beams, return_proba):
+        """The reference's tensor-op formulation of pq.py:626-713, op for op (bit-identical to the reference on
+        the CPU golden vectors, tests/test_host_logic.py)."""
         codebook = self.get_codebook().detach().to(doc_emb.device)
+        rq = self.pq_type == "rq"
+        if self.pq_type == "opq":  # pq.py:630-631
+            doc_emb = torch.matmul(doc_emb, self.rotate.detach().to(doc_emb.device).T)
         K = self.subvector_cents
         bs = doc_emb.size(0)
         beam_scores = doc_emb.new_ones(bs, 1)
-        temp_embed = doc_emb.unsqueeze(1).clone()
+        temp_embed = doc_emb.unsqueeze(1).clone() if rq else None
         temp_index = torch.zeros((bs, 1, 1), device=doc_emb.device, dtype=torch.int32)
         for i in range(self.subvector_num):
-            cur_codebook = codebook[i : i + 1].expand(bs, -1, -1).unsqueeze(1)
-            proba = self.compute_scores(temp_embed.unsqueeze(-2), cur_codebook)
+            if rq:
+                cur_codebook = codebook[i : i + 1].expand(bs, -1, -1).unsqueeze(1)
+                proba = self.compute_scores(temp_embed.unsqueeze(-2), cur_codebook)
+            else:  # pq.py:654-660
+                cur_codebook = codebook[i].unsqueeze(0).expand(bs, -1, -1)
+                cur_embed = doc_emb[:, i * self.last_dim : (i + 1) * self.last_dim].unsqueeze(1)
+                proba = self.compute_scores(cur_embed, cur_codebook)
             proba = F.softmax(proba, dim=-1)
-            if self.rq_topk_score == "prod":
+            if not rq:
+                proba = beam_scores.unsqueeze(-1) * proba.unsqueeze(1)  # pq.py:669
+            elif self.rq_topk_score == "prod":
                 proba = beam_scores.unsqueeze(-1) * proba
             proba = proba.view(bs, -1)
             prev = beam_scores.size(1)
@@ -279,14 +346,14 @@ class ProductQuantization(nn.Module):
                 beam_scores = proba.gather(1, top)
                 temp_index = torch.cat(
                     [temp_index.gather(1, prev_beams.expand(-1, -1, temp_index.size(-1))), cur_code.unsqueeze(-1)], dim=-1)
-                if i != self.subvector_num - 1:
+                if rq and i != self.subvector_num - 1:
                     temp_embed = temp_embed.gather(1, prev_beams.expand(-1, -1, temp_embed.size(-1))) \
                         - codebook[i][cur_code][..., : self.last_dim]
             else:
                 beam_scores = proba
                 temp_index = torch.cat(
                     [temp_index.repeat_interleave(K, dim=1), code_of.unsqueeze(-1).unsqueeze(0).expand(bs, -1, -1)], dim=-1)
-                if i != self.subvector_num - 1:
+                if rq and i != self.subvector_num - 1:
                     temp_embed = temp_embed.repeat_interleave(K, dim=1) - codebook[i][code_of][..., : self.last_dim]
         assert beam_scores.size(1) == num_beams
         topk_label = temp_index[:, :, 1:]
@@ -312,7 +379,33 @@ class ProductQuantization(nn.Module):
     # training-time forward (tensor ops; not on the index hot path)       #
     # ------------------------------------------------------------------ #
     def forward(self, vecs, return_loss=True):
-        """pq.py:307-369 (`forward_rq`): (proba [B,M,K], index [B,M], loss)."""
+        """pq.py:307-319: (proba, index, loss); EMA codebook update when training with pq_update_method='ema'."""
+        if self.pq_type == "rq":
+            proba, index, loss = self.forward_rq(vecs, return_loss)
+        else:
+            proba, index, loss = self.forward_pq(vecs, return_loss)
+        if self.training and self.pq_update_method == "ema":
+            self.ema_update(vecs, index)
+        return proba, index, loss
+
+    def forward_pq(self, vecs, return_loss=True):
+        """pq.py:321-337: (proba [B,M,K], index [B,M], loss)."""
+        if self.pq_type == "opq":
+            vecs = torch.matmul(vecs, self.rotate.T)
+        vecs = vecs.view(vecs.size(0), self.subvector_num, -1)
+        codebook = self.get_codebook().unsqueeze(0).expand(vecs.size(0), -1, -1, -1)
+        proba = self.compute_scores(vecs.unsqueeze(-2), codebook)
+        index = proba.max(dim=-1)[1]
+        loss = None
+        if return_loss and self.centroid_update_loss == "reconstruct":  # pq.py:329-333
+            reconstruct_emb = self.get_reconstruct_vector(index).view(index.shape[0], self.subvector_num, self.last_dim)
+            loss = ((vecs - reconstruct_emb) ** 2).mean()
+        return proba, index, loss
+
+    def forward_rq(self, vecs, return_loss=True):
+        """pq.py:339-369: (proba [B,M,K], index [B,M], loss).  Like the reference, `vecs -= centroid`
+        (pq.py:357) subtracts IN PLACE: the caller's tensor holds the residual before the last level afterwards —
+        `ema_update` (called from `forward` with the same tensor) relies on it."""
         allproba, index = [], []
         codebook = self.get_codebook()
         use_rec = self.centroid_update_loss == "reconstruct"
@@ -327,20 +420,101 @@ class ProductQuantization(nn.Module):
             if use_rec:
                 errors.append(vecs.detach() - cur_centroid)
             if i != self.subvector_num - 1:
-                vecs = vecs - cur_centroid.detach()
+                vecs -= cur_centroid.detach()
         proba = torch.stack(allproba, dim=1)
         index = torch.stack(index, dim=1)
         loss = (torch.stack(errors) ** 2).mean() if (return_loss and use_rec) else None
         return proba, index, loss
 
+    # ------------------------------------------------------------------ #
+    # EMA codebook update                                                 #
+    # ------------------------------------------------------------------ #
+    @torch.no_grad()
+    def ema_sums_counts(self, vectors: torch.Tensor, idxs: torch.Tensor):
+        """pq.py:373-393: per (level, centroid) sums of the vectors assigned to it and the assignment counts,
+        as `(vectors_sum_per_cluster [M,K,last_dim], cluster_size [M,K])`.  The reference builds a one-hot
+        matrix and a bmm; here each level is one `mevi_accumulate_by_code` pass (deterministic shared-memory
+        accumulators, csrc/kmeans.cu).  For 'rq' every level sums the SAME `vectors` (pq.py:375-377 expands the
+        input across levels), for 'pq'/'opq' level j sums sub-vector j."""
+        M, K, w = self.subvector_num, self.subvector_cents, self.last_dim
+        ctx = _lib.get_context(vectors.device)
+        if self.pq_type == "opq":
+            vectors = torch.matmul(vectors, self.rotate.to(vectors.device).T)
+        vectors = vectors.detach().float().contiguous()
+        codes = idxs.reshape(-1, M).to(torch.int32).contiguous()
+        sums = torch.empty((M, K, w), dtype=torch.float32, device=vectors.device)
+        counts = torch.empty((M, K), dtype=torch.float32, device=vectors.device)
+        buf = torch.empty(K * w + K, dtype=torch.float32, device=vectors.device)
+        for j in range(M):
+            x = vectors if self.pq_type == "rq" else vectors[:, j * w : (j + 1) * w].contiguous()
+            ctx.accumulate_by_code(x, codes[:, j], K, buf, assign_stride=M)
+            sums[j].copy_(buf[: K * w].view(K, w))
+            counts[j].copy_(buf[K * w :])
+        return sums, counts
+
+    @torch.no_grad()
+    def ema_update(self, vectors, idxs):
+        """pq.py:371-433.  Sums/counts on the device (`ema_sums_counts`), ONE all-reduce of each when
+        torch.distributed is up (pq.py:395-397), then the reference's EMA / restart / normalisation steps on the
+        [M,K,*] buffers."""
+        M, K, w = self.subvector_num, self.subvector_cents, self.last_dim
+        vectors_sum_per_cluster, cluster_size = self.ema_sums_counts(vectors, idxs)
+        if _dist_on():
+            dist.all_reduce(vectors_sum_per_cluster, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cluster_size, op=dist.ReduceOp.SUM)
+        dev = self.cluster_size_ema.device
+        self.cluster_size_ema.mul_(self.decay).add_(cluster_size.to(dev), alpha=1 - self.decay)
+        self.embed_ema.mul_(self.decay).add_(vectors_sum_per_cluster.to(dev), alpha=1 - self.decay)
+        if self.restart_unused_codes:  # pq.py:404-423
+            if self.pq_type == "rq":
+                temp = vectors.detach().unsqueeze(1).expand(-1, M, -1)
+            else:
+                v = torch.matmul(vectors, self.rotate.to(vectors.device).T) if self.pq_type == "opq" else vectors
+                temp = v.detach().reshape(-1, M, w)
+            B = temp.shape[0]
+            if B < K:
+                n_repeats = (K + B - 1) // B
+                std = temp.new_ones(w) * 0.01 / np.sqrt(w)
+                temp = temp.repeat(n_repeats, 1, 1)
+                temp = temp + torch.rand_like(temp) * std
+            _vectors_random = torch.stack(
+                [temp[torch.randperm(temp.shape[0], device=temp.device), i][:K] for i in range(M)])
+            if _dist_on():
+                dist.broadcast(_vectors_random, 0)
+            _vectors_random = _vectors_random.to(dev)
+            usage = (self.cluster_size_ema.unsqueeze(-1) >= 1).float()
+            self.embed_ema.mul_(usage).add_(_vectors_random * (1 - usage))
+            usage = usage.squeeze(-1)
+            self.cluster_size_ema.mul_(usage)
+            self.cluster_size_ema.add_(torch.ones_like(self.cluster_size_ema) * (1 - usage))
+        n = self.cluster_size_ema.sum(dim=1, keepdim=True)  # pq.py:426-432
+        normalized_cluster_size = n * (self.cluster_size_ema + self.eps) / (n + K * self.eps)
+        self.codebook.data[:] = (self.embed_ema / normalized_cluster_size.unsqueeze(-1)).to(self.codebook.device)
+
     def get_reconstruct_vector(self, index, codebook=None):
-        """pq.py:768-784, rq: sum of the selected centroids."""
+        """pq.py:768-784: rq = sum of the selected centroids; pq = their concatenation ('opq': rotated back)."""
         if codebook is None:
             codebook = self.get_codebook()[..., : self.last_dim]
         assert index.dim() in (1, 2)
         M = self.subvector_num
         parts = [codebook[j][index[..., j]] for j in range(M)]
-        return torch.stack(parts, dim=-2).sum(dim=-2)
+        vectors = torch.stack(parts, dim=-2)
+        if self.pq_type == "rq":
+            return vectors.sum(dim=-2)
+        vectors = vectors.reshape(*index.shape[:-1], -1)
+        if self.pq_type == "opq":
+            vectors = torch.matmul(vectors, self.rotate)
+        return vectors
+
+
+def _matmul_fp32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """Plain fp32 library GEMM (cuBLAS, TF32 off) for the OPQ rotation of pq.py:259-261."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return torch.matmul(x, w).contiguous()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 def codes_to_dicts(codes: np.ndarray, start: int = 0, return_mapping: bool = True):

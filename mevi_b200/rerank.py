@@ -195,3 +195,48 @@ def save_index_files(cluster_path: str, doc_cluster: dict, mapping: dict) -> Non
         pickle.dump(doc_cluster, fw)
     with open(cluster_path.replace("clus", "mapping"), "wb") as fw:
         pickle.dump(mapping, fw)
+
+
+@torch.no_grad()
+def eval_all_documents(query_embedding, all_embeddings, pool_size: int, batch_size: int = 1 << 20,
+                       device_index: Optional[int] = None):
+    """The `--eval_all_documents` branch of MEVI/main_models.py:3818-3876 (twin tower): the reference walks the
+    corpus in blocks of `encode_batch_size`, scores q @ p^T and keeps a running torch.topk pool over the
+    concatenation.  Here every block goes through `mevi_flat_ip_topk` (tcgen05 prefilter + exact fp32
+    re-score) with `id_base` = the block's first row, and the per-block lists are merged by
+    `mevi_topk_merge`.  `all_embeddings` may be a CUDA tensor (scored where it lies), a host tensor or an
+    np.ndarray / np.memmap (streamed block by block).  With torch.distributed initialised the rows are
+    sharded as pq.py:218-225 and the per-shard pools are all-gathered and merged on every rank.
+    Returns (stack_scores [nq, min(pool_size, N)] fp32 descending, sorted_docs int32) on the device,
+    like the reference's tensors."""
+    ctx = _lib.get_context(device_index)
+    dev = torch.device("cuda", ctx.device)
+    if not isinstance(query_embedding, torch.Tensor):
+        query_embedding = torch.from_numpy(np.ascontiguousarray(query_embedding, dtype=np.float32))
+    Q = query_embedding.to(device=dev, dtype=torch.float32).contiguous()
+    N = all_embeddings.shape[0]
+    rank, world = rank_world()
+    start, end = shard_bounds(N, rank, world) if dist_on() else (0, N)
+    k = int(min(pool_size, N))
+    fan_in = max(2, 16384 // max(k, 1))  # mevi_topk_merge sorts at most 16,384 entries per query
+    parts_s, parts_i = [], []
+    for a in range(start, end, batch_size):
+        b = min(a + batch_size, end)
+        if isinstance(all_embeddings, torch.Tensor):
+            blk = all_embeddings[a:b].to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            blk = torch.from_numpy(np.ascontiguousarray(all_embeddings[a:b], dtype=np.float32)).to(dev)
+        s, i = ctx.flat_ip_topk(Q, blk, k, id_base=a)
+        parts_s.append(s)
+        parts_i.append(i)
+        if len(parts_s) == fan_in:
+            s, i = ctx.topk_merge(torch.stack(parts_s).contiguous(), torch.stack(parts_i).contiguous())
+            parts_s, parts_i = [s], [i]
+    if not parts_s:
+        parts_s = [torch.full((Q.shape[0], k), float("-inf"), device=dev)]
+        parts_i = [torch.full((Q.shape[0], k), -1, dtype=torch.int64, device=dev)]
+    scores, ids = (parts_s[0], parts_i[0]) if len(parts_s) == 1 else ctx.topk_merge(
+        torch.stack(parts_s).contiguous(), torch.stack(parts_i).contiguous())
+    if dist_on():
+        scores, ids = ctx.topk_merge(all_gather_stack(scores).contiguous(), all_gather_stack(ids).contiguous())
+    return scores, ids.to(torch.int32)

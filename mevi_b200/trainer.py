@@ -58,6 +58,40 @@ def _upload_rows(doc_emb, start: int, end: int, device: torch.device, chunk: int
     return out
 
 
+def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev):
+    """One k-means problem on the local rows R [n, w] (all ranks in lockstep): k-means++ seeds from rank 0's
+    sample, `iters` Lloyd iterations with one all-reduce of the fused sums|counts buffer each, then the labels
+    under the FINAL centroids written to `col` (stride `stride`), like sklearn's fit_predict.
+    Returns (centroids [K, w] on the device, iterations run); `inertia` holds the global final inertia."""
+    rank, _ = rank_world()
+    n, w = R.shape
+    C = torch.empty((K, w), dtype=torch.float32, device=dev)
+    if rank == 0:
+        s = min(init_sample, n)
+        idx = np.sort(rs.choice(n, size=s, replace=False)) if s < n else np.arange(n)
+        sample = R[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        C.copy_(torch.from_numpy(kmeanspp_init(sample, K, rs)).to(dev))
+    if dist_on():
+        dist.broadcast(C, 0)
+    prev = math.inf
+    n_it = 0
+    for it in range(iters):
+        be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
+        if dist_on():
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+        be.kmeans_update(buf, C, n_empty)
+        n_it = it + 1
+        cur = float(inertia.item())
+        if prev - cur <= tol * max(cur, 1e-30):
+            break
+        prev = cur
+    be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
+    if dist_on():
+        dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+    return C, n_it
+
+
 @torch.no_grad()
 def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: float = 1e-7, init_sample: int = 16384,
                    mode: str = "auto", device_index: Optional[int] = None, backend=None, metric: str = "l2",
@@ -80,40 +114,54 @@ def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: flo
     info = {"levels": [], "world": world, "rows_local": n}
     for j in range(M):
         t0 = time.time()
-        # ---- seeding on rank 0's shard, shared by broadcast -------------------
-        C = torch.empty((K, d), dtype=torch.float32, device=dev)
-        if rank == 0:
-            s = min(init_sample, n)
-            idx = np.sort(rs.choice(n, size=s, replace=False)) if s < n else np.arange(n)
-            sample = R[torch.from_numpy(idx).to(dev)].cpu().numpy()
-            C.copy_(torch.from_numpy(kmeanspp_init(sample, K, rs)).to(dev))
-        if dist_on():
-            dist.broadcast(C, 0)
-        prev = math.inf
-        n_it = 0
         col = codes[:, j]
-        for it in range(iters):
-            be.kmeans_step(R, C, buf, assign=col, assign_stride=M, inertia=inertia, mode=mode)
-            if dist_on():
-                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-                dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
-            be.kmeans_update(buf, C, n_empty)
-            n_it = it + 1
-            cur = float(inertia.item())
-            if prev - cur <= tol * max(cur, 1e-30):
-                prev = cur
-                break
-            prev = cur
-        # ---- labels from the FINAL centroids (sklearn's fit_predict does the same) ----
-        be.kmeans_step(R, C, buf, assign=col, assign_stride=M, inertia=inertia, mode=mode)
-        if dist_on():
-            dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+        C, n_it = _lloyd_level(be, R, K, col, M, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev)
         codebook[j].copy_(C)
         if j != M - 1:  # pq.py:591-593
             be.residual_update(R, C, col, assign_stride=M)
         info["levels"].append({"level": j, "iters": n_it, "inertia": float(inertia.item()),
                                "mse": float(inertia.item()) / max(N, 1) / d, "seconds": time.time() - t0})
     train_rq_lloyd.last_info = info
+    codes_all = None
+    if gather_codes:
+        counts = [shard_bounds(N, r, world)[1] - shard_bounds(N, r, world)[0] for r in range(world)]
+        g = gather_rows_to_rank0(codes, counts)
+        if g is not None:
+            codes_all = g.cpu().numpy()
+    return codebook, codes_all
+
+
+@torch.no_grad()
+def train_pq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: float = 1e-7, init_sample: int = 16384,
+                   mode: str = "auto", device_index: Optional[int] = None, backend=None, gather_codes: bool = True):
+    """pq branch of MEVI/pq.py:568-581: one independent k-means per sub-vector slice
+    doc_emb[:, j*dsub:(j+1)*dsub].  Same sharding and collectives as train_rq_lloyd.
+    Returns (codebook [M,K,d/M] on the compute device, codes np.int32 [N,M] on rank 0 or None)."""
+    be = backend if backend is not None else _lib.get_context(device_index)
+    dev = be.torch_device if backend is not None else torch.device("cuda", be.device)
+    rank, world = rank_world()
+    N, d = doc_emb.shape
+    assert d % M == 0
+    dsub = d // M
+    start, end = shard_bounds(N, rank, world)
+    n = end - start
+    X = _upload_rows(doc_emb, start, end, dev)
+    codes = torch.zeros((n, M), dtype=torch.int32, device=dev)
+    codebook = torch.empty((M, K, dsub), dtype=torch.float32, device=dev)
+    buf = torch.empty(K * dsub + K, dtype=torch.float32, device=dev)
+    inertia = torch.zeros(1, dtype=torch.float64, device=dev)
+    n_empty = torch.zeros(1, dtype=torch.int32, device=dev)
+    rs = np.random.RandomState(seed)
+    info = {"levels": [], "world": world, "rows_local": n}
+    for j in range(M):
+        t0 = time.time()
+        R = X[:, j * dsub : (j + 1) * dsub].contiguous()
+        C, n_it = _lloyd_level(be, R, K, codes[:, j], M, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev)
+        codebook[j].copy_(C)
+        info["levels"].append({"level": j, "iters": n_it, "inertia": float(inertia.item()),
+                               "mse": float(inertia.item()) / max(N, 1) / dsub, "seconds": time.time() - t0})
+        del R
+    train_pq_lloyd.last_info = info
     codes_all = None
     if gather_codes:
         counts = [shard_bounds(N, r, world)[1] - shard_bounds(N, r, world)[0] for r in range(world)]

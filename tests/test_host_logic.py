@@ -41,8 +41,9 @@ def test_constructor_surface_and_out_of_scope_branches():
     assert tuple(pq.codebook.shape) == (4, 32, 768) and pq.codebook.dtype == torch.float32
     assert pq.subvector_cents == 32 and pq.last_dim == 768 and pq.get_preds is False
     assert "codebook" in pq.state_dict()
-    for bad in (dict(pq_type="pq"), dict(pq_type="opq"), dict(pq_type="rq", dist_mode="iptol2"),
-                dict(pq_type="rq", pq_update_method="ema"), dict(pq_type="rq", tie_nci_pq_centroid=1)):
+    # iptol2 cannot run in the reference either (self.extracol is never created, pq.py:113-117);
+    # tied NCI centroids need the T5 lm_head
+    for bad in (dict(pq_type="rq", dist_mode="iptol2"), dict(pq_type="rq", tie_nci_pq_centroid=1)):
         with pytest.raises(NotImplementedError):
             ProductQuantization(**bad)
 
