@@ -20,6 +20,7 @@
 // blocks.  Roofline: tensor pipe (2*nq*N*d FLOP); L2->SM operand traffic is the practical limiter.
 #include <cuda_fp16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -33,6 +34,7 @@ constexpr int FT_STAGES = 4;
 constexpr int FT_A_BYTES = FT_TM * 128, FT_B_BYTES = FT_TN * 128;
 constexpr int FT_STAGE_BYTES = FT_A_BYTES + FT_B_BYTES;  // 48 KB
 constexpr int FT_THREADS2 = 192;
+constexpr int FT_DEFAULT_CLUSTER = 2;
 constexpr int FT_KEEP = 512;     // approximate candidates kept per query between chunks
 
 enum { FC_SD = 0, FC_SQ, FC_INV, FC_DMAX, FC_CLAMPED, FC_NUM = 8 };
@@ -78,7 +80,8 @@ __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, 
     if (lane == 0 && row < rows) {
       const float nn = sqrtf(nrm);
       if (norms) norms[row] = nn;
-      if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nn));
+      // one address for every row: test with a plain load first so the atomic fires a handful of times, not N times
+      if (max_norm_bits && __float_as_uint(nn) > *(volatile unsigned*)max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(nn));
     }
     if (clamp) atomicExch(clamped, 1);
   }
@@ -120,11 +123,18 @@ struct GemmParams {
   int64_t tile_begin, tile_end;   // doc tiles of this chunk
   int64_t n_end;                  // first invalid doc row
   int nq, n_qblocks, nchunks;
+  int qparts;                     // query-block range of a tile group split into this many work items
   const float* consts; const float* tau; const float* margin;
   int* count; float* cand_score; int32_t* cand_id; int* overflow; int capg;
   int* err_flag;
 };
 
+// CS = CTAs per cluster.  The CS CTAs of a cluster work on CS consecutive doc tiles against the SAME query
+// block: each CTA fetches its own A tile and 1/CS of the B block, the latter multicast into every CTA of the
+// cluster, so the L2 serves (16 + 32/CS) KB per CTA and stage instead of 48 KB (the L2 slice output, ~6300
+// B/clk chip-wide, is what bounds the single-CTA form).  The CTAs therefore advance stage by stage together:
+// a stage's empty barrier collects one tcgen05.commit from every CTA of the cluster.
+template <int CS>
 __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;  // [FT_STAGES][A 16 KB | B 32 KB]
@@ -138,34 +148,63 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < FT_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < FT_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CS); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
     ptx::mbar_fence_init();
   }
   if (warp == 0) ptx::tmem_alloc(tmem_holder, 512);
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();  // peers' barriers are initialised before anything is multicast at them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
 
-  const int64_t n_items = (p.tile_end - p.tile_begin) * p.n_qblocks;
+  const uint32_t crank = CS > 1 ? ptx::cluster_ctarank() : 0u;
+  const int64_t cluster_id = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CS) - 1u);
+  constexpr int B_SLICE = FT_B_BYTES / CS;
+  // Work item = (group of CS doc tiles, part of the query-block range).  A cluster keeps ITS doc tiles for a whole
+  // run of query blocks (first use from HBM, the rest from L2) and starts the run at a cluster-dependent block, so
+  // at any moment the CTAs of the grid ask the L2 for different A tiles and different B blocks.  (Doc-tile-major
+  // order over the whole grid had 28 CTAs miss on the same new A tile at the same moment: 19x the A bytes from HBM.)
+  const int64_t n_groups = (p.tile_end - p.tile_begin + CS - 1) / CS;
+  const int64_t n_items = n_groups * p.qparts;
   const int nchunks = p.nchunks;
+  auto item_range = [&](int64_t w, int64_t& grp, int& qb0, int& len) {
+    grp = w / p.qparts;
+    const int part = (int)(w % p.qparts);
+    qb0 = (int)((int64_t)part * p.n_qblocks / p.qparts);
+    len = (int)((int64_t)(part + 1) * p.n_qblocks / p.qparts) - qb0;
+  };
+  const int stagger = (int)(cluster_id % 61);
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t g = 0;
       bool ok = true;
-      for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x) {
-        const int64_t tile = p.tile_begin + w / p.n_qblocks;
-        const int qb = (int)(w % p.n_qblocks);
+      for (int64_t w = cluster_id; w < n_items && ok; w += n_clusters) {
+        int64_t grp; int qb0, len;
+        item_range(w, grp, qb0, len);
+        int64_t tile = p.tile_begin + grp * CS + crank;
+        if (tile >= p.tile_end) tile = p.tile_end - 1;  // ragged last group: keep the pipeline in step, epilogue skips it
         const __half* a_src = p.Aimg + (size_t)tile * nchunks * FT_TM * FT_KC;
-        const __half* b_src = p.Bimg + (size_t)qb * nchunks * FT_TN * FT_KC;
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const uint32_t s = g % FT_STAGES, ph = (g / FT_STAGES) & 1;
-          if (!ptx::mbar_wait_backoff(&empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); ok = false; break; }
-          ptx::mbar_arrive_expect_tx(&full[s], FT_STAGE_BYTES);
-          ptx::bulk_g2s(ring + (size_t)s * FT_STAGE_BYTES, a_src + (size_t)c * FT_TM * FT_KC, FT_A_BYTES, &full[s]);
-          ptx::bulk_g2s(ring + (size_t)s * FT_STAGE_BYTES + FT_A_BYTES, b_src + (size_t)c * FT_TN * FT_KC, FT_B_BYTES, &full[s]);
+        for (int k = 0; k < len && ok; ++k) {
+          const int qb = qb0 + (k + stagger) % len;
+          const __half* b_src = p.Bimg + (size_t)qb * nchunks * FT_TN * FT_KC;
+          for (int c = 0; c < nchunks; ++c, ++g) {
+            const uint32_t s = g % FT_STAGES, ph = (g / FT_STAGES) & 1;
+            if (!ptx::mbar_wait_backoff(&empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); ok = false; break; }
+            ptx::mbar_arrive_expect_tx(&full[s], FT_STAGE_BYTES);
+            uint8_t* st_a = ring + (size_t)s * FT_STAGE_BYTES;
+            ptx::bulk_g2s(st_a, a_src + (size_t)c * FT_TM * FT_KC, FT_A_BYTES, &full[s]);
+            if (CS == 1) {
+              ptx::bulk_g2s(st_a + FT_A_BYTES, b_src + (size_t)c * FT_TN * FT_KC, FT_B_BYTES, &full[s]);
+            } else {
+              ptx::bulk_g2s_multicast(st_a + FT_A_BYTES + crank * B_SLICE,
+                                      reinterpret_cast<const uint8_t*>(b_src + (size_t)c * FT_TN * FT_KC) + crank * B_SLICE, B_SLICE,
+                                      &full[s], CMASK);
+            }
+          }
         }
       }
     }
@@ -174,24 +213,29 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
       const uint32_t idesc = ptx::umma_idesc_f16_m128(FT_TN);
       uint32_t g = 0, it = 0;
       bool ok = true;
-      for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-        if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 2); ok = false; break; }
-        ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * FT_TN;
-        for (int c = 0; c < nchunks; ++c, ++g) {
-          const uint32_t s = g % FT_STAGES, ph2 = (g / FT_STAGES) & 1;
-          if (!ptx::mbar_wait(&full[s], ph2)) { atomicExch(p.err_flag, 3); ok = false; break; }
+      for (int64_t w = cluster_id; w < n_items && ok; w += n_clusters) {
+        int64_t grp; int qb0, len;
+        item_range(w, grp, qb0, len);
+        for (int k = 0; k < len && ok; ++k, ++it) {
+          const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+          if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 2); ok = false; break; }
           ptx::tc_fence_after_sync();
-          const uint32_t a_ad = ptx::smem_u32(ring + (size_t)s * FT_STAGE_BYTES);
-          const uint32_t b_ad = a_ad + FT_A_BYTES;
+          const uint32_t d_tmem = tmem_base + buf * FT_TN;
+          for (int c = 0; c < nchunks; ++c, ++g) {
+            const uint32_t s = g % FT_STAGES, ph2 = (g / FT_STAGES) & 1;
+            if (!ptx::mbar_wait(&full[s], ph2)) { atomicExch(p.err_flag, 3); ok = false; break; }
+            ptx::tc_fence_after_sync();
+            const uint32_t a_ad = ptx::smem_u32(ring + (size_t)s * FT_STAGE_BYTES);
+            const uint32_t b_ad = a_ad + FT_A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < FT_KC / 16; ++ks)
-            ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_ad + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc,
-                          (c | ks) != 0 ? 1u : 0u);
-          ptx::umma_commit(&empty[s]);
+            for (int ks = 0; ks < FT_KC / 16; ++ks)
+              ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_ad + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc,
+                            (c | ks) != 0 ? 1u : 0u);
+            if (CS == 1) ptx::umma_commit(&empty[s]);
+            else ptx::umma_commit_multicast(&empty[s], CMASK);
+          }
+          if (ok) ptx::umma_commit(&acc_full[buf]);
         }
-        if (ok) ptx::umma_commit(&acc_full[buf]);
       }
     }
   } else {
@@ -199,52 +243,154 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
     const int lg = warp & 3;
     const int etid = tid - 64;  // 0..127
     const float inv = p.consts[FC_INV];
+    const float sdsq = p.consts[FC_SD] * p.consts[FC_SQ];  // power of two: thresholds move to accumulator units exactly
     uint32_t it = 0;
     bool ok = true;
-    for (int64_t w = blockIdx.x; w < n_items && ok; w += gridDim.x, ++it) {
-      const int64_t tile = p.tile_begin + w / p.n_qblocks;
-      const int qb = (int)(w % p.n_qblocks);
-      const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      // thresholds of this query block (tau is fixed during a chunk; stale values only admit more)
-      float* thr = s_thr + buf * FT_TN;
-      for (int j = etid; j < FT_TN; j += 128) {
-        const int q = qb * FT_TN + j;
-        thr[j] = q < p.nq ? p.tau[q] - p.margin[q] : CUDART_INF_F;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (!ptx::mbar_wait_backoff(&acc_full[buf], ph, 64)) { atomicExch(p.err_flag, 4); ok = false; break; }
-      ptx::tc_fence_after_sync();
+    for (int64_t w = cluster_id; w < n_items && ok; w += n_clusters) {
+      int64_t grp; int qb0, len;
+      item_range(w, grp, qb0, len);
+      const int64_t tile = p.tile_begin + grp * CS + crank;
       const int64_t doc = tile * FT_TM + lg * 32 + lane;
-      const bool doc_ok = doc < p.n_end;
-      const uint32_t taddr = tmem_base + buf * FT_TN + ((uint32_t)(lg * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < FT_TN; c0 += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld32(taddr + c0, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float sc = __uint_as_float(r[j]) * inv;
-          if (doc_ok && !(sc < thr[c0 + j])) {
-            const int q = qb * FT_TN + c0 + j;
-            const int slot = atomicAdd(&p.count[q], 1);
+      const bool doc_ok = doc < p.n_end && tile < p.tile_end;
+      for (int k = 0; k < len && ok; ++k, ++it) {
+        const int qb = qb0 + (k + stagger) % len;
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        // thresholds of this query block (tau is fixed during a chunk; stale values only admit more)
+        float* thr = s_thr + buf * FT_TN;
+        for (int j = etid; j < FT_TN; j += 128) {
+          const int q = qb * FT_TN + j;
+          thr[j] = q < p.nq ? (p.tau[q] - p.margin[q]) * sdsq : CUDART_INF_F;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (!ptx::mbar_wait_backoff(&acc_full[buf], ph, 64)) { atomicExch(p.err_flag, 4); ok = false; break; }
+        ptx::tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + buf * FT_TN + ((uint32_t)(lg * 32) << 16);
+        // one (query column, warp) append: one atomic per warp and query, not per document
+        auto append = [&](int col, bool pass, float acc) {
+          const unsigned m = __ballot_sync(MEVI_FULL_MASK, pass);
+          if (!m) return;
+          const int q = qb * FT_TN + col;
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&p.count[q], __popc(m));
+          base = __shfl_sync(MEVI_FULL_MASK, base, leader);
+          if (pass) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
             if (slot < p.capg) {
-              p.cand_score[(int64_t)q * p.capg + slot] = sc;
+              p.cand_score[(int64_t)q * p.capg + slot] = acc * inv;
               p.cand_id[(int64_t)q * p.capg + slot] = (int32_t)doc;
             } else {
               *p.overflow = 1;
             }
           }
+        };
+        // The common case (no document of this warp beats any of the 32 thresholds) must cost ~1 instruction per
+        // accumulator: vector threshold loads, one predicate per element, ONE vote per 32 columns.  The next 32
+        // columns are already on their way from tensor memory while these are tested.
+        auto test32 = [&](const uint32_t (&r)[32], int c0) {
+          const float4* t4 = reinterpret_cast<const float4*>(thr + c0);
+          bool any = false;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = t4[j4];
+            any |= !(__uint_as_float(r[4 * j4 + 0]) < t.x);
+            any |= !(__uint_as_float(r[4 * j4 + 1]) < t.y);
+            any |= !(__uint_as_float(r[4 * j4 + 2]) < t.z);
+            any |= !(__uint_as_float(r[4 * j4 + 3]) < t.w);
+          }
+          if (!__any_sync(MEVI_FULL_MASK, any && doc_ok)) return;
+          // some document passes: per-lane column mask, then only the columns that have a passing document
+          unsigned mk = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mk |= (!(__uint_as_float(r[j]) < thr[c0 + j]) ? 1u : 0u) << j;
+          if (!doc_ok) mk = 0;
+          unsigned cols = __reduce_or_sync(MEVI_FULL_MASK, mk);
+          if (__popc(cols) > 10) {  // first chunks: most columns pass somewhere
+#pragma unroll
+            for (int j = 0; j < 32; ++j) append(c0 + j, (mk >> j) & 1u, __uint_as_float(r[j]));
+          } else {
+            while (cols) {  // warp-uniform
+              const int j = __ffs(cols) - 1;
+              cols &= cols - 1;
+              // r[j] for a run-time j without spilling r[] to local memory: 5-level select tree
+              uint32_t a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) a16[i] = (j & 16) ? r[i + 16] : r[i];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a8[i] = (j & 8) ? a16[i + 8] : a16[i];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a4[i] = (j & 4) ? a8[i + 4] : a8[i];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) a2[i] = (j & 2) ? a4[i + 2] : a4[i];
+              const uint32_t v = (j & 1) ? a2[1] : a2[0];
+              append(c0 + j, (mk >> j) & 1u, __uint_as_float(v));
+            }
+          }
+        };
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld32(taddr, ra);
+#pragma unroll 1
+        for (int c0 = 0; c0 < FT_TN; c0 += 64) {
+          ptx::tmem_ld_wait();
+          ptx::tmem_ld32(taddr + c0 + 32, rb);
+          test32(ra, c0);
+          ptx::tmem_ld_wait();
+          if (c0 + 64 < FT_TN) ptx::tmem_ld32(taddr + c0 + 64, ra);
+          test32(rb, c0 + 32);
         }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
       }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();  // no CTA leaves while peers may still multicast into it
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+template <int CS>
+int launch_flat_gemm(mevi_ctx* ctx, const GemmParams& p, size_t smem, int max_clusters, cudaStream_t st) {
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_gemm_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t groups = (p.tile_end - p.tile_begin + CS - 1) / CS;
+  const int64_t items = groups * p.qparts;
+  const int clusters = (int)(items < max_clusters ? items : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CS));
+  cfg.blockDim = dim3(FT_THREADS2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MEVI_CUDA(ctx, cudaLaunchKernelEx(&cfg, flat_gemm_kernel<CS>, p));
+  return MEVI_OK;
+}
+
+// co-resident clusters of CS CTAs (1 CTA per SM): 148/CS unless a GPC cannot be tiled exactly
+template <int CS>
+int flat_max_clusters(mevi_ctx* ctx, size_t smem) {
+  if (CS == 1) return ctx->sm_count;
+  if (cudaFuncSetAttribute(flat_gemm_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ctx->sm_count / CS * CS));
+  cfg.blockDim = dim3(FT_THREADS2);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, flat_gemm_kernel<CS>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
 }
 
 // one CTA per query: sort approximate candidates, keep FT_KEEP, tau = k-th approximate score;
@@ -258,7 +404,9 @@ __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, co
   int cnt = count[q];
   if (cnt > capg) cnt = capg;
   if (cnt == 0) return;
-  for (int i = threadIdx.x; i < capg; i += blockDim.x) {
+  int nsort = 64;  // next power of two >= cnt: after the first chunks a query holds `keep` + a few new candidates
+  while (nsort < cnt) nsort <<= 1;
+  for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
     if (i < cnt) {
       s_score[i] = cand_score[(int64_t)q * capg + i];
       s_id[i] = cand_id[(int64_t)q * capg + i];
@@ -268,7 +416,7 @@ __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, co
     }
   }
   __syncthreads();
-  block_bitonic_sort<int32_t>(s_score, s_id, capg);
+  block_bitonic_sort<int32_t>(s_score, s_id, nsort);
   const int kept = cnt < keep ? cnt : keep;
   for (int i = threadIdx.x; i < kept; i += blockDim.x) {
     cand_score[(int64_t)q * capg + i] = s_score[i];
@@ -391,7 +539,11 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   p.consts = consts; p.tau = tau; p.margin = margin; p.count = count; p.cand_score = cand_score; p.cand_id = cand_id;
   p.overflow = flags; p.capg = capg; p.err_flag = flags + 1;
   const size_t smem_gemm = (size_t)FT_STAGES * FT_STAGE_BYTES + 2 * FT_TN * 4 + (2 * FT_STAGES + 4) * 8 + 16 + 1024;
-  MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm));
+  // cluster size: MEVI_FLAT_CLUSTER=1|2|4 overrides the default
+  int cs = FT_DEFAULT_CLUSTER;
+  if (const char* e = getenv("MEVI_FLAT_CLUSTER")) cs = atoi(e);
+  int max_clusters = cs == 4 ? flat_max_clusters<4>(ctx, smem_gemm) : cs == 2 ? flat_max_clusters<2>(ctx, smem_gemm) : 0;
+  if (max_clusters <= 0) { cs = 1; max_clusters = ctx->sm_count; }
   const size_t smem_compact = (size_t)capg * 8;
   MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
 
@@ -402,9 +554,15 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
     const int64_t end = pos + chunk_tiles < n_tiles ? pos + chunk_tiles : n_tiles;
     p.tile_begin = pos;
     p.tile_end = end;
-    const int64_t items = (end - pos) * n_qblocks;
-    const int grid = (int)(items < ctx->sm_count ? items : ctx->sm_count);
-    flat_gemm_kernel<<<grid, FT_THREADS2, smem_gemm, st>>>(p);
+    {  // enough work items for ~3 per cluster: split the query-block range of a tile group when groups are few
+      const int64_t groups = (end - pos + cs - 1) / cs;
+      int64_t parts = groups >= 3 * (int64_t)max_clusters ? 1 : (3 * (int64_t)max_clusters + groups - 1) / groups;
+      p.qparts = (int)(parts > n_qblocks ? n_qblocks : parts);
+    }
+    const int rc = cs == 4 ? launch_flat_gemm<4>(ctx, p, smem_gemm, max_clusters, st)
+                 : cs == 2 ? launch_flat_gemm<2>(ctx, p, smem_gemm, max_clusters, st)
+                           : launch_flat_gemm<1>(ctx, p, smem_gemm, max_clusters, st);
+    if (rc != MEVI_OK) return rc;
     flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(tau, margin, count, cand_score, cand_id, flags, capg, k, FT_KEEP);
     MEVI_CUDA(ctx, cudaGetLastError());
     MEVI_COUNT_LAUNCH(ctx, 2);
