@@ -248,7 +248,8 @@ def our_arm(args, rank, local_rank, world):
     except Exception:
         avail = 64 << 30
     n_e2e = n
-    while n_e2e * D * 4 * 1.3 > avail * 0.6 and n_e2e > 1 << 18:
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))  # every rank of the node pins its own host copy
+    while n_e2e * D * 4 * 1.3 > avail * 0.6 / max(1, local_world) and n_e2e > 1 << 18:
         n_e2e //= 2
     pq = ProductQuantization("rq", M_LEVELS, 5, "l2", D, "kmeans", "grad")
     pq.kernel_mode = args.mode
@@ -407,14 +408,25 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
         t_perm = time.perf_counter() - t0
         res = {}
 
+        from mevi_b200.dist_utils import all_gather_stack
+
         def rr():
-            res["out"] = ctx.cluster_rerank(Q, D_leaf, index.leaf_offsets, index.leaf_docids, ql, TOPK, leaf_ordered=True)
+            # documents are sharded: every rank scores the candidates it owns for ALL queries, then the per-shard
+            # top-k lists are all-gathered and merged on every rank (the same sequence as ClusterReranker.rerank)
+            sc, ids, nc = ctx.cluster_rerank(Q, D_leaf, index.leaf_offsets, index.leaf_docids, ql, TOPK, id_base=rank * n,
+                                             leaf_ordered=True)
+            if world > 1:
+                sc, ids = ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
+            res["out"] = (sc, ids, nc)
 
         ms = timed(rr, 2)
         ncand = res["out"][2].to(torch.float64)
         gathered = float(ncand.sum().item()) * D * 4
         out["rerank"] = {
-            "metric": "rerank_queries_per_sec", "value": world * NQ_MARCO / (ms / 1e3), "unit": "queries/s",
+            "metric": "rerank_queries_per_sec", "value": NQ_MARCO / (ms / 1e3), "unit": "queries/s",
+            "corpus_docs": world * n, "sharding": f"documents row-sharded over {world} GPU(s); all-gather of [nq,k] (score,id) + merge "
+                                                  "inside the timed region" if world > 1 else "single GPU, no collective",
+            "candidates_scored_per_sec": world * float(ncand.sum().item()) / (ms / 1e3),
             "ms_per_step": ms, "queries": NQ_MARCO, "leaves_per_query": LEAVES, "topk": TOPK,
             "candidates_mean": float(ncand.mean().item()), "candidates_max": float(ncand.max().item()),
             "empty_leaf_fraction": float((ql < 0).float().mean().item()), "n_leaves": index.n_leaves,
@@ -441,11 +453,22 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
 
         ms = timed(km, 3)
         bytes_ = n * D * 4
-        out["kmeans_iteration"] = {"ms": ms, "docs_per_sec": world * n / (ms / 1e3), "allreduce_bytes": (K_CENTS * D + K_CENTS) * 4,
-                                   "roofline": {"bound": "hbm", "achieved": bytes_ / (ms / 1e3) / 1e9, "peak": hbm_peak,
-                                                "unit": "GB/s", "frac": bytes_ / (ms / 1e3) / 1e9 / hbm_peak,
-                                                "note": "algorithmic bytes = 4*d per doc per iteration (assign+accumulate read the shard twice)"}}
-        del assign
+        # the two kernels of an iteration, each against the HBM roofline of ITS pass over the shard
+        a2 = assign.view(n, 1)
+        ms_assign = timed(lambda: ctx.rq_encode(X, C[None], metric="l2", mode=args.mode, codes=a2), 3)
+        ms_accum = timed(lambda: ctx.accumulate_by_code(X, assign, K_CENTS, buf), 3)
+
+        def roof(ms_k, nbytes, note):
+            return {"bound": "hbm", "achieved": nbytes / (ms_k / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": nbytes / (ms_k / 1e3) / 1e9 / hbm_peak, "ms": ms_k, "note": note}
+
+        out["kmeans_iteration"] = {
+            "ms": ms, "docs_per_sec": world * n / (ms / 1e3), "allreduce_bytes": (K_CENTS * D + K_CENTS) * 4,
+            "roofline": roof(ms, bytes_, "whole iteration against ONE pass over the shard (4*d bytes per doc); the iteration "
+                                         "makes two passes (assign, then accumulate), see DESIGN.md for why they are not fused"),
+            "kernels": {"assign (rq_encode, M=1)": roof(ms_assign, bytes_ + n * 4, "reads the shard once, writes int32 assignments"),
+                        "accumulate_by_code": roof(ms_accum, bytes_ + n * 4, "reads the shard and the assignments once")}}
+        del assign, a2
     except Exception as e:
         out["kmeans_iteration"] = {"error": repr(e)[:300]}
 
@@ -456,19 +479,24 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
         g.manual_seed(4321)
         Q = torch.empty((NQ_MARCO, D), device=dev).normal_(generator=g)
 
-        def fl():
-            ctx.flat_ip_topk(Q, X[:shard], TOPK, mode=args.mode)
+        from mevi_b200.dist_utils import all_gather_stack
 
-        ms = timed(fl, 1)
+        def fl():
+            sc, ids = ctx.flat_ip_topk(Q, X[:shard], TOPK, id_base=rank * shard, mode=args.mode)
+            if world > 1:  # docs sharded: all-gather of per-shard top-k + merge (faiss_search.search under torch.distributed)
+                ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
+
+        ms = timed(fl, 2)
         flops = 2.0 * NQ_MARCO * shard * D
-        tf32_peak = bf16_peak / 2.0
-        out["flat_ip"] = {"ms": ms, "docs": shard, "queries": NQ_MARCO, "topk": TOPK,
-                          "queries_per_sec_at_this_shard": NQ_MARCO / (ms / 1e3),
-                          "roofline": {"bound": "tensor", "achieved": flops / (ms / 1e3) / 1e12, "peak": tf32_peak,
-                                       "unit": "TFLOP/s", "frac": flops / (ms / 1e3) / 1e12 / tf32_peak,
-                                       "note": "FLOPs = 2*nq*N*d (algorithmic); peak = measured bf16 cuBLAS / 2 (TF32-equivalent dense "
-                                               "rate for fp32 data); the kernel is a single-pass fp16 tcgen05 prefilter + exact fp32 "
-                                               "re-score, time includes the fp32->fp16 image pass, compactions and the re-score"}}
+        ach = flops / (ms / 1e3) / 1e12
+        out["flat_ip"] = {"ms": ms, "docs_per_gpu": shard, "corpus_docs": world * shard, "queries": NQ_MARCO, "topk": TOPK,
+                          "queries_per_sec": NQ_MARCO / (ms / 1e3), "pairs_per_sec": world * NQ_MARCO * shard / (ms / 1e3),
+                          "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                                       "frac_of_tf32_equivalent_peak": ach / (bf16_peak / 2.0),
+                                       "note": "FLOPs = 2*nq*N*d (algorithmic); peak = measured 16-bit cuBLAS burst rate (the kernel's MMAs "
+                                               "are fp16 tcgen05, one pass); inputs and results are fp32, for which the dense rate would be "
+                                               "half of that (TF32) - both fractions given; the time is the WHOLE call: fp32->fp16 image "
+                                               "pass, GEMM with prefilter epilogue, compactions, exact fp32 re-score"}}
     except Exception as e:
         out["flat_ip"] = {"error": repr(e)[:300]}
     return out

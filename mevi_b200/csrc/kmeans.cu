@@ -15,6 +15,8 @@
 // are then reduced in a fixed order.  No float atomics, so sums are
 // bit-reproducible for a given (n, grid) and ranks stay in lockstep.
 // Roofline: HBM (one more read of the shard: 4*d bytes per row + 4 B assignment).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -32,10 +34,8 @@ namespace {
 constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_TILE = 256;
-#ifndef MEVI_KA_STAGES
-#define MEVI_KA_STAGES 2
-#endif
-constexpr int KA_STAGES = MEVI_KA_STAGES;  // shared-memory stages of the accumulate kernel (KA_STAGES-1 bulk copies in flight)
+constexpr int KA_MAX_STAGES = 8;
+constexpr int KA_DEFAULT_STAGES = 2;  // shared-memory stages of the accumulate kernel (stages-1 bulk copies in flight)
 
 // Column-owner accumulation (skew-proof and deterministic).  The CTA keeps the running [K][d] fp32
 // sums in shared memory; thread t owns column t of every centroid.  Rows arrive in sub-tiles — one
@@ -44,19 +44,21 @@ constexpr int KA_STAGES = MEVI_KA_STAGES;  // shared-memory stages of the accumu
 // the accumulator row of the row's centroid (a CTA-uniform index, so the access stays conflict-free).
 // All threads work on every row, so one dominant cluster (the reference-trained codebooks put >80 %
 // of N(0,1) rows into two centroids) costs nothing extra; the summation order is the row order.
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
-                                                                  const int32_t* __restrict__ assign,
-                                                                  int64_t assign_stride, int K, int sub_rows,
-                                                                  float* __restrict__ partial_sums,     // [grid][K][d]
-                                                                  int32_t* __restrict__ partial_counts)  // [grid][K]
+template <int NT>  // NT column-owner threads + one loader warp
+__global__ void __launch_bounds__(NT + 32, 1) kmeans_accumulate_kernel(const float* __restrict__ R, int64_t n, int d,
+                                                                       const int32_t* __restrict__ assign,
+                                                                       int64_t assign_stride, int K, int sub_rows,
+                                                                       int KA_STAGES,
+                                                                       float* __restrict__ partial_sums,     // [grid][K][d]
+                                                                       int32_t* __restrict__ partial_counts)  // [grid][K]
 {
   extern __shared__ __align__(128) unsigned char km_smem[];  // [KA_STAGES][sub_rows][d] fp32, then acc [K][d]
-  __shared__ __align__(8) uint64_t full_bar[KA_STAGES];
-  __shared__ int s_assign[KA_STAGES][32];
+  __shared__ __align__(8) uint64_t full_bar[KA_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[KA_MAX_STAGES];
+  __shared__ int s_assign[KA_MAX_STAGES][32];
   __shared__ int s_count_total[64];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool owner = tid < d;  // this thread owns column tid of every centroid's running sum
   // sub-tiles are dealt round-robin (CTA b takes sub-tiles b, b+G, ...): neighbouring SMs stream
   // neighbouring memory, like the encode kernel; the per-CTA order is still fixed -> reproducible
@@ -66,55 +68,60 @@ __global__ void __launch_bounds__(NT, 1) kmeans_accumulate_kernel(const float* _
   const size_t stage_bytes = (size_t)sub_rows * d * sizeof(float);
   float* s_acc = reinterpret_cast<float*>(km_smem + KA_STAGES * stage_bytes);
 
-  for (int i = tid; i < K * d; i += NT) s_acc[i] = 0.f;
-  for (int i = tid; i < 64; i += NT) s_count_total[i] = 0;
+  for (int i = tid; i < K * d; i += NT + 32) s_acc[i] = 0.f;
+  for (int i = tid; i < 64; i += NT + 32) s_count_total[i] = 0;
   if (tid == 0) {
-    for (int s = 0; s < KA_STAGES; ++s) ptx::mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < KA_STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], NT / 32);
+    }
     ptx::mbar_fence_init();
   }
   __syncthreads();
-  auto issue = [&](int64_t i) {  // thread 0: bulk copy of sub-tile i into stage i % KA_STAGES
-    const int64_t r0 = (blockIdx.x + i * gridDim.x) * sub_rows;
-    const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
-    const uint32_t bytes = (uint32_t)rows * (uint32_t)d * 4u;
-    const int s = (int)(i % KA_STAGES);
-    ptx::mbar_arrive_expect_tx(&full_bar[s], bytes);
-    ptx::bulk_g2s(km_smem + (size_t)s * stage_bytes, R + r0 * d, bytes, &full_bar[s]);
-  };
-  auto load_assign = [&](int64_t i) {  // threads 0..sub_rows-1: assignments of sub-tile i -> s_assign[i % KA_STAGES]
-    const int64_t r = (blockIdx.x + i * gridDim.x) * sub_rows + tid;
-    if (tid < sub_rows && r < row_end) {
-      int a = assign[r * assign_stride];
-      a = a < 0 ? 0 : (a >= K ? K - 1 : a);
-      s_assign[i % KA_STAGES][tid] = a;
-      atomicAdd(&s_count_total[a], 1);
+  // No CTA-wide barrier inside the loop: the loader warp runs ahead (assignment loads from global memory and the bulk
+  // copy of the rows are both off the owners' critical path), owners drift freely and hand stages back per warp.
+  if (warp == NT / 32) {
+    for (int64_t i = 0; i < nsub; ++i) {
+      const int s = (int)(i % KA_STAGES);
+      const int64_t r0 = (blockIdx.x + i * gridDim.x) * sub_rows;
+      const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
+      int a = 0;
+      if (lane < rows) {  // issued before the wait: the load latency overlaps it
+        a = assign[(r0 + lane) * assign_stride];
+        a = a < 0 ? 0 : (a >= K ? K - 1 : a);
+      }
+      if (i >= KA_STAGES) ptx::mbar_wait_backoff(&empty_bar[s], (uint32_t)(((i / KA_STAGES) - 1) & 1), 32);
+      if (lane < rows) {
+        s_assign[s][lane] = a;
+        atomicAdd(&s_count_total[a], 1);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)d * 4u;
+        ptx::mbar_arrive_expect_tx(&full_bar[s], bytes);
+        ptx::bulk_g2s(km_smem + (size_t)s * stage_bytes, R + r0 * d, bytes, &full_bar[s]);
+      }
     }
-  };
-  for (int64_t i = 0; i < KA_STAGES - 1 && i < nsub; ++i) {
-    if (tid == 0) issue(i);
-    load_assign(i);
+  } else {
+    float* my_acc = s_acc + tid;
+    for (int64_t i = 0; i < nsub; ++i) {
+      const int64_t r0 = (blockIdx.x + i * gridDim.x) * sub_rows;
+      const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
+      const int stg = (int)(i % KA_STAGES);
+      ptx::mbar_wait(&full_bar[stg], (uint32_t)((i / KA_STAGES) & 1));
+      if (owner) {
+        const float* base = reinterpret_cast<const float*>(km_smem + (size_t)stg * stage_bytes) + tid;
+        const int* as = s_assign[stg];
+        // the row's centroid is a CTA-uniform value, so the dynamically indexed accumulator row costs
+        // nothing in shared memory; rows are added in order -> the sum is reproducible
+        for (int r = 0; r < rows; ++r) my_acc[(size_t)as[r] * d] += base[(size_t)r * d];
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[stg]);
+    }
   }
-  for (int64_t i = 0; i < nsub; ++i) {
-    const int64_t r0 = (blockIdx.x + i * gridDim.x) * sub_rows;
-    const int rows = (int)((row_end - r0) < sub_rows ? (row_end - r0) : sub_rows);
-    if (i + KA_STAGES - 1 < nsub) {  // that stage was released by the barrier that ended iteration i-1
-      if (tid == 0) issue(i + KA_STAGES - 1);
-      load_assign(i + KA_STAGES - 1);
-    }
-    const int stg = (int)(i % KA_STAGES);
-    ptx::mbar_wait(&full_bar[stg], (uint32_t)((i / KA_STAGES) & 1));
-    __syncthreads();  // s_assign[stg] (written at least one iteration ago) is visible
-    if (owner) {
-      const float* base = reinterpret_cast<const float*>(km_smem + (size_t)stg * stage_bytes) + tid;
-      const int* as = s_assign[stg];
-      float* my_acc = s_acc + tid;
-      // the row's centroid is a CTA-uniform value, so the dynamically indexed accumulator row costs
-      // nothing in shared memory; rows are added in order -> the sum is reproducible
-      for (int r = 0; r < rows; ++r) my_acc[(size_t)as[r] * d] += base[(size_t)r * d];
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < K * d; i += NT) partial_sums[(int64_t)blockIdx.x * K * d + i] = s_acc[i];
+  __syncthreads();
+  for (int i = tid; i < K * d; i += NT + 32) partial_sums[(int64_t)blockIdx.x * K * d + i] = s_acc[i];
   if (tid < K) partial_counts[(int64_t)blockIdx.x * K + tid] = s_count_total[tid];
 }
 
@@ -181,21 +188,21 @@ __global__ void residual_update_kernel(float* __restrict__ R, int64_t n, int d4,
 
 template <int NT>
 cudaError_t launch_accumulate_nt(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
-                                 float* ps, int32_t* pc, int sub_rows, size_t smem, cudaStream_t st) {
+                                 float* ps, int32_t* pc, int sub_rows, int stages, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kmeans_accumulate_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kmeans_accumulate_kernel<NT><<<G, NT, smem, st>>>(R, n, d, assign, stride, K, sub_rows, ps, pc);
+  kmeans_accumulate_kernel<NT><<<G, NT + 32, smem, st>>>(R, n, d, assign, stride, K, sub_rows, stages, ps, pc);
   return cudaGetLastError();
 }
 
 cudaError_t launch_accumulate(const float* R, int64_t n, int d, const int32_t* assign, int64_t stride, int K, int G,
-                              float* ps, int32_t* pc, int sub_rows, size_t smem, cudaStream_t st) {
+                              float* ps, int32_t* pc, int sub_rows, int stages, size_t smem, cudaStream_t st) {
   // one thread per column
-  if (d <= 128) return launch_accumulate_nt<128>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
-  if (d <= 256) return launch_accumulate_nt<256>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
-  if (d <= 512) return launch_accumulate_nt<512>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
-  if (d <= 768) return launch_accumulate_nt<768>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
-  return launch_accumulate_nt<1024>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+  if (d <= 128) return launch_accumulate_nt<128>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, stages, smem, st);
+  if (d <= 256) return launch_accumulate_nt<256>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, stages, smem, st);
+  if (d <= 512) return launch_accumulate_nt<512>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, stages, smem, st);
+  if (d <= 768) return launch_accumulate_nt<768>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, stages, smem, st);
+  return launch_accumulate_nt<992>(R, n, d, assign, stride, K, G, ps, pc, sub_rows, stages, smem, st);
 }
 
 // per-centroid sums|counts of the rows of R under a given assignment -> sums_counts [K*d + K]
@@ -204,9 +211,13 @@ int accumulate_by_code(mevi_ctx* ctx, const float* R, int64_t n, int d, const in
   const int64_t kd = (int64_t)K * d;
   // shared-memory budget: [K][d] accumulators + KA_STAGES stages of sub_rows rows
   const size_t acc_bytes = (size_t)kd * sizeof(float);
+  int KA_STAGES = KA_DEFAULT_STAGES;
+  if (const char* e = getenv("MEVI_KA_STAGES")) KA_STAGES = atoi(e);
+  if (KA_STAGES < 2) KA_STAGES = 2;
+  if (KA_STAGES > KA_MAX_STAGES) KA_STAGES = KA_MAX_STAGES;
   int sub_rows = acc_bytes + 4096 < 220 * 1024 ? (int)((220 * 1024 - acc_bytes) / ((size_t)KA_STAGES * d * 4)) : 0;
   if (sub_rows > 32) sub_rows = 32;
-  const bool fast = K <= 64 && d <= 1024 && d % 4 == 0 && sub_rows >= 4 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
+  const bool fast = K <= 64 && d <= 992 && d % 4 == 0 && sub_rows >= 4 && (reinterpret_cast<uintptr_t>(R) & 15) == 0;
   if (fast) {
     int G = ctx->sm_count;  // one CTA per SM (shared-memory stages), persistent
     int64_t max_g = (n + sub_rows - 1) / sub_rows;
@@ -219,7 +230,7 @@ int accumulate_by_code(mevi_ctx* ctx, const float* R, int64_t n, int d, const in
     float* ps = (float*)ws;
     int32_t* pc = (int32_t*)(ws + ps_bytes);
     const size_t smem = (size_t)KA_STAGES * sub_rows * d * 4 + acc_bytes + 128;
-    cudaError_t e = launch_accumulate(R, n, d, assign, stride, K, G, ps, pc, sub_rows, smem, st);
+    cudaError_t e = launch_accumulate(R, n, d, assign, stride, K, G, ps, pc, sub_rows, KA_STAGES, smem, st);
     if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "kmeans_accumulate launch: %s", cudaGetErrorString(e));
     int threads = 256;
     int blocks = (int)((kd + K + threads - 1) / threads);
