@@ -455,8 +455,8 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
         bytes_ = n * D * 4
         # the two kernels of an iteration, each against the HBM roofline of ITS pass over the shard
         a2 = assign.view(n, 1)
-        ms_assign = timed(lambda: ctx.rq_encode(X, C[None], metric="l2", mode=args.mode, codes=a2), 3)
-        ms_accum = timed(lambda: ctx.accumulate_by_code(X, assign, K_CENTS, buf), 3)
+        ms_assign = timed(lambda: ctx.rq_encode(X, C[None], metric="l2", mode=args.mode, codes=a2), 5)
+        ms_accum = timed(lambda: ctx.accumulate_by_code(X, assign, K_CENTS, buf), 5)
 
         def roof(ms_k, nbytes, note):
             return {"bound": "hbm", "achieved": nbytes / (ms_k / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

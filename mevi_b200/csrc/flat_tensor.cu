@@ -12,7 +12,7 @@
 //
 // Data path.  One streaming pass converts D (and Q) to fp16 "images": [tile][K chunk][rows][64 halfs]
 // with the 128-byte XOR swizzle UMMA expects, so every pipeline stage is ONE contiguous block fetched
-// by a single bulk async copy (no tensor maps).  GEMM CTA (persistent, 192 threads): warp 0 = bulk-copy
+// by a single bulk async copy (no tensor maps).  GEMM CTA (persistent, 320 threads): warp 0 = bulk-copy
 // producer (A: 128 docs x 64, 16 KB; B: 256 queries x 64, 32 KB; 4 stages), warp 1 = one thread issuing
 // tcgen05.mma M=128 N=256 K=16, accumulators double-buffered in TMEM (2 x 256 columns), warps 2-5 =
 // epilogue: tcgen05.ld, compare with the per-query threshold, rare atomic append.  Work items are
@@ -33,7 +33,8 @@ constexpr int FT_KC = 64;        // K elements per chunk (128-byte rows)
 constexpr int FT_STAGES = 4;
 constexpr int FT_A_BYTES = FT_TM * 128, FT_B_BYTES = FT_TN * 128;
 constexpr int FT_STAGE_BYTES = FT_A_BYTES + FT_B_BYTES;  // 48 KB
-constexpr int FT_THREADS2 = 192;
+constexpr int FT_EPI_WARPS = 8;   // two per TMEM lane group, 128 of the 256 accumulator columns each
+constexpr int FT_THREADS2 = 64 + 32 * FT_EPI_WARPS;
 constexpr int FT_DEFAULT_CLUSTER = 2;
 constexpr int FT_KEEP = 512;     // approximate candidates kept per query between chunks
 
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < FT_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CS); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], FT_EPI_WARPS); }
     ptx::mbar_fence_init();
   }
   if (warp == 0) ptx::tmem_alloc(tmem_holder, 512);
@@ -239,9 +240,10 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
       }
     }
   } else {
-    // ===== epilogue (warps 2..5; TMEM lane group = warp % 4) =====
+    // ===== epilogue (warps 2..9; TMEM lane group = warp % 4; warps 2-5 take columns 0..127, warps 6-9 the rest) =====
     const int lg = warp & 3;
-    const int etid = tid - 64;  // 0..127
+    const int chalf = (warp - 2) >> 2;
+    const int etid = tid - 64;  // 0..255
     const float inv = p.consts[FC_INV];
     const float sdsq = p.consts[FC_SD] * p.consts[FC_SQ];  // power of two: thresholds move to accumulator units exactly
     uint32_t it = 0;
@@ -257,25 +259,23 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         // thresholds of this query block (tau is fixed during a chunk; stale values only admit more)
         float* thr = s_thr + buf * FT_TN;
-        for (int j = etid; j < FT_TN; j += 128) {
+        for (int j = etid; j < FT_TN; j += 32 * FT_EPI_WARPS) {
           const int q = qb * FT_TN + j;
           thr[j] = q < p.nq ? (p.tau[q] - p.margin[q]) * sdsq : CUDART_INF_F;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * FT_EPI_WARPS) : "memory");
         if (!ptx::mbar_wait_backoff(&acc_full[buf], ph, 64)) { atomicExch(p.err_flag, 4); ok = false; break; }
         ptx::tc_fence_after_sync();
         const uint32_t taddr = tmem_base + buf * FT_TN + ((uint32_t)(lg * 32) << 16);
-        // one (query column, warp) append: one atomic per warp and query, not per document
-        auto append = [&](int col, bool pass, float acc) {
-          const unsigned m = __ballot_sync(MEVI_FULL_MASK, pass);
-          if (!m) return;
-          const int q = qb * FT_TN + col;
-          const int leader = __ffs(m) - 1;
-          int base = 0;
-          if (lane == leader) base = atomicAdd(&p.count[q], __popc(m));
-          base = __shfl_sync(MEVI_FULL_MASK, base, leader);
-          if (pass) {
-            const int slot = base + __popc(m & ((1u << lane) - 1u));
+        // Appends of one 32x32 block (32 documents = lanes, 32 queries = columns).  Lane j owns column j: it gets
+        // the mask of passing documents, makes ONE atomicAdd for the column (all columns of the block in flight
+        // together: one atomic round trip per block, not per column), then the passing lanes store.
+        auto store_col = [&](int col, unsigned mk, int j, int base_l, unsigned mym, float acc) {
+          const int b0 = __shfl_sync(MEVI_FULL_MASK, base_l, j);
+          const unsigned m = __shfl_sync(MEVI_FULL_MASK, mym, j);
+          if ((mk >> j) & 1u) {
+            const int q = qb * FT_TN + col;
+            const int slot = b0 + __popc(m & ((1u << lane) - 1u));
             if (slot < p.capg) {
               p.cand_score[(int64_t)q * p.capg + slot] = acc * inv;
               p.cand_id[(int64_t)q * p.capg + slot] = (int32_t)doc;
@@ -304,14 +304,30 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
 #pragma unroll
           for (int j = 0; j < 32; ++j) mk |= (!(__uint_as_float(r[j]) < thr[c0 + j]) ? 1u : 0u) << j;
           if (!doc_ok) mk = 0;
-          unsigned cols = __reduce_or_sync(MEVI_FULL_MASK, mk);
-          if (__popc(cols) > 10) {  // first chunks: most columns pass somewhere
+          const unsigned cols = __reduce_or_sync(MEVI_FULL_MASK, mk);
+          const bool dense = __popc(cols) > 10;  // first chunks: most columns pass somewhere
+          unsigned mym = 0;  // lane j: documents (lanes) passing column j
+          if (dense) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) append(c0 + j, (mk >> j) & 1u, __uint_as_float(r[j]));
+            for (int j = 0; j < 32; ++j) {
+              const unsigned m = __ballot_sync(MEVI_FULL_MASK, (mk >> j) & 1u);
+              if (lane == j) mym = m;
+            }
           } else {
-            while (cols) {  // warp-uniform
-              const int j = __ffs(cols) - 1;
-              cols &= cols - 1;
+            for (unsigned c = cols; c; c &= c - 1) {  // warp-uniform
+              const int j = __ffs(c) - 1;
+              const unsigned m = __ballot_sync(MEVI_FULL_MASK, (mk >> j) & 1u);
+              if (lane == j) mym = m;
+            }
+          }
+          int base_l = 0;
+          if (mym) base_l = atomicAdd(&p.count[qb * FT_TN + c0 + lane], __popc(mym));
+          if (dense) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) store_col(c0 + j, mk, j, base_l, mym, __uint_as_float(r[j]));
+          } else {
+            for (unsigned c = cols; c; c &= c - 1) {
+              const int j = __ffs(c) - 1;
               // r[j] for a run-time j without spilling r[] to local memory: 5-level select tree
               uint32_t a16[16], a8[8], a4[4], a2[2];
 #pragma unroll
@@ -323,19 +339,20 @@ __global__ void __launch_bounds__(FT_THREADS2, 1) flat_gemm_kernel(GemmParams p)
 #pragma unroll
               for (int i = 0; i < 2; ++i) a2[i] = (j & 2) ? a4[i + 2] : a4[i];
               const uint32_t v = (j & 1) ? a2[1] : a2[0];
-              append(c0 + j, (mk >> j) & 1u, __uint_as_float(v));
+              store_col(c0 + j, mk, j, base_l, mym, __uint_as_float(v));
             }
           }
         };
         uint32_t ra[32], rb[32];
-        ptx::tmem_ld32(taddr, ra);
+        const int cbeg = chalf * (FT_TN / 2), cend = cbeg + FT_TN / 2;
+        ptx::tmem_ld32(taddr + cbeg, ra);
 #pragma unroll 1
-        for (int c0 = 0; c0 < FT_TN; c0 += 64) {
+        for (int c0 = cbeg; c0 < cend; c0 += 64) {
           ptx::tmem_ld_wait();
           ptx::tmem_ld32(taddr + c0 + 32, rb);
           test32(ra, c0);
           ptx::tmem_ld_wait();
-          if (c0 + 64 < FT_TN) ptx::tmem_ld32(taddr + c0 + 64, ra);
+          if (c0 + 64 < cend) ptx::tmem_ld32(taddr + c0 + 64, ra);
           test32(rb, c0 + 32);
         }
         ptx::tc_fence_before_sync();

@@ -620,6 +620,7 @@ __global__ void residual_from_codes_kernel(const float* __restrict__ X, int64_t 
 
 #include "rq_tensor3.cuh"
 #include "rq_tensor4.cuh"
+constexpr bool V4_EARLY_DEFAULT = false;  // flipped once verified on hardware
 #include "rq_tensor5.cuh"
 
 }  // namespace
@@ -745,10 +746,18 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     const v4::Smem4 L4 = v4::smem4_layout(M, K, NT);
     const size_t smem4 = (size_t)L4.total + 1024;
     const int grid4 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+    // early accumulator release (register-preloading epilogue): K == 32; MEVI_RQ_EARLY=0|1 overrides the default
+    bool early4 = (K == 32) && V4_EARLY_DEFAULT;
+    if (const char* e = getenv("MEVI_RQ_EARLY")) early4 = (K == 32) && atoi(e) != 0;
 #define MEVI_LAUNCH_RQ_TENSOR4(MM)                                                                                          \
   do {                                                                                                                      \
-    MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
-    v4::rq_tensor4_kernel<MM><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                                 \
+    if (early4) {                                                                                                           \
+      MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+      v4::rq_tensor4_kernel<MM, true><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                         \
+    } else {                                                                                                                \
+      MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+      v4::rq_tensor4_kernel<MM, false><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                        \
+    }                                                                                                                       \
   } while (0)
     switch (M) {
       case 1: MEVI_LAUNCH_RQ_TENSOR4(1); break;

@@ -28,6 +28,10 @@ constexpr int X_STAGE4 = TM4 * KC4 * 4;  // 32 KB
 constexpr int THREADS4 = 640;
 constexpr int EPI_WARPS4 = 8;
 constexpr uint32_t A_COL0 = 256;         // first TMEM column of the operand stages
+// setmaxnreg budgets per warpgroup (launch: 96 x 640 = 61,440 of 65,536): control warps 0-3, converter warps 4-11,
+// epilogue warps 12-19.  The epilogue copies its row's WHOLE accumulator (128 columns) into registers and hands the
+// TMEM buffer back before it computes, so the next tile's MMAs never wait for the 4-level argmin.
+constexpr int REGS4_CTRL = 32, REGS4_CONV = 64, REGS4_EPI = 160;  // must redistribute the LAUNCH allocation: 128*C + 256*V + 256*E <= 96*640 = 61,440
 
 struct Smem4 {
   int x_off, b_off, gram_off, cn2_off, e1_off, lvl_off, stats_off, bar_off, holder_off, total;
@@ -124,7 +128,8 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
   }
 }
 
-template <int M>
+// EARLY: K == 32 only.  Register split by setmaxnreg + whole-row accumulator preload in the epilogue (see REGS4_*).
+template <int M, bool EARLY>
 __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.K, NT = p.NT;
@@ -181,6 +186,8 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
 
   // The three control warps walk their loops with all 32 lanes (operands stay warp-uniform) and issue from one
   // elected lane: `if (lane == 0)` would wrap every TMA / tcgen05 instruction in an R2UR waterfall loop.
+  constexpr bool early = EARLY;  // accumulators preloaded into registers (needs the register split)
+  if (EARLY && warp < 4) reg_dec<REGS4_CTRL>();
   if (warp == 0) {
     uint32_t s = 0, ph = 0, tix = 0, it = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -268,11 +275,13 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
       }
     }
   } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+    if (EARLY) reg_dec<REGS4_CONV>();
     if (p.consts[C_SX] == 1.f)
       converter_loop4<false>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
     else
       converter_loop4<true>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
   } else if (warp >= EPI_WARP0) {
+    if (EARLY) reg_inc<REGS4_EPI>();
     const int ew = warp - EPI_WARP0;
     const float m2inv = (p.metric == MEVI_METRIC_L2 ? -2.f : -1.f) * p.consts[C_INV];
     const bool l2 = p.metric == MEVI_METRIC_L2;
@@ -295,6 +304,50 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
         float last_best = 0.f;
 #pragma unroll
         for (int j = 0; j < M; ++j) code[j] = 0;
+        if (early) {
+          // K == 32: the row's whole accumulator -> registers, TMEM buffer released, THEN the greedy argmin
+          uint32_t acc[M][32];
+#pragma unroll
+          for (int j = 0; j < M; ++j) ptx::tmem_ld32(taddr + j * 32, acc[j]);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
+          if (lane == 0) ptx::mbar_arrive(acc_empty);
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            const float* gj = sGram + (j * (j - 1) / 2) * 32 * 33;
+            const float* grow[M > 1 ? M - 1 : 1];
+#pragma unroll
+            for (int m = 0; m < j; ++m) grow[m] = gj + (m * 32 + code[m]) * 33;
+            float c1 = CUDART_INF_F, u1 = CUDART_INF_F, u2 = CUDART_INF_F;
+#pragma unroll
+            for (int kk = 0; kk < 32; ++kk) {
+              float base = l2 ? sCn2[j * 32 + kk] : 0.f;
+              float g = 0.f;
+#pragma unroll
+              for (int m = 0; m < j; ++m) g += grow[m][kk];
+              base = l2 ? fmaf(2.f, g, base) : g;
+              const float dk = fmaf(__uint_as_float(acc[j][kk]), m2inv, base);
+              acc[j][kk] = __float_as_uint(dk);
+              c1 = fminf(c1, dk);
+              const float u = fmaf(nxn, sE1[j * 32 + kk], dk);
+              u2 = fminf(u2, fmaxf(u1, u));
+              u1 = fminf(u1, u);
+            }
+            int ci = 0;
+#pragma unroll
+            for (int kk = 31; kk >= 0; --kk)
+              if (__uint_as_float(acc[j][kk]) == c1) ci = kk;
+            code[j] = ci;
+            const float eb = xn * sE1[j * 32 + ci];
+            const float ub = fmaf(nxn, sE1[j * 32 + ci], c1);
+            const float other_lo = (ub == u1) ? u2 : u1;
+            const bool clear = other_lo > c1 + eb + sLvl[j * 4 + 1];
+            if (!clear && flag_level < 0) flag_level = j;
+            last_best = c1;
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < M; ++j) {
           if (p.debug & 4) break;
@@ -340,6 +393,7 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
           if (!clear && flag_level < 0) flag_level = j;
           last_best = m1;
         }
+        }
         if (row < p.n) {
           int32_t* dst = p.codes + row * p.codes_stride;
           if (M == 4 && p.codes_stride == 4) {
@@ -356,10 +410,12 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
           if (p.inertia) inertia_acc += (double)(l2 ? fmaxf(last_best + xn2, 0.f) : -last_best);
         }
       }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
-      if (lane == 0) ptx::mbar_arrive(acc_empty);
+      if (!early) {
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
+        if (lane == 0) ptx::mbar_arrive(acc_empty);
+      }
     }
     if (p.inertia) {
 #pragma unroll

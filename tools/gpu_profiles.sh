@@ -2,8 +2,8 @@
 # ncu evidence for profiles/: launch list of the bench command + full captures of the dominant kernels
 set -u
 mkdir -p gpurun_out
-echo "== launch list"; timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.json 2> gpurun_out/bench_under_ncu.err; echo "rc=$?"
-echo "== full capture: rq_tensor3 at bench size"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:rq_tensor3_kernel -s 3 -c 1 -o gpurun_out/prof_rq_encode python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > /dev/null 2> gpurun_out/prof_rq.err; echo "rc=$?"
+echo "== launch list"; timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.json 2> gpurun_out/bench_under_ncu.err; echo "rc=$?"
+echo "== full capture: rq_tensor4 (default K1 kernel) at bench size"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:rq_tensor4_kernel -s 3 -c 1 -f -o gpurun_out/prof_rq_encode python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > /dev/null 2> gpurun_out/prof_rq.err; echo "rc=$?"
 cat > /tmp/others.py <<'PY'
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
@@ -30,5 +30,16 @@ Q2 = torch.randn((6980, 768), device="cuda")
 for _ in range(2): ctx.flat_ip_topk(Q2, X, 100, mode="tensor")
 torch.cuda.synchronize()
 PY
-echo "== full capture: other kernels"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rerank_stream_kernel|kmeans_accumulate_kernel|flat_gemm_kernel|rq_exact_group_kernel|rq_tensor3_kernel<1>" -c 14 -o gpurun_out/prof_others python /tmp/others.py > /dev/null 2> gpurun_out/prof_others.err; echo "rc=$?"
+echo "== full capture: other kernels"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rerank_stream_kernel|kmeans_accumulate_kernel|rq_exact_group_kernel|rq_tensor4_kernel<1>|to_fp16_image_kernel|flat_rescore_kernel|flat_tensor_compact_kernel" -c 16 -f -o gpurun_out/prof_others python /tmp/others.py > /dev/null 2> gpurun_out/prof_others.err; echo "rc=$?"
+# the largest flat GEMM launch of a call (6th of 7; the second call = launches 7..13)
+cat > /tmp/fl.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+import mevi_b200
+ctx = mevi_b200.get_context(0)
+Q = torch.randn((6980, 768), device="cuda"); D = torch.randn((1 << 22, 768), device="cuda")
+for _ in range(2): ctx.flat_ip_topk(Q, D, 100, mode="tensor")
+torch.cuda.synchronize()
+PY
+echo "== full capture: flat GEMM"; timeout 300 ncu --set full --clock-control none --import-source on -k regex:flat_gemm_kernel -s 12 -c 1 -f -o gpurun_out/prof_flat_gemm python /tmp/fl.py > /dev/null 2> gpurun_out/prof_flat.err; echo "rc=$?"
 ls -la gpurun_out/*.ncu-rep

@@ -55,7 +55,7 @@ launches(os.path.join(G, "launches_bench.csv"), os.path.join(OUT, "r01_launches_
 seen = set()
 with open(os.path.join(OUT, "r01_ncu_kernels.md"), "w") as fw:
     fw.write("# ncu --set full --clock-control none  (one launch per kernel; B200, round 1)\n")
-    fw.write("rq_tensor3_kernel<4> captured inside `bench.py` at the bench size (8,841,823 x 768); the others on 2,000,000 x 768.\n")
+    fw.write("rq_tensor4_kernel<4> (the default K1 kernel) captured inside `bench.py` at the bench size (8,841,823 x 768); flat_gemm_kernel = the largest launch of a 6,980 x 4,194,304 search; the others on 2,000,000 x 768.\n")
     rows = kernels(os.path.join(G, "prof_rq_encode.ncu-rep"), fw, seen)
     H = rows[0]; r = rows[2]
     rd = float(r[H.index("dram__bytes_read.sum")]); wr = float(r[H.index("dram__bytes_write.sum")])
@@ -63,6 +63,8 @@ with open(os.path.join(OUT, "r01_ncu_kernels.md"), "w") as fw:
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     traffic = rd * mult[ur] + wr * mult[uw]
     kernels(os.path.join(G, "prof_others.ncu-rep"), fw, seen)
-json.dump({"rq_encode_dram_bytes_per_launch": traffic, "source": "profiles/r01_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of rq_tensor3_kernel<4>, one launch at the bench size)"},
+    if os.path.isfile(os.path.join(G, "prof_flat_gemm.ncu-rep")):
+        kernels(os.path.join(G, "prof_flat_gemm.ncu-rep"), fw, seen)
+json.dump({"rq_encode_dram_bytes_per_launch": traffic, "source": "profiles/r01_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of rq_tensor4_kernel<4>, one launch at the bench size)"},
           open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print("traffic", traffic)
