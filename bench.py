@@ -467,7 +467,10 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
             "roofline": roof(ms, bytes_, "whole iteration against ONE pass over the shard (4*d bytes per doc); the iteration "
                                          "makes two passes (assign, then accumulate), see DESIGN.md for why they are not fused"),
             "kernels": {"assign (rq_encode, M=1)": roof(ms_assign, bytes_ + n * 4, "reads the shard once, writes int32 assignments"),
-                        "accumulate_by_code": roof(ms_accum, bytes_ + n * 4, "reads the shard and the assignments once")}}
+                        "accumulate_by_code": roof(ms_accum, bytes_ + n * 4, "reads the shard and the assignments once; timed as 5 "
+                                                   "back-to-back launches, which runs slower than the same launch inside the "
+                                                   "iteration (iteration ms - assign ms is the in-step cost)")},
+            "accumulate_in_step_ms_estimate": ms - ms_assign}
         del assign, a2
     except Exception as e:
         out["kmeans_iteration"] = {"error": repr(e)[:300]}

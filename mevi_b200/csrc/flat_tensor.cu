@@ -56,26 +56,37 @@ __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, 
     const int r = (int)(row - tile * rows_per_tile);
     float nrm = 0.f;
     bool clamp = false;
-    for (int u = lane; u < units; u += 32) {
-      float v[8];
-      if (row < rows) {
-        const float4 a = ld_stream_f4(X + row * d + u * 8), b = ld_stream_f4(X + row * d + u * 8 + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
+    // four 32-byte units per lane in flight before anything is converted (d = 768 -> the whole row in one round)
+    for (int u0 = lane; u0 < units; u0 += 128) {
+      float4 va[4], vb[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int u = u0 + 32 * i;
+        if (u < units && row < rows) {
+          va[i] = ld_stream_f4(X + row * d + u * 8);
+          vb[i] = ld_stream_f4(X + row * d + u * 8 + 4);
+        } else {
+          va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[i] = va[i];
+        }
       }
-      __half h[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        nrm = fmaf(v[e], v[e], nrm);
-        float t = v[e] * s;
-        if (fabsf(t) > 65000.f) { t = copysignf(65000.f, t); clamp = true; }
-        h[e] = __float2half_rn(t);
+      for (int i = 0; i < 4; ++i) {
+        const int u = u0 + 32 * i;
+        if (u >= units) break;
+        const float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+        __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          nrm = fmaf(v[e], v[e], nrm);
+          float t = v[e] * s;
+          if (fabsf(t) > 65000.f) { t = copysignf(65000.f, t); clamp = true; }
+          h[e] = __float2half_rn(t);
+        }
+        const int chunk = u / 8, uu = u & 7;
+        __half* dst = img + (((size_t)tile * nchunks + chunk) * rows_per_tile + r) * FT_KC + ((uu ^ (r & 7)) * 8);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
       }
-      const int chunk = u / 8, uu = u & 7;
-      __half* dst = img + (((size_t)tile * nchunks + chunk) * rows_per_tile + r) * FT_KC + ((uu ^ (r & 7)) * 8);
-      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
     }
     nrm = warp_sum(nrm);
     if (lane == 0 && row < rows) {
@@ -450,6 +461,8 @@ __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, co
 // one CTA per query: exact fp32 re-score of the surviving candidates, sort, emit the k best
 __global__ void __launch_bounds__(256) flat_rescore_kernel(const float* __restrict__ Q, const float* __restrict__ D, int d,
                                                            const int* __restrict__ count, const int32_t* __restrict__ cand_id,
+                                                           const float* __restrict__ cand_score, const float* __restrict__ tau,
+                                                           const float* __restrict__ margin,
                                                            int capg, int k, int keep_pow2, int64_t id_base,
                                                            float* __restrict__ scores, int64_t* __restrict__ ids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -463,7 +476,11 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(const float* __restri
     s_id[i] = 0x7fffffff;
   }
   __syncthreads();
+  // a member of the exact top-k has an approximate score >= (k-th approximate score) - margin: the rest of the kept
+  // list (sorted by approximate score) cannot matter and is not fetched
+  const float window = tau[q] - margin[q];
   for (int i = warp; i < cnt; i += 8) {
+    if (cand_score[(int64_t)q * capg + i] < window) break;
     const int32_t row = cand_id[(int64_t)q * capg + i];
     float acc = 0.f;
     for (int c4 = lane * 4; c4 < d; c4 += 128) {  // same summation pattern as the dense scorer
@@ -564,8 +581,10 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   const size_t smem_compact = (size_t)capg * 8;
   MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
 
-  // chunks of document tiles growing geometrically: the first can never overflow the candidate buffers
-  int64_t chunk_tiles = (capg - FT_KEEP) / FT_TM;
+  // chunks of document tiles growing geometrically: the first (no thresholds yet, every score is appended) is small,
+  // so its compaction sorts 1,024 and not 4,096 candidates per query; it can never overflow the candidate buffers
+  int64_t chunk_tiles = 8;
+  static_assert(8 * FT_TM <= 4096 - FT_KEEP, "first chunk must fit the candidate buffer");
   int64_t pos = 0;
   while (pos < n_tiles) {
     const int64_t end = pos + chunk_tiles < n_tiles ? pos + chunk_tiles : n_tiles;
@@ -594,7 +613,8 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "flat tensor kernel pipeline time-out (code %d)", h_flags[1]);
   if (h_flags[0] || h_flags[2]) return MEVI_OK;  // guarantee not established: caller falls back to fp32
   const size_t smem_rescore = (size_t)FT_KEEP * 8;
-  flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D, d, count, cand_id, capg, k, FT_KEEP, id_base, scores, ids);
+  flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D, d, count, cand_id, cand_score, tau, margin, capg, k, FT_KEEP, id_base, scores,
+                                                     ids);
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
   *fell_back = 0;

@@ -620,7 +620,7 @@ __global__ void residual_from_codes_kernel(const float* __restrict__ X, int64_t 
 
 #include "rq_tensor3.cuh"
 #include "rq_tensor4.cuh"
-constexpr bool V4_EARLY_DEFAULT = false;  // flipped once verified on hardware
+constexpr int V4_PRE_DEFAULT = 0;  // levels decided after the early TMEM release (0 = off)
 #include "rq_tensor5.cuh"
 
 }  // namespace
@@ -746,18 +746,21 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     const v4::Smem4 L4 = v4::smem4_layout(M, K, NT);
     const size_t smem4 = (size_t)L4.total + 1024;
     const int grid4 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
-    // early accumulator release (register-preloading epilogue): K == 32; MEVI_RQ_EARLY=0|1 overrides the default
-    bool early4 = (K == 32) && V4_EARLY_DEFAULT;
-    if (const char* e = getenv("MEVI_RQ_EARLY")) early4 = (K == 32) && atoi(e) != 0;
+    // early accumulator release (epilogue decides the last PRE levels from registers): K == 32 only;
+    // MEVI_RQ_EARLY=0|2|3|4 overrides the default
+    int pre4 = (K == 32) ? V4_PRE_DEFAULT : 0;
+    if (const char* e = getenv("MEVI_RQ_EARLY")) pre4 = (K == 32) ? atoi(e) : 0;
+#define MEVI_LAUNCH_RQ_TENSOR4_P(MM, PP)                                                                                     \
+  do {                                                                                                                      \
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+    v4::rq_tensor4_kernel<MM, PP><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                             \
+  } while (0)
 #define MEVI_LAUNCH_RQ_TENSOR4(MM)                                                                                          \
   do {                                                                                                                      \
-    if (early4) {                                                                                                           \
-      MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
-      v4::rq_tensor4_kernel<MM, true><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                         \
-    } else {                                                                                                                \
-      MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
-      v4::rq_tensor4_kernel<MM, false><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                        \
-    }                                                                                                                       \
+    if (pre4 >= 4) MEVI_LAUNCH_RQ_TENSOR4_P(MM, 4);                                                                         \
+    else if (pre4 == 3) MEVI_LAUNCH_RQ_TENSOR4_P(MM, 3);                                                                    \
+    else if (pre4 >= 1) MEVI_LAUNCH_RQ_TENSOR4_P(MM, 2);                                                                    \
+    else MEVI_LAUNCH_RQ_TENSOR4_P(MM, 0);                                                                                   \
   } while (0)
     switch (M) {
       case 1: MEVI_LAUNCH_RQ_TENSOR4(1); break;
@@ -766,6 +769,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
       default: MEVI_LAUNCH_RQ_TENSOR4(4); break;
     }
 #undef MEVI_LAUNCH_RQ_TENSOR4
+#undef MEVI_LAUNCH_RQ_TENSOR4_P
   } else if (use_v3) {
     // third-generation kernel: TMA-fed fp32 ring, 256-row tiles, 64B-swizzle operands (rq_tensor3.cuh)
     CUtensorMap tmap;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick K1 check: tensor path vs direct fp32 kernel on 1M rows, then time at the bench size (tight timeouts: a hang must not eat the budget)
-timeout 100 python /dev/stdin <<'PY'
+MEVI_RQ_EARLY=${MEVI_RQ_EARLY:-1} timeout 100 python /dev/stdin <<'PY'
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 import mevi_b200
