@@ -490,10 +490,18 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
                 ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
 
         ms = timed(fl, 2)
+        # parity of the tensor path with the direct fp32 search (both product kernels) on a slice of the queries
+        nchk = 256
+        s_t, i_t = ctx.flat_ip_topk(Q[:nchk], X[:shard], TOPK, mode=args.mode)
+        s_e, i_e = ctx.flat_ip_topk(Q[:nchk], X[:shard], TOPK, mode="exact")
+        parity = {"queries": nchk, "ids_identical_fraction": float((i_t == i_e).float().mean().item()),
+                  "max_rel_score_diff": float(((s_t - s_e).abs() / s_e.abs().clamp_min(1e-6)).max().item()),
+                  "note": "tensor-prefilter path vs fp32 CUDA-core path; ids may differ only at fp32 score ties"}
         flops = 2.0 * NQ_MARCO * shard * D
         ach = flops / (ms / 1e3) / 1e12
         out["flat_ip"] = {"ms": ms, "docs_per_gpu": shard, "corpus_docs": world * shard, "queries": NQ_MARCO, "topk": TOPK,
                           "queries_per_sec": NQ_MARCO / (ms / 1e3), "pairs_per_sec": world * NQ_MARCO * shard / (ms / 1e3),
+                          "parity_vs_fp32_kernel": parity,
                           "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                                        "frac_of_tf32_equivalent_peak": ach / (bf16_peak / 2.0),
                                        "note": "FLOPs = 2*nq*N*d (algorithmic); peak = measured 16-bit cuBLAS burst rate (the kernel's MMAs "

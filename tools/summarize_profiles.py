@@ -55,7 +55,7 @@ launches(os.path.join(G, "launches_bench.csv"), os.path.join(OUT, "r01_launches_
 seen = set()
 with open(os.path.join(OUT, "r01_ncu_kernels.md"), "w") as fw:
     fw.write("# ncu --set full --clock-control none  (one launch per kernel; B200, round 1)\n")
-    fw.write("rq_tensor4_kernel<4> (the default K1 kernel) captured inside `bench.py` at the bench size (8,841,823 x 768); flat_gemm_kernel = the largest launch of a 6,980 x 4,194,304 search; the others on 2,000,000 x 768.\n")
+    fw.write("rq_tensor4_kernel<4> (the default K1 kernel) captured inside `bench.py` at the bench size (8,841,823 x 768); flat_gemm_kernel = the 6,144-doc-tile chunk (6th of 7 launches) of a 6,980 x 4,194,304 search; the others on 2,000,000 x 768.\n")
     rows = kernels(os.path.join(G, "prof_rq_encode.ncu-rep"), fw, seen)
     H = rows[0]; r = rows[2]
     rd = float(r[H.index("dram__bytes_read.sum")]); wr = float(r[H.index("dram__bytes_write.sum")])
