@@ -162,6 +162,40 @@ int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, i
                         const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
                         int32_t* n_candidates, void* stream);
 
+/* mevi_cluster_rerank restricted to the first max_rows candidate rows of every query (leaf-ordered layout, ids =
+ * rows of D_leaf): the exact top-k of a prefix of the candidates.  Its k-th score is a lower bound of the query's
+ * final k-th score - the starting threshold of the grouped re-rank below.                                         */
+int mevi_cluster_rerank_prefix(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int64_t n, int d,
+                               const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                               const int32_t* query_leaves, int L, int k, int64_t max_rows, float* scores, int64_t* ids,
+                               int32_t* n_candidates, void* stream);
+
+/* ---- cluster-restricted re-rank as leaf-grouped GEMMs (tensor cores) ------ *
+ * replaces: the same loop, MEVI/main_models.py:3915-4014.  A leaf selected by many queries is read ONCE and
+ * scored against all of them: per leaf a [documents of the leaf] x [queries that chose it] fp16 tcgen05 GEMM whose
+ * scores are a prefilter with a rigorous margin; survivors are re-scored in exact fp32 (same contract as the flat
+ * search).  Index side, once: tiles of 128 rows of D_leaf that never straddle a leaf
+ *   src_index [n_tiles*128] int32   row of D_leaf per image row, -1 = padding
+ *   Aimg      [n_tiles][d/64][128][64] fp16 (n_tiles*128*d*2 bytes, caller-owned)
+ *   absmax_out, maxnorm_out (host)  scale source and largest document norm; absmax_out < 0: the image cannot
+ *                                   carry the guarantee (fp16 range), keep mevi_cluster_rerank.
+ * Call side: _begin (query scale, margins, thresholds from tau0 [nq] device or NULL), one _round per batch of
+ * (leaf, query) pairs, _finish.  A round takes
+ *   tile_row0, tile_nrows [n_tiles] int32; item_tile, item_group [n_items] int32 work items (tile, query group);
+ *   group_qid [n_groups*64] int32 query index per column of a group, -1 = padding.
+ * _finish: *fell_back = 1 when the guarantee could not be established (margin window overflow): the caller runs
+ * mevi_cluster_rerank instead; else scores [nq,k] fp32 descending, rows [nq,k] int64 rows of D_leaf, -1 padded.
+ * The state between _begin and _finish lives in the context: one grouped call at a time per context.            */
+int mevi_rerank_grouped_image(mevi_ctx* ctx, const float* D_leaf, int64_t n, int d, const int32_t* src_index,
+                              int64_t n_tiles, void* Aimg, float* absmax_out, float* maxnorm_out, void* stream);
+int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, int d, float d_absmax, float d_maxnorm,
+                              const float* tau0, void* stream);
+int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, int d, const void* Aimg, const int32_t* tile_row0,
+                              const int32_t* tile_nrows, const int32_t* item_tile, const int32_t* item_group,
+                              int64_t n_items, const int32_t* group_qid, int64_t n_groups, int k, void* stream);
+int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int d, int k, float* scores,
+                               int64_t* rows, int* fell_back, void* stream);
+
 /* out[i,:] = D[rows[i],:] for i < m: builds the leaf-ordered copy of the document matrix
  * (rows = the CSR's leaf_docids).  Replaces the per-leaf memmap fancy-index gather of
  * MEVI/main_models.py:3944 (IndexedData.__getitem__, 1011-1017) with a one-time permutation.  */

@@ -38,6 +38,11 @@ SYMBOLS = {
     "mevi_rq_beam_search": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mevi_build_inverted_lists": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
+    "mevi_cluster_rerank_prefix": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
+    "mevi_rerank_grouped_image": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, C.POINTER(_f), C.POINTER(_f), _vp]),
+    "mevi_rerank_grouped_begin": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
+    "mevi_rerank_grouped_round": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "mevi_rerank_grouped_finish": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
     "mevi_gather_rows": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "mevi_flat_ip_topk": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
     "mevi_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
@@ -342,6 +347,77 @@ class Context:
                                              self._stream())
             )
         return scores, ids, ncand
+
+    # ---- grouped (tensor-core) re-rank ------------------------------------------
+    def cluster_rerank_prefix(self, Q, D_leaf, leaf_offsets, leaf_docids, query_leaves, k, max_rows):
+        """Exact top-k over the first `max_rows` candidate rows of every query (ids = rows of D_leaf)."""
+        import torch
+
+        Q = self._dev(Q, torch.float32, "Q")
+        D = self._dev(D_leaf, torch.float32, "D_leaf")
+        lo = self._dev(leaf_offsets, torch.int64, "leaf_offsets")
+        ld = self._dev(leaf_docids, torch.int32, "leaf_docids")
+        ql = self._dev(query_leaves, torch.int32, "query_leaves")
+        nq, d = Q.shape
+        scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
+        ncand = torch.empty(nq, dtype=torch.int32, device=Q.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_cluster_rerank_prefix(self.handle, _ptr(Q), nq, _ptr(D), D.shape[0], d, _ptr(lo),
+                                                            lo.numel() - 1, _ptr(ld), _ptr(ql), ql.shape[1], int(k),
+                                                            int(max_rows), _ptr(scores), _ptr(ids), _ptr(ncand), self._stream()))
+        return scores, ids, ncand
+
+    def rerank_grouped_image(self, D_leaf, src_index, n_tiles):
+        """fp16 tile image of the leaf-ordered matrix -> (image uint8 tensor, absmax, maxnorm); absmax < 0: unusable."""
+        import torch
+
+        D = self._dev(D_leaf, torch.float32, "D_leaf")
+        si = self._dev(src_index, torch.int32, "src_index")
+        n, d = D.shape
+        assert si.numel() == n_tiles * 128
+        img = torch.empty(n_tiles * 128 * d * 2, dtype=torch.uint8, device=D.device)
+        a, m = C.c_float(0.0), C.c_float(0.0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_image(self.handle, _ptr(D), n, d, _ptr(si), int(n_tiles), _ptr(img),
+                                                           C.byref(a), C.byref(m), self._stream()))
+        return img, float(a.value), float(m.value)
+
+    def rerank_grouped_begin(self, Q, d_absmax, d_maxnorm, tau0=None):
+        import torch
+
+        Q = self._dev(Q, torch.float32, "Q")
+        if tau0 is not None:
+            self._dev(tau0, torch.float32, "tau0")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_begin(self.handle, _ptr(Q), Q.shape[0], Q.shape[1], float(d_absmax),
+                                                           float(d_maxnorm), _ptr(tau0), self._stream()))
+
+    def rerank_grouped_round(self, Q, img, tile_row0, tile_nrows, item_tile, item_group, group_qid, k):
+        import torch
+
+        for name, t in (("tile_row0", tile_row0), ("tile_nrows", tile_nrows), ("item_tile", item_tile),
+                        ("item_group", item_group), ("group_qid", group_qid)):
+            self._dev(t, torch.int32, name)
+        assert group_qid.numel() % 64 == 0 and item_tile.numel() == item_group.numel()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_round(self.handle, _ptr(Q), Q.shape[0], Q.shape[1], _ptr(img), _ptr(tile_row0),
+                                                           _ptr(tile_nrows), _ptr(item_tile), _ptr(item_group),
+                                                           item_tile.numel(), _ptr(group_qid), group_qid.numel() // 64, int(k),
+                                                           self._stream()))
+
+    def rerank_grouped_finish(self, Q, D_leaf, k):
+        """-> (scores, rows, fell_back)."""
+        import torch
+
+        nq, d = Q.shape
+        scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        rows = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
+        fb = C.c_int(1)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_finish(self.handle, _ptr(Q), nq, _ptr(D_leaf), d, int(k), _ptr(scores),
+                                                            _ptr(rows), C.byref(fb), self._stream()))
+        return scores, rows, bool(fb.value)
 
     def flat_ip_topk(self, Q, D, k, id_base=0, mode="auto"):
         import torch

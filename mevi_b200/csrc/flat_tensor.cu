@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -44,16 +45,19 @@ enum { FC_SD = 0, FC_SQ, FC_INV, FC_DMAX, FC_CLAMPED, FC_NUM = 8 };
 __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, int d, int rows_per_tile,
                                      const float* __restrict__ consts, int scale_slot, __half* __restrict__ img,
                                      float* __restrict__ norms, unsigned* __restrict__ max_norm_bits,
-                                     int* __restrict__ clamped, int64_t padded_rows) {
+                                     int* __restrict__ clamped, int64_t padded_rows,
+                                     const int32_t* __restrict__ src_index = nullptr) {  // image row -> row of X, -1 = zero row
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float s = consts[scale_slot];
   const int units = d / 8;  // 16-byte units per row
   const int nchunks = d / FT_KC;
-  for (int64_t row = warp_global; row < padded_rows; row += n_warps) {
-    const int64_t tile = row / rows_per_tile;
-    const int r = (int)(row - tile * rows_per_tile);
+  for (int64_t prow = warp_global; prow < padded_rows; prow += n_warps) {
+    const int64_t tile = prow / rows_per_tile;
+    const int r = (int)(prow - tile * rows_per_tile);
+    // `row` is the source row; without an index it is the image row itself (rows past the end are zero-filled)
+    const int64_t row = src_index ? (src_index[prow] >= 0 ? (int64_t)src_index[prow] : rows) : prow;
     float nrm = 0.f;
     bool clamp = false;
     // four 32-byte units per lane in flight before anything is converted (d = 768 -> the whole row in one round)
@@ -452,7 +456,8 @@ __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, co
   }
   if (threadIdx.x == 0) {
     count[q] = kept;
-    const float t = (cnt >= k) ? s_score[k - 1] : -CUDART_INF_F;
+    // never below a bound the caller already had (the grouped re-rank starts from a lower bound of the k-th score)
+    const float t = fmaxf(tau[q], (cnt >= k) ? s_score[k - 1] : -CUDART_INF_F);
     tau[q] = t;
     if (cnt > keep && !(s_score[keep] < t - margin[q])) *overflow = 1;
   }
@@ -615,6 +620,367 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   const size_t smem_rescore = (size_t)FT_KEEP * 8;
   flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D, d, count, cand_id, cand_score, tau, margin, capg, k, FT_KEEP, id_base, scores,
                                                      ids);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  *fell_back = 0;
+  return MEVI_OK;
+}
+
+// =====================================================================================================
+// K3g — cluster-restricted re-rank as LEAF-GROUPED GEMMs on the tensor cores.
+//
+// The streaming kernel of rerank.cu reads every candidate row once per query that selected its leaf
+// (main_models.py:3915-4014 does the same, one matmul per (query, leaf)).  With L = 100 leaves a query
+// scores ~150k documents, and a leaf is selected by ~30 queries, so the rows of a leaf can be read ONCE
+// and scored against all the queries that selected it: per leaf a [docs of the leaf] x [queries that
+// chose it] GEMM.  Same numerics contract as K2: fp16 tcgen05 scores are a prefilter with a rigorous
+// margin, survivors are re-scored in exact fp32 in the dense scorer's summation order, and anything
+// that cannot be guaranteed (margin window overflow, fp16 clamp) makes the caller fall back to the
+// streaming kernel.
+//   index side (once): document tiles of 128 rows that never straddle a leaf (tile_row0 / tile_nrows),
+//     fp16 image [tile][K chunk][128][64] of the leaf-ordered matrix;
+//   call side: (leaf, query) pairs sorted by leaf and cut into groups of <= 64 queries (group_qid),
+//     work items (tile of the leaf, group of the leaf); thresholds start from a lower bound tau0 of every
+//     query's k-th best score (exact top-k of a prefix of its candidates, mevi_cluster_rerank_prefix) and
+//     tighten between rounds of pairs, exactly like the chunks of the flat search.
+// GEMM CTA: 320 threads, A 16 KB + B 8 KB per stage, 8 stages, tcgen05.mma M=128 N=64 K=16, two 64-column
+// accumulator buffers in TMEM, 8 epilogue warps (lane group x 32-column half).
+namespace {
+
+constexpr int GR_TN = 64;
+constexpr int GR_STAGES = 8;
+constexpr int GR_B_BYTES = GR_TN * 128;
+constexpr int GR_STAGE_BYTES = FT_A_BYTES + GR_B_BYTES;  // 24 KB
+constexpr int GR_EPI_WARPS = 8;
+constexpr int GR_THREADS = 64 + 32 * GR_EPI_WARPS;
+constexpr int GR_CAPG = 4096;
+
+struct GroupedParams {
+  const __half* Aimg; const __half* Bimg;
+  const int32_t* item_tile; const int32_t* item_group; int64_t n_items;
+  const int32_t* tile_row0; const int32_t* tile_nrows;
+  const int32_t* group_qid;  // [n_groups][GR_TN], -1 = padding
+  int nchunks;
+  const float* consts; const float* tau; const float* margin;
+  int* count; float* cand_score; int32_t* cand_id; int* overflow; int capg;
+  int* err_flag;
+};
+
+__global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;  // [GR_STAGES][A 16 KB | B 8 KB]
+  float* s_thr = reinterpret_cast<float*>(smem + (size_t)GR_STAGES * GR_STAGE_BYTES);  // [2][GR_TN]
+  int* s_qid = reinterpret_cast<int*>(s_thr + 2 * GR_TN);                               // [2][GR_TN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qid + 2 * GR_TN);
+  uint64_t* full = bars;
+  uint64_t* empty = full + GR_STAGES;
+  uint64_t* acc_full = empty + GR_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GR_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], GR_EPI_WARPS); }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_holder, 2 * GR_TN);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+  const int nchunks = p.nchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      bool ok = true;
+      for (int64_t w = blockIdx.x; w < p.n_items && ok; w += gridDim.x) {
+        const __half* a_src = p.Aimg + (size_t)p.item_tile[w] * nchunks * FT_TM * FT_KC;
+        const __half* b_src = p.Bimg + (size_t)p.item_group[w] * nchunks * GR_TN * FT_KC;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t s = g % GR_STAGES, ph = (g / GR_STAGES) & 1;
+          if (!ptx::mbar_wait_backoff(&empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); ok = false; break; }
+          ptx::mbar_arrive_expect_tx(&full[s], GR_STAGE_BYTES);
+          uint8_t* st_a = ring + (size_t)s * GR_STAGE_BYTES;
+          ptx::bulk_g2s(st_a, a_src + (size_t)c * FT_TM * FT_KC, FT_A_BYTES, &full[s]);
+          ptx::bulk_g2s(st_a + FT_A_BYTES, b_src + (size_t)c * GR_TN * FT_KC, GR_B_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16_m128(GR_TN);
+      uint32_t g = 0, it = 0;
+      bool ok = true;
+      for (int64_t w = blockIdx.x; w < p.n_items && ok; w += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+        if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 2); ok = false; break; }
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * GR_TN;
+        for (int c = 0; c < nchunks; ++c, ++g) {
+          const uint32_t s = g % GR_STAGES, ph2 = (g / GR_STAGES) & 1;
+          if (!ptx::mbar_wait(&full[s], ph2)) { atomicExch(p.err_flag, 3); ok = false; break; }
+          ptx::tc_fence_after_sync();
+          const uint32_t a_ad = ptx::smem_u32(ring + (size_t)s * GR_STAGE_BYTES);
+          const uint32_t b_ad = a_ad + FT_A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < FT_KC / 16; ++ks)
+            ptx::umma_f16(d_tmem, ptx::umma_desc_sw128(a_ad + ks * 32), ptx::umma_desc_sw128(b_ad + ks * 32), idesc,
+                          (c | ks) != 0 ? 1u : 0u);
+          ptx::umma_commit(&empty[s]);
+        }
+        if (ok) ptx::umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: warp -> (TMEM lane group = warp % 4, 32-column half) =====
+    const int lg = warp & 3;
+    const int c0 = ((warp - 2) >> 2) * 32;
+    const int etid = tid - 64;
+    const float inv = p.consts[FC_INV];
+    const float sdsq = p.consts[FC_SD] * p.consts[FC_SQ];
+    uint32_t it = 0;
+    bool ok = true;
+    for (int64_t w = blockIdx.x; w < p.n_items && ok; w += gridDim.x, ++it) {
+      const int tile = p.item_tile[w], grp = p.item_group[w];
+      const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+      float* thr = s_thr + buf * GR_TN;
+      int* qid = s_qid + buf * GR_TN;
+      if (etid < GR_TN) {
+        const int q = p.group_qid[(int64_t)grp * GR_TN + etid];
+        qid[etid] = q;
+        thr[etid] = q >= 0 ? (p.tau[q] - p.margin[q]) * sdsq : CUDART_INF_F;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * GR_EPI_WARPS) : "memory");
+      if (!ptx::mbar_wait_backoff(&acc_full[buf], ph, 64)) { atomicExch(p.err_flag, 4); ok = false; break; }
+      ptx::tc_fence_after_sync();
+      const int r = lg * 32 + lane;
+      const bool doc_ok = r < p.tile_nrows[tile];
+      const int32_t doc = p.tile_row0[tile] + r;  // row of the leaf-ordered matrix
+      uint32_t acc[32];
+      ptx::tmem_ld32(tmem_base + buf * GR_TN + c0 + ((uint32_t)(lg * 32) << 16), acc);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);  // accumulators are in registers: hand the buffer back first
+      const float4* t4 = reinterpret_cast<const float4*>(thr + c0);
+      bool any = false;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 t = t4[j4];
+        any |= !(__uint_as_float(acc[4 * j4 + 0]) < t.x);
+        any |= !(__uint_as_float(acc[4 * j4 + 1]) < t.y);
+        any |= !(__uint_as_float(acc[4 * j4 + 2]) < t.z);
+        any |= !(__uint_as_float(acc[4 * j4 + 3]) < t.w);
+      }
+      if (__any_sync(MEVI_FULL_MASK, any && doc_ok)) {
+        unsigned mk = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mk |= (!(__uint_as_float(acc[j]) < thr[c0 + j]) ? 1u : 0u) << j;
+        if (!doc_ok) mk = 0;
+        unsigned mym = 0;  // lane j: documents (lanes) passing column j
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const unsigned m = __ballot_sync(MEVI_FULL_MASK, (mk >> j) & 1u);
+          if (lane == j) mym = m;
+        }
+        const int myq = qid[c0 + lane];
+        int base_l = 0;
+        if (mym && myq >= 0) base_l = atomicAdd(&p.count[myq], __popc(mym));
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int b0 = __shfl_sync(MEVI_FULL_MASK, base_l, j);
+          const unsigned m = __shfl_sync(MEVI_FULL_MASK, mym, j);
+          const int q = __shfl_sync(MEVI_FULL_MASK, myq, j);
+          if (((mk >> j) & 1u) && q >= 0) {
+            const int slot = b0 + __popc(m & ((1u << lane) - 1u));
+            if (slot < p.capg) {
+              p.cand_score[(int64_t)q * p.capg + slot] = __uint_as_float(acc[j]) * inv;
+              p.cand_id[(int64_t)q * p.capg + slot] = doc;
+            } else {
+              *p.overflow = 1;
+            }
+          }
+        }
+      }
+      // the threshold / query-id slots of this buffer are rewritten two items later: every epilogue warp
+      // passes the named barrier of the NEXT item before that, so no extra synchronisation is needed here
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 2 * GR_TN);
+}
+
+__global__ void gr_set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+inline unsigned gr_f32_bits(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+__global__ void gr_row_norm_kernel(const float* __restrict__ X, int rows, int d, float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float a = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 v = ldg_f4(X + (int64_t)row * d + c);
+    a = fmaf(v.x, v.x, a); a = fmaf(v.y, v.y, a); a = fmaf(v.z, v.z, a); a = fmaf(v.w, v.w, a);
+  }
+  a = warp_sum(a);
+  if (lane == 0) norms[row] = sqrtf(a);
+}
+
+__global__ void gr_init_kernel(float* tau, const float* tau0, int* count, int* flags, int nq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) {
+    const float t = tau0 ? tau0[i] : -CUDART_INF_F;
+    tau[i] = (t == t) ? t : -CUDART_INF_F;
+    count[i] = 0;
+  }
+  if (i < 4) flags[i] = 0;
+}
+
+struct GrState {
+  float* consts; unsigned* absmax; int* flags; float* tau; float* margin; float* qnorm; int* count;
+  float* cand_score; int32_t* cand_id;
+};
+
+// the per-call state lives in one scratch slot from _begin to _finish (same layout recomputed by each entry point)
+bool gr_state(mevi_ctx* ctx, int nq, GrState* s) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t o_consts = take(FC_NUM * 4), o_abs = take(16), o_flags = take(16), o_tau = take((size_t)nq * 4),
+               o_margin = take((size_t)nq * 4), o_qnorm = take((size_t)nq * 4), o_cnt = take((size_t)nq * 4),
+               o_cs = take((size_t)nq * GR_CAPG * 4), o_ci = take((size_t)nq * GR_CAPG * 4);
+  char* ws = (char*)mevi_ws(ctx, WS_TOPK_AUX, off);
+  if (!ws) return false;
+  s->consts = (float*)(ws + o_consts); s->absmax = (unsigned*)(ws + o_abs); s->flags = (int*)(ws + o_flags);
+  s->tau = (float*)(ws + o_tau); s->margin = (float*)(ws + o_margin); s->qnorm = (float*)(ws + o_qnorm);
+  s->count = (int*)(ws + o_cnt); s->cand_score = (float*)(ws + o_cs); s->cand_id = (int32_t*)(ws + o_ci);
+  return true;
+}
+
+}  // namespace
+
+// fp16 image of the leaf-ordered matrix, tiles of 128 rows that never straddle a leaf.
+//   src_index [n_tiles*128] int32: row of D_leaf for every image row, -1 = padding
+//   absmax_out / maxnorm_out (host): the two numbers _begin needs (scale of the image, largest document norm)
+extern "C" int mevi_rerank_grouped_image(mevi_ctx* ctx, const float* D_leaf, int64_t n, int d, const int32_t* src_index,
+                                         int64_t n_tiles, void* Aimg, float* absmax_out, float* maxnorm_out, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, D_leaf && src_index && Aimg && absmax_out && maxnorm_out, "NULL argument");
+  MEVI_REQUIRE(ctx, mevi_flat_tensor_supported(ctx, d, 1), "grouped re-rank needs sm_100 and d %% 64 == 0 (got d=%d)", d);
+  MEVI_REQUIRE(ctx, n > 0 && n < (int64_t)2147483647 && n_tiles > 0, "bad sizes");
+  char* ws = (char*)mevi_ws(ctx, WS_MISC, 512);
+  if (!ws) return MEVI_ERR_NOMEM;
+  float* consts = (float*)ws;                 // FC_NUM floats
+  unsigned* absmax2 = (unsigned*)(ws + 64);   // [0] D absmax, [1] unused (1.0), [2] max doc norm
+  int* flags = (int*)(ws + 128);
+  MEVI_CUDA(ctx, cudaMemsetAsync(ws, 0, 512, st));
+  const int64_t sample_rows = 4096;
+  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(D_leaf, n, d, n > sample_rows ? n / sample_rows : 1, absmax2);
+  gr_set_u32_kernel<<<1, 1, 0, st>>>(absmax2 + 1, gr_f32_bits(1.0f));
+  flat_consts_kernel<<<1, 32, 0, st>>>(absmax2, consts);
+  to_fp16_image_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(D_leaf, n, d, FT_TM, consts, FC_SD, (__half*)Aimg, nullptr, absmax2 + 2,
+                                                          flags, n_tiles * FT_TM, src_index);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 4);
+  unsigned h[4] = {0, 0, 0, 0};
+  int h_flag = 0;
+  MEVI_CUDA(ctx, cudaMemcpyAsync(h, absmax2, sizeof(h), cudaMemcpyDeviceToHost, st));
+  MEVI_CUDA(ctx, cudaMemcpyAsync(&h_flag, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+  float a, m;
+  memcpy(&a, &h[0], 4);
+  memcpy(&m, &h[2], 4);
+  *absmax_out = h_flag ? -1.f : a;  // a clamped image cannot carry the guarantee: the caller keeps the streaming kernel
+  *maxnorm_out = m;
+  return MEVI_OK;
+}
+
+// start of a grouped re-rank call: query scale / norms / margins, thresholds from tau0 (device, may be NULL)
+extern "C" int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, int d, float d_absmax, float d_maxnorm,
+                                         const float* tau0, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, Q && nq > 0 && d_absmax >= 0.f, "bad argument");
+  GrState s;
+  if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
+  gr_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.tau, tau0, s.count, s.flags, nq);
+  gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 0, gr_f32_bits(d_absmax));
+  gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 1, 0u);
+  gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 2, gr_f32_bits(d_maxnorm));
+  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(Q, nq, d, 1, s.absmax + 1);
+  flat_consts_kernel<<<1, 32, 0, st>>>(s.absmax, s.consts);
+  gr_row_norm_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, d, s.qnorm);
+  flat_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.qnorm, nq, s.absmax + 2, s.margin);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 8);
+  return MEVI_OK;
+}
+
+// one round: gather the query image of the round's groups, run the grouped GEMM, tighten the thresholds
+extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, int d, const void* Aimg,
+                                         const int32_t* tile_row0, const int32_t* tile_nrows, const int32_t* item_tile,
+                                         const int32_t* item_group, int64_t n_items, const int32_t* group_qid,
+                                         int64_t n_groups, int k, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, Q && Aimg && tile_row0 && tile_nrows, "NULL argument");
+  MEVI_REQUIRE(ctx, k >= 1 && k <= FT_KEEP / 2, "k must be in [1, %d]", FT_KEEP / 2);
+  if (n_items <= 0 || n_groups <= 0) return MEVI_OK;
+  MEVI_REQUIRE(ctx, item_tile && item_group && group_qid, "NULL argument");
+  GrState s;
+  if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
+  const int nchunks = d / FT_KC;
+  __half* Bimg = (__half*)mevi_ws(ctx, WS_TOPK_PART, (size_t)n_groups * GR_TN * d * 2);
+  if (!Bimg) return MEVI_ERR_NOMEM;
+  to_fp16_image_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(Q, nq, d, GR_TN, s.consts, FC_SQ, Bimg, nullptr, nullptr, s.flags + 2,
+                                                          n_groups * GR_TN, group_qid);
+  GroupedParams p;
+  p.Aimg = (const __half*)Aimg; p.Bimg = Bimg; p.item_tile = item_tile; p.item_group = item_group; p.n_items = n_items;
+  p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.group_qid = group_qid; p.nchunks = nchunks;
+  p.consts = s.consts; p.tau = s.tau; p.margin = s.margin; p.count = s.count; p.cand_score = s.cand_score;
+  p.cand_id = s.cand_id; p.overflow = s.flags; p.capg = GR_CAPG; p.err_flag = s.flags + 1;
+  const size_t smem = (size_t)GR_STAGES * GR_STAGE_BYTES + 2 * GR_TN * 8 + (2 * GR_STAGES + 4) * 8 + 16 + 1024;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(n_items < ctx->sm_count ? n_items : ctx->sm_count);
+  grouped_gemm_kernel<<<grid, GR_THREADS, smem, st>>>(p);
+  const size_t smem_compact = (size_t)GR_CAPG * 8;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
+  flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(s.tau, s.margin, s.count, s.cand_score, s.cand_id, s.flags, GR_CAPG, k,
+                                                            FT_KEEP);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 3);
+  return MEVI_OK;
+}
+
+// end of the call: *fell_back = 1 when the guarantee could not be established (the caller then runs the streaming
+// kernel); otherwise scores [nq,k] fp32 descending and rows [nq,k] int64 = rows of the leaf-ordered matrix (-1 padded)
+extern "C" int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int d, int k,
+                                          float* scores, int64_t* rows, int* fell_back, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, Q && D_leaf && scores && rows && fell_back, "NULL argument");
+  *fell_back = 1;
+  GrState s;
+  if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
+  int h_flags[4] = {0, 0, 0, 0};
+  MEVI_CUDA(ctx, cudaMemcpyAsync(h_flags, s.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+  if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "grouped re-rank pipeline time-out (code %d)", h_flags[1]);
+  if (h_flags[0] || h_flags[2]) return MEVI_OK;
+  const size_t smem_rescore = (size_t)FT_KEEP * 8;
+  flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D_leaf, d, s.count, s.cand_id, s.cand_score, s.tau, s.margin, GR_CAPG, k,
+                                                     FT_KEEP, 0, scores, rows);
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
   *fell_back = 0;

@@ -42,6 +42,7 @@ struct RerankParams {
   int64_t id_base;
   float* out_scores; int64_t* out_ids;  // [nq*S, k]
   int32_t* n_candidates;
+  int64_t max_rows;  // > 0: only the first max_rows candidate rows of every query (prefix of its leaf list)
 };
 
 __device__ __forceinline__ void compact_buffer(float* s_score, int32_t* s_id, int* s_count, float* s_tau, int k, int cap) {
@@ -249,8 +250,9 @@ __global__ void __launch_bounds__(RS_THREADS) rerank_stream_kernel(RerankParams 
     }
   }
   __syncthreads();
-  const int64_t C = s_prefix[p.L];
+  int64_t C = s_prefix[p.L];
   if (s == 0 && tid == 0 && p.n_candidates) p.n_candidates[q] = (int32_t)(C > 0x7fffffff ? 0x7fffffff : C);
+  if (p.max_rows > 0 && C > p.max_rows) C = p.max_rows;
   const int64_t lo = C * s / p.S, hi = C * (s + 1) / p.S;
 
   if (warp == 0) {
@@ -455,10 +457,35 @@ int mevi_topk_merge_launch(mevi_ctx* ctx, const float* in_s, const int64_t* in_i
 
 extern "C" {
 
+static int cluster_rerank_impl(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int d_layout,
+                               const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                               const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
+                               int32_t* n_candidates, int64_t max_rows, void* stream);
+
 int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int d_layout,
                         const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
                         const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
                         int32_t* n_candidates, void* stream) {
+  return cluster_rerank_impl(ctx, Q, nq, D, n, d, d_layout, leaf_offsets, n_leaves, leaf_docids, query_leaves, L, k, id_base,
+                             scores, ids, n_candidates, 0, stream);
+}
+
+// Same, restricted to the first max_rows candidate rows of every query (leaf-ordered layout only): the exact top-k
+// of a prefix of the candidates.  Its k-th score is a lower bound of the query's final k-th score — the starting
+// threshold of the grouped re-rank (mevi_rerank_grouped_begin).
+int mevi_cluster_rerank_prefix(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int64_t n, int d,
+                               const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                               const int32_t* query_leaves, int L, int k, int64_t max_rows, float* scores, int64_t* ids,
+                               int32_t* n_candidates, void* stream) {
+  if (ctx && max_rows <= 0) return mevi_set_error(ctx, MEVI_ERR_INVALID, "max_rows must be positive");
+  return cluster_rerank_impl(ctx, Q, nq, D_leaf, n, d, 1, leaf_offsets, n_leaves, leaf_docids, query_leaves, L, k, 0, scores, ids,
+                             n_candidates, max_rows, stream);
+}
+
+static int cluster_rerank_impl(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int d_layout,
+                               const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                               const int32_t* query_leaves, int L, int k, int64_t id_base, float* scores, int64_t* ids,
+                               int32_t* n_candidates, int64_t max_rows, void* stream) {
   MEVI_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -480,6 +507,7 @@ int mevi_cluster_rerank(mevi_ctx* ctx, const float* Q, int nq, const float* D, i
   p.leaf_offsets = leaf_offsets; p.n_leaves = n_leaves; p.leaf_docids = leaf_docids;
   p.query_leaves = query_leaves; p.L = L; p.k = k; p.cap = cap; p.S = S; p.id_base = id_base;
   p.n_candidates = n_candidates;
+  p.max_rows = max_rows;
   if (S == 1) {
     p.out_scores = scores;
     p.out_ids = ids;

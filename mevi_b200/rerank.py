@@ -126,17 +126,97 @@ class ClusterIndex:
         return cluster, mapping
 
 
+
+# ---- leaf-grouped (tensor-core) re-rank: host-side planning ------------------------------------------------
+GROUP_COLS = 64      # queries per GEMM column group (GR_TN in csrc/flat_tensor.cu)
+TILE_ROWS = 128      # document rows per GEMM tile (UMMA M)
+
+
+def build_leaf_tiles(leaf_offsets: torch.Tensor):
+    """Tiles of TILE_ROWS rows of the leaf-ordered matrix that never straddle a leaf.
+    -> (tile_row0 int32 [T], tile_nrows int32 [T], leaf_tile0 int64 [n_leaves+1], src_index int32 [T*128], -1 = padding)."""
+    off = leaf_offsets.to(torch.int64)
+    dev = off.device
+    sizes = off[1:] - off[:-1]
+    tpl = (sizes + TILE_ROWS - 1) // TILE_ROWS
+    leaf_tile0 = torch.zeros(off.numel(), dtype=torch.int64, device=dev)
+    torch.cumsum(tpl, 0, out=leaf_tile0[1:])
+    T = int(leaf_tile0[-1].item())
+    tile_leaf = torch.repeat_interleave(torch.arange(sizes.numel(), device=dev), tpl)
+    local = torch.arange(T, device=dev) - leaf_tile0[tile_leaf]
+    row0 = off[tile_leaf] + local * TILE_ROWS
+    nrows = torch.minimum(off[tile_leaf + 1] - row0, torch.full_like(row0, TILE_ROWS))
+    r = torch.arange(TILE_ROWS, device=dev)
+    src = row0[:, None] + r[None, :]
+    src = torch.where(r[None, :] < nrows[:, None], src, torch.full_like(src, -1))
+    return (row0.to(torch.int32).contiguous(), nrows.to(torch.int32).contiguous(), leaf_tile0,
+            src.to(torch.int32).reshape(-1).contiguous())
+
+
+def plan_grouped_rounds(leaf_offsets: torch.Tensor, leaf_tile0: torch.Tensor, ql: torch.Tensor, round_rows: Sequence[int]):
+    """(leaf, query) pairs of `ql` [nq, L] (CSR leaf index, -1 = none) -> per round the work of the grouped GEMM.
+
+    A pair belongs to round r when the candidate rows listed BEFORE it in its query's leaf list number less than
+    round_rows[r] (and not less than round_rows[r-1]); the last round takes the rest.  Per round: pairs sorted by
+    leaf, each leaf's queries cut into groups of GROUP_COLS columns, one work item per (tile of the leaf, group).
+    -> list of (item_tile int32 [I], item_group int32 [I], group_qid int32 [G*GROUP_COLS], -1 = padding)."""
+    dev = ql.device
+    off = leaf_offsets.to(torch.int64)
+    sizes = off[1:] - off[:-1]
+    nq, L = ql.shape
+    valid = ql >= 0
+    qsz = torch.where(valid, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=dev))
+    before = torch.cumsum(qsz, 1) - qsz
+    bounds = torch.tensor(list(round_rows), dtype=torch.int64, device=dev)
+    rnd = torch.bucketize(before, bounds, right=True)  # rows before < round_rows[0] -> 0, ...
+    qidx = torch.arange(nq, device=dev)[:, None].expand(nq, L)
+    tpl = leaf_tile0[1:] - leaf_tile0[:-1]
+    out = []
+    for r in range(len(round_rows) + 1):
+        m = valid & (rnd == r)
+        leaf = ql[m].long()
+        q = qidx[m]
+        if leaf.numel() == 0:
+            out.append((torch.zeros(0, dtype=torch.int32, device=dev),) * 2 + (torch.zeros(0, dtype=torch.int32, device=dev),))
+            continue
+        order = torch.argsort(leaf, stable=True)
+        leaf, q = leaf[order], q[order]
+        uleaf, cnt = torch.unique_consecutive(leaf, return_counts=True)
+        run0 = torch.cumsum(cnt, 0) - cnt                                   # first pair of every leaf run
+        gpl = (cnt + GROUP_COLS - 1) // GROUP_COLS                          # groups per leaf
+        grp0 = torch.cumsum(gpl, 0) - gpl
+        G = int(gpl.sum().item())
+        run_of_pair = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), cnt)
+        pos = torch.arange(leaf.numel(), device=dev) - run0[run_of_pair]
+        grp_of_pair = grp0[run_of_pair] + pos // GROUP_COLS
+        group_qid = torch.full((G, GROUP_COLS), -1, dtype=torch.int32, device=dev)
+        group_qid[grp_of_pair, pos % GROUP_COLS] = q.to(torch.int32)
+        group_leaf = torch.repeat_interleave(uleaf, gpl)
+        ntl = tpl[group_leaf]                                               # tiles of the group's leaf
+        item_group = torch.repeat_interleave(torch.arange(G, device=dev), ntl)
+        item0 = torch.cumsum(ntl, 0) - ntl
+        item_tile = leaf_tile0[group_leaf[item_group]] + (torch.arange(item_group.numel(), device=dev) - item0[item_group])
+        out.append((item_tile.to(torch.int32).contiguous(), item_group.to(torch.int32).contiguous(),
+                    group_qid.reshape(-1).contiguous()))
+    return out
+
+
 class ClusterReranker:
     """Holds a (shard of the) doc-embedding matrix on the device plus its inverted lists."""
 
+    BOOTSTRAP_ROWS = 2048           # prefix of every query's candidates scored exactly for the first thresholds
+    ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
+
     def __init__(self, all_embeddings, index: ClusterIndex, device_index: Optional[int] = None,
-                 leaf_ordered: bool = True):
+                 leaf_ordered: bool = True, mode: Optional[str] = None, D_leaf: Optional[torch.Tensor] = None):
         """`leaf_ordered=True` (default) keeps a copy of the matrix permuted into CSR order so that each
         leaf is one contiguous byte range (streamed with bulk async copies); False gathers candidate
         rows one by one from the document-ordered matrix."""
         self.ctx = _lib.get_context(device_index if device_index is not None else index.device.index)
         dev = torch.device("cuda", self.ctx.device)
-        if isinstance(all_embeddings, torch.Tensor):
+        if D_leaf is not None:  # the caller already holds the leaf-ordered copy (ctx.gather_rows(D, index.leaf_docids))
+            D = None
+        elif isinstance(all_embeddings, torch.Tensor):
             D = all_embeddings.to(device=dev, dtype=torch.float32).contiguous()
         else:
             from .trainer import _upload_rows
@@ -144,7 +224,28 @@ class ClusterReranker:
             D = _upload_rows(all_embeddings, 0, all_embeddings.shape[0], dev)
         self.index = index
         self.leaf_ordered = bool(leaf_ordered)
-        self.D = self.ctx.gather_rows(D, index.leaf_docids) if self.leaf_ordered else D
+        if D_leaf is not None:
+            assert leaf_ordered and D_leaf.is_cuda and D_leaf.dtype == torch.float32 and D_leaf.is_contiguous()
+            self.D = D_leaf
+        else:
+            self.D = self.ctx.gather_rows(D, index.leaf_docids) if self.leaf_ordered else D
+        # "stream": one pass over every query's candidates (rerank.cu); "grouped": every leaf read once and scored against
+        # all the queries that chose it on the tensor cores (flat_tensor.cu, K3g), falling back to "stream" per call when
+        # the prefilter guarantee cannot be established
+        import os
+
+        self.mode = mode or os.environ.get("MEVI_RERANK_MODE", "stream")
+        if self.mode not in ("stream", "grouped"):
+            raise ValueError(f"unknown re-rank mode {self.mode!r}")
+        self._grouped = None
+        self.last_path = None
+        if self.mode == "grouped":
+            if not self.leaf_ordered:
+                raise ValueError("mode='grouped' needs the leaf-ordered layout")
+            row0, nrows, leaf_tile0, src = build_leaf_tiles(index.leaf_offsets)
+            img, absmax, maxnorm = self.ctx.rerank_grouped_image(self.D, src, row0.numel())
+            del src
+            self._grouped = dict(row0=row0, nrows=nrows, leaf_tile0=leaf_tile0, img=img, absmax=absmax, maxnorm=maxnorm)
 
     @torch.no_grad()
     def rerank(self, query_embedding, dec, topk: int = 100):
@@ -156,14 +257,45 @@ class ClusterReranker:
             query_embedding = torch.from_numpy(np.ascontiguousarray(query_embedding, dtype=np.float32))
         Q = query_embedding.to(device=dev, dtype=torch.float32).contiguous()
         ql = self.index.lookup(dec)
-        scores, ids, ncand = self.ctx.cluster_rerank(Q, self.D, self.index.leaf_offsets, self.index.leaf_docids, ql, topk,
-                                                     id_base=self.index.id_base, leaf_ordered=self.leaf_ordered)
+        out = self._rerank_grouped(Q, ql, topk) if self._grouped is not None else None
+        if out is None:
+            self.last_path = "stream"
+            out = self.ctx.cluster_rerank(Q, self.D, self.index.leaf_offsets, self.index.leaf_docids, ql, topk,
+                                          id_base=self.index.id_base, leaf_ordered=self.leaf_ordered)
+        scores, ids, ncand = out
         if dist_on():
             s_all = all_gather_stack(scores)
             i_all = all_gather_stack(ids)
             scores, ids = self.ctx.topk_merge(s_all.contiguous(), i_all.contiguous())
             torch.distributed.all_reduce(ncand)
         return scores, ids, ncand
+
+
+def _rerank_grouped(self, Q, ql, topk):
+    """Leaf-grouped tensor-core path; None when it does not apply or could not establish its guarantee."""
+    g = self._grouped
+    if g["absmax"] < 0 or topk > 256 or Q.shape[0] == 0:
+        return None
+    ctx, idx = self.ctx, self.index
+    off = idx.leaf_offsets
+    sizes = off[1:] - off[:-1]
+    ncand = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device)).sum(1)
+    # first thresholds: exact k-th score of a prefix of every query's candidates (a lower bound of the final k-th score)
+    s0, _, _ = ctx.cluster_rerank_prefix(Q, self.D, off, idx.leaf_docids, ql, topk, self.BOOTSTRAP_ROWS)
+    tau0 = s0[:, topk - 1].contiguous()
+    ctx.rerank_grouped_begin(Q, g["absmax"], g["maxnorm"], tau0)
+    for item_tile, item_group, group_qid in plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS):
+        if item_tile.numel():
+            ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk)
+    scores, rows, fell_back = ctx.rerank_grouped_finish(Q, self.D, topk)
+    if fell_back:
+        return None
+    self.last_path = "grouped"
+    ids = torch.where(rows >= 0, idx.leaf_docids[rows.clamp(min=0)].to(torch.int64) + idx.id_base, torch.full_like(rows, -1))
+    return scores, ids, ncand.clamp(max=0x7FFFFFFF).to(torch.int32)
+
+
+ClusterReranker._rerank_grouped = _rerank_grouped
 
 
 def hn_lines(texts: Sequence[str], scores, ids, gt_outputs: Optional[Sequence[str]] = None) -> List[str]:

@@ -44,6 +44,55 @@ def test_rerank_matches_oracle(case, nb, k, leaf_ordered):
     assert (np.diff(np.where(np.isfinite(scores), scores, -1e30), axis=1) <= 0).all()
 
 
+@pytest.mark.parametrize("nb,k", [(10, 100), (100, 100), (100, 7)])
+def test_grouped_tensor_rerank_matches_oracle(case, nb, k):
+    """K3g: every leaf read once and scored against all the queries that chose it (tcgen05 prefilter + exact fp32
+    re-score) must return what the per-query loop of main_models.py:3915-4014 returns."""
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    if case.d % 64:
+        pytest.skip("tensor path needs d % 64 == 0")
+    dec = case.load(f"beam{nb}_labels.npy")
+    clus = case.pickle("rqclus.pkl")
+    rr = ClusterReranker(dev(case.X), ClusterIndex.from_codes(case.codes, case.K), mode="grouped")
+    rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS = 256, (600, 3000)  # small corpus: still exercise three rounds
+    scores, ids, ncand = rr.rerank(case.Q, dec, topk=k)
+    assert rr.last_path == "grouped"
+    scores, ids, ncand = scores.cpu().numpy(), ids.cpu().numpy(), ncand.cpu().numpy()
+    ref = oracle.cluster_rerank(case.Q, case.X, clus, dec, topk=k)
+    s_ref = np.full((len(ref), k), -np.inf, np.float32)
+    i_ref = np.full((len(ref), k), -1, np.int64)
+    for q, (d_, s_, nd) in enumerate(ref):
+        s_ref[q, : len(s_)] = s_
+        i_ref[q, : len(d_)] = d_
+        assert ncand[q] == nd
+    X64, Q64 = case.X.astype(np.float64), case.Q.astype(np.float64)
+    assert_topk_equivalent(scores, ids, s_ref, i_ref, rtol=1e-5, atol=1e-4,
+                           pool_scores=lambda q, doc: float(X64[doc] @ Q64[q]))
+
+
+def test_grouped_rerank_falls_back_when_the_margin_window_overflows(gauss):
+    """Near-duplicate documents put more candidates inside the fp16 margin than the buffers keep: the grouped path must
+    notice and the call must still return the exact answer (through the streaming kernel)."""
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    X = gauss.X.copy()
+    nd = 2500  # near-duplicates: all of them inside the fp16 margin window, far more than the 512 the compaction keeps
+    X[:nd] = X[0] + 1e-6 * np.arange(nd, dtype=np.float32)[:, None]
+    codes = np.ascontiguousarray(gauss.codes.copy())
+    codes[:nd] = codes[0]
+    clus, _ = oracle.document_cluster(codes)
+    dec = np.repeat(codes[None, :1, :], 4, axis=0)  # four queries, all asking for that one leaf
+    Q = np.repeat(X[:1], 4, axis=0) * np.float32(1.0)
+    rr = ClusterReranker(dev(X), ClusterIndex.from_codes(codes, gauss.K), mode="grouped")
+    scores, ids, ncand = rr.rerank(Q, dec, topk=100)
+    assert rr.last_path == "stream"
+    ref = oracle.cluster_rerank(Q, X, clus, dec, topk=100)
+    for q, (d_, s_, nd) in enumerate(ref):
+        assert int(ncand[q]) == nd
+        np.testing.assert_allclose(scores[q].cpu().numpy(), s_, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("leaf_ordered", [True, False])
 def test_rerank_split_path_and_empty_leaves(gauss, leaf_ordered):
     """Few queries -> several CTAs per query + merge; leaves that hold no document are legal."""

@@ -108,3 +108,43 @@ def test_text_formats_match_reference_writers(tmp_path):
     p = tmp_path / "emb.bin"
     arr.tofile(p)
     assert np.array_equal(faiss_search.read(str(p), 4), arr)
+
+
+def test_grouped_rerank_plan_covers_every_pair_tile_exactly_once():
+    """Host planning of the leaf-grouped re-rank (mevi_b200/rerank.py): tiles never straddle a leaf, every
+    (query, leaf) pair meets every tile of its leaf exactly once, in the round its preceding candidate count puts it."""
+    import torch
+
+    from mevi_b200.rerank import GROUP_COLS, build_leaf_tiles, plan_grouped_rounds
+
+    rs = np.random.RandomState(0)
+    sizes = rs.randint(1, 700, size=50)
+    sizes[3], sizes[7], sizes[9], sizes[11] = 1, 128, 129, 3000
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64))
+    row0, nrows, lt0, src = build_leaf_tiles(off)
+    assert torch.equal(torch.sort(src[src >= 0]).values.long(), torch.arange(int(off[-1])))
+    for t in range(row0.numel()):
+        a, b = int(row0[t]), int(row0[t]) + int(nrows[t])
+        leaf = int(torch.searchsorted(off, torch.tensor(a), right=True)) - 1
+        assert off[leaf] <= a and b <= off[leaf + 1] and 1 <= b - a <= 128
+    nq, L = 300, 20
+    ql = torch.from_numpy(np.stack([rs.choice(50, size=L, replace=False) for _ in range(nq)]).astype(np.int32))
+    ql[5, 3] = -1
+    ql[8, :] = -1
+    seen = []
+    for r, (it, ig, gq) in enumerate(plan_grouped_rounds(off, lt0, ql, (2000,))):
+        gq = gq.view(-1, GROUP_COLS)
+        for i in range(it.numel()):
+            t, g = int(it[i]), int(ig[i])
+            leaf = int(np.searchsorted(lt0.numpy(), t, side="right")) - 1
+            seen += [(r, q, leaf, t) for q in gq[g][gq[g] >= 0].tolist()]
+    exp = set()
+    for q in range(nq):
+        cum = 0
+        for j in range(L):
+            leaf = int(ql[q, j])
+            if leaf < 0:
+                continue
+            exp |= {(0 if cum < 2000 else 1, q, leaf, t) for t in range(int(lt0[leaf]), int(lt0[leaf + 1]))}
+            cum += int(sizes[leaf])
+    assert len(seen) == len(set(seen)) and set(seen) == exp
