@@ -8,7 +8,7 @@
 // A CTA stages a tile of 32 rows in shared memory (coalesced 128-bit loads, row pitch d+4 floats so the
 // per-lane 128-bit reads below are conflict-free); lane = row, each warp takes sub-vectors j = warp, warp+8, ...
 // and walks the K centroids of codebook[j] with warp-uniform (broadcast) 128-bit loads.
-// Roofline: FP32 issue (3*K*d flops per row against 4*d bytes).
+// Roofline: FP32 issue (3*K*d flops per row against 4*d bytes).  Measured (8,841,823 x 768, bench `widened_rows`).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -26,6 +26,10 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __re
   const int pitch = d + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d4 = d >> 2, ds4 = dsub >> 2;
+  const int nparts = M >= PQ_THREADS / 32 ? 1 : (PQ_THREADS / 32) / M;
+  const int ntasks = M * nparts;
+  float* s_bs = sx + PQ_ROWS * pitch;                       // [ntasks][PQ_ROWS] best score of a task
+  int* s_bi = reinterpret_cast<int*>(s_bs + ntasks * PQ_ROWS);  // [ntasks][PQ_ROWS] its centroid
   const int64_t n_tiles = (n + PQ_ROWS - 1) / PQ_ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t r0 = tile * PQ_ROWS;
@@ -38,37 +42,63 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __re
       *reinterpret_cast<float4*>(sx + r * pitch + 4 * c) = v;
     }
     __syncthreads();
-    for (int j = warp; j < M; j += PQ_THREADS / 32) {
+    // task = (sub-vector j, slice of the K centroids): with fewer than 8 sub-vectors the K range is cut so that all
+    // eight warps work.  Two centroids at a time, four partial sums each: eight independent FMA chains per lane
+    // (one serial chain per centroid left the FP32 pipe waiting on its own latency).
+    for (int task = warp; task < ntasks; task += PQ_THREADS / 32) {
+      const int j = task / nparts, part = task - j * nparts;
+      const int k0 = (int)((int64_t)part * K / nparts), k1 = (int)((int64_t)(part + 1) * K / nparts);
       const float4* xr = reinterpret_cast<const float4*>(sx + lane * pitch + j * dsub);
       const float4* cj = reinterpret_cast<const float4*>(cb + (int64_t)j * K * dsub);
       float best = -CUDART_INF_F;
-      int besti = 0;
-      for (int k = 0; k < K; ++k) {
-        const float4* ck = cj + (int64_t)k * ds4;
-        float acc = 0.f;
+      int besti = k0;
+      for (int k = k0; k < k1; k += 2) {
+        const bool two = k + 1 < k1;
+        const float4* ca = cj + (int64_t)k * ds4;
+        const float4* cbk = cj + (int64_t)(two ? k + 1 : k) * ds4;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 4
         for (int e = 0; e < ds4; ++e) {
-          const float4 a = xr[e];
-          const float4 b = __ldg(ck + e);
+          const float4 x = xr[e];
+          const float4 u = __ldg(ca + e);
+          const float4 v = __ldg(cbk + e);
           if (L2) {
-            const float t0 = a.x - b.x, t1 = a.y - b.y, t2 = a.z - b.z, t3 = a.w - b.w;
-            acc = fmaf(t0, t0, acc);
-            acc = fmaf(t1, t1, acc);
-            acc = fmaf(t2, t2, acc);
-            acc = fmaf(t3, t3, acc);
+            const float t0 = x.x - u.x, t1 = x.y - u.y, t2 = x.z - u.z, t3 = x.w - u.w;
+            const float w0 = x.x - v.x, w1 = x.y - v.y, w2 = x.z - v.z, w3 = x.w - v.w;
+            a0 = fmaf(t0, t0, a0); a1 = fmaf(t1, t1, a1); a2 = fmaf(t2, t2, a2); a3 = fmaf(t3, t3, a3);
+            b0 = fmaf(w0, w0, b0); b1 = fmaf(w1, w1, b1); b2 = fmaf(w2, w2, b2); b3 = fmaf(w3, w3, b3);
           } else {
-            acc = fmaf(a.x, b.x, acc);
-            acc = fmaf(a.y, b.y, acc);
-            acc = fmaf(a.z, b.z, acc);
-            acc = fmaf(a.w, b.w, acc);
+            a0 = fmaf(x.x, u.x, a0); a1 = fmaf(x.y, u.y, a1); a2 = fmaf(x.z, u.z, a2); a3 = fmaf(x.w, u.w, a3);
+            b0 = fmaf(x.x, v.x, b0); b1 = fmaf(x.y, v.y, b1); b2 = fmaf(x.z, v.z, b2); b3 = fmaf(x.w, v.w, b3);
           }
         }
-        const float s = L2 ? -acc : acc;
-        if (s > best) {  // strict: the lowest index wins exact ties
-          best = s;
+        const float sa = (a0 + a1) + (a2 + a3), sb = (b0 + b1) + (b2 + b3);
+        const float s0 = L2 ? -sa : sa, s1 = L2 ? -sb : sb;
+        if (s0 > best) {  // strict: the lowest index wins exact ties
+          best = s0;
           besti = k;
         }
+        if (two && s1 > best) {
+          best = s1;
+          besti = k + 1;
+        }
       }
-      if (lane < rows) codes[(r0 + lane) * M + j] = besti;
+      s_bs[task * PQ_ROWS + lane] = best;
+      s_bi[task * PQ_ROWS + lane] = besti;
+    }
+    __syncthreads();
+    for (int i = tid; i < PQ_ROWS * M; i += PQ_THREADS) {  // consecutive threads -> consecutive code words
+      const int r = i / M, j = i - r * M;
+      float best = s_bs[(j * nparts) * PQ_ROWS + r];
+      int besti = s_bi[(j * nparts) * PQ_ROWS + r];
+      for (int part = 1; part < nparts; ++part) {  // slices ascend in k: strict > keeps the lowest index on ties
+        const float sc = s_bs[(j * nparts + part) * PQ_ROWS + r];
+        if (sc > best) {
+          best = sc;
+          besti = s_bi[(j * nparts + part) * PQ_ROWS + r];
+        }
+      }
+      if (r < rows) codes[(r0 + r) * M + j] = besti;
     }
   }
 }
@@ -88,10 +118,11 @@ extern "C" int mevi_pq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, c
   MEVI_REQUIRE(ctx, dsub % 4 == 0, "sub-vector width %d must be a multiple of 4", dsub);
   MEVI_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0,
                "X and codebook must be 16-byte aligned");
-  const size_t smem = (size_t)PQ_ROWS * (d + 4) * sizeof(float);
+  const int nparts = M >= PQ_THREADS / 32 ? 1 : (PQ_THREADS / 32) / M;
+  const size_t smem = (size_t)PQ_ROWS * (d + 4) * sizeof(float) + (size_t)M * nparts * PQ_ROWS * 8;
   MEVI_REQUIRE(ctx, smem <= 220 * 1024, "embedding width %d too large for the row tile", d);
   const int64_t n_tiles = (n + PQ_ROWS - 1) / PQ_ROWS;
-  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  const int per_sm = smem <= 112 * 1024 ? 2 : 1;
   const int64_t max_grid = (int64_t)ctx->sm_count * per_sm;
   const int grid = (int)(n_tiles < max_grid ? n_tiles : max_grid);
   if (metric == MEVI_METRIC_L2) {

@@ -191,11 +191,16 @@ def plan_grouped_rounds(leaf_offsets: torch.Tensor, leaf_tile0: torch.Tensor, ql
         grp_of_pair = grp0[run_of_pair] + pos // GROUP_COLS
         group_qid = torch.full((G, GROUP_COLS), -1, dtype=torch.int32, device=dev)
         group_qid[grp_of_pair, pos % GROUP_COLS] = q.to(torch.int32)
-        group_leaf = torch.repeat_interleave(uleaf, gpl)
-        ntl = tpl[group_leaf]                                               # tiles of the group's leaf
-        item_group = torch.repeat_interleave(torch.arange(G, device=dev), ntl)
-        item0 = torch.cumsum(ntl, 0) - ntl
-        item_tile = leaf_tile0[group_leaf[item_group]] + (torch.arange(item_group.numel(), device=dev) - item0[item_group])
+        # work items, per leaf TILE-major: a document tile (196 KB) comes from HBM once and meets all the query groups of
+        # its leaf back to back; the groups' images (98 KB each) are what gets re-read, and they stay in L2
+        ntl = tpl[uleaf]
+        ipl = ntl * gpl                                                     # items per leaf
+        item0 = torch.cumsum(ipl, 0) - ipl
+        leaf_of_item = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), ipl)
+        local = torch.arange(leaf_of_item.numel(), device=dev) - item0[leaf_of_item]
+        g_of = gpl[leaf_of_item]
+        item_tile = leaf_tile0[uleaf[leaf_of_item]] + local // g_of
+        item_group = grp0[leaf_of_item] + local % g_of
         out.append((item_tile.to(torch.int32).contiguous(), item_group.to(torch.int32).contiguous(),
                     group_qid.reshape(-1).contiguous()))
     return out
@@ -239,6 +244,10 @@ class ClusterReranker:
             raise ValueError(f"unknown re-rank mode {self.mode!r}")
         self._grouped = None
         self.last_path = None
+        if os.environ.get("MEVI_RERANK_BOOTSTRAP"):
+            self.BOOTSTRAP_ROWS = int(os.environ["MEVI_RERANK_BOOTSTRAP"])
+        if os.environ.get("MEVI_RERANK_ROUNDS"):
+            self.ROUND_ROWS = tuple(int(v) for v in os.environ["MEVI_RERANK_ROUNDS"].split(","))
         if self.mode == "grouped":
             if not self.leaf_ordered:
                 raise ValueError("mode='grouped' needs the leaf-ordered layout")
