@@ -209,6 +209,8 @@ def plan_grouped_rounds(leaf_offsets: torch.Tensor, leaf_tile0: torch.Tensor, ql
 class ClusterReranker:
     """Holds a (shard of the) doc-embedding matrix on the device plus its inverted lists."""
 
+    AUTO_MIN_DOCS = 1 << 18         # mode='auto': corpora below this stay on the streaming kernel (no tile image)
+    AUTO_QUERIES_PER_LEAF = 4       # mode='auto': grouped path when nq*L >= this many (query, leaf) pairs per leaf
     BOOTSTRAP_ROWS = 2048           # prefix of every query's candidates scored exactly for the first thresholds
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
 
@@ -239,8 +241,10 @@ class ClusterReranker:
         # the prefilter guarantee cannot be established
         import os
 
-        self.mode = mode or os.environ.get("MEVI_RERANK_MODE", "stream")
-        if self.mode not in ("stream", "grouped"):
+        # "auto" (default): build the tile image when the corpus is large enough for leaf sharing to matter and it fits, and
+        # take the grouped path per call when the queries share leaves (>= AUTO_QUERIES_PER_LEAF (query, leaf) pairs per leaf)
+        self.mode = mode or os.environ.get("MEVI_RERANK_MODE", "auto")
+        if self.mode not in ("stream", "grouped", "auto"):
             raise ValueError(f"unknown re-rank mode {self.mode!r}")
         self._grouped = None
         self.last_path = None
@@ -248,9 +252,14 @@ class ClusterReranker:
             self.BOOTSTRAP_ROWS = int(os.environ["MEVI_RERANK_BOOTSTRAP"])
         if os.environ.get("MEVI_RERANK_ROUNDS"):
             self.ROUND_ROWS = tuple(int(v) for v in os.environ["MEVI_RERANK_ROUNDS"].split(","))
-        if self.mode == "grouped":
-            if not self.leaf_ordered:
-                raise ValueError("mode='grouped' needs the leaf-ordered layout")
+        build_image = self.mode == "grouped"
+        if self.mode == "grouped" and not self.leaf_ordered:
+            raise ValueError("mode='grouped' needs the leaf-ordered layout")
+        if self.mode == "auto" and self.leaf_ordered and self.D.shape[0] >= self.AUTO_MIN_DOCS and self.D.shape[1] % 64 == 0:
+            n_leaves = int(index.leaf_offsets.numel()) - 1
+            img_bytes = (self.D.shape[0] + 128 * n_leaves) * self.D.shape[1] * 2  # upper bound incl. per-leaf padding
+            build_image = torch.cuda.mem_get_info(dev)[0] >= 2 * img_bytes + (4 << 30)
+        if build_image:
             row0, nrows, leaf_tile0, src = build_leaf_tiles(index.leaf_offsets)
             img, absmax, maxnorm = self.ctx.rerank_grouped_image(self.D, src, row0.numel())
             del src
@@ -266,7 +275,9 @@ class ClusterReranker:
             query_embedding = torch.from_numpy(np.ascontiguousarray(query_embedding, dtype=np.float32))
         Q = query_embedding.to(device=dev, dtype=torch.float32).contiguous()
         ql = self.index.lookup(dec)
-        out = self._rerank_grouped(Q, ql, topk) if self._grouped is not None else None
+        use_grouped = self._grouped is not None and (
+            self.mode == "grouped" or ql.numel() >= self.AUTO_QUERIES_PER_LEAF * max(1, self.index.n_leaves))
+        out = self._rerank_grouped(Q, ql, topk) if use_grouped else None
         if out is None:
             self.last_path = "stream"
             out = self.ctx.cluster_rerank(Q, self.D, self.index.leaf_offsets, self.index.leaf_docids, ql, topk,

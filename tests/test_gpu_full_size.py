@@ -149,3 +149,47 @@ def test_inverted_lists_partition_the_corpus(corpus):
         key = key * K + codes[:, j].long()
     leaf_of_pos = torch.repeat_interleave(torch.arange(index.n_leaves, device=ids.device), (off[1:] - off[:-1]))
     assert torch.equal(index.leaf_keys[leaf_of_pos], key[ids.long()])
+
+
+def test_rerank_auto_mode_takes_the_grouped_path_and_equals_the_streaming_kernel(corpus):
+    """Default ClusterReranker at the bench shape: 2,048 queries x 100 leaves share leaves (~9 pairs per leaf), so the
+    leaf-grouped tensor path runs; its answer must be the streaming kernel's (ids modulo fp32 score ties)."""
+    from mevi_b200.pq import ProductQuantization
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    X, cb, codes = corpus
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 60 << 30:
+        pytest.skip("needs ~50 GB more HBM for the leaf-ordered copy and its fp16 image")
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(4321)
+    nq, L, k = 2048, 100, 100
+    Q = torch.empty((nq, D), device="cuda:0").normal_(generator=g)
+    pq = ProductQuantization("rq", M, 5, "l2", D, "kmeans", "grad")
+    with torch.no_grad():
+        pq.codebook.copy_(cb.cpu())
+    dec = torch.cat([pq.beam_search(Q[a : a + 128], L) for a in range(0, nq, 128)])
+    rr = ClusterReranker(X, ClusterIndex.from_codes(codes, K))
+    assert rr.mode == "auto" and rr._grouped is not None
+    s_g, i_g, n_g = rr.rerank(Q, dec, topk=k)
+    assert rr.last_path == "grouped"
+    rr.mode = "stream"
+    saved, rr._grouped = rr._grouped, None
+    s_s, i_s, n_s = rr.rerank(Q, dec, topk=k)
+    rr._grouped = saved
+    assert rr.last_path == "stream" and torch.equal(n_g, n_s)
+    assert torch.equal(s_g, s_s)  # exact fp32 re-score in the same summation order
+    differ = (i_g != i_s)
+    assert float(differ.float().mean()) < 1e-3
+    # where ids differ the two documents tie in score
+    if bool(differ.any()):
+        q_idx, pos = differ.nonzero(as_tuple=True)
+        a = (X[i_g[q_idx, pos]] * Q[q_idx]).sum(1)
+        b = (X[i_s[q_idx, pos]] * Q[q_idx]).sum(1)
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max())
+    # a few queries that share few leaves stay on the streaming kernel
+    rr.mode = "auto"
+    rr.rerank(Q[:64], dec[:64], topk=k)
+    assert rr.last_path == "stream"
+    del rr
+    torch.cuda.empty_cache()

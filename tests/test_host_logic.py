@@ -148,3 +148,25 @@ def test_grouped_rerank_plan_covers_every_pair_tile_exactly_once():
             exp |= {(0 if cum < 2000 else 1, q, leaf, t) for t in range(int(lt0[leaf]), int(lt0[leaf + 1]))}
             cum += int(sizes[leaf])
     assert len(seen) == len(set(seen)) and set(seen) == exp
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU arithmetic, oracle port) must print ONE JSON line with the
+    keys the driver reads, without touching CUDA."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-sample", "2048"], capture_output=True, text=True, timeout=300,
+                         env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "rq_encode_docs_per_sec" and j["unit"] == "docs/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 1
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"] == {"value": j["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
