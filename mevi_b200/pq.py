@@ -26,6 +26,7 @@ Differences that are deliberate:
 """
 from __future__ import annotations
 
+import os
 import os.path as osp
 from collections import defaultdict
 from typing import Optional
@@ -159,6 +160,15 @@ class ProductQuantization(nn.Module):
         dev = torch.device("cuda", ctx.device)
         cb = self.get_codebook().detach().to(dev).contiguous()
         rot_t = self.rotate.detach().to(dev).T.contiguous() if self.pq_type == "opq" else None
+        # Opt-in (MEVI_PQ_VIA_RQ=1, not yet measured on hardware): sub-vector centroids zero-padded to the full width have
+        # orthogonal supports, so the RQ residual corrections vanish and the RQ tensor kernel returns the PQ codes (up to
+        # fp32 ties; identity checked on the oracle in tests/test_modes_cpu.py).  Shapes the tensor kernel accepts only.
+        M, K, dsub = cb.shape
+        padded = None
+        if os.environ.get("MEVI_PQ_VIA_RQ") == "1" and M * K <= 128 and K % 32 == 0 and (M * dsub) % 64 == 0:
+            padded = torch.zeros((M, K, M * dsub), dtype=torch.float32, device=dev)
+            for j in range(M):
+                padded[j, :, j * dsub : (j + 1) * dsub] = cb[j]
         step = 1 << 18
         for a in range(start, ending, step):
             b = min(a + step, ending)
@@ -168,7 +178,10 @@ class ProductQuantization(nn.Module):
                 x = torch.from_numpy(np.ascontiguousarray(doc_embeddings[a:b], dtype=np.float32)).to(dev)
             if rot_t is not None:
                 x = _matmul_fp32(x, rot_t)
-            codes = ctx.pq_encode(x, cb, metric=self.dist_mode)
+            if padded is not None:
+                codes = ctx.rq_encode(x, padded, metric=self.dist_mode, mode="auto")
+            else:
+                codes = ctx.pq_encode(x, cb, metric=self.dist_mode)
             cluster[a - start : b - start].copy_(codes.to(cluster.device))
 
     @torch.no_grad()

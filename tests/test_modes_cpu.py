@@ -98,3 +98,25 @@ def test_oracle_eval_all_documents_is_streaming_flat_topk(data):
     assert i.dtype == np.int32 and s.shape == (Q.shape[0], 50)
     np.testing.assert_allclose(s, s2, rtol=1e-5, atol=1e-5)
     assert (np.sort(i, 1) == np.sort(i2, 1)).mean() > 0.99
+
+
+def test_pq_encode_equals_rq_encode_on_a_block_padded_codebook():
+    """Design check for moving the PQ encode onto the RQ tensor kernel: zero-padding sub-vector
+    centroid (j,k) to the full width makes the levels' supports orthogonal, so the residual corrections vanish
+    (r_j . c = x . c) and the greedy RQ encode of pq.py:281-305 returns the PQ codes of pq.py:249-279 — up to fp32
+    ties, because the padded direct-form distance adds the same constant to every centroid of a level."""
+    from oracle import oracle
+
+    rs = np.random.RandomState(3)
+    n, d, M, K = 4000, 96, 4, 32
+    X = rs.standard_normal((n, d)).astype(np.float32)
+    cb = rs.standard_normal((M, K, d // M)).astype(np.float32)
+    padded = np.zeros((M, K, d), np.float32)
+    for j in range(M):
+        padded[j, :, j * (d // M):(j + 1) * (d // M)] = cb[j]
+    pq_codes = oracle.pq_encode(X, cb, dist_mode="l2")
+    rq_codes = oracle.rq_encode(X, padded, batch_size=512)
+    differ = np.nonzero((pq_codes != rq_codes).any(axis=1))[0]
+    assert len(differ) <= 2e-3 * n
+    ties, real = oracle.classify_pq_mismatches(X, cb, pq_codes, rq_codes)
+    assert real == 0, (ties, real)
