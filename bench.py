@@ -12,7 +12,11 @@ collective (weak scaling: every rank owns one MSMARCO-shape block).
 The JSON line also carries `roofline` (dominant kernel vs measured HBM peak), `e2e` (same metric
 through the reference-shaped Python entry point with HOST buffers, copies inside the timed region),
 `cpu_baseline` (the reference's CPU arithmetic, oracle port, bounded sample), `clocks`, `gpu_launches`
-and `extra` (re-rank queries/s, k-means iteration, flat-IP search — the other BASELINE configs).
+and `extra` — the other BASELINE configs, each with its own roofline: `rerank` (streaming kernel) and
+`rerank_grouped` (leaf-grouped tensor GEMMs, with parity against the streaming kernel), `kmeans_iteration`
+(whole iteration + per-kernel), `flat_ip` (with parity against the fp32 kernel), `widened_rows` (PQ encode,
+device beam search, inverted lists, leaf-order permutation).  At N > 1 the re-rank and flat extras are
+doc-sharded: all-gather of per-shard top-k + merge inside their timed regions.
 """
 from __future__ import annotations
 
