@@ -58,6 +58,12 @@ const char* mevi_last_error(mevi_ctx* ctx);
  * [4]=1 if the tcgen05 path is usable on this device (cc 10.x), [5]=L2 bytes,
  * [6]=kernels this context has launched so far (its own kernels; library sorts excluded) */
 int mevi_device_info(mevi_ctx* ctx, int64_t info[8]);
+/* Synchronise `stream` and report what the asynchronous launches before it found: the pipelined kernels bound every
+ * mbarrier wait; a time-out (a protocol bug or a hung copy engine, never seen in normal operation) makes the kernel
+ * bail out, overwrite its codes with -1 and set a device error word.  Returns MEVI_ERR_CUDA with a message in that
+ * case, MEVI_OK otherwise.  The same condition is also reported by the next call on the context and by every call that
+ * synchronises on its own (mevi_rq_encode_host, mevi_flat_ip_topk, mevi_rerank_grouped_finish).                  */
+int mevi_ctx_check(mevi_ctx* ctx, void* stream);
 
 /* ---- RQ encode ---------------------------------------------------------- *
  * replaces: MEVI/pq.py:281-305 get_rq_document_cluster (+124-131 compute_scores,
@@ -71,7 +77,9 @@ int mevi_device_info(mevi_ctx* ctx, int64_t info[8]);
  *                     (pq.py:304-305 subtracts after every level), or NULL
  *   stats_or_null     int64[8] DEVICE out: [0]=rows re-decided by the exact
  *                     fix-up because their prefilter top-2 gap was inside the
- *                     error bound (tensor mode), [1]=rows processed; rest 0   */
+ *                     error bound (tensor mode), [1]=rows processed, [2]=(row, level)
+ *                     decisions the hi.hi prefilter left open and the epilogue
+ *                     refined with fp32 dot products (generation 6); rest 0   */
 int mevi_rq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K,
                    int metric, int mode, int32_t* codes, float* residual_or_null, int64_t* stats_or_null,
                    void* stream);

@@ -28,6 +28,7 @@ SYMBOLS = {
     "mevi_ctx_destroy": (None, [_vp]),
     "mevi_last_error": (C.c_char_p, [_vp]),
     "mevi_device_info": (_i, [_vp, C.POINTER(_i64)]),
+    "mevi_ctx_check": (_i, [_vp, _vp]),
     "mevi_rq_encode": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mevi_rq_encode_host": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "mevi_kmeans_step": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
@@ -119,6 +120,17 @@ class Context:
         info = (C.c_int64 * 8)()
         self._check(self.lib.mevi_device_info(self.handle, info))
         return int(info[6])
+
+    def check(self):
+        """Synchronise the current stream and raise MeviError if a kernel of an earlier asynchronous call reported a
+        pipeline time-out (mevi_ctx_check)."""
+        with self._device_guard():
+            self._check(self.lib.mevi_ctx_check(self.handle, self._stream()))
+
+    def _device_guard(self):
+        import torch
+
+        return torch.cuda.device(self.device)
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:

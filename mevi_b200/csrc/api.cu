@@ -61,9 +61,36 @@ void* mevi_pinned(mevi_ctx* ctx, int slot, size_t bytes) {
   return p;
 }
 
+int mevi_publish_errors(mevi_ctx* ctx, cudaStream_t st) {
+  MEVI_CUDA(ctx, cudaMemcpyAsync((void*)ctx->host_err, ctx->dev_err, MEVI_ERRSLOTS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return MEVI_OK;
+}
+
+int mevi_deferred_error(mevi_ctx* ctx) {
+  static const char* const who[MEVI_ERRSLOTS] = {"tensor RQ encode", "cluster re-rank", "kernel", "kernel", "kernel", "kernel", "kernel", "kernel"};
+  for (int i = 0; i < MEVI_ERRSLOTS; ++i) {
+    const int code = ctx->host_err[i];
+    if (code != 0) {
+      for (int j = 0; j < MEVI_ERRSLOTS; ++j) ctx->host_err[j] = 0;
+      cudaMemset(ctx->dev_err, 0, MEVI_ERRSLOTS * sizeof(int));
+      return mevi_set_error(ctx, MEVI_ERR_CUDA,
+                            "%s: a pipeline wait timed out on the device (code %d); the results of that launch are invalid "
+                            "(codes were overwritten with -1, top-k lists are incomplete)", who[i], code);
+    }
+  }
+  return MEVI_OK;
+}
+
 extern "C" {
 
 int mevi_abi_version(void) { return MEVI_ABI_VERSION; }
+
+int mevi_ctx_check(mevi_ctx* ctx, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  MEVI_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+  return mevi_deferred_error(ctx);
+}
 
 int mevi_ctx_create(int device, mevi_ctx** out) {
   if (!out) return MEVI_ERR_INVALID;
@@ -88,6 +115,16 @@ int mevi_ctx_create(int device, mevi_ctx** out) {
   ctx->l2_bytes = (size_t)prop.l2CacheSize;
   for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking);
   for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->aux_event[i], cudaEventDisableTiming);
+  int* herr = nullptr;
+  if (cudaMalloc(&ctx->dev_err, MEVI_ERRSLOTS * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&herr, MEVI_ERRSLOTS * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();
+    mevi_ctx_destroy(ctx);
+    return MEVI_ERR_NOMEM;
+  }
+  ctx->host_err = herr;
+  cudaMemset(ctx->dev_err, 0, MEVI_ERRSLOTS * sizeof(int));
+  for (int i = 0; i < MEVI_ERRSLOTS; ++i) ctx->host_err[i] = 0;
   *out = ctx;
   return MEVI_OK;
 }
@@ -100,6 +137,8 @@ void mevi_ctx_destroy(mevi_ctx* ctx) {
     if (ctx->ws[i]) cudaFree(ctx->ws[i]);
   for (int i = 0; i < 4; ++i)
     if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+  if (ctx->dev_err) cudaFree(ctx->dev_err);
+  if (ctx->host_err) cudaFreeHost((void*)ctx->host_err);
   for (int i = 0; i < 2; ++i)
     if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
   for (int i = 0; i < 4; ++i)

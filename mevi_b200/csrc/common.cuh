@@ -42,10 +42,21 @@ struct mevi_ctx {
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
   cudaEvent_t aux_event[4] = {nullptr, nullptr, nullptr, nullptr};
   void* tmap_encode_fn = nullptr;  // cuTensorMapEncodeTiled, resolved lazily
+  // Device-side error words (a bounded mbarrier wait that times out sets one and the kernel bails out) and their
+  // pinned host mirror.  Asynchronous entry points copy dev_err -> host_err at the end of their launch sequence;
+  // the mirror is inspected at the start of the next call, after every synchronising call, and by mevi_ctx_check.
+  int* dev_err = nullptr;            // [MEVI_ERRSLOTS]
+  volatile int* host_err = nullptr;  // [MEVI_ERRSLOTS], cudaMallocHost
   int64_t launches = 0;            // kernels launched by this context (reported by mevi_device_info)
 };
 
+enum { MEVI_ERRSLOT_RQ = 0, MEVI_ERRSLOT_RERANK = 1, MEVI_ERRSLOT_OTHER = 2, MEVI_ERRSLOTS = 8 };
+
 int mevi_set_error(mevi_ctx* ctx, int code, const char* fmt, ...);
+// enqueue the dev_err -> host_err copy on `st` (end of an asynchronous launch sequence)
+int mevi_publish_errors(mevi_ctx* ctx, cudaStream_t st);
+// MEVI_OK, or MEVI_ERR_CUDA (message set, error words cleared) if a kernel of an earlier launch reported a time-out
+int mevi_deferred_error(mevi_ctx* ctx);
 // grow-on-demand scratch; returns nullptr (and sets the error) on failure
 void* mevi_ws(mevi_ctx* ctx, int slot, size_t bytes);
 void* mevi_pinned(mevi_ctx* ctx, int slot, size_t bytes);

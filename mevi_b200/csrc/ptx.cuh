@@ -117,6 +117,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
                "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

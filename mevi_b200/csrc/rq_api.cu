@@ -116,7 +116,7 @@ int mevi_rq_encode_host(mevi_ctx* ctx, const float* X_host, int64_t n, int d, co
     MEVI_CUDA(ctx, cudaMemcpyAsync(stats_host_or_null, stats_dev, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, s_comp));
   MEVI_CUDA(ctx, cudaStreamSynchronize(s_copy));
   MEVI_CUDA(ctx, cudaStreamSynchronize(s_comp));
-  return MEVI_OK;
+  return mevi_deferred_error(ctx);  // a pipeline time-out in any chunk's kernel fails the call
 }
 
 }  // extern "C"

@@ -1,4 +1,6 @@
-// rq_tensor4.cuh — K1, fourth generation: the document operand goes through TENSOR MEMORY.
+// rq_tensor4.cuh — K1, split-fp16 kernel (generation 4): the document operand goes through TENSOR MEMORY.
+// Serves the shapes generation 6 (rq_tensor6.cuh) does not take: M = 1 (the k-means assignment, which runs at the HBM
+// roofline here), K > 32, d % 128 != 0.
 //
 // Same algorithm / error model / work-list protocol as the earlier generations (rq_tensor.cu).  v3 is bound
 // by shared-memory bandwidth (70 % of the LSU data pipe: TMA writes + converter loads + converter stores +
@@ -28,14 +30,6 @@ constexpr int X_STAGE4 = TM4 * KC4 * 4;  // 32 KB
 constexpr int THREADS4 = 640;
 constexpr int EPI_WARPS4 = 8;
 constexpr uint32_t A_COL0 = 256;         // first TMEM column of the operand stages
-// setmaxnreg budgets per warpgroup (launch: 96 x 640 = 61,440 of 65,536): control warps 0-3, converter warps 4-11,
-// epilogue warps 12-19.  The epilogue copies its row's WHOLE accumulator (128 columns) into registers and hands the
-// TMEM buffer back before it computes, so the next tile's MMAs never wait for the 4-level argmin.
-// must redistribute the LAUNCH allocation: 128*C + 256*V + 256*E <= 96*640 = 61,440 (an inc beyond it never returns)
-template <int PRE> struct Regs4 { static constexpr bool split = false; static constexpr int ctrl = 96, conv = 96, epi = 96; };
-template <> struct Regs4<3> { static constexpr bool split = true; static constexpr int ctrl = 32, conv = 80, epi = 136; };
-template <> struct Regs4<4> { static constexpr bool split = true; static constexpr int ctrl = 32, conv = 64, epi = 160; };
-
 struct Smem4 {
   int x_off, b_off, gram_off, cn2_off, e1_off, lvl_off, stats_off, bar_off, holder_off, total;
 };
@@ -131,10 +125,7 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
   }
 }
 
-// PRE > 0 (K == 32 only): the epilogue decides the first M-PRE levels straight from tensor memory, then copies the
-// remaining PRE levels' accumulator columns into registers and hands the TMEM buffer back BEFORE deciding them, so the
-// next tile's MMAs wait for a fraction of the epilogue only.  PRE >= 3 needs the setmaxnreg register split (Regs4).
-template <int M, int PRE>
+template <int M>
 __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int K = p.K, NT = p.NT;
@@ -191,9 +182,6 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
 
   // The three control warps walk their loops with all 32 lanes (operands stay warp-uniform) and issue from one
   // elected lane: `if (lane == 0)` would wrap every TMA / tcgen05 instruction in an R2UR waterfall loop.
-  constexpr bool early = PRE > 0;
-  using RG = Regs4<(PRE > M ? M : PRE)>;
-  if (RG::split && warp < 4) reg_dec<RG::ctrl>();
   if (warp == 0) {
     uint32_t s = 0, ph = 0, tix = 0, it = 0;
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
@@ -266,6 +254,7 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
 #pragma unroll
             for (int ks = 0; ks < KC4 / 16; ++ks) {
               ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, (c | ks) != 0 ? 1u : 0u);
+              if (p.debug & 32) continue;  // experiment: hi.hi only (a third of the tensor work; results are approximate)
               ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_lo + ks * 32), idesc, 1u);
               ptx::umma_f16_ts(d_tmem, a_lo + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, 1u);
             }
@@ -281,13 +270,11 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
       }
     }
   } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
-    if (RG::split) reg_dec<RG::conv>();
     if (p.consts[C_SX] == 1.f)
       converter_loop4<false>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
     else
       converter_loop4<true>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
   } else if (warp >= EPI_WARP0) {
-    if (RG::split) reg_inc<RG::epi>();
     const int ew = warp - EPI_WARP0;
     const float m2inv = (p.metric == MEVI_METRIC_L2 ? -2.f : -1.f) * p.consts[C_INV];
     const bool l2 = p.metric == MEVI_METRIC_L2;
@@ -310,62 +297,6 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
         float last_best = 0.f;
 #pragma unroll
         for (int j = 0; j < M; ++j) code[j] = 0;
-        if constexpr (early) {
-          constexpr int NPRE = PRE > M ? M : PRE;  // trailing levels decided from registers
-          constexpr int J0 = M - NPRE;
-          // one level (K == 32) from 32 accumulator registers; the distances overwrite them
-          auto level = [&](int j, uint32_t (&a)[32]) {
-            const float* gj = sGram + (j * (j - 1) / 2) * 32 * 33;
-            const float* grow[M > 1 ? M - 1 : 1];
-#pragma unroll
-            for (int m = 0; m < M - 1; ++m)
-              if (m < j) grow[m] = gj + (m * 32 + code[m]) * 33;
-            float c1 = CUDART_INF_F, u1 = CUDART_INF_F, u2 = CUDART_INF_F;
-#pragma unroll
-            for (int kk = 0; kk < 32; ++kk) {
-              float base = l2 ? sCn2[j * 32 + kk] : 0.f;
-              float g = 0.f;
-#pragma unroll
-              for (int m = 0; m < M - 1; ++m)
-                if (m < j) g += grow[m][kk];
-              base = l2 ? fmaf(2.f, g, base) : g;
-              const float dk = fmaf(__uint_as_float(a[kk]), m2inv, base);
-              a[kk] = __float_as_uint(dk);
-              c1 = fminf(c1, dk);
-              const float u = fmaf(nxn, sE1[j * 32 + kk], dk);
-              u2 = fminf(u2, fmaxf(u1, u));
-              u1 = fminf(u1, u);
-            }
-            int ci = 0;
-#pragma unroll
-            for (int kk = 31; kk >= 0; --kk)
-              if (__uint_as_float(a[kk]) == c1) ci = kk;
-            code[j] = ci;
-            const float eb = xn * sE1[j * 32 + ci];
-            const float ub = fmaf(nxn, sE1[j * 32 + ci], c1);
-            const float other_lo = (ub == u1) ? u2 : u1;
-            const bool clear = other_lo > c1 + eb + sLvl[j * 4 + 1];
-            if (!clear && flag_level < 0) flag_level = j;
-            last_best = c1;
-          };
-#pragma unroll
-          for (int j = 0; j < J0; ++j) {  // still holding the TMEM buffer
-            uint32_t a0[32];
-            ptx::tmem_ld32(taddr + j * 32, a0);
-            ptx::tmem_ld_wait();
-            level(j, a0);
-          }
-          uint32_t acc[NPRE][32];
-#pragma unroll
-          for (int j = 0; j < NPRE; ++j) ptx::tmem_ld32(taddr + (J0 + j) * 32, acc[j]);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before_sync();
-          __syncwarp();
-          trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
-          if (lane == 0) ptx::mbar_arrive(acc_empty);
-#pragma unroll
-          for (int j = 0; j < NPRE; ++j) level(J0 + j, acc[j]);
-        } else {
 #pragma unroll
         for (int j = 0; j < M; ++j) {
           if (p.debug & 4) break;
@@ -411,7 +342,6 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
           if (!clear && flag_level < 0) flag_level = j;
           last_best = m1;
         }
-        }
         if (row < p.n) {
           int32_t* dst = p.codes + row * p.codes_stride;
           if (M == 4 && p.codes_stride == 4) {
@@ -428,12 +358,10 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
           if (p.inertia) inertia_acc += (double)(l2 ? fmaxf(last_best + xn2, 0.f) : -last_best);
         }
       }
-      if (!early) {
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
-        if (lane == 0) ptx::mbar_arrive(acc_empty);
-      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      trace_ev(p, warp, lane, tix, it, 255, 1);  // accumulators drained
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
     }
     if (p.inertia) {
 #pragma unroll
@@ -446,23 +374,6 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
   __syncthreads();
   trace_clock(p, 1);
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
-inline int make_x_tensormap4(mevi_ctx* ctx, const float* X, int64_t n, int d, CUtensorMap* out) {
-  if (!ctx->tmap_encode_fn) {
-    CUtensorMap dummy;
-    int rc = v3::make_x_tensormap(ctx, X, n, d, &dummy);  // resolves the driver entry point
-    if (rc != MEVI_OK) return rc;
-  }
-  const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n};
-  const cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)KC4, (cuuint32_t)TM4};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = ((v3::EncodeTiledFn)ctx->tmap_encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estr,
-                                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return mevi_set_error(ctx, MEVI_ERR_CUDA, "cuTensorMapEncodeTiled (128B swizzle) failed with %d", (int)r);
-  return MEVI_OK;
 }
 
 }  // namespace v4

@@ -3,14 +3,15 @@
 Same constructor, method names, argument meaning, side effects (`self.codebook`,
 `self.last_preds`, `self.get_preds`) and on-disk formats as the reference
 (MEVI/pq.py:15-741): `pq_type in ('rq','pq','opq')` (the shipped scripts use
-'rq'), `dist_mode in ('l2','ip')`, `pq_init_method in ('none','kmeans')`,
+'rq'), `dist_mode in ('l2','ip')`, `pq_init_method in ('none','kmeans','avg')`,
 `pq_update_method in ('grad','kmeans','ema','fixpq',...)`.  The hot arithmetic
 runs in hand-written CUDA kernels through the C ABI (include/mevi_b200.h);
 PyTorch only owns memory, streams and the process group.  Branches that need
 packages or state the reference itself does not have here raise
 NotImplementedError instead of silently doing something else: faiss index
-import/export (`pq_init_method='faiss'`, and with it the only way the reference
-obtains an OPQ rotation), tied NCI centroids (T5 lm_head), and
+import/export (`pq_init_method='faiss'`, `pq_update_method='faiss'`, `codebook_from_index`,
+`build_faiss_index`, `unsupervised_update_codebook_faiss` — and with them the only way the
+reference obtains an OPQ rotation), tied NCI centroids (T5 lm_head), `do_sample` beam search, and
 `dist_mode='iptol2'`, which the reference cannot run either — it writes to
 `self.extracol`, an attribute that is never created (pq.py:113-117), so every
 iptol2 path dies with AttributeError.
@@ -222,10 +223,19 @@ class ProductQuantization(nn.Module):
             return
         if self.pq_init_method == "faiss":
             raise NotImplementedError("pq_init_method='faiss' (faiss ResidualQuantizer import) is out of scope")
-        if self.pq_init_method == "avg":
-            raise NotImplementedError("pq_init_method='avg' is out of scope")
-        assert self.pq_init_method.endswith("kmeans")
         use_file = index_file is not None and osp.isfile(index_file)
+        if self.pq_init_method == "avg":  # pq.py:471-482
+            if rank == 0:
+                if use_file:
+                    self.codebook.copy_(torch.load(index_file, map_location="cpu"))
+                else:
+                    torch.nn.init.normal_(self.codebook.data, mean=0.0, std=0.01)
+                print(f"Intializing codebook using average document embedding after {use_file} use file...")
+                self.init_pq_using_document_cluster(doc_emb, pq_cluster_path, encode_batch_size)
+            if _dist_on():
+                self._broadcast_codebook()
+            return
+        assert self.pq_init_method.endswith("kmeans")
         if not use_file:
             self.get_preds = True
         if use_file:
@@ -254,13 +264,14 @@ class ProductQuantization(nn.Module):
     @torch.no_grad()
     def unsupervised_update_codebook(self, doc_emb, rank, seed, align=False):
         """pq.py:526-542."""
-        if align:
-            raise NotImplementedError("align_codebook (pq.py:600-611) is out of scope")
         if self.pq_update_method == "faiss":
             raise NotImplementedError("pq_update_method='faiss' is out of scope")
         if self.pq_update_method.endswith("kmeans"):
             self.get_preds = True
+            ori_codebook = self.codebook.detach().clone() if align else None
             self.unsupervised_update_codebook_manually(doc_emb, seed, self.pq_update_method)
+            if align:  # pq.py:540-541
+                self.align_codebook(ori_codebook)
 
     @torch.no_grad()
     def unsupervised_update_codebook_manually(self, doc_emb, seed, kmeans_method):
@@ -519,6 +530,117 @@ class ProductQuantization(nn.Module):
         if self.pq_type == "opq":
             vectors = torch.matmul(vectors, self.rotate)
         return vectors
+
+
+    def get_reconstruct_loss_for_embeddings(self, embeddings, labels):
+        """pq.py:743-766: mean squared reconstruction error of `embeddings` [B,d] under codes `labels` [B,M]
+        ('rq': the running residual after every level, stacked; 'pq': against the concatenated centroids)."""
+        assert labels.dim() == 2
+        codebook = self.get_codebook()[..., : self.last_dim]
+        vectors = torch.stack([codebook[j][labels[:, j]] for j in range(self.subvector_num)], dim=1)  # [B,M,last_dim]
+        if self.pq_type == "pq":
+            diff = embeddings - vectors.reshape(labels.shape[0], -1)
+        elif self.pq_type == "rq":
+            diffs, cur = [], embeddings
+            for i in range(self.subvector_num):
+                cur = cur - vectors[:, i, :]
+                diffs.append(cur)
+            diff = torch.stack(diffs, 1)
+        else:
+            assert False  # pq.py:761-762: the reference has no opq branch here either
+        return (diff ** 2).mean()
+
+    def get_reconstruct_vector_matrix_multiply(self, index):
+        """pq.py:786-799: soft reconstruction, `index` [bs, M, K] weights over the centroids of every level."""
+        bs = index.shape[0]
+        codebook = self.get_codebook()[..., : self.last_dim]
+        w = index.reshape(-1, self.subvector_cents).unsqueeze(1)
+        cbx = codebook.unsqueeze(0).expand(bs, -1, -1, -1).reshape(-1, self.subvector_cents, self.last_dim)
+        output = torch.bmm(w, cbx).squeeze(1).view(bs, self.subvector_num, self.last_dim)
+        if self.pq_type == "rq":
+            return torch.sum(output, dim=1)
+        return output.view(bs, -1)
+
+    @torch.no_grad()
+    def align_codebook(self, ori_codebook):
+        """pq.py:600-611: per level, permute the new centroids so that they line up with `ori_codebook` under the
+        score-maximising assignment (scipy's Hungarian solver, as the reference)."""
+        from scipy.optimize import linear_sum_assignment
+
+        new_codebook = self.codebook.new(*self.codebook.shape)
+        for ori, cur, new in zip(ori_codebook, self.codebook, new_codebook):
+            scores = self.compute_scores(ori.unsqueeze(0), cur.unsqueeze(1)).cpu().numpy()
+            assign = linear_sum_assignment(scores, maximize=True)
+            for cid, oid in zip(*assign):
+                new[oid] = cur[cid]
+        self.codebook.copy_(new_codebook)
+
+    @torch.no_grad()
+    def init_pq_using_document_cluster(self, doc_emb, cluster, batch_size):
+        """pq.py:488-524: codebook[i][k] = mean of the (residual) embeddings of the documents whose code at level i
+        is k, taken from an existing `rqclus*.pkl` / `pqclus*.pkl`; 'rq' subtracts the mean before the next level.
+        `cluster` is the pickle path (as in the reference) or the dictionary itself.  The per-code means are one
+        `mevi_accumulate_by_code` pass per level on the device (fp32 sums / counts; the reference accumulates
+        sum/ndocs in float64), the residual update is `mevi_residual_update`.  Codes absent from the dictionary keep
+        their previous centroid, as in the reference."""
+        import pickle
+
+        assert self.dist_mode in ("l2",)
+        assert self.pq_type in ("pq", "rq")
+        if isinstance(cluster, (str, os.PathLike)):
+            with open(cluster, "rb") as fr:
+                cluster = pickle.load(fr)
+        ctx = self._ctx()
+        dev = torch.device("cuda", ctx.device)
+        M, K, w = self.subvector_num, self.subvector_cents, self.last_dim
+        n = doc_emb.shape[0]
+        codes = np.full((n, M), -1, dtype=np.int32)
+        for key, docs in cluster.items():
+            codes[np.asarray(docs, dtype=np.int64)] = np.asarray(key, dtype=np.int32)
+        member = torch.from_numpy((codes[:, 0] >= 0)).to(dev)
+        rows = torch.nonzero(member).squeeze(1)
+        X = torch.from_numpy(np.ascontiguousarray(np.asarray(doc_emb), dtype=np.float32)).to(dev)
+        X = X[rows].contiguous() if rows.numel() != n else X
+        cdev = torch.from_numpy(codes).to(dev)[rows].contiguous()
+        buf = torch.empty(K * w + K, dtype=torch.float32, device=dev)
+        for i in range(M):
+            part = X if self.pq_type == "rq" else X[:, i * w : (i + 1) * w].contiguous()
+            ctx.accumulate_by_code(part, cdev[:, i], K, buf, assign_stride=M)
+            sums, counts = buf[: K * w].view(K, w), buf[K * w :]
+            seen = counts > 0
+            cent = self.codebook.data[i].to(dev).clone()
+            cent[seen] = sums[seen] / counts[seen].unsqueeze(1)
+            self.codebook.data[i].copy_(cent.cpu())
+            if self.pq_type == "rq" and i != M - 1:
+                ctx.residual_update(X, cent.contiguous(), cdev[:, i], assign_stride=M)
+
+    # ---- faiss-backed branches of the reference: explicit scope cuts (faiss is not part of this path) ----------
+    def augment_xb(self, xb, phi=None):  # pq.py:82-87 (iptol2 helper; numpy only)
+        norms = np.sum((xb ** 2), axis=-1)
+        if phi is None:
+            phi = np.max(norms)
+        return np.hstack((xb, np.sqrt(phi - norms)[..., np.newaxis]))
+
+    def augment_xq(self, xq):  # pq.py:89-95
+        if isinstance(xq, torch.Tensor):
+            return torch.cat((xq, xq.new_zeros(*xq.shape[:-1], 1)), dim=-1)
+        return np.concatenate((xq, np.zeros((*xq.shape[:-1], 1), dtype=xq.dtype)), axis=-1)
+
+    def wrapped_augment_xb(self, xb, index=None):  # pq.py:97-119
+        if self.dist_mode != "iptol2":
+            return xb
+        raise NotImplementedError("dist_mode='iptol2' (pq.py:113-117 writes to a self.extracol that is never created)")
+
+    def codebook_from_index(self, index, index_file=None):  # pq.py:143-173
+        raise NotImplementedError("codebook_from_index reads a faiss index (faiss.read_index / index.rq.codebooks): "
+                                  "faiss import/export is out of scope; load a .pt codebook through initialize()")
+
+    def build_faiss_index(self, doc_embeddings, save_path=None):  # pq.py:175-198
+        raise NotImplementedError("build_faiss_index trains a faiss RQ/PQ/OPQ index: out of scope; use "
+                                  "initialize(..., pq_init_method='kmeans') for the device trainer")
+
+    def unsupervised_update_codebook_faiss(self, doc_emb, seed):  # pq.py:544-548
+        raise NotImplementedError("pq_update_method='faiss' is out of scope")
 
 
 def _matmul_fp32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:

@@ -58,18 +58,57 @@ def _upload_rows(doc_emb, start: int, end: int, device: torch.device, chunk: int
     return out
 
 
-def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev):
-    """One k-means problem on the local rows R [n, w] (all ranks in lockstep): k-means++ seeds from rank 0's
-    sample, `iters` Lloyd iterations with one all-reduce of the fused sums|counts buffer each, then the labels
-    under the FINAL centroids written to `col` (stride `stride`), like sklearn's fit_predict.
+def _init_sample(R, init_sample: int, rs: np.random.RandomState, dev):
+    """Rows for the k-means++ seeding, drawn from EVERY shard (init_sample // world rows per rank, seeded per rank) and
+    gathered to rank 0 — a corpus stored in some order must not be seeded from its first N/world rows only.
+    Returns a host float32 array on rank 0, None elsewhere.  Every rank draws from its own RandomState stream so
+    the sample is reproducible for a given (seed, world)."""
+    rank, world = rank_world()
+    n = R.shape[0]
+    per = max(1, init_sample // world)
+    s = min(per, n)
+    rs_r = np.random.RandomState(rs.randint(1 << 30) + 7919 * rank) if world > 1 else rs
+    idx = np.sort(rs_r.choice(n, size=s, replace=False)) if s < n else np.arange(n)
+    mine = R[torch.from_numpy(idx).to(dev)].contiguous()
+    if world == 1:
+        return mine.cpu().numpy()
+    counts = torch.tensor([s], dtype=torch.int64, device=dev)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts)
+    g = gather_rows_to_rank0(mine, [int(c.item()) for c in all_counts])
+    return g.cpu().numpy() if g is not None else None
+
+
+def _reseed_empty(R, C, buf, K, rs: np.random.RandomState, dev):
+    """Empty clusters (count 0 after the all-reduce, so every rank sees the same set) are re-seeded from rows of rank
+    0's shard chosen with the trainer's RandomState, then broadcast: sklearn relocates empty / low-count centres too
+    (MiniBatchKMeans reassignment_ratio, pq.py:559-560); leaving them in place wastes codes for good."""
+    w = C.shape[1]
+    empty = torch.nonzero(buf[K * w :] <= 0).squeeze(1)
+    if empty.numel() == 0:
+        return 0
+    rank, _ = rank_world()
+    if rank == 0:
+        n = R.shape[0]
+        pick = rs.choice(n, size=int(empty.numel()), replace=n < int(empty.numel()))
+        C[empty] = R[torch.from_numpy(np.asarray(pick, dtype=np.int64)).to(dev)]
+    if dist_on():
+        dist.broadcast(C, 0)
+    return int(empty.numel())
+
+
+def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev, check_every=5):
+    """One k-means problem on the local rows R [n, w] (all ranks in lockstep): k-means++ seeds from a sample of all
+    shards, `iters` Lloyd iterations with ONE all-reduce of the fused sums|counts buffer each, then the labels under
+    the FINAL centroids written to `col` (stride `stride`), like sklearn's fit_predict.  Convergence (relative inertia
+    decrease <= tol) and empty clusters are looked at every `check_every` iterations only: that is the one point where
+    the host waits for the device (an all-reduce of the inertia scalar + `.item()`).
     Returns (centroids [K, w] on the device, iterations run); `inertia` holds the global final inertia."""
     rank, _ = rank_world()
     n, w = R.shape
     C = torch.empty((K, w), dtype=torch.float32, device=dev)
+    sample = _init_sample(R, init_sample, rs, dev)
     if rank == 0:
-        s = min(init_sample, n)
-        idx = np.sort(rs.choice(n, size=s, replace=False)) if s < n else np.arange(n)
-        sample = R[torch.from_numpy(idx).to(dev)].cpu().numpy()
         C.copy_(torch.from_numpy(kmeanspp_init(sample, K, rs)).to(dev))
     if dist_on():
         dist.broadcast(C, 0)
@@ -79,16 +118,21 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
         be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
         if dist_on():
             dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-            dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
         be.kmeans_update(buf, C, n_empty)
         n_it = it + 1
-        cur = float(inertia.item())
-        if prev - cur <= tol * max(cur, 1e-30):
-            break
-        prev = cur
+        if n_it % check_every == 0 or n_it == iters:
+            if dist_on():
+                dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+            cur = float(inertia.item())  # the host waits for the device here (and only here)
+            reseeded = _reseed_empty(R, C, buf, K, rs, dev) if int(n_empty.item()) > 0 and n_it < iters else 0
+            if not reseeded and prev - cur <= tol * max(cur, 1e-30):
+                break
+            prev = cur
     be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
     if dist_on():
         dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+    if hasattr(be, "check"):
+        be.check()
     return C, n_it
 
 
