@@ -199,27 +199,54 @@ __device__ __noinline__ int4 refine_rows6(const float* __restrict__ X, const flo
         float rb = CUDART_INF_F, vb = CUDART_INF_F, v1 = CUDART_INF_F, v2 = CUDART_INF_F;
         int rbi = 0;
         while (cm != 0u) {
-          const int k = __ffs(cm) - 1;
+          // two candidates per round: the row and both centroid rows are requested in ONE batch of independent loads
+          // (18 x 16 B per lane), so a round exposes one memory latency, not one per 128 columns
+          const int ka = __ffs(cm) - 1;
           cm &= cm - 1;
-          const float* cr = cb + (size_t)(j * K + k) * d;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 6
-          for (int i = lane * 4; i < d; i += 128) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(xr + i));
-            const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + i));
-            acc.x = fmaf(xv.x, cv.x, acc.x);
-            acc.y = fmaf(xv.y, cv.y, acc.y);
-            acc.z = fmaf(xv.z, cv.z, acc.z);
-            acc.w = fmaf(xv.w, cv.w, acc.w);
-          }
-          float sdot = (acc.x + acc.y) + (acc.z + acc.w);
+          const bool two = cm != 0u;
+          const int kb = two ? __ffs(cm) - 1 : ka;
+          cm &= cm - 1;  // (0 & ... stays 0)
+          const float* ca = cb + (size_t)(j * K + ka) * d;
+          const float* cbp = cb + (size_t)(j * K + kb) * d;
+          float4 aa = make_float4(0.f, 0.f, 0.f, 0.f), ab = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int b0 = lane * 4; b0 < d; b0 += 768) {
+            float4 xv[6], va[6], vb4[6];
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(MEVI_FULL_MASK, sdot, o);
-          const float dr = fmaf(sdot, mf, base_of(k));
-          const float v = fmaf(nxn, sE1[j * K + k], dr);
-          if (dr < rb) { rb = dr; rbi = k; vb = v; }  // ascending k, strict: lowest index among equals
-          v2 = fminf(v2, fmaxf(v1, v));
-          v1 = fminf(v1, v);
+            for (int t = 0; t < 6; ++t) {
+              const int idx = b0 + t * 128;
+              const bool in = idx < d;
+              xv[t] = in ? __ldg(reinterpret_cast<const float4*>(xr + idx)) : z;
+              va[t] = in ? __ldg(reinterpret_cast<const float4*>(ca + idx)) : z;
+              vb4[t] = (in && two) ? __ldg(reinterpret_cast<const float4*>(cbp + idx)) : z;
+            }
+#pragma unroll
+            for (int t = 0; t < 6; ++t) {
+              aa.x = fmaf(xv[t].x, va[t].x, aa.x);
+              aa.y = fmaf(xv[t].y, va[t].y, aa.y);
+              aa.z = fmaf(xv[t].z, va[t].z, aa.z);
+              aa.w = fmaf(xv[t].w, va[t].w, aa.w);
+              ab.x = fmaf(xv[t].x, vb4[t].x, ab.x);
+              ab.y = fmaf(xv[t].y, vb4[t].y, ab.y);
+              ab.z = fmaf(xv[t].z, vb4[t].z, ab.z);
+              ab.w = fmaf(xv[t].w, vb4[t].w, ab.w);
+            }
+          }
+          float sa = (aa.x + aa.y) + (aa.z + aa.w), sb = (ab.x + ab.y) + (ab.z + ab.w);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sa += __shfl_xor_sync(MEVI_FULL_MASK, sa, o);
+            sb += __shfl_xor_sync(MEVI_FULL_MASK, sb, o);
+          }
+          auto take = [&](int k, float sdot) {
+            const float dr = fmaf(sdot, mf, base_of(k));
+            const float v = fmaf(nxn, sE1[j * K + k], dr);
+            if (dr < rb) { rb = dr; rbi = k; vb = v; }  // ascending k, strict: lowest index among equals
+            v2 = fminf(v2, fmaxf(v1, v));
+            v1 = fminf(v1, v);
+          };
+          take(ka, sa);
+          if (two) take(kb, sb);
         }
         resolved = ((vb == v1) ? v2 : v1) > rb + xn * sE1[j * K + rbi] + sLvl[j * 4 + 1];
         best = rbi;
