@@ -12,11 +12,20 @@ collective (weak scaling: every rank owns one MSMARCO-shape block).
 The JSON line also carries `roofline` (dominant kernel vs measured HBM peak), `e2e` (same metric
 through the reference-shaped Python entry point with HOST buffers, copies inside the timed region),
 `cpu_baseline` (the reference's CPU arithmetic, oracle port, bounded sample), `clocks`, `gpu_launches`
-and `extra` — the other BASELINE configs, each with its own roofline: `rerank` (streaming kernel) and
-`rerank_grouped` (leaf-grouped tensor GEMMs, with parity against the streaming kernel), `kmeans_iteration`
-(whole iteration + per-kernel), `flat_ip` (with parity against the fp32 kernel), `widened_rows` (PQ encode,
-device beam search, inverted lists, leaf-order permutation).  At N > 1 the re-rank and flat extras are
-doc-sharded: all-gather of per-shard top-k + merge inside their timed regions.
+and, as its LAST key, `summary`: one compact entry per BASELINE config with ms / value / roofline fraction,
+measured in the same run (verbose details go to stderr and gpurun_out/bench_details.json):
+  enc_strong    ONE 8,841,823-row corpus split over the N ranks by the pq.py:218-225 rule (strong scaling)
+  train         full train_rq_lloyd on that sharded corpus: 4 levels x 25 Lloyd iterations, one all-reduce each
+  km_it         one k-means iteration on the rank's shard: assign + accumulate kernels, all-reduce timed alone (ar_ms)
+  rr_stream / rr_group   cluster-restricted re-rank, 6,980 queries x 100 leaves -> top-100 over the sharded corpus
+                (all-gather + merge inside the timed region at N > 1, timed alone as ag_ms); frac_img = reuse-aware
+                roofline (fp16 tile image bytes / time / HBM peak), frac_nr = no-reuse byte count of SURVEY 8d
+  rr_clust      the same on the clustered corpus of SURVEY 8d (4,096-Gaussian mixture, sigma 0.3, seed 99)
+  enc_nq / flat_nq       NQ shape (21,015,324 x 768 over the N ranks): encode, exact flat IP top-100 of 3,610 queries
+  flat          exact flat IP top-100, 6,980 queries x the sharded MSMARCO-shape corpus
+  wid           SURVEY 8f rows (PQ encode, beam search, inverted lists)
+  cpu           reference CPU legs on the host cores (bounded samples), N = 1 only
+  dist_check    N > 1: sharded flat / re-rank / training results equal the single-GPU ones on a small problem
 """
 from __future__ import annotations
 
@@ -34,6 +43,7 @@ sys.path.insert(0, ROOT)
 
 N_MARCO, D, M_LEVELS, K_CENTS = 8841823, 768, 4, 32
 NQ_MARCO, TOPK, LEAVES = 6980, 100, 100
+N_NQ, NQ_NQ = 21015324, 3610  # NQ-DPR corpus (dataprocess/NQ_dpr/get_inverse_answers.py:17), NQ-test queries
 GOLDEN_CB = os.path.join(ROOT, "tests", "golden", "gauss768", "codebook.pt")
 
 
@@ -130,7 +140,8 @@ def load_codebook():
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation of the path (torch CPU ops of pq.py:281-305, batch 128
     as main_models.py:3208) on the host cores — the oracle port, since the reference is Python and
-    /root/reference does not exist on the GPU box."""
+    /root/reference does not exist on the GPU box.  Each step encodes a bounded sample of the workload:
+    up to --ref-sample rows (default 1,048,576), shrunk so that the whole run stays within ~2.5 minutes."""
     if rank != 0:
         return
     import numpy as np
@@ -140,11 +151,15 @@ def reference_arm(args, rank, world):
 
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference uses every core
     torch.manual_seed(1234)
-    S = args.ref_sample
-    X = torch.randn(S, D).numpy()
     cb = load_codebook()
+    probe = torch.randn(32768, D).numpy()
     for _ in range(max(args.warmup, 1)):
-        oracle.rq_encode(X[: min(S, 8192)], cb, batch_size=128)
+        oracle.rq_encode(probe[:8192], cb, batch_size=128)
+    t0 = time.perf_counter()
+    oracle.rq_encode(probe, cb, batch_size=128)
+    rate = len(probe) / (time.perf_counter() - t0)
+    S = int(min(args.ref_sample, max(65536, rate * 150.0 / max(args.steps, 1))))
+    X = torch.randn(S, D).numpy()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         codes = oracle.rq_encode(X, cb, batch_size=128)
@@ -165,6 +180,18 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def r3(x):
+    """3-4 significant digits for the compact summary."""
+    if x is None:
+        return None
+    x = float(x)
+    if x == 0 or x != x:
+        return x
+    from math import floor, log10
+
+    return round(x, max(0, 3 - int(floor(log10(abs(x))))))
+
+
 # --------------------------------------------------------------------------- #
 def our_arm(args, rank, local_rank, world):
     import numpy as np
@@ -172,6 +199,7 @@ def our_arm(args, rank, local_rank, world):
     import torch.distributed as dist
 
     import mevi_b200
+    from mevi_b200.dist_utils import all_gather_stack, shard_bounds
     from mevi_b200.pq import ProductQuantization
 
     torch.cuda.set_device(local_rank)
@@ -213,6 +241,7 @@ def our_arm(args, rank, local_rank, world):
     stop.record()
     barrier()
     t_wall1 = time.time()
+    ctx.check()
     launches = ctx.launches - l0
     ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -223,12 +252,14 @@ def our_arm(args, rank, local_rank, world):
     value = world * n / (ms_step / 1e3)
     _, stats = ctx.rq_encode(X[: min(n, 1 << 20)], cb, mode=args.mode, return_stats=True)
     flagged_frac = float(stats[0].item()) / max(1, int(stats[1].item()))
+    refined_frac = float(stats[2].item()) / max(1, int(stats[1].item()))
     checksum = int(codes.to(torch.int64).sum().item())
 
     # kernel-vs-kernel agreement of the fast path with the exact path on a sample (both product kernels)
-    ns = min(n, 1 << 18)
-    exact = ctx.rq_encode(X[:ns], cb, mode="exact")
-    mismatch = int((exact != codes[:ns]).any(dim=1).sum().item())
+    ns_chk = min(n, 1 << 18)
+    exact = ctx.rq_encode(X[:ns_chk], cb, mode="exact")
+    mismatch = int((exact != codes[:ns_chk]).any(dim=1).sum().item())
+    del exact
 
     algo_bytes = n * D * 4 + n * M_LEVELS * 4
     achieved = algo_bytes / (ms_step / 1e3) / 1e9
@@ -284,15 +315,42 @@ def our_arm(args, rank, local_rank, world):
            "codes_equal_device_path": e2e_ok}
     del Xh, Xh_np, cluster
 
-    extra = {}
+    # host sample for the CPU legs (taken before the corpus is reused by the other configs)
+    cpu_sample_path = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_sample_path = save_cpu_sample(X, codes)
+
+    summary, details = {}, {}
+    summary["n"] = world
+    summary["enc"] = {"ms": r3(ms_step), "frac": r3(achieved / hbm_peak)}
+    details["enc"] = {"flagged_fraction": flagged_frac, "refined_fraction": refined_frac}
     if not args.no_extras:
-        extra = run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak)
+        if world > 1:
+            try:
+                summary["dist_check"] = dist_check(ctx, dev, rank, world)
+            except Exception as e:
+                summary["dist_check"] = "error: " + repr(e)[:100]
+        run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, summary, details)
+        del X, codes
+        torch.cuda.empty_cache()
+        if not args.no_nq:
+            run_nq(args, ctx, cb, dev, rank, world, hbm_peak, bf16_peak, summary, details)
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_leg(X, cb_cpu)
+    if cpu_sample_path is not None:
+        legs = cpu_legs(cpu_sample_path)
+        cpu_baseline = legs.pop("encode", None)
+        summary["cpu"] = legs.get("summary", {"error": legs.get("error")})
+        details["cpu_legs"] = legs
 
     if rank == 0:
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"bench_details_n{world}.json"), "w") as fw:
+                json.dump(details, fw, indent=1)
+        except Exception:
+            pass
+        log("details: " + json.dumps(details))
         line = {
             "metric": "rq_encode_docs_per_sec", "value": value, "unit": "docs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,7 +362,8 @@ def our_arm(args, rank, local_rank, world):
                        "timing": "CUDA events on the launch stream, max over ranks"},
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline, "clocks": clocks, "gpu_launches": launches,
             "codes_checksum": checksum, "prefilter_flagged_fraction": flagged_frac,
-            "fast_vs_exact_kernel_mismatch_rows": {"rows": ns, "mismatch": mismatch}, "extra": extra,
+            "fast_vs_exact_kernel_mismatch_rows": {"rows": ns_chk, "mismatch": mismatch},
+            "summary": summary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -312,22 +371,27 @@ def our_arm(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def cpu_baseline_leg(X, cb_cpu):
-    """Reference CPU arithmetic (oracle port of pq.py:281-305, batch 128) on a bounded sample of the
-    same corpus (~10-30 s of CPU work).  Runs in a CHILD process that never initialises CUDA: inside a
-    CUDA process every munmap of the 12.6 MB torch temporaries goes through the UVM notifier and the
-    CPU path runs ~10x slower than the reference would on its own."""
+# --------------------------------------------------------------------------- #
+def save_cpu_sample(X, codes):
+    """First rows of the bench corpus + their codes -> /dev/shm for the CUDA-free child process."""
     import tempfile
 
     import numpy as np
 
-    S = int(min(1 << 18, X.shape[0]))
+    S = int(min(1 << 19, X.shape[0]))
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    path = os.path.join(shm, f"mevi_bench_sample_{os.getpid()}.npy")
-    np.save(path, X[:S].cpu().numpy())
+    path = os.path.join(shm, f"mevi_bench_sample_{os.getpid()}.npz")
+    np.savez(path, X=X[:S].cpu().numpy(), codes=codes[:S].cpu().numpy())
+    return path
+
+
+def cpu_legs(path):
+    """Reference CPU arithmetic on bounded samples of the same workloads, in a CHILD process that never
+    initialises CUDA: inside a CUDA process every munmap of the 12.6 MB torch temporaries goes through the
+    UVM notifier and the CPU path runs ~10x slower than the reference would on its own."""
     try:
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-baseline-child", "--sample-file", path],
-                             capture_output=True, text=True, timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+                             capture_output=True, text=True, timeout=900, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
         line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
         return json.loads(line)
     except Exception as e:
@@ -340,44 +404,356 @@ def cpu_baseline_leg(X, cb_cpu):
 
 
 def cpu_baseline_child(args):
+    """BASELINE.md section 4 on the host cores (oracle = the reference's arithmetic; the only place bench.py runs it):
+    B2 encode (pq.py:281-305, batch 128), B1/B3 one level of the reference build (sklearn MiniBatchKMeans with the
+    reference's hyper-parameters, pq.py:551-598) on 100k rows, B4 the re-rank loop (main_models.py:3915-4014) and
+    B5 flat IP (faiss IndexFlatIP semantics in numpy), each on a bounded sample."""
     import numpy as np
     import torch
 
     from oracle import oracle
 
     torch.set_num_threads(os.cpu_count() or 1)
-    sample = np.load(args.sample_file)
+    z = np.load(args.sample_file)
+    X, codes = z["X"], z["codes"]
     cb_cpu = load_codebook()
+    cores = torch.get_num_threads()
+    out = {}
+    # ---- B2: encode
+    sample = X[: 1 << 18]
     oracle.rq_encode(sample[:8192], cb_cpu, batch_size=128)  # warm-up (allocator, threads)
     t0 = time.perf_counter()
     oracle.rq_encode(sample[:32768], cb_cpu, batch_size=128)
     rate = 32768 / (time.perf_counter() - t0)
-    reps = int(max(1, min(64, round(rate * 15.0 / len(sample)))))
+    reps = int(max(1, min(64, round(rate * 12.0 / len(sample)))))
     t0 = time.perf_counter()
     for _ in range(reps):
         oracle.rq_encode(sample, cb_cpu, batch_size=128)
     dt = time.perf_counter() - t0
-    print(json.dumps({"value": len(sample) * reps / dt, "unit": "docs/s", "cores": torch.get_num_threads(), "kind": "port",
-                      "sample": f"first {len(sample)} rows of the bench corpus x {reps} passes, torch CPU restatement of "
-                                f"pq.py:281-305 (batch 128) in a CUDA-free child process, {dt:.1f} s",
-                      "host_cpus": os.cpu_count()}), flush=True)
+    out["encode"] = {"value": len(sample) * reps / dt, "unit": "docs/s", "cores": cores, "kind": "port",
+                     "sample": f"first {len(sample)} rows of the bench corpus x {reps} passes, torch CPU restatement of "
+                               f"pq.py:281-305 (batch 128) in a CUDA-free child process, {dt:.1f} s",
+                     "host_cpus": os.cpu_count()}
+    summ = {"cores": cores, "enc_docs_s": r3(out["encode"]["value"])}
+    # ---- B1/B3: one level of the reference build on 100k x 768
+    try:
+        t0 = time.perf_counter()
+        oracle.rq_build_reference(X[:100000], M_LEVELS, K_CENTS, 41, levels=1)
+        dt = time.perf_counter() - t0
+        out["build"] = {"seconds_per_level": dt, "rows": 100000, "levels_timed": 1, "kind": "port",
+                        "note": "sklearn MiniBatchKMeans(n_init=100, batch 1000, max_iter 300), pq.py:557-563; the reference "
+                                "runs 4 such levels on rank 0, cost almost independent of N"}
+        summ["build_s_lvl"] = r3(dt)
+    except Exception as e:
+        out["build"] = {"error": repr(e)[:200]}
+    # ---- B4: re-rank loop on the sample corpus (queries x 100 leaves)
+    try:
+        clus, _ = oracle.document_cluster(codes)
+        rs = np.random.RandomState(4321)
+        nq = 24
+        Q = rs.standard_normal((nq, D)).astype(np.float32)
+        dec, _ = oracle.beam_search(torch.as_tensor(cb_cpu), torch.from_numpy(Q), LEAVES)
+        oracle.cluster_rerank(Q[:2], X, clus, dec[:2].numpy(), topk=TOPK)
+        t0 = time.perf_counter()
+        res = oracle.cluster_rerank(Q, X, clus, dec.numpy(), topk=TOPK)
+        dt = time.perf_counter() - t0
+        ncand = float(np.mean([r[2] for r in res]))
+        out["rerank"] = {"queries_per_sec": nq / dt, "candidates_per_sec": nq * ncand / dt, "corpus_rows": int(len(X)),
+                         "candidates_mean": ncand, "queries": nq, "kind": "port",
+                         "note": "main_models.py:3915-4014 restated (dict lookup, row gather, q.P^T in 1024-row chunks, "
+                                 "descending sort); candidate counts scale with the corpus, compare candidates/s"}
+        summ["rr_cand_s"] = r3(nq * ncand / dt)
+    except Exception as e:
+        out["rerank"] = {"error": repr(e)[:200]}
+    # ---- B5: flat IP
+    try:
+        rs = np.random.RandomState(4321)
+        nq = 256
+        Q = rs.standard_normal((nq, D)).astype(np.float32)
+        oracle.flat_ip_topk_partition(Q[:8], X[:65536], TOPK)
+        t0 = time.perf_counter()
+        oracle.flat_ip_topk_partition(Q, X, TOPK)
+        dt = time.perf_counter() - t0
+        out["flat_ip"] = {"pairs_per_sec": nq * len(X) / dt, "tflops": 2.0 * nq * len(X) * D / dt / 1e12, "queries": nq,
+                          "corpus_rows": int(len(X)), "kind": "port",
+                          "note": "numpy sgemm blocks + argpartition top-k (faiss IndexFlatIP semantics, BASELINE.md B5; faiss is not installable here)"}
+        summ["flat_pairs_s"] = r3(nq * len(X) / dt)
+    except Exception as e:
+        out["flat_ip"] = {"error": repr(e)[:200]}
+    out["summary"] = summ
+    print(json.dumps(out), flush=True)
 
 
-def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
-    """The other BASELINE.json configs, each one short: (iv) cluster-restricted re-rank of 6,980
-    queries x 100 leaves -> top-100; (iii) one k-means iteration with the sums|counts all-reduce;
-    (v) exact flat inner-product top-100 on a bounded shard."""
+# --------------------------------------------------------------------------- #
+def run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, summary, details):
+    """The other BASELINE.json configs on the stated shapes (see the module docstring).  Every leg is wrapped: a
+    failure becomes an `error` entry, never a lost headline line."""
+    import numpy as np
     import torch
     import torch.distributed as dist
 
+    from mevi_b200.dist_utils import all_gather_stack, shard_bounds
     from mevi_b200.pq import ProductQuantization
-    from mevi_b200.rerank import ClusterIndex
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+    from mevi_b200.trainer import train_rq_lloyd
 
-    n = X.shape[0]
-    out = {}
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
 
-    def timed(fn, reps):
-        fn()
+    def timed(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def leg(name):
+        def deco(fn):
+            try:
+                t0 = time.time()
+                fn()
+                log(f"[rank {rank}] leg {name}: {time.time() - t0:.1f} s")
+            except Exception as e:  # a leg must never kill the headline line
+                import traceback
+
+                summary[name] = {"error": repr(e)[:160]}
+                details[name] = {"error": traceback.format_exc()[-1500:]}
+                torch.cuda.synchronize()
+            return fn
+        return deco
+
+    # ---- the strong-scaling shard: ONE 8,841,823-row corpus over the N ranks (pq.py:218-225) -----------------
+    s0, s1 = shard_bounds(N_MARCO if args.docs == N_MARCO else args.docs, rank, world)
+    ns = s1 - s0
+    n_total = N_MARCO if args.docs == N_MARCO else args.docs
+    Xs, codes_s = X[:ns], codes[:ns]
+    shard_bytes = ns * D * 4
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)
+    Q = torch.empty((NQ_MARCO, D), device=dev).normal_(generator=g)
+    state = {}
+
+    @leg("enc_strong")
+    def _():
+        ms = timed(lambda: ctx.rq_encode(Xs, cb, metric="l2", mode=args.mode, codes=codes_s), max(3, min(args.steps, 10)))
+        summary["enc_strong"] = {"ms": r3(ms), "docs_s": r3(n_total / (ms / 1e3)), "frac": r3((shard_bytes + ns * 16) / (ms / 1e3) / 1e9 / hbm_peak)}
+        details["enc_strong"] = {"rows_total": n_total, "rows_this_rank": ns}
+
+    # collectives, timed alone (SURVEY 8d "Collectives")
+    ar_ms = ag_ms = None
+    if world > 1:
+        buf = torch.zeros(K_CENTS * D + K_CENTS, device=dev)
+        ar_ms = timed(lambda: dist.all_reduce(buf), 50, warm=5)
+        sc0 = torch.zeros((NQ_MARCO, TOPK), device=dev)
+        id0 = torch.zeros((NQ_MARCO, TOPK), dtype=torch.int64, device=dev)
+        ag_ms = timed(lambda: (all_gather_stack(sc0), all_gather_stack(id0)), 20, warm=3)
+        mg_ms = timed(lambda: ctx.topk_merge(all_gather_stack(sc0).contiguous(), all_gather_stack(id0).contiguous()), 10, warm=2)
+        details["collectives"] = {"allreduce_98KB_ms": ar_ms, "allgather_topk_ms": ag_ms, "allgather_plus_merge_ms": mg_ms}
+
+    @leg("km_it")
+    def _():
+        C = cb[0].clone()
+        buf = torch.empty(K_CENTS * D + K_CENTS, device=dev)
+        assign = torch.empty(ns, dtype=torch.int32, device=dev)
+
+        def km():
+            ctx.kmeans_step(Xs, C, buf, assign=assign, mode=args.mode)
+            if world > 1:
+                dist.all_reduce(buf)
+            ctx.kmeans_update(buf, C)
+
+        ms = timed(km, 5)
+        a2 = assign.view(ns, 1)
+        ms_assign = timed(lambda: ctx.rq_encode(Xs, C[None], metric="l2", mode=args.mode, codes=a2), 5)
+        ms_accum = timed(lambda: ctx.accumulate_by_code(Xs, assign, K_CENTS, buf), 5)
+        fr = lambda m: (shard_bytes + ns * 4) / (m / 1e3) / 1e9 / hbm_peak
+        summary["km_it"] = {"ms": r3(ms), "frac": r3(shard_bytes / (ms / 1e3) / 1e9 / hbm_peak), "assign_ms": r3(ms_assign),
+                            "accum_ms": r3(ms_accum), "ar_ms": r3(ar_ms)}
+        details["km_it"] = {"assign_frac": fr(ms_assign), "accum_frac": fr(ms_accum), "rows_total": n_total,
+                            "note": "frac = ONE pass over the shard / iteration time; the iteration makes two passes"}
+
+    @leg("train")
+    def _():
+        sync_all()
+        t0 = time.perf_counter()
+        cbt, _ = train_rq_lloyd(Xs, M=M_LEVELS, K=K_CENTS, seed=41, iters=25, tol=None, mode=args.mode, device_index=dev.index,
+                                presharded=True)
+        sync_all()
+        dt = time.perf_counter() - t0
+        info = train_rq_lloyd.last_info
+        iters = sum(l["iters"] for l in info["levels"])
+        loop = sum(l["loop_ms_per_iter"] * l["iters"] for l in info["levels"]) / iters
+        summary["train"] = {"s": r3(dt), "iters": iters, "loop_ms_per_it": r3(loop), "mse": r3(info["levels"][-1]["mse"])}
+        details["train"] = info
+        del cbt
+
+    @leg("rr")
+    def _():
+        pq = ProductQuantization("rq", M_LEVELS, 5, "l2", D, "kmeans", "grad")
+        with torch.no_grad():
+            pq.codebook.copy_(cb.cpu())
+        ctx.rq_encode(Xs, cb, metric="l2", mode=args.mode, codes=codes_s)
+        dec = torch.cat([pq.beam_search(Q[a : a + 1024], LEAVES) for a in range(0, NQ_MARCO, 1024)])
+        index = ClusterIndex.from_codes(codes_s, K_CENTS, id_base=s0, device_index=dev.index)
+        ql = index.lookup(dec)
+        D_leaf = ctx.gather_rows(Xs, index.leaf_docids)
+        res = {}
+
+        def rr():
+            sc, ids, nc = ctx.cluster_rerank(Q, D_leaf, index.leaf_offsets, index.leaf_docids, ql, TOPK, id_base=s0, leaf_ordered=True)
+            if world > 1:
+                sc, ids = ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
+            res["out"] = (sc, ids, nc)
+
+        ms = timed(rr, 2)
+        ncand = res["out"][2].to(torch.float64)
+        if world > 1:
+            dist.all_reduce(ncand)
+        cand_total = float(ncand.sum().item())
+        gathered_local = float(res["out"][2].to(torch.float64).sum().item()) * D * 4
+        summary["rr_stream"] = {"ms": r3(ms), "qps": r3(NQ_MARCO / (ms / 1e3)), "frac": r3(gathered_local / (ms / 1e3) / 1e9 / hbm_peak),
+                                "cand_mean": r3(cand_total / NQ_MARCO), "ag_ms": r3(ag_ms)}
+        details["rr_stream"] = {"cand_max": float(ncand.max().item()), "empty_leaf_fraction": float((ql < 0).float().mean().item()),
+                                "n_leaves_this_rank": index.n_leaves, "rows_total": n_total}
+        # independent check of the streaming kernel: fp32 matmul (TF32 off) + topk over the candidate rows of 4 queries
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            sc_k, id_k, _ = ctx.cluster_rerank(Q, D_leaf, index.leaf_offsets, index.leaf_docids, ql, TOPK, id_base=s0, leaf_ordered=True)
+            worst = 0.0
+            for qi in (0, 1, NQ_MARCO // 2, NQ_MARCO - 1):
+                lv = ql[qi][ql[qi] >= 0].long()
+                rows = torch.cat([torch.arange(int(index.leaf_offsets[l]), int(index.leaf_offsets[l + 1]), device=dev) for l in lv.tolist()])
+                sref = torch.topk(D_leaf[rows] @ Q[qi], min(TOPK, rows.numel())).values
+                worst = max(worst, float(((sc_k[qi, : sref.numel()] - sref).abs() / sref.abs().clamp_min(1e-6)).max().item()))
+            summary["rr_stream"]["chk_rel"] = r3(worst)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        # ---- leaf-grouped GEMM formulation (K3g): every leaf read once for all the queries that chose it
+        t0 = time.perf_counter()
+        rrg = ClusterReranker(None, index, mode="grouped", D_leaf=D_leaf)
+        torch.cuda.synchronize()
+        t_img = time.perf_counter() - t0
+        gres = {}
+
+        def rg():
+            gres["out"] = rrg.rerank(Q, dec, topk=TOPK)  # includes the all-gather + merge when torch.distributed is up
+
+        ms_g = timed(rg, 3)
+        sg, ig, _ = gres["out"]
+        ss, is_, _ = res["out"]
+        fin = torch.isfinite(sg) & torch.isfinite(ss)
+        img_bytes = float(rrg._grouped["img"].numel()) if rrg._grouped is not None else 0.0
+        summary["rr_group"] = {"ms": r3(ms_g), "qps": r3(NQ_MARCO / (ms_g / 1e3)), "path": rrg.last_path,
+                               "frac_img": r3(img_bytes / (ms_g / 1e3) / 1e9 / hbm_peak),
+                               "frac_nr": r3(gathered_local / (ms_g / 1e3) / 1e9 / hbm_peak),
+                               "ids_eq": r3(float((ig == is_).float().mean().item()))}
+        details["rr_group"] = {"max_abs_score_diff_vs_stream": float((sg - ss)[fin].abs().max().item()) if bool(fin.any()) else 0.0,
+                               "tile_image_build_s": t_img, "tile_image_bytes": img_bytes}
+        del rrg, D_leaf, index, ql, dec
+
+    @leg("flat")
+    def _():
+        def fl():
+            sc, ids = ctx.flat_ip_topk(Q, Xs[: min(ns, args.flat_docs)], TOPK, id_base=s0, mode=args.mode)
+            if world > 1:  # docs sharded: all-gather of per-shard top-k + merge (faiss_search.search under torch.distributed)
+                ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
+
+        rows = min(ns, args.flat_docs)
+        ms = timed(fl, 2)
+        tf = 2.0 * NQ_MARCO * rows * D / (ms / 1e3) / 1e12
+        nchk = 128
+        s_t, i_t = ctx.flat_ip_topk(Q[:nchk], Xs[:rows], TOPK, mode=args.mode)
+        s_e, i_e = ctx.flat_ip_topk(Q[:nchk], Xs[:rows], TOPK, mode="exact")
+        summary["flat"] = {"ms": r3(ms), "tf": r3(tf), "frac": r3(tf / bf16_peak)}
+        details["flat"] = {"rows_this_rank": rows, "pairs_per_sec": world * NQ_MARCO * rows / (ms / 1e3),
+                           "ids_identical_vs_fp32_kernel": float((i_t == i_e).float().mean().item())}
+
+    @leg("wid")
+    def _():
+        wid = {}
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(77)
+        for Mp, Kp in ((4, 32), (24, 256)):
+            cbp = torch.empty((Mp, Kp, D // Mp), device=dev).normal_(generator=gq)
+            cp = torch.empty((ns, Mp), dtype=torch.int32, device=dev)
+            ms_pq = timed(lambda: ctx.pq_encode(Xs, cbp, metric="l2", codes=cp), 2)
+            wid[f"pq{Mp}x{Kp}"] = r3((shard_bytes + ns * Mp * 4) / (ms_pq / 1e3) / 1e9 / hbm_peak)
+            details.setdefault("wid", {})[f"pq_encode_M{Mp}_K{Kp}_ms"] = ms_pq
+            del cbp, cp
+        ms_beam = timed(lambda: ctx.rq_beam_search(Q, cb, LEAVES, metric="l2", prod=True), 3)
+        wid["beam_ms"] = r3(ms_beam)
+        ms_inv = timed(lambda: ctx.build_inverted_lists(codes_s, K_CENTS), 3)
+        wid["inv_ms"] = r3(ms_inv)
+        summary["wid"] = wid
+
+    # ---- clustered corpus of SURVEY 8d: mixture of 4,096 Gaussians, sigma 0.3, seed 99 (the shard is regenerated in place)
+    @leg("rr_clust")
+    def _():
+        gc = torch.Generator(device=dev)
+        gc.manual_seed(99)
+        centers = torch.empty((4096, D), device=dev).normal_(generator=gc)  # same centres on every rank
+        gl = torch.Generator(device=dev)
+        gl.manual_seed(99 + 1000 * (rank + 1))
+        stepr = 1 << 20
+        for a in range(0, ns, stepr):
+            b = min(a + stepr, ns)
+            lab = torch.randint(0, 4096, (b - a,), device=dev, generator=gl)
+            Xs[a:b].normal_(generator=gl).mul_(0.3).add_(centers[lab])
+        cbc, codes_c = train_rq_lloyd(Xs, M=M_LEVELS, K=K_CENTS, seed=41, iters=10, tol=None, mode=args.mode,
+                                      device_index=dev.index, presharded=True)
+        pq = ProductQuantization("rq", M_LEVELS, 5, "l2", D, "kmeans", "grad")
+        with torch.no_grad():
+            pq.codebook.copy_(cbc.cpu())
+        ctx.rq_encode(Xs, cbc, metric="l2", mode=args.mode, codes=codes_s)
+        dec = torch.cat([pq.beam_search(Q[a : a + 1024], LEAVES) for a in range(0, NQ_MARCO, 1024)])
+        index = ClusterIndex.from_codes(codes_s, K_CENTS, id_base=s0, device_index=dev.index)
+        sizes = (index.leaf_offsets[1:] - index.leaf_offsets[:-1]).to(torch.float64)
+        ql = index.lookup(dec)
+        nc = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.float64, device=dev)).sum(1)
+        if world > 1:
+            dist.all_reduce(nc)
+        D_leaf = ctx.gather_rows(Xs, index.leaf_docids)
+        rrg = ClusterReranker(None, index, mode="grouped", D_leaf=D_leaf)
+        out = {"cand_mean": r3(float(nc.mean().item())), "cand_max": r3(float(nc.max().item())),
+               "empty": r3(float((ql < 0).float().mean().item()))}
+        details["rr_clust"] = {"n_leaves_this_rank": index.n_leaves, "rows_total": n_total, "train": train_rq_lloyd.last_info}
+        # a small call first: if the grouped path cannot establish its guarantee here (near-duplicate documents inside a
+        # mixture component overflow the margin window) it falls back to the streaming kernel; all 6,980 queries then run
+        # only if that stays within a few seconds
+        nq_c = 256
+        rrg.rerank(Q[:nq_c], dec[:nq_c], topk=TOPK)
+        stream_s = float(nc.sum().item()) / world * D * 4 / 5e12
+        if rrg.last_path == "grouped" or stream_s < 3.0:
+            nq_c = NQ_MARCO
+        ms_c = timed(lambda: rrg.rerank(Q[:nq_c], dec[:nq_c], topk=TOPK), 2)
+        out.update({"ms": r3(ms_c), "queries": nq_c, "qps": r3(nq_c / (ms_c / 1e3)), "path": rrg.last_path,
+                    "tf": r3(2.0 * float(nc[:nq_c].sum().item()) * D / world / (ms_c / 1e3) / 1e12)})
+        summary["rr_clust"] = out
+        del rrg, D_leaf, index, ql, dec
+
+    return
+
+
+def run_nq(args, ctx, cb, dev, rank, world, hbm_peak, bf16_peak, summary, details):
+    import torch
+    import torch.distributed as dist
+
+    from mevi_b200.dist_utils import all_gather_stack, shard_bounds
+
+    def timed(fn, reps, warm=1):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -392,194 +768,87 @@ def run_extras(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- (iv) re-rank ---------------------------------------------------------------------
     try:
+        s0, s1 = shard_bounds(N_NQ, rank, world)
+        nn = s1 - s0
+        free = torch.cuda.mem_get_info(dev)[0]
+        need = nn * D * 4 * 1.55 + (6 << 30)  # rows + fp16 image of the flat search + slack
+        if free < need:
+            summary["enc_nq"] = {"error": f"needs {need / 2**30:.0f} GiB, {free / 2**30:.0f} free"}
+            return
+        Xn = make_corpus(nn, D, dev, 777 + rank)
+        cn = torch.empty((nn, M_LEVELS), dtype=torch.int32, device=dev)
+        ms = timed(lambda: ctx.rq_encode(Xn, cb, metric="l2", mode=args.mode, codes=cn), 5)
+        summary["enc_nq"] = {"ms": r3(ms), "frac": r3((nn * D * 4 + nn * 16) / (ms / 1e3) / 1e9 / hbm_peak)}
+        details["enc_nq"] = {"rows_total": N_NQ, "rows_this_rank": nn, "docs_per_sec": N_NQ / (ms / 1e3)}
+        del cn
         g = torch.Generator(device=dev)
-        g.manual_seed(4321)
-        Q = torch.empty((NQ_MARCO, D), device=dev).normal_(generator=g)
-        pq = ProductQuantization("rq", M_LEVELS, 5, "l2", D, "kmeans", "grad")
-        with torch.no_grad():
-            pq.codebook.copy_(cb.cpu())
-        dec = torch.cat([pq.beam_search(Q[a : a + 128], LEAVES) for a in range(0, NQ_MARCO, 128)])
-        t0 = time.perf_counter()
-        index = ClusterIndex.from_codes(codes, K_CENTS, id_base=0, device_index=dev.index)
-        torch.cuda.synchronize()
-        t_index = time.perf_counter() - t0
-        ql = index.lookup(dec)
-        t0 = time.perf_counter()
-        D_leaf = ctx.gather_rows(X, index.leaf_docids)  # one-time permutation into CSR (leaf) order
-        torch.cuda.synchronize()
-        t_perm = time.perf_counter() - t0
-        res = {}
-
-        from mevi_b200.dist_utils import all_gather_stack
-
-        def rr():
-            # documents are sharded: every rank scores the candidates it owns for ALL queries, then the per-shard
-            # top-k lists are all-gathered and merged on every rank (the same sequence as ClusterReranker.rerank)
-            sc, ids, nc = ctx.cluster_rerank(Q, D_leaf, index.leaf_offsets, index.leaf_docids, ql, TOPK, id_base=rank * n,
-                                             leaf_ordered=True)
-            if world > 1:
-                sc, ids = ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
-            res["out"] = (sc, ids, nc)
-
-        ms = timed(rr, 2)
-        ncand = res["out"][2].to(torch.float64)
-        gathered = float(ncand.sum().item()) * D * 4
-        out["rerank"] = {
-            "metric": "rerank_queries_per_sec", "value": NQ_MARCO / (ms / 1e3), "unit": "queries/s",
-            "corpus_docs": world * n, "sharding": f"documents row-sharded over {world} GPU(s); all-gather of [nq,k] (score,id) + merge "
-                                                  "inside the timed region" if world > 1 else "single GPU, no collective",
-            "candidates_scored_per_sec": world * float(ncand.sum().item()) / (ms / 1e3),
-            "ms_per_step": ms, "queries": NQ_MARCO, "leaves_per_query": LEAVES, "topk": TOPK,
-            "candidates_mean": float(ncand.mean().item()), "candidates_max": float(ncand.max().item()),
-            "empty_leaf_fraction": float((ql < 0).float().mean().item()), "n_leaves": index.n_leaves,
-            "index_build_s": t_index, "leaf_order_permutation_s": t_perm, "layout": "documents stored in CSR (leaf) order; leaves streamed with bulk async copies",
-            "roofline": {"bound": "hbm", "achieved": gathered / (ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": gathered / (ms / 1e3) / 1e9 / hbm_peak, "traffic": None,
-                         "note": "bytes = sum_q candidates_q * 4*d, no cross-query reuse assumed"},
-        }
-        # ---- same workload, leaf-grouped GEMM formulation (K3g): every leaf read once for all the queries that chose it
-        try:
-            from mevi_b200.rerank import ClusterReranker
-
-            t0 = time.perf_counter()
-            rrg = ClusterReranker(None, index, mode="grouped", D_leaf=D_leaf)
-            torch.cuda.synchronize()
-            t_img = time.perf_counter() - t0
-            gres = {}
-
-            def rg():
-                gres["out"] = rrg.rerank(Q, dec, topk=TOPK)  # includes the all-gather + merge when torch.distributed is up
-
-            ms_g = timed(rg, 3)
-            sg, ig, _ = gres["out"]
-            ss, is_, _ = res["out"]
-            fin = torch.isfinite(sg) & torch.isfinite(ss)
-            out["rerank_grouped"] = {
-                "metric": "rerank_queries_per_sec", "value": NQ_MARCO / (ms_g / 1e3), "unit": "queries/s", "ms_per_step": ms_g,
-                "path": rrg.last_path, "corpus_docs": world * n, "tile_image_build_s": t_img,
-                "speedup_vs_streaming_kernel": ms / ms_g,
-                "formulation": "per leaf a [docs of the leaf] x [queries that chose it] fp16 tcgen05 GEMM (prefilter with a rigorous "
-                               "margin) + exact fp32 re-score; thresholds bootstrapped from the exact top-k of a 2,048-row prefix; "
-                               "falls back to the streaming kernel when the guarantee cannot be established",
-                "parity_vs_streaming_kernel": None if world > 1 else {
-                    "ids_identical_fraction": float((ig == is_).float().mean().item()),
-                    "max_abs_score_diff": float((sg - ss)[fin].abs().max().item()) if bool(fin.any()) else 0.0,
-                    "note": "ids may differ only where two documents tie in fp32 score"},
-                "roofline": {"bound": "hbm", "achieved": gathered / (ms_g / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": gathered / (ms_g / 1e3) / 1e9 / hbm_peak,
-                             "note": "same no-reuse byte count as the streaming kernel (sum_q candidates_q * 4*d) as the numerator: "
-                                     "> 1 because a leaf's rows are read once for ~30 queries (SURVEY 8d, crossover note)"}}
-            del rrg
-        except Exception as e:
-            out["rerank_grouped"] = {"error": repr(e)[:300]}
-        del index, ql, dec, D_leaf
-    except Exception as e:  # extras must never kill the headline line
-        out["rerank"] = {"error": repr(e)[:300]}
-
-    # ---- (iii) k-means iteration ----------------------------------------------------------
-    try:
-        C = cb[0].clone()
-        buf = torch.empty(K_CENTS * D + K_CENTS, device=dev)
-        assign = torch.empty(n, dtype=torch.int32, device=dev)
-
-        def km():
-            ctx.kmeans_step(X, C, buf, assign=assign, mode=args.mode)
-            if world > 1:
-                dist.all_reduce(buf)
-            ctx.kmeans_update(buf, C)
-
-        ms = timed(km, 3)
-        bytes_ = n * D * 4
-        # the two kernels of an iteration, each against the HBM roofline of ITS pass over the shard
-        a2 = assign.view(n, 1)
-        ms_assign = timed(lambda: ctx.rq_encode(X, C[None], metric="l2", mode=args.mode, codes=a2), 5)
-        ms_accum = timed(lambda: ctx.accumulate_by_code(X, assign, K_CENTS, buf), 5)
-
-        def roof(ms_k, nbytes, note):
-            return {"bound": "hbm", "achieved": nbytes / (ms_k / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": nbytes / (ms_k / 1e3) / 1e9 / hbm_peak, "ms": ms_k, "note": note}
-
-        out["kmeans_iteration"] = {
-            "ms": ms, "docs_per_sec": world * n / (ms / 1e3), "allreduce_bytes": (K_CENTS * D + K_CENTS) * 4,
-            "roofline": roof(ms, bytes_, "whole iteration against ONE pass over the shard (4*d bytes per doc); the iteration "
-                                         "makes two passes (assign, then accumulate), see DESIGN.md for why they are not fused"),
-            "kernels": {"assign (rq_encode, M=1)": roof(ms_assign, bytes_ + n * 4, "reads the shard once, writes int32 assignments"),
-                        "accumulate_by_code": roof(ms_accum, bytes_ + n * 4, "reads the shard and the assignments once; timed as 5 "
-                                                   "back-to-back launches, which runs slower than the same launch inside the "
-                                                   "iteration (iteration ms - assign ms is the in-step cost)")},
-            "accumulate_in_step_ms_estimate": ms - ms_assign}
-        del assign, a2
-    except Exception as e:
-        out["kmeans_iteration"] = {"error": repr(e)[:300]}
-
-    # ---- (v) flat IP on a bounded shard ----------------------------------------------------
-    try:
-        shard = min(n, args.flat_docs)
-        g = torch.Generator(device=dev)
-        g.manual_seed(4321)
-        Q = torch.empty((NQ_MARCO, D), device=dev).normal_(generator=g)
-
-        from mevi_b200.dist_utils import all_gather_stack
+        g.manual_seed(4322)
+        Qn = torch.empty((NQ_NQ, D), device=dev).normal_(generator=g)
+        piece = 1 << 22
 
         def fl():
-            sc, ids = ctx.flat_ip_topk(Q, X[:shard], TOPK, id_base=rank * shard, mode=args.mode)
-            if world > 1:  # docs sharded: all-gather of per-shard top-k + merge (faiss_search.search under torch.distributed)
-                ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
+            run = None
+            for a in range(0, nn, piece):
+                b = min(a + piece, nn)
+                s, i = ctx.flat_ip_topk(Qn, Xn[a:b], TOPK, id_base=s0 + a, mode=args.mode)
+                run = (s, i) if run is None else ctx.topk_merge(torch.stack([run[0], s]), torch.stack([run[1], i]))
+            if world > 1:
+                ctx.topk_merge(all_gather_stack(run[0]).contiguous(), all_gather_stack(run[1]).contiguous())
 
         ms = timed(fl, 2)
-        # parity of the tensor path with the direct fp32 search (both product kernels) on a slice of the queries
-        nchk = 256
-        s_t, i_t = ctx.flat_ip_topk(Q[:nchk], X[:shard], TOPK, mode=args.mode)
-        s_e, i_e = ctx.flat_ip_topk(Q[:nchk], X[:shard], TOPK, mode="exact")
-        parity = {"queries": nchk, "ids_identical_fraction": float((i_t == i_e).float().mean().item()),
-                  "max_rel_score_diff": float(((s_t - s_e).abs() / s_e.abs().clamp_min(1e-6)).max().item()),
-                  "note": "tensor-prefilter path vs fp32 CUDA-core path; ids may differ only at fp32 score ties"}
-        flops = 2.0 * NQ_MARCO * shard * D
-        ach = flops / (ms / 1e3) / 1e12
-        out["flat_ip"] = {"ms": ms, "docs_per_gpu": shard, "corpus_docs": world * shard, "queries": NQ_MARCO, "topk": TOPK,
-                          "queries_per_sec": NQ_MARCO / (ms / 1e3), "pairs_per_sec": world * NQ_MARCO * shard / (ms / 1e3),
-                          "parity_vs_fp32_kernel": parity,
-                          "roofline": {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                                       "frac_of_tf32_equivalent_peak": ach / (bf16_peak / 2.0),
-                                       "note": "FLOPs = 2*nq*N*d (algorithmic); peak = measured 16-bit cuBLAS burst rate (the kernel's MMAs "
-                                               "are fp16 tcgen05, one pass); inputs and results are fp32, for which the dense rate would be "
-                                               "half of that (TF32) - both fractions given; the time is the WHOLE call: fp32->fp16 image "
-                                               "pass, GEMM with prefilter epilogue, compactions, exact fp32 re-score"}}
+        tf = 2.0 * NQ_NQ * nn * D / (ms / 1e3) / 1e12
+        summary["flat_nq"] = {"ms": r3(ms), "qps": r3(NQ_NQ / (ms / 1e3)), "tf": r3(tf), "frac": r3(tf / bf16_peak)}
+        details["flat_nq"] = {"rows_total": N_NQ, "queries": NQ_NQ, "piece_rows": piece}
     except Exception as e:
-        out["flat_ip"] = {"error": repr(e)[:300]}
+        import traceback
 
-    # ---- the callers / modes either side of the path, same measurement bar ------------------
-    try:
-        wid = {}
-        hbm = lambda ms_k, nbytes: {"ms": ms_k, "GB/s": nbytes / (ms_k / 1e3) / 1e9, "frac_of_hbm_peak": nbytes / (ms_k / 1e3) / 1e9 / hbm_peak}
-        # f4: pq/opq encode (pq.py:249-279): M sub-vectors x K centroids, one pass over the shard
-        gq = torch.Generator(device=dev)
-        gq.manual_seed(77)
-        for Mp, Kp in ((4, 32), (24, 256)):
-            cbp = torch.empty((Mp, Kp, D // Mp), device=dev).normal_(generator=gq)
-            cp = torch.empty((n, Mp), dtype=torch.int32, device=dev)
-            ms_pq = timed(lambda: ctx.pq_encode(X, cbp, metric="l2", codes=cp), 3)
-            wid[f"pq_encode_M{Mp}_K{Kp}"] = dict(hbm(ms_pq, n * D * 4 + n * Mp * 4), docs_per_sec=world * n / (ms_pq / 1e3))
-            del cbp, cp
-        # f3: rq beam search on the device (pq.py:613-713), 100 beams per query, all queries in one call
-        gq.manual_seed(4321)
-        Qb = torch.empty((NQ_MARCO, D), device=dev).normal_(generator=gq)
-        ms_beam = timed(lambda: ctx.rq_beam_search(Qb, cb, LEAVES, metric="l2", prod=True), 3)
-        wid["rq_beam_search"] = {"ms": ms_beam, "queries_per_sec": NQ_MARCO / (ms_beam / 1e3), "beams": LEAVES,
-                                 "note": "leaf producer of the re-rank (not in its timed region)"}
-        # f1: inverted lists from codes (pq.py:236-242): sort by leaf key -> CSR + permutation
-        ms_inv = timed(lambda: ctx.build_inverted_lists(codes, K_CENTS), 3)
-        wid["build_inverted_lists"] = {"ms": ms_inv, "docs_per_sec": world * n / (ms_inv / 1e3)}
-        # f1: one-time permutation of the corpus into leaf order (read + write of the shard)
-        docids, _ = ctx.build_inverted_lists(codes, K_CENTS)
-        ms_perm = timed(lambda: ctx.gather_rows(X, docids), 2)
-        wid["leaf_order_permutation"] = hbm(ms_perm, 2 * n * D * 4)
-        out["widened_rows"] = wid
-    except Exception as e:
-        out["widened_rows"] = {"error": repr(e)[:300]}
-    return out
+        summary.setdefault("flat_nq", {"error": repr(e)[:160]})
+        details["nq_error"] = traceback.format_exc()[-1500:]
+
+
+def dist_check(ctx, dev, rank, world):
+    """N > 1: the sharded paths give the single-GPU answers on a small problem (product kernels on both sides)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mevi_b200.dist_utils import all_gather_stack, shard_bounds
+    from mevi_b200.pq import ProductQuantization
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+    from mevi_b200.trainer import train_rq_lloyd
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    n, d = 60001, 768
+    Xall = torch.empty((n, d), device=dev).normal_(generator=g)  # same seed on every rank -> same corpus
+    Qs = torch.empty((64, d), device=dev).normal_(generator=g)
+    s, e = shard_bounds(n, rank, world)
+    # training: every rank ends with the same codebook
+    cbk, codes_l = train_rq_lloyd(Xall[s:e], M=4, K=32, seed=41, iters=5, tol=None, device_index=dev.index, presharded=True)
+    allcb = all_gather_stack(cbk)
+    ok_train = all(bool(torch.equal(allcb[0], allcb[r])) for r in range(world))
+    # flat: sharded + merged == single GPU
+    sc, ids = ctx.flat_ip_topk(Qs, Xall[s:e].contiguous(), 100, id_base=s)
+    sc, ids = ctx.topk_merge(all_gather_stack(sc).contiguous(), all_gather_stack(ids).contiguous())
+    s1, i1 = ctx.flat_ip_topk(Qs, Xall, 100)
+    ok_flat = float((i1 == ids).float().mean().item()) > 0.995 and bool(torch.allclose(s1, sc, rtol=1e-5, atol=2e-4))
+    # re-rank: sharded + merged == single GPU
+    codes_all = ctx.rq_encode(Xall, cbk)
+    pq = ProductQuantization("rq", 4, 5, "l2", d, "kmeans", "grad")
+    with torch.no_grad():
+        pq.codebook.copy_(cbk.cpu())
+    dec = pq.beam_search(Qs, 20)
+    rr = ClusterReranker(Xall[s:e].contiguous(), ClusterIndex.from_codes(codes_all[s:e].contiguous(), 32, id_base=s, device_index=dev.index))
+    sc, ids, nc = rr.rerank(Qs, dec, topk=100)
+    full = ClusterIndex.from_codes(codes_all, 32, device_index=dev.index)
+    s0_, i0_, n0_ = ctx.cluster_rerank(Qs, Xall, full.leaf_offsets, full.leaf_docids, full.lookup(dec), 100)
+    ok_rr = float((i0_ == ids).float().mean().item()) > 0.995 and bool((n0_ == nc).all()) and bool(torch.allclose(s0_, sc, rtol=1e-5, atol=2e-4))
+    flags = torch.tensor([int(ok_train), int(ok_flat), int(ok_rr)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    names = ["train", "flat", "rerank"]
+    bad = [nm for nm, f in zip(names, flags.tolist()) if not f]
+    return "ok" if not bad else "FAILED:" + ",".join(bad)
 
 
 def main():
@@ -591,9 +860,10 @@ def main():
     ap.add_argument("--sample-file", type=str, default=None)
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--docs", type=int, default=N_MARCO, help="rows per GPU (default: MSMARCO 8,841,823)")
-    ap.add_argument("--flat-docs", type=int, default=1 << 22)
-    ap.add_argument("--ref-sample", type=int, default=65536)
+    ap.add_argument("--flat-docs", type=int, default=N_MARCO, help="rows per GPU of the MSMARCO-shape flat search")
+    ap.add_argument("--ref-sample", type=int, default=1 << 20)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-nq", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

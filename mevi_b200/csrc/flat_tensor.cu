@@ -615,6 +615,7 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   int h_flags[4] = {0, 0, 0, 0};
   MEVI_CUDA(ctx, cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
   MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+  if (int drc = mevi_deferred_error(ctx)) return drc;  // a kernel of this (or an earlier asynchronous) launch timed out
   if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "flat tensor kernel pipeline time-out (code %d)", h_flags[1]);
   if (h_flags[0] || h_flags[2]) return MEVI_OK;  // guarantee not established: caller falls back to fp32
   const size_t smem_rescore = (size_t)FT_KEEP * 8;
@@ -895,6 +896,7 @@ extern "C" int mevi_rerank_grouped_image(mevi_ctx* ctx, const float* D_leaf, int
   MEVI_CUDA(ctx, cudaMemcpyAsync(h, absmax2, sizeof(h), cudaMemcpyDeviceToHost, st));
   MEVI_CUDA(ctx, cudaMemcpyAsync(&h_flag, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
   MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+  if (int drc = mevi_deferred_error(ctx)) return drc;  // a kernel of this (or an earlier asynchronous) launch timed out
   float a, m;
   memcpy(&a, &h[0], 4);
   memcpy(&m, &h[2], 4);
@@ -976,6 +978,7 @@ extern "C" int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq,
   int h_flags[4] = {0, 0, 0, 0};
   MEVI_CUDA(ctx, cudaMemcpyAsync(h_flags, s.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
   MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+  if (int drc = mevi_deferred_error(ctx)) return drc;  // a kernel of this (or an earlier asynchronous) launch timed out
   if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "grouped re-rank pipeline time-out (code %d)", h_flags[1]);
   if (h_flags[0] || h_flags[2]) return MEVI_OK;
   const size_t smem_rescore = (size_t)FT_KEEP * 8;

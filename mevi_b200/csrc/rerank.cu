@@ -43,7 +43,17 @@ struct RerankParams {
   float* out_scores; int64_t* out_ids;  // [nq*S, k]
   int32_t* n_candidates;
   int64_t max_rows;  // > 0: only the first max_rows candidate rows of every query (prefix of its leaf list)
+  int* err_flag;     // set when a bounded pipeline wait times out (the top-k lists of that launch are then incomplete)
 };
+
+// after the launch sequence: a time-out must not leave a plausible but truncated result behind
+__global__ void poison_topk_kernel(const int* __restrict__ err, float* __restrict__ scores, int64_t* __restrict__ ids, int64_t total) {
+  if (*err == 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    scores[i] = __int_as_float(0x7fc00000);  // NaN
+    ids[i] = -1;
+  }
+}
 
 __device__ __forceinline__ void compact_buffer(float* s_score, int32_t* s_id, int* s_count, float* s_tau, int k, int cap) {
   __syncthreads();
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(RS_THREADS) rerank_stream_kernel(RerankParams 
           const int nrows = (int)((b - a) < RS_ROWS ? (b - a) : RS_ROWS);
           const int64_t row = s_leafbeg[t] + (a - s_prefix[t]);
           const uint32_t st = g % RS_STAGES, ph = (g / RS_STAGES) & 1;
-          if (!ptx::mbar_wait(&empty_bar[st], ph ^ 1)) { ok = false; break; }
+          if (!ptx::mbar_wait(&empty_bar[st], ph ^ 1)) { atomicExch(p.err_flag, 1); ok = false; break; }
           s_meta_row[st] = (int)row;
           s_meta_n[st] = nrows;
           const uint32_t bytes = (uint32_t)nrows * row_bytes;
@@ -277,9 +287,13 @@ __global__ void __launch_bounds__(RS_THREADS) rerank_stream_kernel(RerankParams 
       }
       // sentinel: tells the consumers the stream has ended
       const uint32_t st = g % RS_STAGES, ph = (g / RS_STAGES) & 1;
-      if (ok && ptx::mbar_wait(&empty_bar[st], ph ^ 1)) {
-        s_meta_n[st] = 0;
-        ptx::mbar_arrive(&full_bar[st]);
+      if (ok) {
+        if (ptx::mbar_wait(&empty_bar[st], ph ^ 1)) {
+          s_meta_n[st] = 0;
+          ptx::mbar_arrive(&full_bar[st]);
+        } else {
+          atomicExch(p.err_flag, 2);
+        }
       }
     }
   } else {
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(RS_THREADS) rerank_stream_kernel(RerankParams 
     uint32_t g = 0;
     for (;; ++g) {
       const uint32_t st = g % RS_STAGES, ph = (g / RS_STAGES) & 1;
-      if (!ptx::mbar_wait(&full_bar[st], ph)) break;
+      if (!ptx::mbar_wait(&full_bar[st], ph)) { atomicExch(p.err_flag, 3); break; }
       const int nrows = s_meta_n[st];
       if (nrows == 0) break;
       if (cw < nrows) {
@@ -495,6 +509,7 @@ static int cluster_rerank_impl(mevi_ctx* ctx, const float* Q, int nq, const floa
   MEVI_REQUIRE(ctx, L >= 1 && L <= 4096, "L must be in [1, 4096] (got %d)", L);
   MEVI_REQUIRE(ctx, n < (int64_t)2147483647, "shard too large for int32 row ids");
   if (nq <= 0) return MEVI_OK;
+  if (int rc = mevi_deferred_error(ctx)) return rc;
   MEVI_REQUIRE(ctx, d_layout == 0 || d_layout == 1, "d_layout must be 0 (document order) or 1 (CSR / leaf order)");
   const int cap = next_pow2(k + 2 * RR_SUPER);
   int S = (4 * ctx->sm_count + nq - 1) / nq;
@@ -508,6 +523,7 @@ static int cluster_rerank_impl(mevi_ctx* ctx, const float* Q, int nq, const floa
   p.query_leaves = query_leaves; p.L = L; p.k = k; p.cap = cap; p.S = S; p.id_base = id_base;
   p.n_candidates = n_candidates;
   p.max_rows = max_rows;
+  p.err_flag = ctx->dev_err + MEVI_ERRSLOT_RERANK;
   if (S == 1) {
     p.out_scores = scores;
     p.out_ids = ids;
@@ -539,9 +555,12 @@ static int cluster_rerank_impl(mevi_ctx* ctx, const float* Q, int nq, const floa
   MEVI_COUNT_LAUNCH(ctx, 1);
   if (S > 1) {
     // lists of one query are contiguous: [q][s][k]  -> shard_stride = k, list_stride = S*k
-    return mevi_topk_merge_launch(ctx, p.out_scores, p.out_ids, S, nq, k, (int64_t)S * k, (int64_t)k, scores, ids, st);
+    int rc = mevi_topk_merge_launch(ctx, p.out_scores, p.out_ids, S, nq, k, (int64_t)S * k, (int64_t)k, scores, ids, st);
+    if (rc != MEVI_OK) return rc;
   }
-  return MEVI_OK;
+  poison_topk_kernel<<<ctx->sm_count, 256, 0, st>>>(p.err_flag, scores, ids, (int64_t)nq * k);
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  return mevi_publish_errors(ctx, st);
 }
 
 int mevi_gather_rows(mevi_ctx* ctx, const float* D, int64_t n, int d, const int32_t* rows, int64_t m, float* out,

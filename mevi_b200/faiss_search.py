@@ -25,6 +25,15 @@ def _is_flat(param: str) -> bool:
     return param.strip().lower() in ("flat", "flatip", "idmap,flat")
 
 
+def _is_approximate(param: str) -> bool:
+    """IVF*/HNSW*/PQ* factory strings: approximate faiss indexes whose result is a SUBSET of the exact one."""
+    p = param.strip().lower()
+    return any(tok.startswith(("ivf", "hnsw", "pq", "opq", "lsh", "imi")) for tok in p.split(","))
+
+
+FAISS_PAD_SCORE = float(np.finfo(np.float32).min)  # faiss pads inner-product results with -3.4028235e38, id -1
+
+
 @torch.no_grad()
 def search(query, doc, dim, topk, param, piece_rows: int = 1 << 21, mode: str = "auto",
            device_index: Optional[int] = None):
@@ -34,8 +43,11 @@ def search(query, doc, dim, topk, param, piece_rows: int = 1 << 21, mode: str = 
     With torch.distributed initialised the documents are row-sharded (pq.py:218-225 rule), each
     rank searches its block and the per-shard lists are all-gathered and merged."""
     if not _is_flat(param):
-        raise NotImplementedError(
-            f"param={param!r}: only the exact 'Flat' index is implemented (approximate HNSW/IVF are out of scope)")
+        if not _is_approximate(param):
+            raise NotImplementedError(f"param={param!r}: not a faiss index string this module understands")
+        # The reference CLI defaults to 'IVF100,Flat' (faiss_search.py:88).  An approximate index returns a subset of
+        # the exact neighbours; the exact search below is always at least as good and on a B200 faster than training one.
+        print(f"Param {param}: approximate faiss indexes are not built here; running the exact 'Flat' search instead.")
     ctx = _lib.get_context(device_index)
     dev = torch.device("cuda", ctx.device)
     print(f"Param {param} trained: True.")
@@ -63,7 +75,9 @@ def search(query, doc, dim, topk, param, piece_rows: int = 1 << 21, mode: str = 
         run_i = torch.full((Q.shape[0], topk), -1, dtype=torch.int64, device=dev)
     if dist_on():
         run_s, run_i = ctx.topk_merge(all_gather_stack(run_s).contiguous(), all_gather_stack(run_i).contiguous())
-    return run_s.cpu().numpy(), run_i.cpu().numpy()
+    dists, indices = run_s.cpu().numpy(), run_i.cpu().numpy()
+    dists[indices < 0] = FAISS_PAD_SCORE  # the library pads with -inf; faiss with the lowest float (to_file prints it)
+    return dists, indices
 
 
 def to_file(query_path, output_path, dists, indices):  # faiss_search.py:71-77

@@ -326,14 +326,26 @@ class ProductQuantization(nn.Module):
             num_beams = num_return_sequences
         if do_sample:
             raise NotImplementedError("do_sample=True (torch.multinomial branch, pq.py:686-688) is out of scope")
-        if self.pq_type == "rq" and doc_emb.is_cuda:
+        if self.pq_type == "rq" and doc_emb.is_cuda and self._beam_kernel_fits(int(num_beams), doc_emb.shape[-1]):
             ctx = _lib.get_context(doc_emb.device)
             cb = self.get_codebook().detach().to(doc_emb.device).contiguous()
             labels, scores = ctx.rq_beam_search(doc_emb.contiguous().float(), cb, int(num_beams), metric=self.dist_mode,
                                                 prod=(self.rq_topk_score == "prod"))
             labels = labels.long()  # pq.py: the int32 seed column is promoted by cat with int64 codes
             return (labels, scores) if return_proba else labels
+        # shapes beyond the kernel's shared-memory state (e.g. 8-bit codebooks with 100 beams: 25,600 candidates per
+        # level) and the pq/opq branch run the reference's tensor-op formulation on the input's device
         return self._beam_search_tensor_ops(doc_emb, num_beams, return_proba)
+
+    def _beam_kernel_fits(self, num_beams: int, d: int) -> bool:
+        """The limits `mevi_rq_beam_search` enforces (csrc/beam.cu): M*K <= 2048, num_beams*K <= 16384 (rounded up to a
+        power of two) and a per-query state below 200 KB of shared memory."""
+        M, K = self.subvector_num, self.subvector_cents
+        cap = 1
+        while cap < num_beams * K:
+            cap <<= 1
+        smem = 8 * (M * K + 2 * num_beams) + 4 * (d + 2 * num_beams + cap) + 4 * (cap + 2 * num_beams * M)
+        return M * K <= 2048 and cap <= 16384 and smem <= 200 * 1024 and float(K) ** M >= num_beams
 
     def _beam_search_tensor_ops(self, doc_emb, num_beams, return_proba):
         """The reference's tensor-op formulation of pq.py:626-713, op for op (bit-identical to the reference on

@@ -24,26 +24,29 @@ from . import _lib
 from .dist_utils import dist_on, gather_rows_to_rank0, rank_world, shard_bounds
 
 
-def kmeanspp_init(sample: np.ndarray, K: int, rs: np.random.RandomState) -> np.ndarray:
-    """k-means++ seeding (D^2 sampling) on a small host sample, float64 arithmetic.
-    The reference seeds with sklearn's init='k-means++' (pq.py:559); this is the
-    textbook algorithm, seeded by `random_state=seed` like the reference."""
-    x = np.asarray(sample, dtype=np.float64)
+def kmeanspp_init(sample, K: int, rs: np.random.RandomState) -> torch.Tensor:
+    """k-means++ seeding (D^2 sampling) on a small sample, float64 arithmetic, on the device the sample lives on
+    (32 passes over a 16,384 x 768 sample are seconds of numpy but milliseconds of device time).  The reference
+    seeds with sklearn's init='k-means++' (pq.py:559); this is the textbook algorithm, with every random number
+    drawn from `rs` (`random_state=seed` like the reference) so the seeds depend only on (seed, sample)."""
+    x = torch.as_tensor(sample).to(torch.float64)
     n = x.shape[0]
-    centers = np.empty((K, x.shape[1]), dtype=np.float64)
+    centers = torch.empty((K, x.shape[1]), dtype=torch.float64, device=x.device)
     first = int(rs.randint(n))
+    u = rs.random_sample(K)  # one uniform per further centre, drawn up front
     centers[0] = x[first]
     d2 = ((x - centers[0]) ** 2).sum(1)
     for k in range(1, K):
-        tot = d2.sum()
+        cum = torch.cumsum(d2, 0)
+        tot = float(cum[-1].item())
         if not np.isfinite(tot) or tot <= 0:
-            idx = int(rs.randint(n))
+            idx = int(u[k] * n) % n
         else:
-            idx = int(np.searchsorted(np.cumsum(d2), rs.random_sample() * tot))
+            idx = int(torch.searchsorted(cum, torch.tensor(u[k] * tot, dtype=torch.float64, device=x.device)).item())
             idx = min(idx, n - 1)
         centers[k] = x[idx]
-        d2 = np.minimum(d2, ((x - centers[k]) ** 2).sum(1))
-    return centers.astype(np.float32)
+        d2 = torch.minimum(d2, ((x - centers[k]) ** 2).sum(1))
+    return centers.to(torch.float32)
 
 
 def _upload_rows(doc_emb, start: int, end: int, device: torch.device, chunk: int = 1 << 19) -> torch.Tensor:
@@ -61,8 +64,8 @@ def _upload_rows(doc_emb, start: int, end: int, device: torch.device, chunk: int
 def _init_sample(R, init_sample: int, rs: np.random.RandomState, dev):
     """Rows for the k-means++ seeding, drawn from EVERY shard (init_sample // world rows per rank, seeded per rank) and
     gathered to rank 0 — a corpus stored in some order must not be seeded from its first N/world rows only.
-    Returns a host float32 array on rank 0, None elsewhere.  Every rank draws from its own RandomState stream so
-    the sample is reproducible for a given (seed, world)."""
+    Returns a float32 tensor (on the compute device) on rank 0, None elsewhere.  Every rank draws from its own
+    RandomState stream so the sample is reproducible for a given (seed, world)."""
     rank, world = rank_world()
     n = R.shape[0]
     per = max(1, init_sample // world)
@@ -71,12 +74,12 @@ def _init_sample(R, init_sample: int, rs: np.random.RandomState, dev):
     idx = np.sort(rs_r.choice(n, size=s, replace=False)) if s < n else np.arange(n)
     mine = R[torch.from_numpy(idx).to(dev)].contiguous()
     if world == 1:
-        return mine.cpu().numpy()
+        return mine
     counts = torch.tensor([s], dtype=torch.int64, device=dev)
     all_counts = [torch.zeros_like(counts) for _ in range(world)]
     dist.all_gather(all_counts, counts)
     g = gather_rows_to_rank0(mine, [int(c.item()) for c in all_counts])
-    return g.cpu().numpy() if g is not None else None
+    return g
 
 
 def _reseed_empty(R, C, buf, K, rs: np.random.RandomState, dev):
@@ -109,11 +112,13 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
     C = torch.empty((K, w), dtype=torch.float32, device=dev)
     sample = _init_sample(R, init_sample, rs, dev)
     if rank == 0:
-        C.copy_(torch.from_numpy(kmeanspp_init(sample, K, rs)).to(dev))
+        C.copy_(kmeanspp_init(sample, K, rs))
+    del sample
     if dist_on():
         dist.broadcast(C, 0)
     prev = math.inf
     n_it = 0
+    t_loop = time.perf_counter()
     for it in range(iters):
         be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
         if dist_on():
@@ -125,9 +130,10 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
                 dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
             cur = float(inertia.item())  # the host waits for the device here (and only here)
             reseeded = _reseed_empty(R, C, buf, K, rs, dev) if int(n_empty.item()) > 0 and n_it < iters else 0
-            if not reseeded and prev - cur <= tol * max(cur, 1e-30):
+            if not reseeded and tol is not None and prev - cur <= tol * max(cur, 1e-30):
                 break
             prev = cur
+    _lloyd_level.last_loop_seconds = time.perf_counter() - t_loop  # ends on the .item() of the last check: device time
     be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
     if dist_on():
         dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
@@ -137,17 +143,27 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
 
 
 @torch.no_grad()
-def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: float = 1e-7, init_sample: int = 16384,
+def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: Optional[float] = 1e-7, init_sample: int = 16384,
                    mode: str = "auto", device_index: Optional[int] = None, backend=None, metric: str = "l2",
-                   gather_codes: bool = True):
+                   gather_codes: bool = True, presharded: bool = False):
     """Returns (codebook [M,K,d] fp32 tensor on the compute device, codes np.int32 [N,M] on rank 0 or None).
-    k-means is always L2 (as sklearn's in the reference), whatever `metric` the encoder uses later."""
+    k-means is always L2 (as sklearn's in the reference), whatever `metric` the encoder uses later.
+    `presharded=True`: `doc_emb` already is THIS rank's row block (a device tensor the caller sharded with the
+    pq.py:218-225 rule) instead of the whole corpus; codes are then returned as the local device tensor.
+    `tol=None` runs exactly `iters` iterations per level."""
     be = backend if backend is not None else _lib.get_context(device_index)
     dev = be.torch_device if backend is not None else torch.device("cuda", be.device)
     rank, world = rank_world()
-    N, d = doc_emb.shape
-    start, end = shard_bounds(N, rank, world)
-    n = end - start
+    if presharded:
+        n, d = doc_emb.shape
+        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+        if dist_on():
+            dist.all_reduce(cnt)
+        N, start, end = int(cnt.item()), 0, n
+    else:
+        N, d = doc_emb.shape
+        start, end = shard_bounds(N, rank, world)
+        n = end - start
     R = _upload_rows(doc_emb, start, end, dev)
     codes = torch.zeros((n, M), dtype=torch.int32, device=dev)
     codebook = torch.empty((M, K, d), dtype=torch.float32, device=dev)
@@ -164,8 +180,11 @@ def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: flo
         if j != M - 1:  # pq.py:591-593
             be.residual_update(R, C, col, assign_stride=M)
         info["levels"].append({"level": j, "iters": n_it, "inertia": float(inertia.item()),
-                               "mse": float(inertia.item()) / max(N, 1) / d, "seconds": time.time() - t0})
+                               "mse": float(inertia.item()) / max(N, 1) / d, "seconds": time.time() - t0,
+                               "loop_ms_per_iter": getattr(_lloyd_level, "last_loop_seconds", 0.0) / max(n_it, 1) * 1e3})
     train_rq_lloyd.last_info = info
+    if presharded:
+        return codebook, codes
     codes_all = None
     if gather_codes:
         counts = [shard_bounds(N, r, world)[1] - shard_bounds(N, r, world)[0] for r in range(world)]

@@ -1,5 +1,5 @@
 """Multi-GPU functional check (NCCL, one process per GPU): sharded Lloyd training, doc-sharded flat search with
-all-gather merge, doc-sharded cluster re-rank.  Launch: torchrun --nproc-per-node 2 tools/dist_check.py"""
+all-gather merge, doc-sharded cluster re-rank.  Launch: torchrun --nproc-per-node 2 tests/dist_check.py"""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

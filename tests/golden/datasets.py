@@ -15,6 +15,8 @@ CASES = {
     "gauss768": ("gauss", 3000, 768, 4, 5, 1234),
     "mix768": ("mix", 3000, 768, 4, 5, 99),
     "small64": ("gauss", 2000, 64, 3, 4, 7),
+    # BASELINE.json configs[0]: synthetic 100k x 768 (make_golden_100k.py; codebook + codes only)
+    "gauss100k": ("gauss", 100000, 768, 4, 5, 1234),
 }
 QUERY_SEED = 4321
 N_QUERIES = 32

@@ -72,8 +72,14 @@ def test_search_dropin_pieces_id_base_and_file(tmp_path, gauss):
     assert dists.dtype == np.float32 and indices.dtype == np.int64 and dists.shape == (32, 100)
     s_ref, i_ref = oracle.flat_ip_topk(gauss.Q, gauss.X, 100)
     assert_topk_equivalent(dists, indices, s_ref, i_ref, rtol=1e-5, atol=2e-4)
+    # approximate index strings (the reference CLI default is 'IVF100,Flat') run the exact search, with a printed note
+    d2, i2 = faiss_search.search(gauss.Q, gauss.X, gauss.d, 100, "IVF100,Flat")
+    assert np.array_equal(i2, indices) and np.array_equal(d2, dists)
     with pytest.raises(NotImplementedError):
-        faiss_search.search(gauss.Q, gauss.X, gauss.d, 100, "HNSW256")
+        faiss_search.search(gauss.Q, gauss.X, gauss.d, 100, "no-such-index")
+    # fewer documents than k: faiss pads with the lowest float and id -1 (to_file prints them)
+    d3, i3 = faiss_search.search(gauss.Q[:2], gauss.X[:7], gauss.d, 10, "Flat")
+    assert (i3[:, 7:] == -1).all() and (d3[:, 7:] == np.finfo(np.float32).min).all() and (i3[:, :7] >= 0).all()
     qf = tmp_path / "q.tsv"
     qf.write_text("".join(f"query {i}\t{i}\n" for i in range(32)))
     out = tmp_path / "out.txt"

@@ -206,6 +206,24 @@ def test_beam_search_kernel_matches_tensor_op_formulation(gauss, metric, prod, n
         assert (lab[:, 0].cpu().numpy() == codes).mean() > 0.99
 
 
+def test_beam_search_beyond_the_kernel_limits_falls_back_to_tensor_ops():
+    """8-bit codebooks with 100 beams (25,600 candidates per level) exceed the kernel's shared-memory state: the drop-in
+    runs the reference's tensor-op formulation on the device instead of raising (pq.py:613-713 handles any shape)."""
+    from mevi_b200.pq import ProductQuantization
+
+    rs = np.random.RandomState(11)
+    d = 64
+    pq = ProductQuantization("rq", 2, 8, "l2", d, "kmeans", "grad")
+    with torch.no_grad():
+        pq.codebook.copy_(torch.tensor(rs.standard_normal((2, 256, d)).astype(np.float32)))
+    assert not pq._beam_kernel_fits(100, d) and pq._beam_kernel_fits(10, d)
+    Q = rs.standard_normal((5, d)).astype(np.float32) * 0.3
+    lab, sc = pq.beam_search(dev(Q), 100, return_proba=True)
+    lab_ref, sc_ref = pq._beam_search_tensor_ops(torch.tensor(Q), 100, True)
+    assert lab.is_cuda and tuple(lab.shape) == (5, 100, 2)
+    _beam_compare(lab.cpu().numpy(), sc.cpu().numpy(), lab_ref.numpy(), sc_ref.numpy(), rtol=2e-3)
+
+
 def test_beam_search_rejects_more_beams_than_leaves():
     from mevi_b200 import _lib
 

@@ -19,6 +19,6 @@ def test_sharded_paths_on_two_gpus():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py")],
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0 and "DIST CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -157,3 +157,42 @@ def test_badly_scaled_and_outlier_rows_still_exact(gauss):
     for mode in tensor_modes(c, gauss.d, gauss.M, gauss.K):
         codes = c.rq_encode(dev(X), dev(gauss.codebook), mode=mode).cpu().numpy()
         _check(X, gauss.codebook, codes, ref)
+
+
+def test_config_i_100k_golden_codes():
+    """BASELINE.json configs[0] (100k x 768, reference-built codebook): every kernel mode against the reference's codes."""
+    import json
+    import os
+
+    import datasets
+    from conftest import GOLDEN
+
+    d = os.path.join(GOLDEN, "gauss100k")
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    X = datasets.case_docs("gauss100k")
+    assert datasets.sha256(X) == meta["x_sha256"]
+    cb = torch.load(os.path.join(d, "codebook.pt"), map_location="cpu", weights_only=False).detach().numpy()
+    want = np.load(os.path.join(d, "codes_u8.npy")).astype(np.int32)
+    c = ctx()
+    for mode in tensor_modes(c, 768, 4, 32):
+        codes, stats = c.rq_encode(dev(X), dev(cb), mode=mode, return_stats=True)
+        rep = _check(X, cb, codes.cpu().numpy(), want)
+        print("gauss100k", mode, "mismatch", rep["n_mismatch"], "ties", rep["n_ties"], "stats", stats.tolist()[:3])
+
+
+def test_generation6_kernel_matches_the_exact_kernel(monkeypatch, gauss):
+    """The hi.hi prefilter + in-epilogue refinement kernel (MEVI_RQ_KERNEL=6, opt-in): same codes as the direct kernel."""
+    c = ctx()
+    rs = np.random.RandomState(3)
+    X = rs.standard_normal((50000, 768)).astype(np.float32)
+    X[::7] *= 3.0
+    X[5] = 0.0
+    for M in (2, 3, 4):
+        cb = gauss.codebook[:M].copy()
+        want = c.rq_encode(dev(X), dev(cb), mode="exact").cpu().numpy()
+        monkeypatch.setenv("MEVI_RQ_KERNEL", "6")
+        got, stats = c.rq_encode(dev(X), dev(cb), mode="tensor", return_stats=True)
+        monkeypatch.delenv("MEVI_RQ_KERNEL")
+        c.check()
+        assert int(stats[2].item()) > 0  # the refinement path ran
+        _check(X, cb, got.cpu().numpy(), want)

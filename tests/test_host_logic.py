@@ -81,8 +81,8 @@ def test_kmeanspp_seeding_is_seeded_and_spread():
     rs = np.random.RandomState(0)
     centers = rs.standard_normal((8, 16)) * 10
     x = (centers[rs.randint(0, 8, 2000)] + rs.standard_normal((2000, 16)) * 0.1).astype(np.float32)
-    a = kmeanspp_init(x, 8, np.random.RandomState(41))
-    b = kmeanspp_init(x, 8, np.random.RandomState(41))
+    a = kmeanspp_init(x, 8, np.random.RandomState(41)).numpy()
+    b = kmeanspp_init(torch.from_numpy(x), 8, np.random.RandomState(41)).numpy()
     assert np.array_equal(a, b) and a.dtype == np.float32
     # one seed per well-separated blob
     owner = ((a[:, None, :] - centers[None]) ** 2).sum(-1).argmin(1)
@@ -170,3 +170,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert j["higher_is_better"] is True and j["value"] > 0 and j["steps"] == 1
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": "docs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_oracle_flat_search_partition_form_equals_sort_form():
+    rs = np.random.RandomState(1)
+    Q = rs.standard_normal((32, 48)).astype(np.float32)
+    Dm = rs.standard_normal((9000, 48)).astype(np.float32)
+    for docs, k, block in ((Dm, 100, 2048), (Dm[:50], 100, 65536), (Dm, 1000, 4096)):
+        a = oracle.flat_ip_topk(Q, docs, k, block=block)
+        b = oracle.flat_ip_topk_partition(Q, docs, k, block=block)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])

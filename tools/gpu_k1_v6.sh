@@ -42,4 +42,4 @@ run("v6 again")
 ctx.check()
 PY
 echo "rc=$?"
-timeout 900 python -m pytest tests/test_gpu_rq_encode.py -x -q -m gpu 2>&1 | tail -3
+
