@@ -562,7 +562,11 @@ def run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, 
 
     @leg("km_it")
     def _():
-        C = cb[0].clone()
+        # centroids as the trainer has them: K data rows (k-means++ draws data points), moved by the updates of the
+        # warm-up iteration - balanced clusters, unlike the reference-trained level-0 codebook (80 % of rows in two cells)
+        gk = torch.Generator(device=dev)
+        gk.manual_seed(41)
+        C = Xs[torch.randint(0, ns, (K_CENTS,), device=dev, generator=gk)].clone()
         buf = torch.empty(K_CENTS * D + K_CENTS, device=dev)
         assign = torch.empty(ns, dtype=torch.int32, device=dev)
 

@@ -25,6 +25,7 @@ enum WsSlot {
   WS_HOST_CODES_A,
   WS_HOST_CODES_B,
   WS_MISC,
+  WS_PQ_PAD,        // PQ encode on the tensor path: block-padded codebook
   WS_NUM
 };
 
@@ -47,6 +48,10 @@ struct mevi_ctx {
   // the mirror is inspected at the start of the next call, after every synchronising call, and by mevi_ctx_check.
   int* dev_err = nullptr;            // [MEVI_ERRSLOTS]
   volatile int* host_err = nullptr;  // [MEVI_ERRSLOTS], cudaMallocHost
+  // set by mevi_pq_encode around its call of the RQ tensor kernel on the block-padded codebook: the rows the
+  // prefilter flags are then re-decided by the sub-vector kernel (the PQ reference arithmetic), not by rq_exact
+  const float* pq_fix_codebook = nullptr;
+  int pq_fix_dsub = 0;
   int64_t launches = 0;            // kernels launched by this context (reported by mevi_device_info)
 };
 

@@ -10,6 +10,7 @@
 // and walks the K centroids of codebook[j] with warp-uniform (broadcast) 128-bit loads.
 // Roofline: FP32 issue (3*K*d flops per row against 4*d bytes).  Measured (8,841,823 x 768, bench `widened_rows`).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -21,7 +22,13 @@ constexpr int PQ_ROWS = 32;
 template <bool L2>
 __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __restrict__ X, int64_t n, int d,
                                                                const float* __restrict__ cb, int M, int K, int dsub,
-                                                               int32_t* __restrict__ codes) {
+                                                               int32_t* __restrict__ codes,
+                                                               const int32_t* __restrict__ work_rows,   // optional: row ids
+                                                               const int64_t* __restrict__ n_work_dev)  // and their count
+{
+  // work-list form (the arbiter of rows the tensor prefilter flagged): item i is row work_rows[i]; the arithmetic per
+  // (row, sub-vector, centroid) does not depend on the tile a row sits in, so codes equal those of the plain form
+  if (work_rows != nullptr) n = *n_work_dev;
   extern __shared__ __align__(16) float sx[];  // [PQ_ROWS][d + 4]
   const int pitch = d + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -38,7 +45,7 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __re
     for (int i = tid; i < PQ_ROWS * d4; i += PQ_THREADS) {
       const int r = i / d4, c = i - r * d4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows) v = ld_stream_f4(X + (r0 + r) * d + 4 * c);
+      if (r < rows) v = ld_stream_f4(X + (work_rows ? (int64_t)work_rows[r0 + r] : r0 + r) * d + 4 * c);
       *reinterpret_cast<float4*>(sx + r * pitch + 4 * c) = v;
     }
     __syncthreads();
@@ -98,12 +105,64 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __re
           besti = s_bi[(j * nparts + part) * PQ_ROWS + r];
         }
       }
-      if (r < rows) codes[(r0 + r) * M + j] = besti;
+      if (r < rows) codes[(work_rows ? (int64_t)work_rows[r0 + r] : r0 + r) * M + j] = besti;
     }
   }
 }
 
 }  // namespace
+
+static int launch_pq_kernel(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K, int metric,
+                            int32_t* codes, const int32_t* work_rows, const int64_t* n_work_dev, cudaStream_t st) {
+  const int dsub = d / M;
+  const int nparts = M >= PQ_THREADS / 32 ? 1 : (PQ_THREADS / 32) / M;
+  const size_t smem = (size_t)PQ_ROWS * (d + 4) * sizeof(float) + (size_t)M * nparts * PQ_ROWS * 8;
+  MEVI_REQUIRE(ctx, smem <= 220 * 1024, "embedding width %d too large for the row tile", d);
+  const int64_t n_tiles = (n + PQ_ROWS - 1) / PQ_ROWS;
+  const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+  const int64_t max_grid = (int64_t)ctx->sm_count * per_sm;
+  const int grid = (int)(n_tiles < max_grid ? n_tiles : max_grid);
+  if (metric == MEVI_METRIC_L2) {
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(pq_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq_encode_kernel<true><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes, work_rows, n_work_dev);
+  } else {
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(pq_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq_encode_kernel<false><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes, work_rows, n_work_dev);
+  }
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  return MEVI_OK;
+}
+
+// rows the tensor prefilter flagged (work list on the device), re-decided by the sub-vector kernel; n = upper bound
+int mevi_pq_fix_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* pq_codebook, int M, int K, int metric,
+                       int32_t* codes, const int32_t* work_rows, const int64_t* n_work_dev, cudaStream_t st) {
+  // a launch sized for a few flagged rows per thousand; the kernel's tile loop covers whatever the list holds
+  const int64_t bound = n < (int64_t)ctx->sm_count * 2 * PQ_ROWS ? n : (int64_t)ctx->sm_count * 2 * PQ_ROWS;
+  return launch_pq_kernel(ctx, X, bound, d, pq_codebook, M, K, metric, codes, work_rows, n_work_dev, st);
+}
+
+namespace {
+// padded[j][k][:] = 0 except columns [j*dsub, (j+1)*dsub) = codebook[j][k][:]: sub-vector centroids zero-padded to the
+// full width have orthogonal supports across levels, so the RQ residual corrections vanish and the RQ kernel's argmin
+// per level IS the PQ argmin per sub-vector
+__global__ void pq_pad_codebook_kernel(const float* __restrict__ cb, int M, int K, int dsub, float* __restrict__ padded) {
+  const int d = M * dsub;
+  const int64_t total = (int64_t)M * K * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const int64_t jk = i / d;
+    const int j = (int)(jk / K);
+    const int e = c - j * dsub;
+    padded[i] = (e >= 0 && e < dsub) ? cb[jk * dsub + e] : 0.f;
+  }
+}
+}  // namespace
+
+int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* cb, int M, int K, int metric,
+                          int32_t* codes, int64_t codes_stride, float* residual, int64_t* stats, double* inertia,
+                          cudaStream_t st);
+bool mevi_rq_tensor_supported(mevi_ctx* ctx, int d, int M, int K, int metric);
 
 extern "C" int mevi_pq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K,
                               int metric, int32_t* codes, void* stream) {
@@ -118,21 +177,22 @@ extern "C" int mevi_pq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, c
   MEVI_REQUIRE(ctx, dsub % 4 == 0, "sub-vector width %d must be a multiple of 4", dsub);
   MEVI_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0,
                "X and codebook must be 16-byte aligned");
-  const int nparts = M >= PQ_THREADS / 32 ? 1 : (PQ_THREADS / 32) / M;
-  const size_t smem = (size_t)PQ_ROWS * (d + 4) * sizeof(float) + (size_t)M * nparts * PQ_ROWS * 8;
-  MEVI_REQUIRE(ctx, smem <= 220 * 1024, "embedding width %d too large for the row tile", d);
-  const int64_t n_tiles = (n + PQ_ROWS - 1) / PQ_ROWS;
-  const int per_sm = smem <= 112 * 1024 ? 2 : 1;
-  const int64_t max_grid = (int64_t)ctx->sm_count * per_sm;
-  const int grid = (int)(n_tiles < max_grid ? n_tiles : max_grid);
-  if (metric == MEVI_METRIC_L2) {
-    MEVI_CUDA(ctx, cudaFuncSetAttribute(pq_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pq_encode_kernel<true><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes);
-  } else {
-    MEVI_CUDA(ctx, cudaFuncSetAttribute(pq_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pq_encode_kernel<false><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes);
+  // Tensor route (M*K <= 128, the shapes the RQ kernel takes): K1 on the block-padded codebook - one HBM pass at
+  // ~70 % of the roofline instead of an FP32-issue-bound pass at 6 % - with the sub-vector kernel below as the arbiter
+  // of the rows its prefilter flags.  MEVI_PQ_TENSOR=0 keeps everything on the sub-vector kernel.
+  const char* env = getenv("MEVI_PQ_TENSOR");
+  if (!(env && atoi(env) == 0) && n >= 4096 && mevi_rq_tensor_supported(ctx, d, M, K, metric)) {
+    float* padded = (float*)mevi_ws(ctx, WS_PQ_PAD, (size_t)M * K * d * sizeof(float));
+    if (!padded) return MEVI_ERR_NOMEM;
+    pq_pad_codebook_kernel<<<ctx->sm_count, 256, 0, st>>>(codebook, M, K, dsub, padded);
+    MEVI_CUDA(ctx, cudaGetLastError());
+    MEVI_COUNT_LAUNCH(ctx, 1);
+    ctx->pq_fix_codebook = codebook;
+    ctx->pq_fix_dsub = dsub;
+    const int rc = mevi_rq_tensor_assign(ctx, X, n, d, padded, M, K, metric, codes, M, nullptr, nullptr, nullptr, st);
+    ctx->pq_fix_codebook = nullptr;
+    ctx->pq_fix_dsub = 0;
+    return rc;
   }
-  MEVI_CUDA(ctx, cudaGetLastError());
-  MEVI_COUNT_LAUNCH(ctx, 1);
-  return MEVI_OK;
+  return launch_pq_kernel(ctx, X, n, d, codebook, M, K, metric, codes, nullptr, nullptr, st);
 }

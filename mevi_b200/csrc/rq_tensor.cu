@@ -35,6 +35,8 @@ int mevi_rq_exact_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const 
                          int32_t* codes, int64_t codes_stride, float* residual, const int32_t* work_rows,
                          const int32_t* work_levels, const int64_t* n_work_dev, int64_t n_items, double* inertia,
                          cudaStream_t st);
+int mevi_pq_fix_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* pq_codebook, int M, int K, int metric,
+                       int32_t* codes, const int32_t* work_rows, const int64_t* n_work_dev, cudaStream_t st);
 
 namespace {
 
@@ -467,9 +469,16 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   MEVI_COUNT_LAUNCH(ctx, 2);
   if (int rc = mevi_publish_errors(ctx, st)) return rc;
 
-  // exact re-decision of the flagged rows (count stays on the device)
-  int rc = mevi_rq_exact_launch(ctx, X, n, d, cb, M, K, metric, codes, codes_stride, nullptr, work, work + n,
-                                reinterpret_cast<const int64_t*>(work_count), n, nullptr, st);
+  // exact re-decision of the flagged rows (count stays on the device): the fp32 direct-form RQ kernel, or - when this
+  // is a PQ encode running on a block-padded codebook - the sub-vector kernel, so that flagged rows get exactly the
+  // codes mevi_pq_encode's CUDA-core path gives them
+  int rc;
+  if (ctx->pq_fix_codebook != nullptr && codes_stride == M)
+    rc = mevi_pq_fix_launch(ctx, X, n, d, ctx->pq_fix_codebook, M, K, metric, codes, work,
+                            reinterpret_cast<const int64_t*>(work_count), st);
+  else
+    rc = mevi_rq_exact_launch(ctx, X, n, d, cb, M, K, metric, codes, codes_stride, nullptr, work, work + n,
+                              reinterpret_cast<const int64_t*>(work_count), n, nullptr, st);
   if (rc != MEVI_OK) return rc;
   if (stats) {
     finish_stats_kernel<<<1, 32, 0, st>>>(work_count, refine_count, n, stats);

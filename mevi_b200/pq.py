@@ -29,7 +29,6 @@ from __future__ import annotations
 
 import os
 import os.path as osp
-from collections import defaultdict
 from typing import Optional
 
 import numpy as np
@@ -161,16 +160,8 @@ class ProductQuantization(nn.Module):
         dev = torch.device("cuda", ctx.device)
         cb = self.get_codebook().detach().to(dev).contiguous()
         rot_t = self.rotate.detach().to(dev).T.contiguous() if self.pq_type == "opq" else None
-        # Opt-in (MEVI_PQ_VIA_RQ=1; measured once: 12.9x the sub-vector kernel at M=4 K=32, codes equal up to fp32 ties —
-        # DESIGN.md 6b.2; default once a GPU test covers it): sub-vector centroids zero-padded to the full width have
-        # orthogonal supports, so the RQ residual corrections vanish and the RQ tensor kernel returns the PQ codes (up to
-        # fp32 ties; identity checked on the oracle in tests/test_modes_cpu.py).  Shapes the tensor kernel accepts only.
-        M, K, dsub = cb.shape
-        padded = None
-        if os.environ.get("MEVI_PQ_VIA_RQ") == "1" and M * K <= 128 and K % 32 == 0 and (M * dsub) % 64 == 0:
-            padded = torch.zeros((M, K, M * dsub), dtype=torch.float32, device=dev)
-            for j in range(M):
-                padded[j, :, j * dsub : (j + 1) * dsub] = cb[j]
+        # `mevi_pq_encode` itself takes the tensor route when the shape allows it (M*K <= 128: the RQ kernel on a
+        # block-padded codebook, sub-vector kernel as the arbiter of flagged rows; csrc/pq_encode.cu)
         step = 1 << 18
         for a in range(start, ending, step):
             b = min(a + step, ending)
@@ -180,10 +171,7 @@ class ProductQuantization(nn.Module):
                 x = torch.from_numpy(np.ascontiguousarray(doc_embeddings[a:b], dtype=np.float32)).to(dev)
             if rot_t is not None:
                 x = _matmul_fp32(x, rot_t)
-            if padded is not None:
-                codes = ctx.rq_encode(x, padded, metric=self.dist_mode, mode="auto")
-            else:
-                codes = ctx.pq_encode(x, cb, metric=self.dist_mode)
+            codes = ctx.pq_encode(x, cb, metric=self.dist_mode)
             cluster[a - start : b - start].copy_(codes.to(cluster.device))
 
     @torch.no_grad()
@@ -666,17 +654,38 @@ def _matmul_fp32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
 
 
 def codes_to_dicts(codes: np.ndarray, start: int = 0, return_mapping: bool = True):
-    """The dictionaries of pq.py:236-242 from an int code table: python-int tuples,
-    doc ids ascending inside a leaf, leaves in order of first appearance (the
-    insertion order of the reference's defaultdict)."""
-    codes = np.asarray(codes)
-    n = codes.shape[0]
-    tuples = list(map(tuple, codes.tolist()))
-    doc_cluster = defaultdict(list)
-    for k, t in enumerate(tuples):
-        doc_cluster[t].append(k + start)
-    mapping = dict(zip(range(start, start + n), tuples)) if return_mapping else None
-    return dict(doc_cluster), mapping
+    """The dictionaries of pq.py:236-242 from an int code table: python-int tuples, doc ids ascending inside a leaf,
+    leaves in order of first appearance (the insertion order of the reference's defaultdict) - so `pickle.dumps` of
+    the result is byte-identical to the reference's rqclus / rqmapping files.  No per-row interpreter loop: rows are
+    grouped with one stable sort by leaf key, leaves are ordered by their smallest doc id, and python objects are made
+    by `ndarray.tolist()`; the only python-level loop runs over the leaves."""
+    codes = np.ascontiguousarray(codes)
+    n, M = codes.shape
+    if n == 0:
+        return {}, ({} if return_mapping else None)
+    base = int(codes.max()) + 1
+    key = np.zeros(n, dtype=np.int64)
+    for j in range(M):
+        key = key * base + codes[:, j].astype(np.int64)
+    order = np.argsort(key, kind="stable")                     # doc ids ascending inside a leaf
+    skey = key[order]
+    starts = np.flatnonzero(np.concatenate(([True], skey[1:] != skey[:-1])))
+    ends = np.concatenate((starts[1:], [n]))
+    first_doc = order[starts]                                  # a stable sort puts the leaf's smallest row first
+    leaf_order = np.argsort(first_doc, kind="stable")          # first appearance
+    if return_mapping:
+        tuples = list(map(tuple, codes.tolist()))              # one distinct tuple object per row, like tuple(v.tolist())
+        mapping = dict(zip(range(start, start + n), tuples))
+        key_of = lambda g: tuples[first_doc[g]]                # the leaf's key IS its first row's tuple (pq.py:238-240)
+    else:
+        mapping = None
+        firsts = codes[first_doc].tolist()
+        key_of = lambda g: tuple(firsts[g])
+    docs_sorted = order + start
+    doc_cluster = {}
+    for g_ in leaf_order.tolist():
+        doc_cluster[key_of(g_)] = docs_sorted[starts[g_] : ends[g_]].tolist()
+    return doc_cluster, mapping
 
 
 def _cli():

@@ -108,21 +108,29 @@ class ClusterIndex:
 
     # -- reference-format dictionaries ---------------------------------------
     def to_dicts(self):
-        """(rqclus, rqmapping) python dictionaries in the reference's format (global doc ids)."""
+        """(rqclus, rqmapping) python dictionaries in the reference's format and ORDER (global doc ids): leaves in order
+        of first appearance (= ascending smallest doc id, pq.py:236-242), doc ids ascending inside a leaf, mapping in doc
+        order - `pickle.dumps` of either equals the reference's file byte for byte.  One D2H copy of the CSR, numpy
+        grouping, python objects via tolist(); the only interpreter loop runs over the leaves."""
         keys = self.leaf_keys.cpu().numpy()
         offs = self.leaf_offsets.cpu().numpy()
-        docs = self.leaf_docids.cpu().numpy().astype(np.int64) + self.id_base
-        cluster, mapping = {}, {}
-        for i, key in enumerate(keys.tolist()):
-            t = []
-            for _ in range(self.M):
-                t.append(key % self.K)
-                key //= self.K
-            t = tuple(reversed(t))
-            lst = docs[offs[i] : offs[i + 1]].tolist()
-            cluster[t] = lst
-            for dd in lst:
-                mapping[dd] = t
+        local = self.leaf_docids.cpu().numpy().astype(np.int64)
+        n, nl = local.shape[0], keys.shape[0]
+        digits = np.zeros((nl, self.M), dtype=np.int64)
+        k = keys.copy()
+        for j in range(self.M - 1, -1, -1):
+            digits[:, j] = k % self.K
+            k //= self.K
+        leaf_of_pos = np.repeat(np.arange(nl), np.diff(offs))
+        codes = np.empty((n, self.M), dtype=np.int64)
+        codes[local] = digits[leaf_of_pos]                      # code tuple of every local row
+        tuples = list(map(tuple, codes.tolist()))
+        mapping = dict(zip(range(self.id_base, self.id_base + n), tuples))
+        first_doc = local[offs[:-1]] if nl else np.zeros(0, np.int64)
+        docs = local + self.id_base
+        cluster = {}
+        for g_ in np.argsort(first_doc, kind="stable").tolist():
+            cluster[tuples[first_doc[g_]]] = docs[offs[g_] : offs[g_ + 1]].tolist()
         return cluster, mapping
 
 

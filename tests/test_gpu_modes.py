@@ -50,6 +50,32 @@ def test_pq_encode_matches_oracle_shapes(n, d, M, bits):
         assert real == 0 and ties <= max(2, n * M // 5000), (metric, ties, real)
 
 
+@pytest.mark.parametrize("n,d,M,bits,metric", [(40000, 768, 4, 5, "l2"), (40000, 768, 4, 5, "ip"), (20011, 256, 2, 6, "l2"),
+                                               (9000, 128, 2, 5, "l2")])
+def test_pq_encode_tensor_route_equals_subvector_kernel(monkeypatch, n, d, M, bits, metric):
+    """M*K <= 128 and n >= 4096: mevi_pq_encode runs the RQ tensor kernel on the block-padded codebook (default) with the
+    sub-vector kernel as the arbiter of flagged rows.  Codes must equal the oracle's up to fp32 ties (float64 arbiter
+    per sub-vector) and the sub-vector kernel's own codes almost everywhere."""
+    rs = np.random.RandomState(n + d + M)
+    K = 2 ** bits
+    X = rs.standard_normal((n, d)).astype(np.float32)
+    cb = (rs.standard_normal((M, K, d // M)) * 0.7).astype(np.float32)
+    c = ctx()
+    l0 = c.launches
+    codes_t = c.pq_encode(dev(X), dev(cb), metric=metric).cpu().numpy()
+    assert c.launches - l0 >= 8  # the tensor route's preparation kernels ran (the sub-vector path is ONE launch)
+    monkeypatch.setenv("MEVI_PQ_TENSOR", "0")
+    l0 = c.launches
+    codes_s = c.pq_encode(dev(X), dev(cb), metric=metric).cpu().numpy()
+    assert c.launches - l0 == 1
+    monkeypatch.delenv("MEVI_PQ_TENSOR")
+    ref = oracle.pq_encode(X, cb, metric)
+    for got in (codes_t, codes_s):
+        ties, real = oracle.classify_pq_mismatches(X, cb, got, ref, metric)
+        assert real == 0 and ties <= max(2, n * M // 5000), (metric, ties, real)
+    assert (codes_t != codes_s).any(1).mean() < 1e-3
+
+
 def test_pq_and_opq_document_cluster_mirror(data):
     from mevi_b200.pq import ProductQuantization
 

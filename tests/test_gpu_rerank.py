@@ -15,7 +15,16 @@ def test_inverted_lists_equal_reference_dicts(case):
     idx = ClusterIndex.from_codes(case.codes, case.K)
     clus, mapping = idx.to_dicts()
     ref_clus, ref_map = case.pickle("rqclus.pkl"), case.pickle("rqmapping.pkl")
-    assert clus == ref_clus and mapping == ref_map  # same content (dict order differs: sorted by key here)
+    assert clus == ref_clus and mapping == ref_map
+    # ... in the reference's insertion order too, so the pickles written from the device CSR are the reference's bytes
+    import pickle
+
+    assert list(clus) == list(ref_clus) and list(mapping) == list(ref_map)
+    assert pickle.dumps(clus) == pickle.dumps(ref_clus) and pickle.dumps(mapping) == pickle.dumps(ref_map)
+    # a shard with an id base: global doc ids, same rule
+    half = case.n // 2
+    c2, m2 = ClusterIndex.from_codes(case.codes[half:], case.K, id_base=half).to_dicts()
+    assert min(m2) == half and all(m2[i] == ref_map[i] for i in m2) and sum(len(v) for v in c2.values()) == case.n - half
     idx2 = ClusterIndex.from_cluster_dict(ref_clus, case.K)
     assert torch.equal(idx2.leaf_keys, idx.leaf_keys) and torch.equal(idx2.leaf_offsets, idx.leaf_offsets)
     assert torch.equal(idx2.leaf_docids, idx.leaf_docids)
