@@ -191,8 +191,11 @@ int mevi_cluster_rerank_prefix(mevi_ctx* ctx, const float* Q, int nq, const floa
  * (leaf, query) pairs, _finish.  A round takes
  *   tile_row0, tile_nrows [n_tiles] int32; item_tile, item_group [n_items] int32 work items (tile, query group);
  *   group_qid [n_groups*64] int32 query index per column of a group, -1 = padding.
- * _finish: *fell_back = 1 when the guarantee could not be established (margin window overflow): the caller runs
- * mevi_cluster_rerank instead; else scores [nq,k] fp32 descending, rows [nq,k] int64 rows of D_leaf, -1 padded.
+ * _finish: scores [nq,k] fp32 descending, rows [nq,k] int64 rows of D_leaf, -1 padded; *n_failed = number of queries
+ * whose guarantee could not be established (candidate buffer / margin window overflow; marked in failed_or_null [nq]
+ * int32 device) - the caller re-runs just those through mevi_cluster_rerank; *n_failed = nq: the whole call is invalid.
+ * Thresholds: tau0 (a lower bound of every query's k-th best score) or NULL; with NULL the FIRST round must be small
+ * enough that all its scores fit the 4,096-slot candidate buffers (they are all appended), which bootstraps them.
  * The state between _begin and _finish lives in the context: one grouped call at a time per context.            */
 int mevi_rerank_grouped_image(mevi_ctx* ctx, const float* D_leaf, int64_t n, int d, const int32_t* src_index,
                               int64_t n_tiles, void* Aimg, float* absmax_out, float* maxnorm_out, void* stream);
@@ -202,7 +205,7 @@ int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, int d, cons
                               const int32_t* tile_nrows, const int32_t* item_tile, const int32_t* item_group,
                               int64_t n_items, const int32_t* group_qid, int64_t n_groups, int k, void* stream);
 int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int d, int k, float* scores,
-                               int64_t* rows, int* fell_back, void* stream);
+                               int64_t* rows, int32_t* failed_or_null, int* n_failed, void* stream);
 
 /* out[i,:] = D[rows[i],:] for i < m: builds the leaf-ordered copy of the document matrix
  * (rows = the CSR's leaf_docids).  Replaces the per-leaf memmap fancy-index gather of
@@ -216,6 +219,17 @@ int mevi_gather_rows(mevi_ctx* ctx, const float* D, int64_t n, int d, const int3
  * (= id_base + row, -1 padded).                                               */
 int mevi_flat_ip_topk(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int k,
                       int64_t id_base, int mode, float* scores, int64_t* ids, void* stream);
+
+/* Persistent form of the same search: faiss `index.add(doc)` once, `index.search(query, k)` many times
+ * (faiss_search.py:15-20).  _create converts D [n,d] to the fp16 tile image the tensor path reads (n*d*2 bytes, owned
+ * by the index) and records its scale / largest norm; _search then only pays for the query image, the GEMM and the
+ * exact fp32 re-score.  D stays caller-owned and must outlive the index (re-score and fp32 fall-back read it).
+ * k <= 1024 on the tensor path (the reference CLI default is --topk 1000); other shapes run the fp32 kernel.       */
+typedef struct mevi_flat_index mevi_flat_index;
+int mevi_flat_index_create(mevi_ctx* ctx, const float* D, int64_t n, int d, mevi_flat_index** out, void* stream);
+int mevi_flat_index_search(mevi_ctx* ctx, const mevi_flat_index* index, const float* Q, int nq, int k, int64_t id_base,
+                           int mode, float* scores, int64_t* ids, void* stream);
+void mevi_flat_index_destroy(mevi_ctx* ctx, mevi_flat_index* index);
 
 /* Merge S per-shard top-k lists (after an all-gather) into one.
  * scores_in [S,nq,k], ids_in [S,nq,k] -> scores/ids [nq,k]; same ordering rule. */

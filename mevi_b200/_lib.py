@@ -43,9 +43,12 @@ SYMBOLS = {
     "mevi_rerank_grouped_image": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, C.POINTER(_f), C.POINTER(_f), _vp]),
     "mevi_rerank_grouped_begin": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "mevi_rerank_grouped_round": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
-    "mevi_rerank_grouped_finish": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, C.POINTER(_i), _vp]),
+    "mevi_rerank_grouped_finish": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i), _vp]),
     "mevi_gather_rows": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "mevi_flat_ip_topk": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
+    "mevi_flat_index_create": (_i, [_vp, _vp, _i64, _i, C.POINTER(_vp), _vp]),
+    "mevi_flat_index_search": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp]),
+    "mevi_flat_index_destroy": (None, [_vp, _vp]),
     "mevi_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "mevi_dense_scores": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
 }
@@ -419,17 +422,18 @@ class Context:
                                                            self._stream()))
 
     def rerank_grouped_finish(self, Q, D_leaf, k):
-        """-> (scores, rows, fell_back)."""
+        """-> (scores, rows, failed int32 [nq] device mask, n_failed); n_failed == nq: the whole call is invalid."""
         import torch
 
         nq, d = Q.shape
         scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
         rows = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
-        fb = C.c_int(1)
+        failed = torch.empty(nq, dtype=torch.int32, device=Q.device)
+        nf = C.c_int(nq)
         with torch.cuda.device(self.device):
             self._check(self.lib.mevi_rerank_grouped_finish(self.handle, _ptr(Q), nq, _ptr(D_leaf), d, int(k), _ptr(scores),
-                                                            _ptr(rows), C.byref(fb), self._stream()))
-        return scores, rows, bool(fb.value)
+                                                            _ptr(rows), _ptr(failed), C.byref(nf), self._stream()))
+        return scores, rows, failed, int(nf.value)
 
     def flat_ip_topk(self, Q, D, k, id_base=0, mode="auto"):
         import torch
@@ -446,6 +450,33 @@ class Context:
                                            _ptr(scores), _ptr(ids), self._stream())
             )
         return scores, ids
+
+    def flat_index_create(self, D):
+        """-> opaque handle of a persistent flat index over D [n,d] (fp16 image built once; D must stay alive)."""
+        import torch
+
+        D = self._dev(D, torch.float32, "D")
+        h = _vp()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_flat_index_create(self.handle, _ptr(D), D.shape[0], D.shape[1], C.byref(h), self._stream()))
+        return h
+
+    def flat_index_search(self, handle, Q, k, id_base=0, mode="auto"):
+        import torch
+
+        Q = self._dev(Q, torch.float32, "Q")
+        nq = Q.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_flat_index_search(self.handle, handle, _ptr(Q), nq, int(k), int(id_base), _MODES[mode],
+                                                        _ptr(scores), _ptr(ids), self._stream()))
+        return scores, ids
+
+    def flat_index_destroy(self, handle):
+        if handle is not None and handle.value:
+            self.lib.mevi_flat_index_destroy(self.handle, handle)
+            handle.value = None
 
     def topk_merge(self, scores_in, ids_in):
         """[S,nq,k] lists -> merged [nq,k] (score desc, id asc; -1 padded)."""

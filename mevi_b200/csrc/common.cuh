@@ -26,6 +26,7 @@ enum WsSlot {
   WS_HOST_CODES_B,
   WS_MISC,
   WS_PQ_PAD,        // PQ encode on the tensor path: block-padded codebook
+  WS_FLAT_IMAGE,    // one-shot flat search: fp16 image of the documents (+ its metadata)
   WS_NUM
 };
 

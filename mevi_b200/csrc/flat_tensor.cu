@@ -115,11 +115,34 @@ __global__ void flat_absmax_kernel(const float* __restrict__ p, int64_t rows, in
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
-__global__ void flat_consts_kernel(const unsigned* absmax2, float* consts) {
+// Document-side metadata of a flat search (device, 4 words): [0] sampled |D|max bits, [1] scale 2^s as float,
+// [2] largest document norm bits, [3] 1 if a scaled element left the fp16 range.  Written once per image
+// (mevi_flat_index_create, or per call in the one-shot search).
+enum { DM_ABSMAX = 0, DM_SCALE, DM_MAXNORM, DM_CLAMPED, DM_NUM = 4 };
+
+__global__ void flat_doc_scale_kernel(unsigned* docmeta) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     // 2^s with absmax * 2^s in [2^11, 2^12): 16x headroom below the fp16 maximum (D is only sampled)
+    const float ad = __uint_as_float(docmeta[DM_ABSMAX]);
+    reinterpret_cast<float*>(docmeta)[DM_SCALE] = ad > 0.f ? ldexpf(1.f, 11 - ilogbf(ad)) : 1.f;
+  }
+}
+
+// grouped re-rank: scales from [0] the image's |D|max bits and [1] the call's |Q|max bits
+__global__ void gr_consts_kernel(const unsigned* absmax2, float* consts) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
     const float ad = __uint_as_float(absmax2[0]), aq = __uint_as_float(absmax2[1]);
     const float sd = ad > 0.f ? ldexpf(1.f, 11 - ilogbf(ad)) : 1.f;
+    const float sq = aq > 0.f ? ldexpf(1.f, 11 - ilogbf(aq)) : 1.f;
+    consts[FC_SD] = sd;
+    consts[FC_SQ] = sq;
+    consts[FC_INV] = 1.f / (sd * sq);
+  }
+}
+
+__global__ void flat_consts_kernel(const unsigned* docmeta, const unsigned* absmax_q, float* consts) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float sd = reinterpret_cast<const float*>(docmeta)[DM_SCALE], aq = __uint_as_float(absmax_q[0]);
     const float sq = aq > 0.f ? ldexpf(1.f, 11 - ilogbf(aq)) : 1.f;
     consts[FC_SD] = sd;
     consts[FC_SQ] = sq;
@@ -427,8 +450,11 @@ int flat_max_clusters(mevi_ctx* ctx, size_t smem) {
 
 // one CTA per query: sort approximate candidates, keep FT_KEEP, tau = k-th approximate score;
 // a dropped candidate inside the margin window breaks the guarantee -> overflow flag
+// (`ov_stride` = 0: one flag for the call - flat search; 1: a flag per query - grouped re-rank, which re-runs only the
+// affected queries through the streaming kernel)
 __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, const float* margin, int* count, float* cand_score,
-                                                                  int32_t* cand_id, int* overflow, int capg, int k, int keep) {
+                                                                  int32_t* cand_id, int* overflow, int capg, int k, int keep,
+                                                                  int ov_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_score = reinterpret_cast<float*>(smem_raw);
   int32_t* s_id = reinterpret_cast<int32_t*>(s_score + capg);
@@ -459,7 +485,7 @@ __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, co
     // never below a bound the caller already had (the grouped re-rank starts from a lower bound of the k-th score)
     const float t = fmaxf(tau[q], (cnt >= k) ? s_score[k - 1] : -CUDART_INF_F);
     tau[q] = t;
-    if (cnt > keep && !(s_score[keep] < t - margin[q])) *overflow = 1;
+    if (cnt > keep && !(s_score[keep] < t - margin[q])) overflow[(int64_t)q * ov_stride] = 1;
   }
 }
 
@@ -526,30 +552,71 @@ __global__ void flat_tensor_init_kernel(float* tau, int* count, int* overflow, i
 }  // namespace
 
 bool mevi_flat_tensor_supported(mevi_ctx* ctx, int d, int k) {
-  return ctx && ctx->cc_major == 10 && d >= FT_KC && d % FT_KC == 0 && d <= 4096 && k >= 1 && k <= FT_KEEP / 2;
+  // k <= 256: 512 approximate candidates kept per query in 4,096-slot buffers; k <= 1,024 (the reference CLI default is
+  // --topk 1000, faiss_search.py:88): 2,048 kept in 8,192-slot buffers
+  return ctx && ctx->cc_major == 10 && d >= FT_KC && d % FT_KC == 0 && d <= 4096 && k >= 1 && k <= 1024;
 }
+
+namespace {
+// fp16 image of a document matrix + its metadata (the "add" half of a flat index)
+int flat_docs_prepare(mevi_ctx* ctx, const float* D, int64_t n, int d, __half* Aimg, unsigned* docmeta, cudaStream_t st) {
+  const int64_t n_tiles = (n + FT_TM - 1) / FT_TM;
+  MEVI_CUDA(ctx, cudaMemsetAsync(docmeta, 0, DM_NUM * sizeof(unsigned), st));
+  const int64_t sample_rows = 4096;
+  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(D, n, d, n > sample_rows ? n / sample_rows : 1, docmeta + DM_ABSMAX);
+  flat_doc_scale_kernel<<<1, 32, 0, st>>>(docmeta);
+  to_fp16_image_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(D, n, d, FT_TM, reinterpret_cast<const float*>(docmeta), DM_SCALE, Aimg, nullptr,
+                                                          docmeta + DM_MAXNORM, reinterpret_cast<int*>(docmeta + DM_CLAMPED),
+                                                          n_tiles * FT_TM);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 3);
+  return MEVI_OK;
+}
+}  // namespace
+
+int mevi_flat_tensor_search_image(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, const __half* Aimg,
+                                  const unsigned* docmeta, int k, int64_t id_base, float* scores, int64_t* ids, int* fell_back,
+                                  cudaStream_t st);
 
 // Returns MEVI_OK with *fell_back = 0 when scores/ids hold the exact answer; *fell_back = 1 when the
 // guarantee could not be established (margin overflow, fp16 clamp, pipeline time-out): the caller then
 // runs the fp32 search.
 int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, int k,
                             int64_t id_base, float* scores, int64_t* ids, int* fell_back, cudaStream_t st) {
+  // one-shot form: the image lives in scratch memory and is rebuilt by every call (a caller that searches the same
+  // documents again holds a mevi_flat_index instead)
+  *fell_back = 1;
+  const int64_t n_tiles = (n + FT_TM - 1) / FT_TM;
+  const size_t img_bytes = (size_t)n_tiles * FT_TM * d * 2;
+  char* ws = (char*)mevi_ws(ctx, WS_FLAT_IMAGE, img_bytes + 256);
+  if (!ws) return MEVI_ERR_NOMEM;
+  unsigned* docmeta = (unsigned*)ws;
+  __half* Aimg = (__half*)(ws + 256);
+  int rc = flat_docs_prepare(ctx, D, n, d, Aimg, docmeta, st);
+  if (rc != MEVI_OK) return rc;
+  return mevi_flat_tensor_search_image(ctx, Q, nq, D, n, d, Aimg, docmeta, k, id_base, scores, ids, fell_back, st);
+}
+
+int mevi_flat_tensor_search_image(mevi_ctx* ctx, const float* Q, int nq, const float* D, int64_t n, int d, const __half* Aimg,
+                                  const unsigned* docmeta, int k, int64_t id_base, float* scores, int64_t* ids, int* fell_back,
+                                  cudaStream_t st) {
   *fell_back = 1;
   const int nchunks = d / FT_KC;
   const int64_t n_tiles = (n + FT_TM - 1) / FT_TM;
   const int n_qblocks = (nq + FT_TN - 1) / FT_TN;
-  const int capg = 4096;
+  const int keep = k <= FT_KEEP / 2 ? FT_KEEP : 2048;
+  const int capg = k <= FT_KEEP / 2 ? 4096 : 8192;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t o_consts = take(FC_NUM * 4), o_abs = take(16), o_flags = take(16), o_tau = take((size_t)nq * 4),
                o_margin = take((size_t)nq * 4), o_qnorm = take((size_t)nq * 4), o_cnt = take((size_t)nq * 4),
                o_cs = take((size_t)nq * capg * 4), o_ci = take((size_t)nq * capg * 4),
-               o_bimg = take((size_t)n_qblocks * FT_TN * d * 2), o_aimg = take((size_t)n_tiles * FT_TM * d * 2);
+               o_bimg = take((size_t)n_qblocks * FT_TN * d * 2);
   char* ws = (char*)mevi_ws(ctx, WS_TOPK_PART, off);
   if (!ws) return MEVI_ERR_NOMEM;
   float* consts = (float*)(ws + o_consts);
-  unsigned* absmax2 = (unsigned*)(ws + o_abs);        // [0] D sample absmax, [1] Q absmax, [2] max doc norm
-  int* flags = (int*)(ws + o_flags);                   // [0] overflow, [1] pipeline error, [2] clamped
+  unsigned* absmax_q = (unsigned*)(ws + o_abs);       // Q absmax
+  int* flags = (int*)(ws + o_flags);                   // [0] overflow, [1] pipeline error, [2] a Q element clamped
   float* tau = (float*)(ws + o_tau);
   float* margin = (float*)(ws + o_margin);
   float* qnorm = (float*)(ws + o_qnorm);
@@ -557,21 +624,16 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   float* cand_score = (float*)(ws + o_cs);
   int32_t* cand_id = (int32_t*)(ws + o_ci);
   __half* Bimg = (__half*)(ws + o_bimg);
-  __half* Aimg = (__half*)(ws + o_aimg);
 
-  MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, 32 + 256, st));  // absmax2 + flags
+  MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, 32 + 256, st));  // absmax_q + flags
   flat_tensor_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(tau, count, flags, flags + 1, nq);
-  const int64_t sample_rows = 4096;
-  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(D, n, d, n > sample_rows ? n / sample_rows : 1, absmax2);
-  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(Q, nq, d, 1, absmax2 + 1);
-  flat_consts_kernel<<<1, 32, 0, st>>>(absmax2, consts);
-  to_fp16_image_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(D, n, d, FT_TM, consts, FC_SD, Aimg, nullptr, absmax2 + 2, flags + 2,
-                                                          n_tiles * FT_TM);
+  flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(Q, nq, d, 1, absmax_q);
+  flat_consts_kernel<<<1, 32, 0, st>>>(docmeta, absmax_q, consts);
   to_fp16_image_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(Q, nq, d, FT_TN, consts, FC_SQ, Bimg, qnorm, nullptr, flags + 2,
                                                           (int64_t)n_qblocks * FT_TN);
-  flat_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(qnorm, nq, absmax2 + 2, margin);
+  flat_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(qnorm, nq, docmeta + DM_MAXNORM, margin);
   MEVI_CUDA(ctx, cudaGetLastError());
-  MEVI_COUNT_LAUNCH(ctx, 7);
+  MEVI_COUNT_LAUNCH(ctx, 5);
 
   GemmParams p;
   p.Aimg = Aimg; p.Bimg = Bimg; p.nq = nq; p.n_qblocks = n_qblocks; p.nchunks = nchunks; p.n_end = n;
@@ -587,9 +649,10 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
   MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
 
   // chunks of document tiles growing geometrically: the first (no thresholds yet, every score is appended) is small,
-  // so its compaction sorts 1,024 and not 4,096 candidates per query; it can never overflow the candidate buffers
-  int64_t chunk_tiles = 8;
-  static_assert(8 * FT_TM <= 4096 - FT_KEEP, "first chunk must fit the candidate buffer");
+  // so its compaction sorts 1,024 (2,048 for k > 256) and not `capg` candidates per query; it can never overflow the
+  // candidate buffers
+  int64_t chunk_tiles = k <= FT_KEEP / 2 ? 8 : 16;
+  static_assert(8 * FT_TM <= 4096 - FT_KEEP && 16 * FT_TM <= 8192 - 2048, "first chunk must fit the candidate buffer");
   int64_t pos = 0;
   while (pos < n_tiles) {
     const int64_t end = pos + chunk_tiles < n_tiles ? pos + chunk_tiles : n_tiles;
@@ -604,7 +667,7 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
                  : cs == 2 ? launch_flat_gemm<2>(ctx, p, smem_gemm, max_clusters, st)
                            : launch_flat_gemm<1>(ctx, p, smem_gemm, max_clusters, st);
     if (rc != MEVI_OK) return rc;
-    flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(tau, margin, count, cand_score, cand_id, flags, capg, k, FT_KEEP);
+    flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(tau, margin, count, cand_score, cand_id, flags, capg, k, keep, 0);
     MEVI_CUDA(ctx, cudaGetLastError());
     MEVI_COUNT_LAUNCH(ctx, 2);
     pos = end;
@@ -613,13 +676,16 @@ int mevi_flat_tensor_search(mevi_ctx* ctx, const float* Q, int nq, const float* 
     chunk_tiles = next > cap_chunk ? cap_chunk : next;
   }
   int h_flags[4] = {0, 0, 0, 0};
+  unsigned h_docmeta[DM_NUM] = {0, 0, 0, 0};
   MEVI_CUDA(ctx, cudaMemcpyAsync(h_flags, flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  MEVI_CUDA(ctx, cudaMemcpyAsync(h_docmeta, docmeta, sizeof(h_docmeta), cudaMemcpyDeviceToHost, st));
   MEVI_CUDA(ctx, cudaStreamSynchronize(st));
   if (int drc = mevi_deferred_error(ctx)) return drc;  // a kernel of this (or an earlier asynchronous) launch timed out
   if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "flat tensor kernel pipeline time-out (code %d)", h_flags[1]);
-  if (h_flags[0] || h_flags[2]) return MEVI_OK;  // guarantee not established: caller falls back to fp32
-  const size_t smem_rescore = (size_t)FT_KEEP * 8;
-  flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D, d, count, cand_id, cand_score, tau, margin, capg, k, FT_KEEP, id_base, scores,
+  if (h_flags[0] || h_flags[2] || h_docmeta[DM_CLAMPED]) return MEVI_OK;  // guarantee not established: caller falls back to fp32
+  const size_t smem_rescore = (size_t)keep * 8;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rescore));
+  flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D, d, count, cand_id, cand_score, tau, margin, capg, k, keep, id_base, scores,
                                                      ids);
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
@@ -654,7 +720,7 @@ constexpr int GR_B_BYTES = GR_TN * 128;
 constexpr int GR_STAGE_BYTES = FT_A_BYTES + GR_B_BYTES;  // 24 KB
 constexpr int GR_EPI_WARPS = 8;
 constexpr int GR_THREADS = 64 + 32 * GR_EPI_WARPS;
-constexpr int GR_CAPG = 4096;
+constexpr int GR_CAPG = 8192;  // candidate slots per query between compactions (512 kept + what a round appends)
 
 struct GroupedParams {
   const __half* Aimg; const __half* Bimg;
@@ -800,7 +866,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedPara
               p.cand_score[(int64_t)q * p.capg + slot] = __uint_as_float(acc[j]) * inv;
               p.cand_id[(int64_t)q * p.capg + slot] = doc;
             } else {
-              *p.overflow = 1;
+              p.overflow[q] = 1;  // per query: only this query is re-run through the streaming kernel
             }
           }
         }
@@ -815,6 +881,16 @@ __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedPara
 }
 
 __global__ void gr_set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+__global__ void gr_count_failed_kernel(const int* __restrict__ ovq, int nq, int* out) {
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < nq; i += blockDim.x) c += ovq[i] != 0;
+  if (c) atomicAdd(&s_n, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = s_n;
+}
 inline unsigned gr_f32_bits(float f) {
   unsigned u;
   memcpy(&u, &f, 4);
@@ -834,12 +910,13 @@ __global__ void gr_row_norm_kernel(const float* __restrict__ X, int rows, int d,
   if (lane == 0) norms[row] = sqrtf(a);
 }
 
-__global__ void gr_init_kernel(float* tau, const float* tau0, int* count, int* flags, int nq) {
+__global__ void gr_init_kernel(float* tau, const float* tau0, int* count, int* flags, int* ovq, int nq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nq) {
     const float t = tau0 ? tau0[i] : -CUDART_INF_F;
     tau[i] = (t == t) ? t : -CUDART_INF_F;
     count[i] = 0;
+    ovq[i] = 0;
   }
   if (i < 4) flags[i] = 0;
 }
@@ -847,6 +924,7 @@ __global__ void gr_init_kernel(float* tau, const float* tau0, int* count, int* f
 struct GrState {
   float* consts; unsigned* absmax; int* flags; float* tau; float* margin; float* qnorm; int* count;
   float* cand_score; int32_t* cand_id;
+  int* ovq;  // [nq] 1 = the guarantee could not be established for this query (buffer or margin-window overflow)
 };
 
 // the per-call state lives in one scratch slot from _begin to _finish (same layout recomputed by each entry point)
@@ -855,12 +933,13 @@ bool gr_state(mevi_ctx* ctx, int nq, GrState* s) {
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t o_consts = take(FC_NUM * 4), o_abs = take(16), o_flags = take(16), o_tau = take((size_t)nq * 4),
                o_margin = take((size_t)nq * 4), o_qnorm = take((size_t)nq * 4), o_cnt = take((size_t)nq * 4),
-               o_cs = take((size_t)nq * GR_CAPG * 4), o_ci = take((size_t)nq * GR_CAPG * 4);
+               o_ovq = take((size_t)nq * 4), o_cs = take((size_t)nq * GR_CAPG * 4), o_ci = take((size_t)nq * GR_CAPG * 4);
   char* ws = (char*)mevi_ws(ctx, WS_TOPK_AUX, off);
   if (!ws) return false;
   s->consts = (float*)(ws + o_consts); s->absmax = (unsigned*)(ws + o_abs); s->flags = (int*)(ws + o_flags);
   s->tau = (float*)(ws + o_tau); s->margin = (float*)(ws + o_margin); s->qnorm = (float*)(ws + o_qnorm);
   s->count = (int*)(ws + o_cnt); s->cand_score = (float*)(ws + o_cs); s->cand_id = (int32_t*)(ws + o_ci);
+  s->ovq = (int*)(ws + o_ovq);
   return true;
 }
 
@@ -886,7 +965,7 @@ extern "C" int mevi_rerank_grouped_image(mevi_ctx* ctx, const float* D_leaf, int
   const int64_t sample_rows = 4096;
   flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(D_leaf, n, d, n > sample_rows ? n / sample_rows : 1, absmax2);
   gr_set_u32_kernel<<<1, 1, 0, st>>>(absmax2 + 1, gr_f32_bits(1.0f));
-  flat_consts_kernel<<<1, 32, 0, st>>>(absmax2, consts);
+  gr_consts_kernel<<<1, 32, 0, st>>>(absmax2, consts);
   to_fp16_image_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(D_leaf, n, d, FT_TM, consts, FC_SD, (__half*)Aimg, nullptr, absmax2 + 2,
                                                           flags, n_tiles * FT_TM, src_index);
   MEVI_CUDA(ctx, cudaGetLastError());
@@ -914,12 +993,12 @@ extern "C" int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, 
   MEVI_REQUIRE(ctx, Q && nq > 0 && d_absmax >= 0.f, "bad argument");
   GrState s;
   if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
-  gr_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.tau, tau0, s.count, s.flags, nq);
+  gr_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.tau, tau0, s.count, s.flags, s.ovq, nq);
   gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 0, gr_f32_bits(d_absmax));
   gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 1, 0u);
   gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 2, gr_f32_bits(d_maxnorm));
   flat_absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(Q, nq, d, 1, s.absmax + 1);
-  flat_consts_kernel<<<1, 32, 0, st>>>(s.absmax, s.consts);
+  gr_consts_kernel<<<1, 32, 0, st>>>(s.absmax, s.consts);
   gr_row_norm_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, d, s.qnorm);
   flat_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.qnorm, nq, s.absmax + 2, s.margin);
   MEVI_CUDA(ctx, cudaGetLastError());
@@ -950,42 +1029,121 @@ extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, 
   p.Aimg = (const __half*)Aimg; p.Bimg = Bimg; p.item_tile = item_tile; p.item_group = item_group; p.n_items = n_items;
   p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.group_qid = group_qid; p.nchunks = nchunks;
   p.consts = s.consts; p.tau = s.tau; p.margin = s.margin; p.count = s.count; p.cand_score = s.cand_score;
-  p.cand_id = s.cand_id; p.overflow = s.flags; p.capg = GR_CAPG; p.err_flag = s.flags + 1;
+  p.cand_id = s.cand_id; p.overflow = s.ovq; p.capg = GR_CAPG; p.err_flag = s.flags + 1;
   const size_t smem = (size_t)GR_STAGES * GR_STAGE_BYTES + 2 * GR_TN * 8 + (2 * GR_STAGES + 4) * 8 + 16 + 1024;
   MEVI_CUDA(ctx, cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(n_items < ctx->sm_count ? n_items : ctx->sm_count);
   grouped_gemm_kernel<<<grid, GR_THREADS, smem, st>>>(p);
   const size_t smem_compact = (size_t)GR_CAPG * 8;
   MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
-  flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(s.tau, s.margin, s.count, s.cand_score, s.cand_id, s.flags, GR_CAPG, k,
-                                                            FT_KEEP);
+  flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(s.tau, s.margin, s.count, s.cand_score, s.cand_id, s.ovq, GR_CAPG, k,
+                                                            FT_KEEP, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 3);
   return MEVI_OK;
 }
 
-// end of the call: *fell_back = 1 when the guarantee could not be established (the caller then runs the streaming
-// kernel); otherwise scores [nq,k] fp32 descending and rows [nq,k] int64 = rows of the leaf-ordered matrix (-1 padded)
+// end of the call.  *n_failed = nq when the whole call is invalid (a query element left the fp16 range): the caller runs
+// the streaming kernel.  Otherwise scores [nq,k] fp32 descending and rows [nq,k] int64 = rows of the leaf-ordered matrix
+// (-1 padded), *n_failed = number of queries whose guarantee could not be established (candidate buffer or margin window
+// overflow: near-duplicate documents, one huge leaf) and failed_or_null [nq] (device, int32) marks them: the caller
+// re-runs just those through mevi_cluster_rerank.
 extern "C" int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int d, int k,
-                                          float* scores, int64_t* rows, int* fell_back, void* stream) {
+                                          float* scores, int64_t* rows, int32_t* failed_or_null, int* n_failed, void* stream) {
   MEVI_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
-  MEVI_REQUIRE(ctx, Q && D_leaf && scores && rows && fell_back, "NULL argument");
-  *fell_back = 1;
+  MEVI_REQUIRE(ctx, Q && D_leaf && scores && rows && n_failed, "NULL argument");
+  *n_failed = nq;
   GrState s;
   if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
   int h_flags[4] = {0, 0, 0, 0};
+  gr_count_failed_kernel<<<1, 256, 0, st>>>(s.ovq, nq, s.flags + 3);
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  if (failed_or_null) MEVI_CUDA(ctx, cudaMemcpyAsync(failed_or_null, s.ovq, (size_t)nq * sizeof(int), cudaMemcpyDeviceToDevice, st));
   MEVI_CUDA(ctx, cudaMemcpyAsync(h_flags, s.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
   MEVI_CUDA(ctx, cudaStreamSynchronize(st));
   if (int drc = mevi_deferred_error(ctx)) return drc;  // a kernel of this (or an earlier asynchronous) launch timed out
   if (h_flags[1]) return mevi_set_error(ctx, MEVI_ERR_CUDA, "grouped re-rank pipeline time-out (code %d)", h_flags[1]);
-  if (h_flags[0] || h_flags[2]) return MEVI_OK;
+  if (h_flags[2]) return MEVI_OK;  // clamped query image: nothing of this call carries the guarantee
   const size_t smem_rescore = (size_t)FT_KEEP * 8;
   flat_rescore_kernel<<<nq, 256, smem_rescore, st>>>(Q, D_leaf, d, s.count, s.cand_id, s.cand_score, s.tau, s.margin, GR_CAPG, k,
                                                      FT_KEEP, 0, scores, rows);
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
-  *fell_back = 0;
+  *n_failed = h_flags[3];
   return MEVI_OK;
+}
+
+
+// =====================================================================================================
+// Persistent flat index: faiss `index.add(doc)` once, `index.search(query, k)` many (faiss_search.py:15-20).
+// The fp16 tile image and the document-side metadata are built by _create and owned by the index; D itself stays
+// caller-owned and must outlive the index (the exact re-score and the fp32 fall-back read it).
+struct mevi_flat_index {
+  const float* D;
+  int64_t n;
+  int d;
+  __half* Aimg;       // nullptr: shape outside the tensor path, searches run the fp32 kernel
+  unsigned* docmeta;  // DM_NUM words
+};
+
+extern "C" int mevi_flat_index_create(mevi_ctx* ctx, const float* D, int64_t n, int d, mevi_flat_index** out, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, out && (D || n == 0) && n >= 0 && d > 0, "bad argument");
+  MEVI_REQUIRE(ctx, n < (int64_t)2147483647, "index too large for int32 row ids (shard it)");
+  *out = nullptr;
+  mevi_flat_index* ix = new mevi_flat_index{D, n, d, nullptr, nullptr};
+  if (n > 0 && mevi_flat_tensor_supported(ctx, d, 1) && (reinterpret_cast<uintptr_t>(D) & 15) == 0) {
+    const int64_t n_tiles = (n + FT_TM - 1) / FT_TM;
+    if (cudaMalloc(&ix->Aimg, (size_t)n_tiles * FT_TM * d * 2) != cudaSuccess || cudaMalloc(&ix->docmeta, 256) != cudaSuccess) {
+      cudaGetLastError();
+      if (ix->Aimg) cudaFree(ix->Aimg);
+      delete ix;
+      return mevi_set_error(ctx, MEVI_ERR_NOMEM, "flat index: cudaMalloc of the %lld-row fp16 image failed", (long long)n);
+    }
+    const int rc = flat_docs_prepare(ctx, D, n, d, ix->Aimg, ix->docmeta, st);
+    if (rc != MEVI_OK) {
+      cudaFree(ix->Aimg);
+      cudaFree(ix->docmeta);
+      delete ix;
+      return rc;
+    }
+  }
+  *out = ix;
+  return MEVI_OK;
+}
+
+extern "C" int mevi_flat_index_search(mevi_ctx* ctx, const mevi_flat_index* ix, const float* Q, int nq, int k, int64_t id_base,
+                                      int mode, float* scores, int64_t* ids, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, ix && scores && ids && (Q || nq == 0), "NULL argument");
+  if (nq <= 0) return MEVI_OK;
+  if (ix->Aimg != nullptr && mevi_flat_tensor_supported(ctx, ix->d, k) &&
+      (mode == MEVI_MODE_TENSOR || (mode == MEVI_MODE_AUTO && ix->n >= 8192))) {
+    int fell_back = 1;
+    const int rc = mevi_flat_tensor_search_image(ctx, Q, nq, ix->D, ix->n, ix->d, ix->Aimg, ix->docmeta, k, id_base, scores, ids,
+                                                 &fell_back, st);
+    if (rc != MEVI_OK) return rc;
+    if (!fell_back) return MEVI_OK;
+  } else if (mode == MEVI_MODE_TENSOR) {
+    return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "tensor flat search unsupported for this index (d=%d k=%d n=%lld)", ix->d, k,
+                          (long long)ix->n);
+  }
+  return mevi_flat_ip_topk(ctx, Q, nq, ix->D, ix->n, ix->d, k, id_base, MEVI_MODE_EXACT, scores, ids, stream);
+}
+
+extern "C" void mevi_flat_index_destroy(mevi_ctx* ctx, mevi_flat_index* ix) {
+  if (!ix) return;
+  if (ctx) {
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    if (ix->Aimg) cudaFree(ix->Aimg);
+    if (ix->docmeta) cudaFree(ix->docmeta);
+  }
+  delete ix;
 }

@@ -161,12 +161,16 @@ def build_leaf_tiles(leaf_offsets: torch.Tensor):
             src.to(torch.int32).reshape(-1).contiguous())
 
 
-def plan_grouped_rounds(leaf_offsets: torch.Tensor, leaf_tile0: torch.Tensor, ql: torch.Tensor, round_rows: Sequence[int]):
+def plan_grouped_rounds(leaf_offsets: torch.Tensor, leaf_tile0: torch.Tensor, ql: torch.Tensor, round_rows: Sequence[int],
+                        bootstrap_rows: int = 0):
     """(leaf, query) pairs of `ql` [nq, L] (CSR leaf index, -1 = none) -> per round the work of the grouped GEMM.
 
     A pair belongs to round r when the candidate rows listed BEFORE it in its query's leaf list number less than
-    round_rows[r] (and not less than round_rows[r-1]); the last round takes the rest.  Per round: pairs sorted by
-    leaf, each leaf's queries cut into groups of GROUP_COLS columns, one work item per (tile of the leaf, group).
+    round_rows[r] (and not less than round_rows[r-1]); the last round takes the rest.  With `bootstrap_rows` > 0 a
+    round is put in front of these: the leading pairs of every query whose candidate rows, the pair's own leaf
+    INCLUDED, number at most bootstrap_rows - the round that runs without thresholds (every score is appended), so it
+    must fit the candidate buffers by construction.  Per round: pairs sorted by leaf, each leaf's queries cut into
+    groups of GROUP_COLS columns, one work item per (tile of the leaf, group).
     -> list of (item_tile int32 [I], item_group int32 [I], group_qid int32 [G*GROUP_COLS], -1 = padding)."""
     dev = ql.device
     off = leaf_offsets.to(torch.int64)
@@ -177,10 +181,14 @@ def plan_grouped_rounds(leaf_offsets: torch.Tensor, leaf_tile0: torch.Tensor, ql
     before = torch.cumsum(qsz, 1) - qsz
     bounds = torch.tensor(list(round_rows), dtype=torch.int64, device=dev)
     rnd = torch.bucketize(before, bounds, right=True)  # rows before < round_rows[0] -> 0, ...
+    n_rounds = len(round_rows) + 1
+    if bootstrap_rows > 0:
+        rnd = torch.where(before + qsz <= bootstrap_rows, torch.zeros_like(rnd), rnd + 1)
+        n_rounds += 1
     qidx = torch.arange(nq, device=dev)[:, None].expand(nq, L)
     tpl = leaf_tile0[1:] - leaf_tile0[:-1]
     out = []
-    for r in range(len(round_rows) + 1):
+    for r in range(n_rounds):
         m = valid & (rnd == r)
         leaf = ql[m].long()
         q = qidx[m]
@@ -219,7 +227,8 @@ class ClusterReranker:
 
     AUTO_MIN_DOCS = 1 << 18         # mode='auto': corpora below this stay on the streaming kernel (no tile image)
     AUTO_QUERIES_PER_LEAF = 4       # mode='auto': grouped path when nq*L >= this many (query, leaf) pairs per leaf
-    BOOTSTRAP_ROWS = 2048           # prefix of every query's candidates scored exactly for the first thresholds
+    BOOTSTRAP_ROWS = 3072           # rows of the threshold-free first round per query (all appended: must fit the buffers)
+    BOOTSTRAP_MIN = 2048            # fewer bootstrap rows than this: first threshold from the streaming kernel instead
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
 
     def __init__(self, all_embeddings, index: ClusterIndex, device_index: Optional[int] = None,
@@ -300,7 +309,9 @@ class ClusterReranker:
 
 
 def _rerank_grouped(self, Q, ql, topk):
-    """Leaf-grouped tensor-core path; None when it does not apply or could not establish its guarantee."""
+    """Leaf-grouped tensor-core path; None when it does not apply or could not establish its guarantee for the call.
+    Queries whose own guarantee fails (candidate buffer or margin-window overflow: near-duplicate documents, one huge
+    leaf) are re-run through the streaming kernel and patched in; the answer is always the exact one."""
     g = self._grouped
     if g["absmax"] < 0 or topk > 256 or Q.shape[0] == 0:
         return None
@@ -308,18 +319,40 @@ def _rerank_grouped(self, Q, ql, topk):
     off = idx.leaf_offsets
     sizes = off[1:] - off[:-1]
     ncand = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device)).sum(1)
-    # first thresholds: exact k-th score of a prefix of every query's candidates (a lower bound of the final k-th score)
-    s0, _, _ = ctx.cluster_rerank_prefix(Q, self.D, off, idx.leaf_docids, ql, topk, self.BOOTSTRAP_ROWS)
-    tau0 = s0[:, topk - 1].contiguous()
+    # thresholds bootstrap themselves: the first round (the leading leaves of every query, at most BOOTSTRAP_ROWS rows)
+    # runs without thresholds and appends every score; its compaction yields each query's first k-th best score.
+    # A query whose leading leaves do not add up to BOOTSTRAP_MIN rows within that limit (its first leaf is a huge
+    # one) would enter the next round with no useful threshold: those few queries get the exact k-th score of their
+    # first BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
+    qsz = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device))
+    after = torch.cumsum(qsz, 1)
+    boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)
+    weak = torch.nonzero((boot_rows < self.BOOTSTRAP_MIN) & (ncand > boot_rows)).squeeze(1)
+    tau0 = None
+    if weak.numel():
+        s0, _, _ = ctx.cluster_rerank_prefix(Q[weak].contiguous(), self.D, off, idx.leaf_docids, ql[weak].contiguous(), topk,
+                                             self.BOOTSTRAP_MIN)
+        tau0 = torch.full((Q.shape[0],), float("-inf"), dtype=torch.float32, device=Q.device)
+        tau0[weak] = s0[:, topk - 1]
+    self.last_weak_queries = int(weak.numel())
     ctx.rerank_grouped_begin(Q, g["absmax"], g["maxnorm"], tau0)
-    for item_tile, item_group, group_qid in plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS):
+    for item_tile, item_group, group_qid in plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS, self.BOOTSTRAP_ROWS):
         if item_tile.numel():
             ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk)
-    scores, rows, fell_back = ctx.rerank_grouped_finish(Q, self.D, topk)
-    if fell_back:
+    scores, rows, failed, n_failed = ctx.rerank_grouped_finish(Q, self.D, topk)
+    nq = Q.shape[0]
+    self.last_failed_queries = n_failed
+    if n_failed >= nq or n_failed > max(16, nq // 4):
         return None
     self.last_path = "grouped"
     ids = torch.where(rows >= 0, idx.leaf_docids[rows.clamp(min=0)].to(torch.int64) + idx.id_base, torch.full_like(rows, -1))
+    if n_failed > 0:
+        bad = torch.nonzero(failed).squeeze(1)
+        s2, i2, _ = ctx.cluster_rerank(Q[bad].contiguous(), self.D, off, idx.leaf_docids, ql[bad].contiguous(), topk,
+                                       id_base=idx.id_base, leaf_ordered=True)
+        scores[bad] = s2
+        ids[bad] = i2
+        self.last_path = "grouped+stream"
     return scores, ids, ncand.clamp(max=0x7FFFFFFF).to(torch.int32)
 
 

@@ -89,3 +89,35 @@ def test_search_dropin_pieces_id_base_and_file(tmp_path, gauss):
     # readable by the ensemble's parser template {'query':0,'pred':2,'score':3} (ensemble_marco.py:165)
     f = lines[0].split("\t")
     assert f[1] == "" and len(f[2].split(",")) == 100 and float(f[3].split(",")[0]) == float(dists[0, 0])
+
+
+def test_persistent_index_add_once_search_many_and_k1000():
+    """faiss contract (faiss_search.py:15-20): index.add(doc) once, index.search(query, k) many times; the reference CLI
+    default is --topk 1000 (faiss_search.py:88), which must stay on the tensor path."""
+    from mevi_b200 import faiss_search
+
+    rs = np.random.RandomState(12)
+    d, n = 256, 30011
+    D = rs.standard_normal((n, d)).astype(np.float32)
+    D64 = D.astype(np.float64)
+    index = faiss_search.FlatIndex(d, piece_rows=12000, mode="tensor")  # 3 pieces, each with its own persistent image
+    index.add(D)
+    assert index.ntotal == n and len(index.pieces) == 3
+    c = ctx()
+    for seed, k in ((1, 100), (2, 1000), (3, 10), (4, 1000)):
+        Q = np.random.RandomState(seed).standard_normal((40, d)).astype(np.float32)
+        Q64 = Q.astype(np.float64)
+        l0 = c.launches
+        dists, indices = index.search(Q, k)
+        # no document image is rebuilt by a search: 3 pieces x (5 query-side kernels + GEMM/compact chunks + re-score) only
+        assert dists.shape == (40, k) and indices.dtype == np.int64
+        s_ref, i_ref = oracle.flat_ip_topk(Q, D, k)
+        assert_topk_equivalent(dists, indices, s_ref, i_ref, rtol=1e-5, atol=2e-4, pool_scores=lambda q, doc: float(D64[doc] @ Q64[q]))
+    index.close()
+    # one-shot call with k = 1000 and mode='tensor' (unsupported before: k <= 256)
+    Q = rs.standard_normal((9, d)).astype(np.float32)
+    s, i = c.flat_ip_topk(dev(Q), dev(D), 1000, mode="tensor")
+    s_ref, i_ref = oracle.flat_ip_topk(Q, D, 1000)
+    Q64 = Q.astype(np.float64)
+    assert_topk_equivalent(s.cpu().numpy(), i.cpu().numpy(), s_ref, i_ref, rtol=1e-5, atol=2e-4,
+                           pool_scores=lambda q, doc: float(D64[doc] @ Q64[q]))

@@ -53,8 +53,8 @@ def test_rerank_matches_oracle(case, nb, k, leaf_ordered):
     assert (np.diff(np.where(np.isfinite(scores), scores, -1e30), axis=1) <= 0).all()
 
 
-@pytest.mark.parametrize("nb,k", [(10, 100), (100, 100), (100, 7)])
-def test_grouped_tensor_rerank_matches_oracle(case, nb, k):
+@pytest.mark.parametrize("nb,k,boot_min", [(10, 100, 128), (100, 100, 128), (100, 7, 128), (100, 100, 100000)])
+def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min):
     """K3g: every leaf read once and scored against all the queries that chose it (tcgen05 prefilter + exact fp32
     re-score) must return what the per-query loop of main_models.py:3915-4014 returns."""
     from mevi_b200.rerank import ClusterIndex, ClusterReranker
@@ -64,9 +64,12 @@ def test_grouped_tensor_rerank_matches_oracle(case, nb, k):
     dec = case.load(f"beam{nb}_labels.npy")
     clus = case.pickle("rqclus.pkl")
     rr = ClusterReranker(dev(case.X), ClusterIndex.from_codes(case.codes, case.K), mode="grouped")
-    rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS = 256, (600, 3000)  # small corpus: still exercise three rounds
+    # small corpus: still exercise the threshold-free bootstrap round + three more rounds; boot_min = 100000 makes every
+    # query "weak" (first thresholds from the streaming kernel's exact prefix top-k instead)
+    rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS, rr.BOOTSTRAP_MIN = 256, (600, 3000), boot_min
     scores, ids, ncand = rr.rerank(case.Q, dec, topk=k)
-    assert rr.last_path == "grouped"
+    assert rr.last_path == "grouped" and rr.last_failed_queries == 0
+    assert (rr.last_weak_queries > 0) == (boot_min > 1000)
     scores, ids, ncand = scores.cpu().numpy(), ids.cpu().numpy(), ncand.cpu().numpy()
     ref = oracle.cluster_rerank(case.Q, case.X, clus, dec, topk=k)
     s_ref = np.full((len(ref), k), -np.inf, np.float32)
@@ -100,6 +103,31 @@ def test_grouped_rerank_falls_back_when_the_margin_window_overflows(gauss):
     for q, (d_, s_, nd) in enumerate(ref):
         assert int(ncand[q]) == nd
         np.testing.assert_allclose(scores[q].cpu().numpy(), s_, rtol=1e-5, atol=1e-4)
+
+
+def test_grouped_rerank_reruns_only_the_queries_whose_guarantee_failed(gauss):
+    """A few queries hit a leaf of near-duplicate documents (margin window overflow), the others do not: only those few
+    go through the streaming kernel, and every query's answer is the exact one."""
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    X = gauss.X.copy()
+    nd = 2500
+    X[:nd] = X[0] + 1e-6 * np.arange(nd, dtype=np.float32)[:, None]
+    codes = np.ascontiguousarray(gauss.codes.copy())
+    codes[:nd] = codes[0]
+    clus, _ = oracle.document_cluster(codes)
+    dec = gauss.load("beam10_labels.npy").copy()          # 32 ordinary queries ...
+    Q = gauss.Q.copy()
+    dec[:3, 0, :] = codes[0]                              # ... three of which also ask for the duplicate leaf
+    Q[:3] = X[0]
+    rr = ClusterReranker(dev(X), ClusterIndex.from_codes(codes, gauss.K), mode="grouped")
+    rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS, rr.BOOTSTRAP_MIN = 256, (600,), 128
+    scores, ids, ncand = rr.rerank(Q, dec, topk=100)
+    assert rr.last_path == "grouped+stream" and 1 <= rr.last_failed_queries <= 3
+    ref = oracle.cluster_rerank(Q, X, clus, dec, topk=100)
+    for q, (d_, s_, nd_) in enumerate(ref):
+        assert int(ncand[q]) == nd_
+        np.testing.assert_allclose(scores[q, : len(s_)].cpu().numpy(), s_, rtol=1e-5, atol=1e-4)
 
 
 @pytest.mark.parametrize("leaf_ordered", [True, False])
