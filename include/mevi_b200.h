@@ -178,6 +178,17 @@ int mevi_cluster_rerank_prefix(mevi_ctx* ctx, const float* Q, int nq, const floa
                                const int32_t* query_leaves, int L, int k, int64_t max_rows, float* scores, int64_t* ids,
                                int32_t* n_candidates, void* stream);
 
+/* The same loop keeping EVERY candidate (the shipped recipe runs `--save_hard_neg 8841823`: main_models.py:4012-4014,
+ * 4046-4053 write all candidates, sorted): leaf-ordered layout only.  Candidate number pos of query q, in the
+ * reference's concatenation order (leaf order = beam order, then row order inside the leaf, 3994-3997), goes to
+ * scores/ids[out_offsets[q] + pos]; out_offsets [nq+1] int64 (device) = exclusive prefix sum of the queries' candidate
+ * counts, computed by the caller from leaf_offsets and query_leaves.  Sorting (and the doc_multiclus aggregation of
+ * 3998-4011) is the caller's: a segmented device sort in mevi_b200/rerank.py.                                      */
+int mevi_cluster_rerank_all(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int64_t n, int d,
+                            const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                            const int32_t* query_leaves, int L, int64_t id_base, const int64_t* out_offsets, float* scores,
+                            int64_t* ids, int32_t* n_candidates, void* stream);
+
 /* ---- cluster-restricted re-rank as leaf-grouped GEMMs (tensor cores) ------ *
  * replaces: the same loop, MEVI/main_models.py:3915-4014.  A leaf selected by many queries is read ONCE and
  * scored against all of them: per leaf a [documents of the leaf] x [queries that chose it] fp16 tcgen05 GEMM whose

@@ -40,6 +40,7 @@ SYMBOLS = {
     "mevi_build_inverted_lists": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "mevi_cluster_rerank_prefix": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
+    "mevi_cluster_rerank_all": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mevi_rerank_grouped_image": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, C.POINTER(_f), C.POINTER(_f), _vp]),
     "mevi_rerank_grouped_begin": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "mevi_rerank_grouped_round": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
@@ -362,6 +363,33 @@ class Context:
                                              self._stream())
             )
         return scores, ids, ncand
+
+    def cluster_rerank_all(self, Q, D_leaf, leaf_offsets, leaf_docids, query_leaves, id_base=0):
+        """Scores of ALL candidates of every query, in the reference's concatenation order (unsorted):
+        -> (offsets int64 [nq+1], scores fp32 [total], ids int64 [total], n_candidates int32 [nq])."""
+        import torch
+
+        Q = self._dev(Q, torch.float32, "Q")
+        D = self._dev(D_leaf, torch.float32, "D_leaf")
+        lo = self._dev(leaf_offsets, torch.int64, "leaf_offsets")
+        ld = self._dev(leaf_docids, torch.int32, "leaf_docids")
+        ql = self._dev(query_leaves, torch.int32, "query_leaves")
+        nq, d = Q.shape
+        sizes = lo[1:] - lo[:-1]
+        cnt = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=Q.device)).sum(1)
+        offsets = torch.zeros(nq + 1, dtype=torch.int64, device=Q.device)
+        torch.cumsum(cnt, 0, out=offsets[1:])
+        total = int(offsets[-1].item())
+        scores = torch.empty(total, dtype=torch.float32, device=Q.device)
+        ids = torch.empty(total, dtype=torch.int64, device=Q.device)
+        ncand = cnt.clamp(max=0x7FFFFFFF).to(torch.int32)
+        if total == 0:  # no query has a candidate (all its leaves are empty): nothing to score
+            return offsets, scores, ids, ncand
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_cluster_rerank_all(self.handle, _ptr(Q), nq, _ptr(D), D.shape[0], d, _ptr(lo), lo.numel() - 1,
+                                                         _ptr(ld), _ptr(ql), ql.shape[1], int(id_base), _ptr(offsets), _ptr(scores),
+                                                         _ptr(ids), _ptr(ncand), self._stream()))
+        return offsets, scores, ids, ncand
 
     # ---- grouped (tensor-core) re-rank ------------------------------------------
     def cluster_rerank_prefix(self, Q, D_leaf, leaf_offsets, leaf_docids, query_leaves, k, max_rows):

@@ -439,6 +439,87 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
   }
 }
 
+// Every candidate's score, no top-k: the output mode of the shipped re-rank recipe (`--save_hard_neg 8841823`,
+// MEVI/main_models.py:4012-4014, 4046-4053 keeps ALL candidates, sorted).  Leaf-ordered layout; candidate position pos
+// of query q (leaf order = beam order, then row order inside the leaf - the reference's concatenation order, 3994-3997)
+// goes to out[out_offsets[q] + pos].  One warp per row, summation order of the dense scorer; the caller sorts.
+template <int NCH>
+__global__ void __launch_bounds__(256) rerank_all_kernel(RerankParams p, const int64_t* __restrict__ out_offsets) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int64_t* s_prefix = reinterpret_cast<int64_t*>(smem_raw);  // [L+1]
+  int64_t* s_leafbeg = s_prefix + (p.L + 1);                 // [L]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = (int)(blockIdx.x / p.S), s = (int)(blockIdx.x - (int64_t)q * p.S);
+  const int d = p.d;
+  for (int t = threadIdx.x; t < p.L; t += blockDim.x) {
+    const int leaf = p.query_leaves[(int64_t)q * p.L + t];
+    int64_t b = 0, sz = 0;
+    if (leaf >= 0 && leaf < p.n_leaves) {
+      b = p.leaf_offsets[leaf];
+      sz = p.leaf_offsets[leaf + 1] - b;
+    }
+    s_leafbeg[t] = b;
+    s_prefix[t + 1] = sz;
+  }
+  if (threadIdx.x == 0) s_prefix[0] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t run = 0;
+    for (int t = 1; t <= p.L; ++t) {
+      run += s_prefix[t];
+      s_prefix[t] = run;
+    }
+  }
+  __syncthreads();
+  const int64_t C = s_prefix[p.L];
+  if (s == 0 && threadIdx.x == 0 && p.n_candidates) p.n_candidates[q] = (int32_t)(C > 0x7fffffff ? 0x7fffffff : C);
+  const int64_t lo = C * s / p.S, hi = C * (s + 1) / p.S;
+  const int64_t obase = out_offsets[q];
+  float4 qreg[NCH];
+#pragma unroll
+  for (int t = 0; t < NCH; ++t) {
+    const int c4 = (lane + 32 * t) * 4;
+    qreg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < d) qreg[t] = ldg_f4(p.Q + (int64_t)q * d + c4);
+  }
+  int t_cur = 0;
+  for (int64_t pos = lo + warp; pos < hi; pos += 8) {
+    while (s_prefix[t_cur + 1] <= pos) ++t_cur;  // pos only grows: the leaf cursor moves forward
+    const int64_t row = s_leafbeg[t_cur] + (pos - s_prefix[t_cur]);
+    const float* src = p.D + row * d;
+    float4 v[NCH];
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) {
+      const int c4 = (lane + 32 * t) * 4;
+      v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < d) v[t] = ld_stream_f4(src + c4);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < NCH; ++t) {
+      acc = fmaf(qreg[t].x, v[t].x, acc);
+      acc = fmaf(qreg[t].y, v[t].y, acc);
+      acc = fmaf(qreg[t].z, v[t].z, acc);
+      acc = fmaf(qreg[t].w, v[t].w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      p.out_scores[obase + pos] = acc;
+      p.out_ids[obase + pos] = p.id_base + (int64_t)p.leaf_docids[row];
+    }
+  }
+}
+
+template <int NCH>
+cudaError_t launch_rerank_all(const RerankParams& p, const int64_t* out_offsets, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rerank_all_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  rerank_all_kernel<NCH><<<(unsigned)((int64_t)p.nq * p.S), 256, smem, st>>>(p, out_offsets);
+  return cudaGetLastError();
+}
+
 int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -561,6 +642,38 @@ static int cluster_rerank_impl(mevi_ctx* ctx, const float* Q, int nq, const floa
   poison_topk_kernel<<<ctx->sm_count, 256, 0, st>>>(p.err_flag, scores, ids, (int64_t)nq * k);
   MEVI_COUNT_LAUNCH(ctx, 1);
   return mevi_publish_errors(ctx, st);
+}
+
+int mevi_cluster_rerank_all(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int64_t n, int d,
+                            const int64_t* leaf_offsets, int64_t n_leaves, const int32_t* leaf_docids,
+                            const int32_t* query_leaves, int L, int64_t id_base, const int64_t* out_offsets, float* scores,
+                            int64_t* ids, int32_t* n_candidates, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, Q && D_leaf && leaf_offsets && leaf_docids && query_leaves && out_offsets && scores && ids, "NULL argument");
+  MEVI_REQUIRE(ctx, d > 0 && d % 4 == 0 && d <= 1024, "re-rank needs d %% 4 == 0 and d <= 1024 (got %d)", d);
+  MEVI_REQUIRE(ctx, L >= 1 && L <= 4096, "L must be in [1, 4096] (got %d)", L);
+  if (nq <= 0) return MEVI_OK;
+  int S = (8 * ctx->sm_count + nq - 1) / nq;
+  if (S < 1) S = 1;
+  if (S > 256) S = 256;
+  RerankParams p;
+  p.Q = Q; p.nq = nq; p.D = D_leaf; p.n = n; p.d = d;
+  p.leaf_offsets = leaf_offsets; p.n_leaves = n_leaves; p.leaf_docids = leaf_docids;
+  p.query_leaves = query_leaves; p.L = L; p.k = 0; p.cap = 0; p.S = S; p.id_base = id_base;
+  p.out_scores = scores; p.out_ids = ids; p.n_candidates = n_candidates; p.max_rows = 0;
+  p.err_flag = ctx->dev_err + MEVI_ERRSLOT_RERANK;
+  const size_t smem = (size_t)(2 * L + 1) * sizeof(int64_t);
+  cudaError_t e;
+  if (d <= 128) e = launch_rerank_all<1>(p, out_offsets, smem, st);
+  else if (d <= 256) e = launch_rerank_all<2>(p, out_offsets, smem, st);
+  else if (d <= 512) e = launch_rerank_all<4>(p, out_offsets, smem, st);
+  else if (d <= 768) e = launch_rerank_all<6>(p, out_offsets, smem, st);
+  else e = launch_rerank_all<8>(p, out_offsets, smem, st);
+  if (e != cudaSuccess) return mevi_set_error(ctx, MEVI_ERR_CUDA, "rerank_all launch: %s", cudaGetErrorString(e));
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  return MEVI_OK;
 }
 
 int mevi_gather_rows(mevi_ctx* ctx, const float* D, int64_t n, int d, const int32_t* rows, int64_t m, float* out,

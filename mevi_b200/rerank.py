@@ -308,6 +308,72 @@ class ClusterReranker:
         return scores, ids, ncand
 
 
+@torch.no_grad()
+def _rerank_all(self, query_embedding, dec, multiclus_score_aggr: Optional[str] = None):
+    """The shipped recipe's output mode (`--save_hard_neg <corpus size>`, main_models.py:4012-4014, 4046-4053): EVERY
+    candidate of every query, sorted by score descending, as a CSR over the queries:
+        -> (offsets int64 [nq+1], ids int64 [total], scores fp32 [total]) on the device.
+    `multiclus_score_aggr` in ('add', 'max') is the `--doc_multiclus > 1` aggregation of 3998-4011: a document listed
+    under several of the query's leaves appears once, with its scores added or maximised (`np.unique` + loop there).
+    Scores come from `mevi_cluster_rerank_all` (dense scorer's summation order, bit-equal to the top-k paths); the
+    sort is a segmented device sort, ties ordered by ascending doc id (the reference's CUDA `torch.sort` leaves tie
+    order unspecified).  `--knn_topk_by_step` (3986-3989, a running top-pool_size) is `rerank(topk=pool_size)`."""
+    if not self.leaf_ordered:
+        raise ValueError("rerank_all needs the leaf-ordered layout")
+    if dist_on():
+        raise NotImplementedError("rerank_all under torch.distributed: run it per shard and merge the sorted lists")
+    dev = self.D.device
+    if not isinstance(query_embedding, torch.Tensor):
+        query_embedding = torch.from_numpy(np.ascontiguousarray(query_embedding, dtype=np.float32))
+    Q = query_embedding.to(device=dev, dtype=torch.float32).contiguous()
+    ql = self.index.lookup(dec)
+    offsets, scores, ids, _ = self.ctx.cluster_rerank_all(Q, self.D, self.index.leaf_offsets, self.index.leaf_docids, ql,
+                                                          id_base=self.index.id_base)
+    nq = Q.shape[0]
+    seg = torch.repeat_interleave(torch.arange(nq, device=dev), offsets[1:] - offsets[:-1])
+    if multiclus_score_aggr is not None:
+        if multiclus_score_aggr not in ("add", "max"):
+            raise ValueError("multiclus_score_aggr must be 'add' or 'max' (main_models.py:4002-4009)")
+        span = int(ids.max().item()) + 1 if ids.numel() else 1
+        key, inv = torch.unique(seg * span + ids, return_inverse=True)
+        agg = torch.zeros(key.numel(), dtype=torch.float32, device=dev)
+        if multiclus_score_aggr == "add":
+            agg.scatter_add_(0, inv, scores)
+        else:
+            agg.fill_(float("-inf")).scatter_reduce_(0, inv, scores, reduce="amax")
+        seg, ids, scores = key // span, key % span, agg
+        counts = torch.bincount(seg, minlength=nq)
+        offsets = torch.zeros(nq + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=offsets[1:])
+    # segmented sort: (query asc, score desc, id asc) through three stable passes, least significant key first
+    order = torch.argsort(ids, stable=True)
+    order = order[torch.argsort(scores[order], descending=True, stable=True)]
+    order = order[torch.argsort(seg[order], stable=True)]
+    return offsets, ids[order], scores[order]
+
+
+def hn_lines_all(texts: Sequence[str], offsets, ids, scores, save_hard_neg: Optional[int] = None,
+                 gt_outputs: Optional[Sequence[str]] = None) -> List[str]:
+    """hn lines (main_models.py:4046-4053) from the CSR of `rerank_all`: all candidates, truncated to
+    `[:save_hard_neg]` like the reference's slices."""
+    off = offsets.cpu().numpy()
+    i = ids.cpu().numpy()
+    s = scores.cpu().numpy()
+    lines = []
+    for r, text in enumerate(texts):
+        a, b = int(off[r]), int(off[r + 1])
+        if save_hard_neg is not None:
+            b = min(b, a + int(save_hard_neg))
+        docs = ",".join(str(int(x)) for x in i[a:b])
+        sc = ",".join(str(float(x)) for x in s[a:b])
+        gt = gt_outputs[r] if gt_outputs is not None else ""
+        lines.append("\t".join([text, gt, docs, sc]))
+    return lines
+
+
+ClusterReranker.rerank_all = _rerank_all
+
+
 def _rerank_grouped(self, Q, ql, topk):
     """Leaf-grouped tensor-core path; None when it does not apply or could not establish its guarantee for the call.
     Queries whose own guarantee fails (candidate buffer or margin-window overflow: near-duplicate documents, one huge
