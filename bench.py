@@ -581,8 +581,37 @@ def run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, 
         ms_assign = timed(lambda: ctx.rq_encode(Xs, C[None], metric="l2", mode=args.mode, codes=a2), 5)
         ms_accum = timed(lambda: ctx.accumulate_by_code(Xs, assign, K_CENTS, buf), 5)
         fr = lambda m: (shard_bytes + ns * 4) / (m / 1e3) / 1e9 / hbm_peak
-        summary["km_it"] = {"ms": r3(ms), "frac": r3(shard_bytes / (ms / 1e3) / 1e9 / hbm_peak), "assign_ms": r3(ms_assign),
-                            "accum_ms": r3(ms_accum), "ar_ms": r3(ar_ms)}
+        # one-pass iteration (mevi_kmeans_step_fused): assignment + sums under the previous assignment in one read of the
+        # shard, then the rows whose assignment changed are moved between centroids; steady state = after 3 iterations
+        ms_fused = ms_fpass = changed = None
+        try:
+            a_prev, a_cur = assign, torch.empty_like(assign)
+            moved = torch.empty((ns // 4 + 1, D), device=dev)
+
+            def km_fused():
+                nonlocal a_prev, a_cur, changed
+                ctx.kmeans_step_fused(Xs, C, a_prev, a_cur, buf)
+                ch = torch.nonzero(a_cur != a_prev).squeeze(1)
+                changed = int(ch.numel())
+                if changed > ns // 4:
+                    ctx.accumulate_by_code(Xs, a_cur, K_CENTS, buf)
+                elif changed:
+                    mv = ctx.gather_rows(Xs, ch.to(torch.int32), out=moved)
+                    buf.add_(ctx.accumulate_by_code(mv, a_cur[ch].contiguous(), K_CENTS)).sub_(ctx.accumulate_by_code(mv, a_prev[ch].contiguous(), K_CENTS))
+                if world > 1:
+                    dist.all_reduce(buf)
+                ctx.kmeans_update(buf, C)
+                a_prev, a_cur = a_cur, a_prev
+
+            ms_fused = timed(km_fused, 5, warm=3)
+            ms_fpass = timed(lambda: ctx.kmeans_step_fused(Xs, C, a_prev, a_cur, buf), 5)
+            del moved
+        except Exception as e:
+            details["km_it_fused_error"] = repr(e)[:200]
+        summary["km_it"] = {"ms": r3(ms_fused if ms_fused else ms), "frac": r3(shard_bytes / ((ms_fused if ms_fused else ms) / 1e3) / 1e9 / hbm_peak),
+                            "pass_ms": r3(ms_fpass), "two_pass_ms": r3(ms), "assign_ms": r3(ms_assign), "accum_ms": r3(ms_accum),
+                            "ar_ms": r3(ar_ms)}
+        details["km_it_changed_rows_last"] = changed
         details["km_it"] = {"assign_frac": fr(ms_assign), "accum_frac": fr(ms_accum), "rows_total": n_total,
                             "note": "frac = ONE pass over the shard / iteration time; the iteration makes two passes"}
 

@@ -108,6 +108,21 @@ int mevi_rq_encode_host(mevi_ctx* ctx, const float* X_host, int64_t n, int d, co
 int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K, int mode,
                      int32_t* assign_out_or_null, int64_t assign_stride, float* sums_counts,
                      double* inertia_or_null, void* stream);
+/* ONE pass over the shard for a whole Lloyd iteration (the north star's "centroid GEMM fused with ... per-centroid
+ * sum/count accumulation"): while the tensor kernel assigns the rows to `centroids`, the same streamed tiles are summed
+ * per centroid under the rows' PREVIOUS assignment (known before the pass; the new one is only known after a row's
+ * last column):
+ *   prev_assign [n] int32 (stride prev_stride)   in:  assignment of the previous iteration (values clamped to [0,K))
+ *   assign_out  [n] int32 (stride assign_stride) out: nearest centroid now (a different buffer than prev_assign)
+ *   sums_counts_prev [K*d + K] fp32              out: per-centroid sums | counts of the rows UNDER prev_assign
+ * The caller turns these into the sums under assign_out by adding x to the new and subtracting it from the old
+ * centroid for the rows whose assignment changed (few after the first iterations): mevi_b200/trainer.py does that with
+ * mevi_gather_rows + mevi_accumulate_by_code, in a fixed order - results are bit-reproducible run to run.
+ * MEVI_ERR_UNSUPPORTED for shapes outside K <= 32 (K % 4 == 0), d % 64 == 0, K*d*4 <= ~100 KB, n >= 4096: use
+ * mevi_kmeans_step.  replaces: the same lines as mevi_kmeans_step.                                                  */
+int mevi_kmeans_step_fused(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K,
+                           const int32_t* prev_assign, int64_t prev_stride, int32_t* assign_out, int64_t assign_stride,
+                           float* sums_counts_prev, double* inertia_or_null, void* stream);
 /* centroids[k] = sums[k]/counts[k] where counts[k] > 0 (others unchanged);
  * n_empty_or_null: int32 DEVICE out = number of empty clusters.              */
 int mevi_kmeans_update(mevi_ctx* ctx, const float* sums_counts, int K, int d, float* centroids,

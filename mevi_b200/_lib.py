@@ -32,6 +32,7 @@ SYMBOLS = {
     "mevi_rq_encode": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mevi_rq_encode_host": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "mevi_kmeans_step": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "mevi_kmeans_step_fused": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "mevi_kmeans_update": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "mevi_residual_update": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp]),
     "mevi_accumulate_by_code": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp]),
@@ -231,6 +232,26 @@ class Context:
                                           int(assign_stride), _ptr(sums_counts), _ptr(inertia), self._stream())
             )
 
+    def kmeans_step_fused(self, R, centroids, prev_assign, assign, sums_counts_prev, prev_stride=1, assign_stride=1, inertia=None):
+        """One pass: `assign` = nearest centroid now, `sums_counts_prev` = per-centroid sums|counts of the rows under
+        `prev_assign` (mevi_kmeans_step_fused).  Raises MeviError (MEVI_ERR_UNSUPPORTED) for shapes it does not take."""
+        import torch
+
+        R = self._dev(R, torch.float32, "R")
+        c = self._dev(centroids, torch.float32, "centroids")
+        self._dev(sums_counts_prev, torch.float32, "sums_counts_prev")
+        n, d = R.shape
+        K = c.shape[0]
+        assert sums_counts_prev.numel() == K * d + K
+        assert prev_assign.dtype == torch.int32 and prev_assign.is_cuda and assign.dtype == torch.int32 and assign.is_cuda
+        assert prev_assign.data_ptr() != assign.data_ptr()
+        if inertia is not None:
+            assert inertia.dtype == torch.float64 and inertia.is_cuda
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_kmeans_step_fused(self.handle, _ptr(R), n, d, _ptr(c), K, _ptr(prev_assign), int(prev_stride),
+                                                        _ptr(assign), int(assign_stride), _ptr(sums_counts_prev), _ptr(inertia),
+                                                        self._stream()))
+
     def kmeans_update(self, sums_counts, centroids, n_empty=None):
         import torch
 
@@ -328,13 +349,17 @@ class Context:
             )
         return docids, keys
 
-    def gather_rows(self, D, rows):
-        """out[i] = D[rows[i]] (rows int32 on the device)."""
+    def gather_rows(self, D, rows, out=None):
+        """out[i] = D[rows[i]] (rows int32 on the device); `out`: a preallocated [>= len(rows), d] fp32 buffer to fill."""
         import torch
 
         D = self._dev(D, torch.float32, "D")
         rows = self._dev(rows, torch.int32, "rows")
-        out = torch.empty((rows.numel(), D.shape[1]), dtype=torch.float32, device=D.device)
+        if out is None:
+            out = torch.empty((rows.numel(), D.shape[1]), dtype=torch.float32, device=D.device)
+        else:
+            assert out.shape[0] >= rows.numel() and out.shape[1] == D.shape[1]
+            out = self._dev(out, torch.float32, "out")[: rows.numel()]
         with torch.cuda.device(self.device):
             self._check(self.lib.mevi_gather_rows(self.handle, _ptr(D), D.shape[0], D.shape[1], _ptr(rows), rows.numel(),
                                                   _ptr(out), self._stream()))

@@ -53,6 +53,12 @@ struct mevi_ctx {
   // prefilter flags are then re-decided by the sub-vector kernel (the PQ reference arithmetic), not by rq_exact
   const float* pq_fix_codebook = nullptr;
   int pq_fix_dsub = 0;
+  // set by mevi_kmeans_step_fused around its call of the tensor assignment kernel: the same pass then also accumulates
+  // the rows under their PREVIOUS assignment into per-CTA partial sums | counts ([grid][K][d] floats, [grid][K] ints)
+  const int32_t* km_prev = nullptr;
+  int64_t km_prev_stride = 0;
+  float* km_part_sums = nullptr;
+  int32_t* km_part_counts = nullptr;
   int64_t launches = 0;            // kernels launched by this context (reported by mevi_device_info)
 };
 

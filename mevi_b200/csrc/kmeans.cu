@@ -28,6 +28,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
                           int32_t* codes, int64_t codes_stride, float* residual, int64_t* stats, double* inertia,
                           cudaStream_t st);
 bool mevi_rq_tensor_supported(mevi_ctx* ctx, int d, int M, int K, int metric);
+bool mevi_kmeans_fused_supported(mevi_ctx* ctx, int d, int K);
 
 namespace {
 
@@ -296,6 +297,41 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
   // 2. accumulation
   rc = accumulate_by_code(ctx, R, n, d, assign, stride, K, sums_counts, st);
   if (rc != MEVI_OK) return rc;
+  return MEVI_OK;
+}
+
+int mevi_kmeans_step_fused(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K,
+                           const int32_t* prev_assign, int64_t prev_stride, int32_t* assign_out, int64_t assign_stride,
+                           float* sums_counts_prev, double* inertia_or_null, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, R && centroids && prev_assign && assign_out && sums_counts_prev, "NULL argument");
+  MEVI_REQUIRE(ctx, prev_stride >= 1 && assign_stride >= 1, "strides must be >= 1");
+  MEVI_REQUIRE(ctx, n > 0 && n < (int64_t)2147483647, "n out of range");
+  if (!mevi_kmeans_fused_supported(ctx, d, K) || n < 4096)
+    return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "fused k-means pass unsupported for n=%lld d=%d K=%d (use mevi_kmeans_step)",
+                          (long long)n, d, K);
+  if (inertia_or_null) MEVI_CUDA(ctx, cudaMemsetAsync(inertia_or_null, 0, sizeof(double), st));
+  const int64_t kd = (int64_t)K * d;
+  const int64_t n_tiles = (n + 255) / 256;
+  const int G = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);  // the kernel's grid: one partial per CTA
+  const size_t ps_bytes = (size_t)G * kd * sizeof(float), pc_bytes = (size_t)G * K * sizeof(int32_t);
+  char* ws = (char*)mevi_ws(ctx, WS_KM_PARTIAL, ps_bytes + pc_bytes);
+  if (!ws) return MEVI_ERR_NOMEM;
+  ctx->km_prev = prev_assign;
+  ctx->km_prev_stride = prev_stride;
+  ctx->km_part_sums = (float*)ws;
+  ctx->km_part_counts = (int32_t*)(ws + ps_bytes);
+  const int rc = mevi_rq_tensor_assign(ctx, R, n, d, centroids, 1, K, MEVI_METRIC_L2, assign_out, assign_stride, nullptr, nullptr,
+                                       inertia_or_null, st);
+  ctx->km_prev = nullptr;
+  if (rc != MEVI_OK) return rc;
+  const int threads = 256;
+  kmeans_reduce_partials_kernel<<<(int)((kd + K + threads - 1) / threads), threads, 0, st>>>((const float*)ws, (const int32_t*)(ws + ps_bytes),
+                                                                                             G, K, d, sums_counts_prev);
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  MEVI_CUDA(ctx, cudaGetLastError());
   return MEVI_OK;
 }
 

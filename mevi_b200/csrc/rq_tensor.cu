@@ -56,6 +56,8 @@ struct Params {
   int32_t* codes; int64_t codes_stride;
   int32_t* work_rows; int32_t* work_levels; unsigned long long* work_count;
   unsigned long long* refine_count;  // generation 6: (row, level) decisions refined in the epilogue
+  // fused k-means pass (rq_tensor4_kernel<1, true>): previous assignment in, per-CTA partial sums | counts out
+  const int32_t* prev; int64_t prev_stride; float* part_sums; int32_t* part_counts;
   double* inertia; int* err_flag;
   int64_t n_tiles;
   int debug;  // MEVI_RQ_DEBUG bit mask for pipeline ablations (timing experiments only; results are wrong)
@@ -333,6 +335,13 @@ bool v6_ok(int d, int M, int K) { return M >= 2 && K == 32 && d % 128 == 0 && d 
 
 }  // namespace
 
+// fused k-means pass: the [K][d] accumulators must fit next to a 3-stage fp32 ring
+bool mevi_kmeans_fused_supported(mevi_ctx* ctx, int d, int K) {
+  if (!shape_ok(ctx, d, 1, K, MEVI_METRIC_L2)) return false;
+  if (K > 32 || K % v4::ACC_WARPS != 0 || d % KC32 != 0) return false;
+  return v4::smem4_layout(1, K, K, K * d).total + 1024 <= 227 * 1024;
+}
+
 bool mevi_rq_tensor_supported(mevi_ctx* ctx, int d, int M, int K, int metric) {
   if (!shape_ok(ctx, d, M, K, metric)) return false;
   const int NT = M * K;
@@ -407,6 +416,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   p.codes = codes; p.codes_stride = codes_stride;
   p.work_rows = work; p.work_levels = work + n; p.work_count = work_count; p.refine_count = refine_count;
   p.inertia = inertia; p.err_flag = err_flag;
+  p.prev = nullptr; p.prev_stride = 0; p.part_sums = nullptr; p.part_counts = nullptr;
   {
     const char* dbg = getenv("MEVI_RQ_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
@@ -443,9 +453,19 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     const int grid4 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
 #define MEVI_LAUNCH_RQ_TENSOR4(MM)                                                                                          \
   do {                                                                                                                      \
-    MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
-    v4::rq_tensor4_kernel<MM><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                                 \
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<MM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+    v4::rq_tensor4_kernel<MM, false><<<grid4, v4::THREADS4, smem4, st>>>(p, tmap);                                          \
   } while (0)
+    if (ctx->km_prev != nullptr && M == 1) {
+      // fused k-means pass: assignment + accumulation under the previous assignment in one read of the shard
+      if (!mevi_kmeans_fused_supported(ctx, d, K))
+        return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "fused k-means pass unsupported for d=%d K=%d", d, K);
+      p.prev = ctx->km_prev; p.prev_stride = ctx->km_prev_stride;
+      p.part_sums = ctx->km_part_sums; p.part_counts = ctx->km_part_counts;
+      const size_t smem_acc = (size_t)v4::smem4_layout(1, K, NT, K * d).total + 1024;
+      MEVI_CUDA(ctx, cudaFuncSetAttribute(v4::rq_tensor4_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_acc));
+      v4::rq_tensor4_kernel<1, true><<<grid4, v4::THREADS4_ACC, smem_acc, st>>>(p, tmap);
+    } else
     switch (M) {
       case 1: MEVI_LAUNCH_RQ_TENSOR4(1); break;
       case 2: MEVI_LAUNCH_RQ_TENSOR4(2); break;

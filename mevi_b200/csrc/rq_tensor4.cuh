@@ -25,18 +25,36 @@ namespace v4 {
 constexpr int TM4 = 256;
 constexpr int KC4 = 32;
 constexpr int NSX4 = 4, NSB4 = 4, NSA4 = 4;
+// Fused k-means variant (template argument ACC): the same pass also accumulates the per-centroid sums|counts of the
+// rows under their PREVIOUS assignment (known before the pass), straight from the fp32 TMA stages:
+//   warps 12-15  epilogue (4 warps instead of 8: each takes its TMEM lane quarter of both 128-row halves)
+//   warp 16      sorter: per tile a stable counting sort of the 256 rows by previous code (bucket offsets + row list)
+//                and the steps of the accumulation (every centroid's sorted rows cut into steps of 16)
+//   warps 17-24  accumulators, per K chunk (32 columns) in two phases: A - the steps are dealt round-robin to the 8 warps
+//                (balanced whatever the cluster sizes): 16 sorted rows per step, four independent 16-byte shared loads
+//                per lane, partial sum parked in a staging buffer; B - warp a owns the centroids [K/8 * a, K/8 * (a+1))
+//                and adds their steps' partials in step order to the CTA's [K][d] fp32 accumulators in shared memory.
+//                No atomics, a fixed summation order: bit-reproducible.
+// The accumulators take 96 KB of shared memory (K = 32, d = 768), so the fp32 ring is 3 stages deep instead of 4.
+constexpr int NSX4_ACC = 3;
+constexpr int EPI_WARPS4_ACC = 4;       // fused variant: the (light, single-level) epilogue runs on 4 warps, both halves each
+constexpr int SORT_WARP = 16, ACC_WARP0 = 17, ACC_WARPS = 8;
+constexpr int THREADS4_ACC = 32 * (ACC_WARP0 + ACC_WARPS);  // 800
+constexpr int STEP_ROWS4 = 16;                       // sorted rows per accumulation step
+constexpr int MAX_STEPS4 = TM4 / STEP_ROWS4 + 32;    // every centroid's list is cut into steps of 16 rows: <= 16 + K steps
 static_assert(NSA4 == NSB4, "the A (TMEM) and B (smem) rings share their 'empty' barriers");
 constexpr int X_STAGE4 = TM4 * KC4 * 4;  // 32 KB
 constexpr int THREADS4 = 640;
 constexpr int EPI_WARPS4 = 8;
 constexpr uint32_t A_COL0 = 256;         // first TMEM column of the operand stages
 struct Smem4 {
-  int x_off, b_off, gram_off, cn2_off, e1_off, lvl_off, stats_off, bar_off, holder_off, total;
+  int x_off, b_off, gram_off, cn2_off, e1_off, lvl_off, stats_off, bar_off, holder_off, acc_off, sort_off, total;
 };
-__host__ __device__ inline Smem4 smem4_layout(int M, int K, int NT) {
+// acc_floats > 0: fused k-means variant (3-stage fp32 ring + [K][d] accumulators + sort buffers)
+__host__ __device__ inline Smem4 smem4_layout(int M, int K, int NT, int acc_floats = 0) {
   Smem4 L;
   L.x_off = 0;
-  L.b_off = L.x_off + NSX4 * X_STAGE4;
+  L.b_off = L.x_off + (acc_floats > 0 ? NSX4_ACC : NSX4) * X_STAGE4;
   L.gram_off = L.b_off + NSB4 * (2 * NT) * 64;
   int gram_pad = 0;
   for (int j = 1; j < M; ++j) gram_pad += j * K * (K + 1);
@@ -45,12 +63,20 @@ __host__ __device__ inline Smem4 smem4_layout(int M, int K, int NT) {
   L.lvl_off = L.e1_off + NT * 4;
   L.stats_off = L.lvl_off + 64;
   L.bar_off = (L.stats_off + 2 * TM4 * 4 + 7) & ~7;
-  L.holder_off = L.bar_off + 32 * 8;
-  L.total = L.holder_off + 16;
+  L.holder_off = L.bar_off + 40 * 8;
+  L.acc_off = (L.holder_off + 16 + 127) & ~127;
+  // sort buffers: [2 tile parities] x (row list 256 B + bucket offsets (K+2) ints), then K running counts
+  L.sort_off = L.acc_off + acc_floats * 4;
+  // + zero line (128 B), step tables [2] x (48 centroid bytes + 48 row-count bytes + (K+2) first-step ints), staging
+  // [2][48][128 B], row table [2][48][16] bytes
+  L.total = acc_floats > 0 ? ((L.sort_off + 2 * (TM4 + (K + 2) * 4) + 2 * K * 4 + 15) & ~15) + 128 +
+                                 2 * (MAX_STEPS4 + MAX_STEPS4 + (K + 2) * 4) + 16 + 2 * MAX_STEPS4 * 128 +
+                                 2 * MAX_STEPS4 * STEP_ROWS4
+                           : L.holder_off + 16;
   return L;
 }
 
-template <bool SCALE>
+template <bool SCALE, int NSX>
 __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, float* sStats, uint32_t tmem_base, uint64_t* x_full,
                                                 uint64_t* x_empty, uint64_t* a_full, uint64_t* a_empty, uint64_t* st_full,
                                                 int cw, int lane) {
@@ -107,7 +133,7 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
       trace_ev(p, warp, lane, tix, it, c, 2);  // converted, stores issued
       pending = true;
       pend_stage = as;
-      if (++xs == NSX4) { xs = 0; xph ^= 1; }
+      if (++xs == NSX) { xs = 0; xph ^= 1; }
       if (++as == NSA4) { as = 0; aph ^= 1; }
     }
     // end of tile: publish its last operand stage right away (the MMA needs it to finish the tile)
@@ -125,11 +151,15 @@ __device__ __forceinline__ void converter_loop4(const Params& p, uint8_t* sX, fl
   }
 }
 
-template <int M>
-__global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const __grid_constant__ CUtensorMap tmap) {
+template <int M, bool ACC>
+__global__ void __launch_bounds__(ACC ? THREADS4_ACC : THREADS4, 1)
+rq_tensor4_kernel(Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  static_assert(!ACC || M == 1, "the fused accumulation is the k-means (single level) form");
+  constexpr int NSX = ACC ? NSX4_ACC : NSX4;
+  constexpr int NTHREADS = ACC ? THREADS4_ACC : THREADS4;
   const int K = p.K, NT = p.NT;
-  const Smem4 L = smem4_layout(M, K, NT);
+  const Smem4 L = smem4_layout(M, K, NT, ACC ? K * p.d : 0);
   uint8_t* sX = smem + L.x_off;
   uint8_t* sB = smem + L.b_off;
   float* sGram = reinterpret_cast<float*>(smem + L.gram_off);
@@ -139,8 +169,8 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
   float* sStats = reinterpret_cast<float*>(smem + L.stats_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* x_full = bars;
-  uint64_t* x_empty = x_full + NSX4;
-  uint64_t* a_full = x_empty + NSX4;
+  uint64_t* x_empty = x_full + NSX;
+  uint64_t* a_full = x_empty + NSX;
   uint64_t* a_empty = a_full + NSA4;
   uint64_t* b_full = a_empty + NSA4;
   uint64_t* b_empty = b_full + NSB4;
@@ -153,21 +183,44 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
   const uint32_t b_stage_bytes = (uint32_t)(2 * NT) * 64u;
   const int nchunks = p.d / KC4;
 
-  for (int i = tid; i < p.gram_floats; i += THREADS4) {
+  for (int i = tid; i < p.gram_floats; i += NTHREADS) {
     const int r = i / K, c = i - r * K;
     sGram[r * (K + 1) + c] = p.gram[i];
   }
-  for (int i = tid; i < NT; i += THREADS4) {
+  for (int i = tid; i < NT; i += NTHREADS) {
     sCn2[i] = p.cn2[i];
     sE1[i] = p.e1[i];
   }
-  for (int i = tid; i < M * 4; i += THREADS4) sLvl[i] = p.lvl[i];
+  for (int i = tid; i < M * 4; i += NTHREADS) sLvl[i] = p.lvl[i];
+  // fused k-means accumulation: CTA-wide [K][d] sums, per tile parity a row list + bucket offsets, running counts
+  float* sAcc = reinterpret_cast<float*>(smem + L.acc_off);
+  uint8_t* sPerm = smem + L.sort_off;                                                  // [2][TM4]
+  int* sOff = reinterpret_cast<int*>(smem + L.sort_off + 2 * TM4);                     // [2][K + 2]
+  int* sCnt = sOff + 2 * (K + 2);                                                      // [K] rows per centroid so far (CTA)
+  int* sRun = sCnt + K;                                                                // [K] sorter scratch
+  const uint32_t zero_line = (ptx::smem_u32(sRun + K) + 15u) & ~15u;                   // 128 zero bytes (a row that adds nothing)
+  uint8_t* sTab = smem + (((L.sort_off + 2 * (TM4 + (K + 2) * 4) + 2 * K * 4 + 15) & ~15) + 128);
+  uint8_t* sStepB = sTab;                                                              // [2][MAX_STEPS4] centroid of a step
+  uint8_t* sStepC = sTab + 2 * MAX_STEPS4;                                             // [2][MAX_STEPS4] rows of a step (1..16)
+  int* sStep0 = reinterpret_cast<int*>(sTab + 4 * MAX_STEPS4);                         // [2][K + 2] first step of a centroid; [K] = count
+  float4* sPart = reinterpret_cast<float4*>(sTab + ((2 * (MAX_STEPS4 + MAX_STEPS4 + (K + 2) * 4) + 15) & ~15));  // [2][MAX_STEPS4][8]
+  uint8_t* sRowIdx = reinterpret_cast<uint8_t*>(sPart) + 2 * MAX_STEPS4 * 128;         // [2][MAX_STEPS4][16] row (in the tile) of every step row
+  uint64_t* sort_full = st_full + 2;                                                   // [2]
+  uint64_t* sort_empty = sort_full + 2;                                                // [2]
+  if (ACC) {
+    for (int i = tid; i < K * p.d; i += NTHREADS) sAcc[i] = 0.f;
+    for (int i = tid; i < K; i += NTHREADS) sCnt[i] = 0;
+    if (tid < 32) asm volatile("st.shared.b32 [%0], %1;" ::"r"(zero_line + tid * 4), "r"(0) : "memory");
+  }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < NSX4; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], CONV_WARPS); }
+    for (int s = 0; s < NSX; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], CONV_WARPS + (ACC ? ACC_WARPS : 0)); }
+    if (ACC) {
+      for (int b = 0; b < 2; ++b) { ptx::mbar_init(&sort_full[b], 1); ptx::mbar_init(&sort_empty[b], ACC_WARPS); }
+    }
     for (int s = 0; s < NSA4; ++s) { ptx::mbar_init(&a_full[s], CONV_WARPS); ptx::mbar_init(&a_empty[s], 2); }  // one commit per MMA warp
     for (int s = 0; s < NSB4; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
     ptx::mbar_init(acc_full, 2);
-    ptx::mbar_init(acc_empty, EPI_WARPS4);
+    ptx::mbar_init(acc_empty, ACC ? EPI_WARPS4_ACC : EPI_WARPS4);
     ptx::mbar_init(&st_full[0], CONV_WARPS);
     ptx::mbar_init(&st_full[1], CONV_WARPS);
     ptx::mbar_fence_init();
@@ -196,7 +249,7 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
           ptx::tma_load_2d(sX + (size_t)s * X_STAGE4, &tmap, c * KC4, (int)(tile * TM4), &x_full[s]);
         }
         __syncwarp();
-        if (++s == NSX4) { s = 0; ph ^= 1; }
+        if (++s == NSX) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 3) {
@@ -271,10 +324,186 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
     }
   } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
     if (p.consts[C_SX] == 1.f)
-      converter_loop4<false>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
+      converter_loop4<false, NSX>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
     else
-      converter_loop4<true>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
-  } else if (warp >= EPI_WARP0) {
+      converter_loop4<true, NSX>(p, sX, sStats, tmem_base, x_full, x_empty, a_full, a_empty, st_full, warp - CONV_WARP0, lane);
+  } else if (ACC && warp == SORT_WARP) {
+    // ===== sorter: stable counting sort of the tile's rows by PREVIOUS code; rows past the end go to bucket K =====
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+      if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(&sort_empty[buf], bph ^ 1, 64))) {
+        if (lane == 0) atomicExch(p.err_flag, 8);
+        return;
+      }
+      int code[TM4 / 32];
+#pragma unroll
+      for (int i = 0; i < TM4 / 32; ++i) {
+        const int64_t row = tile * TM4 + i * 32 + lane;
+        int c = K;
+        if (row < p.n) {
+          c = p.prev[row * p.prev_stride];
+          c = c < 0 ? 0 : (c >= K ? K - 1 : c);
+        }
+        code[i] = c;
+      }
+      int* off = sOff + buf * (K + 2);
+      // 1. bucket sizes: the first lane of every group of equal codes adds the group's size (distinct codes, distinct words)
+      if (lane <= K && lane < 32) off[lane] = 0;
+      if (lane == 0) off[K] = 0;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < TM4 / 32; ++i) {
+        const unsigned same = __match_any_sync(MEVI_FULL_MASK, code[i]);
+        if (lane == __ffs(same) - 1) off[code[i]] += __popc(same);
+        __syncwarp();
+      }
+      // 2. exclusive scan over the K (<= 32) buckets, lane = bucket; running counts of the CTA; placement counters
+      const int cnt = lane < K ? off[lane] : 0;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(MEVI_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total_valid = __shfl_sync(MEVI_FULL_MASK, incl, 31);
+      __syncwarp();
+      if (lane < K) {
+        off[lane] = incl - cnt;
+        sCnt[lane] += cnt;
+        sRun[lane] = 0;
+      }
+      if (lane == 0) off[K] = total_valid;
+      __syncwarp();
+      // 3. placement, rows in ascending order inside a bucket (stable): position = bucket start + rows of the bucket
+      //    placed by earlier blocks + rank among the equal codes of this block
+#pragma unroll
+      for (int i = 0; i < TM4 / 32; ++i) {
+        const int c = code[i];
+        const unsigned same = __match_any_sync(MEVI_FULL_MASK, c);
+        if (c < K) sPerm[buf * TM4 + off[c] + sRun[c] + __popc(same & ((1u << lane) - 1u))] = (uint8_t)(i * 32 + lane);
+        __syncwarp();
+        if (c < K && lane == __ffs(same) - 1) sRun[c] += __popc(same);
+        __syncwarp();
+      }
+      // 4. steps: centroid `lane`'s list is cut into ceil(cnt / 16) steps; steps are numbered centroid by centroid
+      {
+        const int nst = lane < K ? (cnt + STEP_ROWS4 - 1) / STEP_ROWS4 : 0;
+        int sincl = nst;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(MEVI_FULL_MASK, sincl, o);
+          if (lane >= o) sincl += v;
+        }
+        int* st0 = sStep0 + buf * (K + 2);
+        if (lane < K) st0[lane] = sincl - nst;
+        if (lane == 31) st0[K] = sincl;
+        for (int t = 0; t < nst; ++t) {
+          sStepB[buf * MAX_STEPS4 + sincl - nst + t] = (uint8_t)lane;
+          sStepC[buf * MAX_STEPS4 + sincl - nst + t] = (uint8_t)(cnt - STEP_ROWS4 * t < STEP_ROWS4 ? cnt - STEP_ROWS4 * t : STEP_ROWS4);
+        }
+      }
+      __syncwarp();
+      // 5. per step the stage offsets of its 16 rows (two steps per pass: lane = (step parity, row of the step))
+      {
+        const int total_steps = sStep0[buf * (K + 2) + K];
+        for (int s2 = 0; s2 < total_steps; s2 += 2) {
+          const int st = s2 + (lane >> 4), t = lane & 15;
+          if (st < total_steps) {
+            const int b = sStepB[buf * MAX_STEPS4 + st];
+            const int q = off[b] + STEP_ROWS4 * (st - sStep0[buf * (K + 2) + b]) + t;
+            sRowIdx[(buf * MAX_STEPS4 + st) * STEP_ROWS4 + t] = q < off[b + 1] ? sPerm[buf * TM4 + q] : (uint8_t)0;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sort_full[buf]);
+    }
+  } else if (ACC && warp >= ACC_WARP0) {
+    // ===== accumulators: sums of the rows under their previous code, from the fp32 stages =====
+    const int aw = warp - ACC_WARP0;
+    const int kb0 = aw * (K / ACC_WARPS), kb1 = (aw + 1) * (K / ACC_WARPS);
+    const int d = p.d;
+    const int g4 = lane >> 3;
+    const uint32_t u8 = (uint32_t)(lane & 7);
+    uint32_t xs = 0, xph = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1, bph = (it >> 1) & 1;
+      if (!ptx::mbar_wait_backoff(&sort_full[buf], bph, 64)) { atomicExch(p.err_flag, 9); return; }
+      const uint8_t* perm = sPerm + buf * TM4;
+      const int* off = sOff + buf * (K + 2);
+      const uint8_t* stepb = sStepB + buf * MAX_STEPS4;
+      const int* step0 = sStep0 + buf * (K + 2);
+      const uint8_t* rowidx = sRowIdx + buf * MAX_STEPS4 * STEP_ROWS4;
+      const uint8_t* stepc = sStepC + buf * MAX_STEPS4;
+      for (int c = 0; c < nchunks; ++c) {
+        if (!ptx::mbar_wait(&x_full[xs], xph)) { atomicExch(p.err_flag, 9); return; }
+        // Phase A (balanced whatever the cluster sizes): the tile's steps are dealt to the 8 warps four at a time.  lane =
+        // (step g = lane / 8 of the four, 16-byte unit u = lane % 8): one LDS.128 per lane covers one row of each of the
+        // four steps x 32 columns per warp instruction.  A group of 8 lanes walks its step's (up to 16) sorted rows four
+        // at a time (rows past the end read the zero line), adds them in a fixed order and parks the 32-column partial
+        // sum in the staging buffer of this chunk's parity.
+        const uint32_t stage_u32 = ptx::smem_u32(sX) + xs * X_STAGE4;
+        float4* part = sPart + (c & 1) * MAX_STEPS4 * 8;
+        const int nsteps = (p.debug & 128) ? 0 : step0[K];
+        for (int base = aw * 4; base < nsteps; base += 4 * ACC_WARPS) {
+          // four steps per warp at a time, one per group of 8 lanes: no cross-lane reduction, 4 independent row streams.
+          // The sorter left every step's 16 row offsets in a table (0xFFFF = past the end of the list -> zero line).
+          const int sidx = base + g4;
+          const bool live = sidx < nsteps;
+          const uint8_t* ro = rowidx + (live ? sidx : 0) * STEP_ROWS4;
+          const int cnt = live ? (int)stepc[sidx] : 0;
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+          for (int t0 = 0; t0 < STEP_ROWS4; t0 += 4) {
+            if (__all_sync(MEVI_FULL_MASK, t0 >= cnt)) break;  // every group's list has ended
+            const uint32_t r4 = *reinterpret_cast<const uint32_t*>(ro + t0);  // four row indices
+            float4 v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const uint32_t r = (r4 >> (8 * t)) & 255u;
+              const uint32_t ad = t0 + t < cnt ? stage_u32 + (r << 7) + ((u8 ^ (r & 7u)) << 4) : zero_line + (u8 << 4);
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[t].x), "=f"(v[t].y), "=f"(v[t].z), "=f"(v[t].w) : "r"(ad));
+            }
+            a0.x += v[0].x; a0.y += v[0].y; a0.z += v[0].z; a0.w += v[0].w;
+            a1.x += v[1].x; a1.y += v[1].y; a1.z += v[1].z; a1.w += v[1].w;
+            a2.x += v[2].x; a2.y += v[2].y; a2.z += v[2].z; a2.w += v[2].w;
+            a3.x += v[3].x; a3.y += v[3].y; a3.z += v[3].z; a3.w += v[3].w;
+          }
+          if (live)
+            part[sidx * 8 + u8] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                                              (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+        }
+        // the fp32 stage is consumed: hand it back, then wait for every warp's partials (named barrier of the 8 warps)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&x_empty[xs]);
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * ACC_WARPS) : "memory");
+        // Phase B: warp a owns the centroids [K/8 * a, K/8 * (a+1)) and adds their steps' partials, in step order, to the
+        // CTA's running sums (lanes 0-7: 32 columns).  The staging buffer of the other parity is free for the next
+        // chunk's phase A: a warp passes the next barrier only after its own phase B.
+        {  // lane = (g: which of the warp's K/8 centroids, u: 16-byte unit of the 32 columns)
+          const int b = kb0 + g4;
+          if (g4 < kb1 - kb0) {
+            const int s0 = step0[b], s1 = step0[b + 1];
+            if (s1 > s0) {
+              float4 a = part[s0 * 8 + u8];
+              for (int t = s0 + 1; t < s1; ++t) {
+                const float4 w = part[t * 8 + u8];
+                a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w;
+              }
+              float4* dst = reinterpret_cast<float4*>(sAcc + (size_t)b * d + c * KC4 + 4 * (int)u8);
+              float4 t4 = *dst;
+              t4.x += a.x; t4.y += a.y; t4.z += a.z; t4.w += a.w;
+              *dst = t4;
+            }
+          }
+        }
+        if (++xs == NSX) { xs = 0; xph ^= 1; }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&sort_empty[buf]);
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + (ACC ? EPI_WARPS4_ACC : EPI_WARPS4)) {
     const int ew = warp - EPI_WARP0;
     const float m2inv = (p.metric == MEVI_METRIC_L2 ? -2.f : -1.f) * p.consts[C_INV];
     const bool l2 = p.metric == MEVI_METRIC_L2;
@@ -285,8 +514,9 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
       if (!ptx::mbar_wait_backoff(acc_full, it & 1, 64) || !ptx::mbar_wait_backoff(&st_full[it & 1], (it >> 1) & 1, 32)) { atomicExch(p.err_flag, 6); ok = false; break; }
       ptx::tc_fence_after_sync();
       trace_ev(p, warp, lane, tix, it, 255, 0);  // accumulators ready
-      {
-        const int h = ew >> 2, q = ew & 3;  // half of the tile, 32-lane quarter of TMEM (== warp % 4)
+      // (fused k-means variant: 4 epilogue warps, each takes its lane quarter of BOTH halves)
+      for (int h = ACC ? 0 : (ew >> 2); h < (ACC ? 2 : (ew >> 2) + 1); ++h) {
+        const int q = ew & 3;  // 32-lane quarter of TMEM (== warp % 4)
         const int rl = h * 128 + q * 32 + lane;
         const float xn2 = sStats[(it & 1) * TM4 + rl];
         const float xn = sqrtf(xn2), nxn = -xn;
@@ -374,6 +604,11 @@ __global__ void __launch_bounds__(THREADS4, 1) rq_tensor4_kernel(Params p, const
   __syncthreads();
   trace_clock(p, 1);
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (ACC) {  // per-CTA partials; reduced in CTA order by kmeans_reduce_partials_kernel (deterministic)
+    const int64_t kd = (int64_t)K * p.d;
+    for (int i = tid; i < kd; i += NTHREADS) p.part_sums[(int64_t)blockIdx.x * kd + i] = sAcc[i];
+    for (int i = tid; i < K; i += NTHREADS) p.part_counts[(int64_t)blockIdx.x * K + i] = sCnt[i];
+  }
 }
 
 }  // namespace v4

@@ -13,6 +13,7 @@ the trainer itself only sequences kernels and collectives.
 from __future__ import annotations
 
 import math
+import os
 import time
 from typing import Optional
 
@@ -22,6 +23,9 @@ import torch.distributed as dist
 
 from . import _lib
 from .dist_utils import dist_on, gather_rows_to_rank0, rank_world, shard_bounds
+
+
+FUSED_LLOYD = os.environ.get("MEVI_KMEANS_FUSED", "1") != "0"  # one-pass Lloyd iterations (mevi_kmeans_step_fused)
 
 
 def kmeanspp_init(sample, K: int, rs: np.random.RandomState) -> torch.Tensor:
@@ -100,7 +104,7 @@ def _reseed_empty(R, C, buf, K, rs: np.random.RandomState, dev):
     return int(empty.numel())
 
 
-def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev, check_every=5):
+def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev, check_every=5, scratch=None):
     """One k-means problem on the local rows R [n, w] (all ranks in lockstep): k-means++ seeds from a sample of all
     shards, `iters` Lloyd iterations with ONE all-reduce of the fused sums|counts buffer each, then the labels under
     the FINAL centroids written to `col` (stride `stride`), like sklearn's fit_predict.  Convergence (relative inertia
@@ -118,9 +122,50 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
         dist.broadcast(C, 0)
     prev = math.inf
     n_it = 0
+    # One pass per iteration where the library offers it (mevi_kmeans_step_fused): the pass that assigns the rows to the
+    # current centroids also sums them under the PREVIOUS iteration's assignment; the rows whose assignment changed
+    # (few after the first iterations) are then moved between their old and new centroid's sums.  The first iteration
+    # has no previous assignment and takes the two-pass step.
+    fused = hasattr(be, "kmeans_step_fused") and n >= 4096 and FUSED_LLOYD
+    a_prev = a_cur = moved_buf = None
+    if fused:
+        # buffers of the one-pass iterations, allocated once per training (not per iteration: the changed-row count differs
+        # every time and a fresh multi-GB allocation per iteration costs more than the pass itself)
+        scratch = scratch if scratch is not None else {}
+        if scratch.get("n") != (n, w):
+            scratch.clear()
+            scratch.update(n=(n, w), a=torch.empty(n, dtype=torch.int32, device=dev), b=torch.empty(n, dtype=torch.int32, device=dev),
+                           moved=torch.empty((n // 4 + 1, w), dtype=torch.float32, device=dev))
+        a_prev, a_cur, moved_buf = scratch["a"], scratch["b"], scratch["moved"]
+    have_prev = False
+    stats = {"fused_iters": 0, "two_pass_iters": 0, "changed_rows": 0}
     t_loop = time.perf_counter()
     for it in range(iters):
-        be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
+        if fused and have_prev:
+            try:
+                be.kmeans_step_fused(R, C, a_prev, a_cur, buf, inertia=inertia)
+            except _lib.MeviError as e:
+                if "unsupported" not in str(e):
+                    raise
+                fused = False
+        if fused and have_prev:
+            changed = torch.nonzero(a_cur != a_prev).squeeze(1)
+            nc = int(changed.numel())
+            stats["changed_rows"] += nc
+            if nc > n // 4:  # cheaper to sum everything again than to move a quarter of the rows
+                be.accumulate_by_code(R, a_cur, K, buf)
+            elif nc > 0:
+                moved = be.gather_rows(R, changed.to(torch.int32), out=moved_buf)
+                plus = be.accumulate_by_code(moved, a_cur[changed].contiguous(), K)
+                minus = be.accumulate_by_code(moved, a_prev[changed].contiguous(), K)
+                buf.add_(plus).sub_(minus)
+            stats["fused_iters"] += 1
+        else:
+            be.kmeans_step(R, C, buf, assign=(a_cur if fused else col), assign_stride=(1 if fused else stride), inertia=inertia, mode=mode)
+            stats["two_pass_iters"] += 1
+        if fused:
+            a_prev, a_cur = a_cur, a_prev
+            have_prev = True
         if dist_on():
             dist.all_reduce(buf, op=dist.ReduceOp.SUM)
         be.kmeans_update(buf, C, n_empty)
@@ -133,6 +178,7 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
             if not reseeded and tol is not None and prev - cur <= tol * max(cur, 1e-30):
                 break
             prev = cur
+    _lloyd_level.last_stats = stats
     _lloyd_level.last_loop_seconds = time.perf_counter() - t_loop  # ends on the .item() of the last check: device time
     be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
     if dist_on():
@@ -172,16 +218,18 @@ def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: Opt
     n_empty = torch.zeros(1, dtype=torch.int32, device=dev)
     rs = np.random.RandomState(seed)
     info = {"levels": [], "world": world, "rows_local": n}
+    scratch = {}
     for j in range(M):
         t0 = time.time()
         col = codes[:, j]
-        C, n_it = _lloyd_level(be, R, K, col, M, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev)
+        C, n_it = _lloyd_level(be, R, K, col, M, rs, iters, tol, init_sample, mode, inertia, buf, n_empty, dev, scratch=scratch)
         codebook[j].copy_(C)
         if j != M - 1:  # pq.py:591-593
             be.residual_update(R, C, col, assign_stride=M)
         info["levels"].append({"level": j, "iters": n_it, "inertia": float(inertia.item()),
                                "mse": float(inertia.item()) / max(N, 1) / d, "seconds": time.time() - t0,
-                               "loop_ms_per_iter": getattr(_lloyd_level, "last_loop_seconds", 0.0) / max(n_it, 1) * 1e3})
+                               "loop_ms_per_iter": getattr(_lloyd_level, "last_loop_seconds", 0.0) / max(n_it, 1) * 1e3,
+                               **getattr(_lloyd_level, "last_stats", {})})
     train_rq_lloyd.last_info = info
     if presharded:
         return codebook, codes

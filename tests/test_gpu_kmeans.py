@@ -101,3 +101,64 @@ def test_trainer_quality_vs_reference_codebook(case):
     assert rep["n_hard"] == 0
     clus, mapping = pq.get_document_cluster_simple(True)
     assert len(mapping) == case.n and sum(len(v) for v in clus.values()) == case.n
+
+
+@pytest.mark.parametrize("n,d,K", [(20000, 768, 32), (4097, 768, 32), (70001, 256, 32), (9000, 512, 32)])
+def test_fused_step_assigns_and_accumulates_in_one_pass(n, d, K):
+    """mevi_kmeans_step_fused: new assignment under C + per-centroid sums|counts of the rows under the PREVIOUS
+    assignment, in one read of the shard.  Against the two-pass kernels (assignment bit-equal, sums to fp32 rounding),
+    a float64 oracle, and itself (bit-reproducible)."""
+    rs = np.random.RandomState(n)
+    X = rs.standard_normal((n, d)).astype(np.float32)
+    X[: n // 3] += 2.0 * rs.standard_normal((1, d)).astype(np.float32)  # skew: a third of the rows share a cluster
+    C0 = X[rs.choice(n, K, replace=False)].copy()
+    C1 = (C0 + 0.05 * rs.standard_normal((K, d))).astype(np.float32)
+    c = ctx()
+    Xd, C0d, C1d = dev(X), dev(C0), dev(C1)
+    buf = torch.empty(K * d + K, device="cuda:0")
+    prev = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    c.kmeans_step(Xd, C0d, buf, assign=prev, mode="tensor")
+    want_assign = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    c.kmeans_step(Xd, C1d, buf, assign=want_assign, mode="tensor")
+    want_prev_sums = c.accumulate_by_code(Xd, prev, K).clone()
+    cur = torch.empty(n, dtype=torch.int32, device="cuda:0")
+    got = torch.empty(K * d + K, device="cuda:0")
+    inertia = torch.zeros(1, dtype=torch.float64, device="cuda:0")
+    c.kmeans_step_fused(Xd, C1d, prev, cur, got, inertia=inertia)
+    c.check()
+    assert torch.equal(cur, want_assign)
+    assert torch.equal(got[K * d :], want_prev_sums[K * d :])  # counts
+    np.testing.assert_allclose(got[: K * d].cpu().numpy(), want_prev_sums[: K * d].cpu().numpy(), rtol=2e-5, atol=2e-3)
+    pa = prev.cpu().numpy()
+    s64 = np.zeros((K, d), np.float64)
+    np.add.at(s64, pa, X.astype(np.float64))
+    np.testing.assert_allclose(got[: K * d].view(K, d).cpu().numpy(), s64, rtol=2e-5, atol=2e-3)
+    _, _, _, i_ref, _ = oracle.lloyd_step(X, C1)
+    assert abs(float(inertia.item()) - i_ref) <= 1e-5 * i_ref
+    got2 = torch.empty_like(got)
+    cur2 = torch.empty_like(cur)
+    c.kmeans_step_fused(Xd, C1d, prev, cur2, got2)
+    assert torch.equal(got, got2) and torch.equal(cur, cur2)
+
+
+def test_trainer_one_pass_iterations_match_two_pass_training(monkeypatch):
+    """train_rq_lloyd with one-pass iterations (fused assign + accumulate, changed rows moved afterwards) against the
+    same training with two passes per iteration: same codes, same codebook up to fp32 summation order."""
+    from mevi_b200 import trainer
+
+    rs = np.random.RandomState(21)
+    centers = rs.standard_normal((40, 768)).astype(np.float32)
+    X = (centers[rs.randint(0, 40, 30000)] + 0.7 * rs.standard_normal((30000, 768))).astype(np.float32)
+    out = {}
+    for fused in (True, False):
+        monkeypatch.setattr(trainer, "FUSED_LLOYD", fused)
+        cb, codes = trainer.train_rq_lloyd(X, M=2, K=32, seed=41, iters=8, tol=None, device_index=0)
+        info = trainer.train_rq_lloyd.last_info
+        out[fused] = (cb.cpu().numpy(), codes, info)
+    assert out[True][2]["levels"][0]["fused_iters"] == 7 and out[False][2]["levels"][0]["fused_iters"] == 0
+    assert out[True][2]["levels"][0]["changed_rows"] > 0
+    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-4, atol=1e-4)
+    assert (out[True][1] != out[False][1]).any(1).mean() < 2e-3
+    m1 = oracle.quantisation_mse(X, out[True][0], out[True][1])
+    m0 = oracle.quantisation_mse(X, out[False][0], out[False][1])
+    assert abs(m1 - m0) <= 1e-4 * m0
