@@ -117,6 +117,36 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+_ORIG_AFFINITY = set()
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the GPU's PCI device):
+    with N ranks each pulling 27 GB of pinned host rows, buffers that all land on one node halve the H2D rate."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        _ORIG_AFFINITY.update(allowed)  # the CPU-baseline child gets every core back
+        cpus &= allowed
+        if not cpus:
+            return "unchanged (no local_cpulist inside the allowed set)"
+        os.sched_setaffinity(0, cpus)
+        node = open(f"{base}/numa_node").read().strip()
+        return f"GPU {bdf} numa_node {node}, {len(cpus)} CPUs"
+    except Exception as e:
+        return f"unchanged ({type(e).__name__}: {e})"[:160]
+
+
 def make_corpus(n, d, device, seed):
     import torch
 
@@ -204,11 +234,13 @@ def our_arm(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # pinned host buffers of the e2e leg then live next to this GPU's PCIe root
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = mevi_b200.get_context(local_rank)
     hbm_peak, bf16_peak, peak_src = measured_peaks()
     n = args.docs
+    log(f"[rank {rank}] host affinity: {numa}")
     log(f"[rank {rank}] generating {n} x {D} fp32 corpus on {torch.cuda.get_device_name(dev)}")
     X = make_corpus(n, D, dev, 1234 + rank)
     cb_cpu = load_codebook()
@@ -390,8 +422,10 @@ def cpu_legs(path):
     initialises CUDA: inside a CUDA process every munmap of the 12.6 MB torch temporaries goes through the
     UVM notifier and the CPU path runs ~10x slower than the reference would on its own."""
     try:
+        restore = (lambda: os.sched_setaffinity(0, _ORIG_AFFINITY)) if _ORIG_AFFINITY else None
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-baseline-child", "--sample-file", path],
-                             capture_output=True, text=True, timeout=900, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+                             capture_output=True, text=True, timeout=900, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""},
+                             preexec_fn=restore)
         line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
         return json.loads(line)
     except Exception as e:

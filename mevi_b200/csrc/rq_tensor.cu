@@ -56,6 +56,9 @@ struct Params {
   int32_t* codes; int64_t codes_stride;
   int32_t* work_rows; int32_t* work_levels; unsigned long long* work_count;
   unsigned long long* refine_count;  // generation 6: (row, level) decisions refined in the epilogue
+  // generation 6, two-kernel form: rows with an open level are dumped (row, state, tensor-core accumulators of all levels)
+  // for rq_refine6_kernel instead of being refined inside the epilogue
+  int32_t* open_rows; int4* open_meta; float* open_t1; unsigned long long* open_count; int64_t open_cap;
   // fused k-means pass (rq_tensor4_kernel<1, true>): previous assignment in, per-CTA partial sums | counts out
   const int32_t* prev; int64_t prev_stride; float* part_sums; int32_t* part_counts;
   double* inertia; int* err_flag;
@@ -417,6 +420,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   p.work_rows = work; p.work_levels = work + n; p.work_count = work_count; p.refine_count = refine_count;
   p.inertia = inertia; p.err_flag = err_flag;
   p.prev = nullptr; p.prev_stride = 0; p.part_sums = nullptr; p.part_counts = nullptr;
+  p.open_rows = nullptr; p.open_meta = nullptr; p.open_t1 = nullptr; p.open_count = nullptr; p.open_cap = 0;
   {
     const char* dbg = getenv("MEVI_RQ_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
@@ -434,10 +438,35 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     p.n_tiles = (n + v6::TM6 - 1) / v6::TM6;
     const size_t smem6 = (size_t)v6::smem6_layout(M, NT).total + 1024;
     const int grid6 = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+    // two-kernel form (default for generation 6; MEVI_RQ_REFINE=inline keeps the refinement inside the epilogue): the open
+    // list holds up to a quarter of the rows (11-12 % are open on N(0,1) data; overflow goes to the exact kernel)
+    const char* rmode = getenv("MEVI_RQ_REFINE");
+    const bool two_kernel = !(rmode && rmode[0] == 'i') && d <= 1024;
+    if (two_kernel) {
+      const int64_t cap = n / 4 + 1024;
+      size_t ooff = 0;
+      auto otake = [&](size_t bytes) { size_t o = ooff; ooff = (ooff + bytes + 255) & ~size_t(255); return o; };
+      const size_t o_cnt2 = otake(8), o_rows = otake((size_t)cap * 4), o_meta = otake((size_t)cap * 16), o_t1 = otake((size_t)cap * M * 32 * 4);
+      char* ows = (char*)mevi_ws(ctx, WS_RQ_OPEN, ooff);
+      if (!ows) return MEVI_ERR_NOMEM;
+      p.open_count = (unsigned long long*)(ows + o_cnt2);
+      p.open_rows = (int32_t*)(ows + o_rows);
+      p.open_meta = (int4*)(ows + o_meta);
+      p.open_t1 = (float*)(ows + o_t1);
+      p.open_cap = cap;
+      MEVI_CUDA(ctx, cudaMemsetAsync(p.open_count, 0, 8, st));
+    }
+    int gram_pad6 = 0;
+    for (int j = 1; j < M; ++j) gram_pad6 += j * 32 * 33;
+    const size_t smem_ref = (size_t)(gram_pad6 + 4 * NT + 16) * 4 + 64;
 #define MEVI_LAUNCH_RQ_TENSOR6(MM)                                                                                          \
   do {                                                                                                                      \
     MEVI_CUDA(ctx, cudaFuncSetAttribute(v6::rq_tensor6_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6)); \
     v6::rq_tensor6_kernel<MM><<<grid6, v6::THREADS6, smem6, st>>>(p, tmap);                                                 \
+    if (two_kernel) {                                                                                                       \
+      v6::rq_refine6_kernel<MM><<<ctx->sm_count * 8, 256, smem_ref, st>>>(p);                                               \
+      MEVI_COUNT_LAUNCH(ctx, 1);                                                                                            \
+    }                                                                                                                       \
   } while (0)
     switch (M) {
       case 2: MEVI_LAUNCH_RQ_TENSOR6(2); break;

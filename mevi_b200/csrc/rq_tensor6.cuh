@@ -494,7 +494,42 @@ __global__ void __launch_bounds__(THREADS6, 1) rq_tensor6_kernel(Params p, const
           if (lane * 32 < d) ptx::prefetch_l2(p.X + (row0 + src) * d + lane * 32);
         }
       }
-      if (__ballot_sync(MEVI_FULL_MASK, openmask != 0u) != 0u && !(p.debug & 64)) {
+      if (p.open_rows != nullptr) {
+        // two-kernel form: rows with an open level leave the pipeline here - their state and the tensor-core
+        // accumulators of every level from the first open one on go to the open list (rq_refine6_kernel finishes them with
+        // thousands of rows in flight instead of one per epilogue warp); the codes written below are provisional for them
+        const unsigned om = __ballot_sync(MEVI_FULL_MASK, openmask != 0u);
+        if (om != 0u) {
+          const int leader = __ffs(om) - 1;
+          unsigned long long base = 0;
+          if (lane == leader) base = atomicAdd(p.open_count, (unsigned long long)__popc(om));
+          base = __shfl_sync(MEVI_FULL_MASK, base, leader);
+          const long long slot = (long long)base + __popc(om & ((1u << lane) - 1u));
+          const bool dump = openmask != 0u && slot < p.open_cap;
+          const int j0 = openmask != 0u ? __ffs(openmask) - 1 : M;
+#pragma unroll
+          for (int j = 0; j < M; ++j) {
+            if (__ballot_sync(MEVI_FULL_MASK, dump && j >= j0) == 0u) continue;
+            uint32_t ra[32];
+            ptx::tmem_ld32(taddr + j * K, ra);
+            ptx::tmem_ld_wait();
+            if (dump && j >= j0) {
+              uint4* dst = reinterpret_cast<uint4*>(p.open_t1 + (slot * M + j) * 32);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) dst[t] = make_uint4(ra[4 * t], ra[4 * t + 1], ra[4 * t + 2], ra[4 * t + 3]);
+            }
+          }
+          if (dump) {
+            unsigned packed = 0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) packed |= (unsigned)code[j] << (8 * j);
+            p.open_rows[slot] = (int32_t)row;
+            p.open_meta[slot] = make_int4((int)packed, j0, __float_as_int(xn), __float_as_int(na));
+          } else if (openmask != 0u) {
+            flag_level = j0;  // the open list is full: the exact kernel takes the row from its first open level
+          }
+        }
+      } else if (__ballot_sync(MEVI_FULL_MASK, openmask != 0u) != 0u && !(p.debug & 64)) {
         unsigned packed = 0;
 #pragma unroll
         for (int j = 0; j < M; ++j) packed |= (unsigned)code[j] << (8 * j);
@@ -544,6 +579,121 @@ __global__ void __launch_bounds__(THREADS6, 1) rq_tensor6_kernel(Params p, const
   __syncthreads();
   trace_clock(p, 1);
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Second kernel of the two-kernel form: one warp per open row, lane = candidate.  The row's tensor-core accumulators of
+// the levels from its first open one on come from the dump (128 B per level, coalesced), the row itself is read once
+// (3 KB, coalesced) and kept in registers; per level the loose bound decides or lists the open candidates, whose exact-input
+// fp32 dot products are computed by the whole warp; the tight bound decides or sends the row to the exact kernel's work list.
+// Thousands of rows are in flight per SM-wave, so the memory latency that stalls the in-epilogue refinement is hidden.
+template <int M>
+__global__ void __launch_bounds__(256) rq_refine6_kernel(Params p) {
+  constexpr int K = 32;
+  extern __shared__ __align__(16) float sm6[];
+  float* sGram = sm6;                       // padded rows of K+1
+  int gram_pad = 0;
+  for (int j = 1; j < M; ++j) gram_pad += j * K * (K + 1);
+  float* sCn2 = sGram + gram_pad;
+  float* sE1 = sCn2 + M * K;
+  float* sEA1 = sE1 + M * K;
+  float* sEA2 = sEA1 + M * K;
+  float* sLvl = sEA2 + M * K;
+  for (int i = threadIdx.x; i < p.gram_floats; i += blockDim.x) sGram[(i / K) * (K + 1) + (i % K)] = p.gram[i];
+  for (int i = threadIdx.x; i < M * K; i += blockDim.x) {
+    sCn2[i] = p.cn2[i];
+    sE1[i] = p.e1[i];
+    sEA1[i] = p.ea1[i];
+    sEA2[i] = p.ea2[i];
+  }
+  for (int i = threadIdx.x; i < M * 4; i += blockDim.x) sLvl[i] = p.lvl[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long n_open = (long long)(*p.open_count < (unsigned long long)p.open_cap ? *p.open_count : (unsigned long long)p.open_cap);
+  const bool l2 = p.metric == MEVI_METRIC_L2;
+  const float mf = l2 ? -2.f : -1.f;
+  const float m2inv = mf * p.consts[C_INV];
+  const int d = p.d, nd = d / 128;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  unsigned n_ref = 0;
+  for (long long slot = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); slot < n_open; slot += warps) {
+    const int row = p.open_rows[slot];
+    const int4 meta = p.open_meta[slot];
+    unsigned packed = (unsigned)meta.x;
+    const int j0 = meta.y;
+    const float xn = __int_as_float(meta.z), na = __int_as_float(meta.w), nxn = -xn;
+    const float* xr = p.X + (int64_t)row * d;
+    float4 xv[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) xv[t] = t < nd ? __ldg(reinterpret_cast<const float4*>(xr + lane * 4 + 128 * t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    int flag = -1;
+    for (int j = j0; j < M && flag < 0; ++j) {
+      const float acc = p.open_t1[(slot * M + j) * 32 + lane];
+      const float* gj = sGram + (j * (j - 1) / 2) * K * (K + 1);
+      float g = 0.f;
+      for (int m = 0; m < j; ++m) g += gj[(m * K + (int)((packed >> (8 * m)) & 255u)) * (K + 1) + lane];
+      const float base = l2 ? fmaf(2.f, g, sCn2[j * K + lane]) : g;
+      const float dk = fmaf(acc, m2inv, base);
+      float c1 = dk;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c1 = fminf(c1, __shfl_xor_sync(MEVI_FULL_MASK, c1, o));
+      const unsigned bm = __ballot_sync(MEVI_FULL_MASK, dk == c1);
+      int best = bm ? __ffs(bm) - 1 : 0;  // lowest index among equals (NaN rows: no lane matches -> unresolved below)
+      const float u = fmaf(nxn, sEA2[j * K + lane], fmaf(na, sEA1[j * K + lane], dk));
+      float other = lane == best ? CUDART_INF_F : u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) other = fminf(other, __shfl_xor_sync(MEVI_FULL_MASK, other, o));
+      const float hi_best = c1 + fmaf(xn, sEA2[j * K + best], -na * sEA1[j * K + best]) + sLvl[j * 4 + 1];
+      bool resolved = bm != 0u && other > hi_best;
+      if (!resolved) {
+        unsigned cm = __ballot_sync(MEVI_FULL_MASK, u <= hi_best);
+        const int nc = __popc(cm);
+        if (bm != 0u && nc >= 2 && nc <= MAX_REFINE) {
+          float rb = CUDART_INF_F, vb = CUDART_INF_F, v1 = CUDART_INF_F, v2 = CUDART_INF_F;
+          int rbi = 0;
+          while (cm != 0u) {
+            const int k = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const float* cr = p.cb + (size_t)(j * K + k) * d + lane * 4;
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              if (t < nd) {
+                const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + 128 * t));
+                a4.x = fmaf(xv[t].x, cv.x, a4.x);
+                a4.y = fmaf(xv[t].y, cv.y, a4.y);
+                a4.z = fmaf(xv[t].z, cv.z, a4.z);
+                a4.w = fmaf(xv[t].w, cv.w, a4.w);
+              }
+            }
+            float sdot = (a4.x + a4.y) + (a4.z + a4.w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(MEVI_FULL_MASK, sdot, o);
+            const float dr = fmaf(sdot, mf, __shfl_sync(MEVI_FULL_MASK, base, k));
+            const float v = fmaf(nxn, sE1[j * K + k], dr);
+            if (dr < rb) { rb = dr; rbi = k; vb = v; }  // ascending k, strict: lowest index among equals
+            v2 = fminf(v2, fmaxf(v1, v));
+            v1 = fminf(v1, v);
+          }
+          resolved = ((vb == v1) ? v2 : v1) > rb + xn * sE1[j * K + rbi] + sLvl[j * 4 + 1];
+          best = rbi;
+          ++n_ref;
+        }
+      }
+      packed = (packed & ~(255u << (8 * j))) | ((unsigned)best << (8 * j));
+      if (!resolved) flag = j;  // the exact kernel re-decides the row from this level on
+    }
+    if (lane == 0) {
+      int32_t* dst = p.codes + (int64_t)row * p.codes_stride;
+#pragma unroll
+      for (int j = 0; j < M; ++j) dst[j] = (int32_t)((packed >> (8 * j)) & 255u);
+      if (flag >= 0) {
+        const unsigned long long w = atomicAdd(p.work_count, 1ull);
+        p.work_rows[w] = row;
+        p.work_levels[w] = flag;
+      }
+    }
+  }
+  if (lane == 0 && n_ref != 0u) atomicAdd(p.refine_count, (unsigned long long)n_ref);
 }
 
 }  // namespace v6
