@@ -463,7 +463,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   do {                                                                                                                      \
     MEVI_CUDA(ctx, cudaFuncSetAttribute(v6::rq_tensor6_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6)); \
     v6::rq_tensor6_kernel<MM><<<grid6, v6::THREADS6, smem6, st>>>(p, tmap);                                                 \
-    if (two_kernel) {                                                                                                       \
+    if (two_kernel && !(p.debug & 256)) {                                                                                   \
       v6::rq_refine6_kernel<MM><<<ctx->sm_count * 8, 256, smem_ref, st>>>(p);                                               \
       MEVI_COUNT_LAUNCH(ctx, 1);                                                                                            \
     }                                                                                                                       \

@@ -1,7 +1,8 @@
 #!/bin/bash
-# K1 generation 6 (hi.hi prefilter + in-epilogue refinement): parity vs the direct fp32 kernel, then timing at the bench size
+# K1 generation 6 (hi.hi prefilter; undecided rows dumped for rq_refine6_kernel, or MEVI_RQ_REFINE=inline): parity vs the direct fp32 kernel, then timing at the bench size
 timeout 600 python - <<'PY'
 import os, sys, torch
+os.environ['MEVI_RQ_KERNEL'] = '6'
 sys.path.insert(0, os.getcwd())
 import mevi_b200
 ctx = mevi_b200.get_context(0)
@@ -34,12 +35,14 @@ def run(tag, reps=20):
 run("v6 default")
 _, st = ctx.rq_encode(X, cb, mode="tensor", return_stats=True); print("stats at 8.84M:", st.tolist()[:3], flush=True)
 e = ctx.rq_encode(X[:300000], cb, mode="exact"); print("mismatch vs exact on 300k:", int((codes[:300000] != e).any(1).sum()), flush=True)
-for dbg, name in ((64, "no refinement"), (4, "no epilogue math"), (2, "no MMA")):
+for dbg, name in ((256, "refine kernel not launched"), (4, "no epilogue math")):
     os.environ["MEVI_RQ_DEBUG"] = str(dbg); run(f"v6 debug={dbg} ({name})", reps=10)
 os.environ["MEVI_RQ_DEBUG"] = "0"
-os.environ["MEVI_RQ_KERNEL"] = "4"; run("v4 (split fp16)", reps=10); del os.environ["MEVI_RQ_KERNEL"]
+os.environ["MEVI_RQ_REFINE"] = "inline"; run("v6 inline refinement", reps=5); del os.environ["MEVI_RQ_REFINE"]
+os.environ["MEVI_RQ_KERNEL"] = "4"; run("v4 (split fp16)", reps=10); os.environ["MEVI_RQ_KERNEL"] = "6"
 run("v6 again")
 ctx.check()
 PY
 echo "rc=$?"
 
+MEVI_RQ_KERNEL=6 timeout 600 python -m pytest tests/test_gpu_rq_encode.py -m gpu -x -q 2>&1 | tail -3
