@@ -24,8 +24,10 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __re
                                                                const float* __restrict__ cb, int M, int K, int dsub,
                                                                int32_t* __restrict__ codes,
                                                                const int32_t* __restrict__ work_rows,   // optional: row ids
-                                                               const int64_t* __restrict__ n_work_dev)  // and their count
+                                                               const int64_t* __restrict__ n_work_dev,  // and their count
+                                                               const int* __restrict__ run_if)          // optional: run only if != 0
 {
+  if (run_if != nullptr && *run_if == 0) return;
   // work-list form (the arbiter of rows the tensor prefilter flagged): item i is row work_rows[i]; the arithmetic per
   // (row, sub-vector, centroid) does not depend on the tile a row sits in, so codes equal those of the plain form
   if (work_rows != nullptr) n = *n_work_dev;
@@ -110,10 +112,64 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_encode_kernel(const float* __re
   }
 }
 
+// Arbiter of the (row, sub-vector) pairs the wide-codebook tensor kernel (pq_tensor.cuh) could not decide: one warp per
+// pair, lane = centroids lane, lane+32, ...; per centroid exactly the arithmetic of pq_encode_kernel (four FMA chains over
+// the elements e = 0, 4, 8, ... combined as (a0 + a1) + (a2 + a3); lowest index on ties), so a re-decided pair gets the
+// code the sub-vector kernel would give it.
+template <bool L2>
+__global__ void __launch_bounds__(256) pq_fix_pairs_kernel(const float* __restrict__ X, int d, const float* __restrict__ cb, int M,
+                                                           int K, int dsub, int32_t* __restrict__ codes,
+                                                           const uint32_t* __restrict__ pairs,
+                                                           const unsigned long long* __restrict__ n_pairs_dev,
+                                                           unsigned long long cap) {
+  const unsigned long long n_pairs = *n_pairs_dev < cap ? *n_pairs_dev : cap;
+  const int lane = threadIdx.x & 31;
+  const int ds4 = dsub >> 2;
+  const unsigned long long warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n_pairs; i += warps) {
+    const uint32_t pr = pairs[i];
+    const int64_t row = pr / (uint32_t)M;
+    const int j = (int)(pr - (uint32_t)row * (uint32_t)M);
+    const float4* xr = reinterpret_cast<const float4*>(X + row * d + j * dsub);
+    const float4* cj = reinterpret_cast<const float4*>(cb + (int64_t)j * K * dsub);
+    float best = -CUDART_INF_F;
+    int besti = 0x7fffffff;
+    for (int k = lane; k < K; k += 32) {
+      const float4* ca = cj + (int64_t)k * ds4;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int e = 0; e < ds4; ++e) {
+        const float4 x = __ldg(xr + e);
+        const float4 u = __ldg(ca + e);
+        if (L2) {
+          const float t0 = x.x - u.x, t1 = x.y - u.y, t2 = x.z - u.z, t3 = x.w - u.w;
+          a0 = fmaf(t0, t0, a0); a1 = fmaf(t1, t1, a1); a2 = fmaf(t2, t2, a2); a3 = fmaf(t3, t3, a3);
+        } else {
+          a0 = fmaf(x.x, u.x, a0); a1 = fmaf(x.y, u.y, a1); a2 = fmaf(x.z, u.z, a2); a3 = fmaf(x.w, u.w, a3);
+        }
+      }
+      const float sa = (a0 + a1) + (a2 + a3);
+      const float s0 = L2 ? -sa : sa;
+      if (s0 > best) {  // ascending k per lane, strict: the lowest index wins exact ties; NaN / -inf scores never win
+        best = s0;
+        besti = k;
+      }
+    }
+    // warp argmax, lowest index among equal scores (no candidate above -inf: code 0, as in the sub-vector kernel)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(MEVI_FULL_MASK, best, o);
+      const int oi = __shfl_xor_sync(MEVI_FULL_MASK, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) codes[row * M + j] = besti == 0x7fffffff ? 0 : besti;
+  }
+}
+
 }  // namespace
 
 static int launch_pq_kernel(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K, int metric,
-                            int32_t* codes, const int32_t* work_rows, const int64_t* n_work_dev, cudaStream_t st) {
+                            int32_t* codes, const int32_t* work_rows, const int64_t* n_work_dev, cudaStream_t st,
+                            const int* run_if = nullptr) {
   const int dsub = d / M;
   const int nparts = M >= PQ_THREADS / 32 ? 1 : (PQ_THREADS / 32) / M;
   const size_t smem = (size_t)PQ_ROWS * (d + 4) * sizeof(float) + (size_t)M * nparts * PQ_ROWS * 8;
@@ -124,10 +180,10 @@ static int launch_pq_kernel(mevi_ctx* ctx, const float* X, int64_t n, int d, con
   const int grid = (int)(n_tiles < max_grid ? n_tiles : max_grid);
   if (metric == MEVI_METRIC_L2) {
     MEVI_CUDA(ctx, cudaFuncSetAttribute(pq_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pq_encode_kernel<true><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes, work_rows, n_work_dev);
+    pq_encode_kernel<true><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes, work_rows, n_work_dev, run_if);
   } else {
     MEVI_CUDA(ctx, cudaFuncSetAttribute(pq_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pq_encode_kernel<false><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes, work_rows, n_work_dev);
+    pq_encode_kernel<false><<<grid, PQ_THREADS, smem, st>>>(X, n, d, codebook, M, K, dsub, codes, work_rows, n_work_dev, run_if);
   }
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 1);
@@ -140,6 +196,21 @@ int mevi_pq_fix_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const fl
   // a launch sized for a few flagged rows per thousand; the kernel's tile loop covers whatever the list holds
   const int64_t bound = n < (int64_t)ctx->sm_count * 2 * PQ_ROWS ? n : (int64_t)ctx->sm_count * 2 * PQ_ROWS;
   return launch_pq_kernel(ctx, X, bound, d, pq_codebook, M, K, metric, codes, work_rows, n_work_dev, st);
+}
+
+// pairs (row * M + sub-vector) of the wide-codebook tensor kernel, re-decided in the sub-vector kernel's arithmetic; if the
+// pair list overflowed (*overflow != 0) the whole matrix is redone by the sub-vector kernel instead
+int mevi_pq_fix_pairs_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* pq_codebook, int M, int K, int metric,
+                             int32_t* codes, const uint32_t* pairs, const unsigned long long* n_pairs_dev, unsigned long long cap,
+                             const int* overflow, cudaStream_t st) {
+  const int dsub = d / M;
+  if (metric == MEVI_METRIC_L2)
+    pq_fix_pairs_kernel<true><<<ctx->sm_count * 8, 256, 0, st>>>(X, d, pq_codebook, M, K, dsub, codes, pairs, n_pairs_dev, cap);
+  else
+    pq_fix_pairs_kernel<false><<<ctx->sm_count * 8, 256, 0, st>>>(X, d, pq_codebook, M, K, dsub, codes, pairs, n_pairs_dev, cap);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  return launch_pq_kernel(ctx, X, n, d, pq_codebook, M, K, metric, codes, nullptr, nullptr, st, overflow);
 }
 
 namespace {
@@ -163,6 +234,9 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
                           int32_t* codes, int64_t codes_stride, float* residual, int64_t* stats, double* inertia,
                           cudaStream_t st);
 bool mevi_rq_tensor_supported(mevi_ctx* ctx, int d, int M, int K, int metric);
+bool mevi_pq_tensor_supported(mevi_ctx* ctx, int64_t n, int d, int M, int K, int metric);
+int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K, int metric,
+                          int32_t* codes, int64_t* stats, cudaStream_t st);
 
 extern "C" int mevi_pq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* codebook, int M, int K,
                               int metric, int32_t* codes, void* stream) {
@@ -194,5 +268,8 @@ extern "C" int mevi_pq_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, c
     ctx->pq_fix_dsub = 0;
     return rc;
   }
+  // wide codebooks (K = 256, sub-vector width 32): the split-fp16 tensor kernel of pq_tensor.cuh
+  if (!(env && atoi(env) == 0) && n >= 4096 && mevi_pq_tensor_supported(ctx, n, d, M, K, metric))
+    return mevi_pq_tensor_encode(ctx, X, n, d, codebook, M, K, metric, codes, nullptr, st);
   return launch_pq_kernel(ctx, X, n, d, codebook, M, K, metric, codes, nullptr, nullptr, st);
 }

@@ -1,0 +1,479 @@
+// pq_tensor.cuh — product-quantiser encode on the tensor cores for the wide codebooks (K = 256 centroids per
+// sub-vector, sub-vector width 32: 24 x 256 at d = 768, 32 x 256 at d = 1024).  Replaces MEVI/pq.py:249-279 for
+// those shapes; the M*K <= 128 shapes ride on K1 (pq_encode.cu), everything else on the fp32 sub-vector kernel.
+//
+// Per sub-vector j the scores  s_k = 2 x_j.c_k - |c_k|^2  ('l2': the reference's -|x_j - c_k|^2 up to the row constant)
+// or  x_j.c_k  ('ip') of 256 centroids are one [rows x 32] . [32 x 256] contraction: split-fp16 (hi.hi + hi.lo + lo.hi,
+// ~2^-22 relative) on tcgen05 with the document operand in TENSOR MEMORY, as in K1 generation 4.  What differs from K1:
+//   * the codebook operand of a sub-vector is 32 KB (K1: 16 KB per chunk for all levels), so it cannot be streamed per
+//     row tile.  The CTA keeps the images of FOUR sub-vectors (128 KB) resident and walks ALL its row tiles for them,
+//     then loads the next four: the document matrix is still read exactly once, in six passes over 512-byte row pieces;
+//   * a unit of work is (128 rows, sub-vector, half of the centroids): N = 128 accumulator columns, THREE buffers in
+//     rotation (unit u -> buffer u % 3) so the MMAs of the next unit run while two units are being drained; MMA warp h
+//     issues the units of half h (two independent issue streams fill each other's commit bubbles);
+//   * the epilogue reduces 256 scores per (row, sub-vector) — 6,144 per row, the issue-bound part of the kernel.  It
+//     takes the argmax AND a bound on every other score without packing indices: the 256 scores are a 32 x 8 matrix
+//     (k = 8 g + j); R_g = max over row g and C_j = max over column j cost one FMNMX3 per two scores each.  The best
+//     score is max R = max C at (g*, j*); every other candidate sits in another row or another column, so
+//     max(second largest R, second largest C) bounds them all.  If best - that bound exceeds the error bound of the
+//     prefilter (+ the fp32 direct form's own rounding) the pair is decided, else (row, sub-vector) goes to a pair list
+//     and the fp32 direct-form arbiter (pq_fix_pairs_kernel) re-decides it with the arithmetic of pq_encode_kernel.
+//
+// Warps: 0 TMA producer ([128 rows x 32 fp32] boxes, 128B swizzle, 4 stages) | 1-2 MMA | 3 codebook-group loader |
+// 4-7 converters (thread = row = TMEM lane; fp32 -> fp16 hi|lo into one of 8 TMEM operand stages; |x_j|^2 on the side) |
+// 8-15 epilogue.  TMEM: [0,384) three accumulator buffers, [384,512) four operand stages.
+// Barriers that several roles wait on in turn (accumulator full / empty) exist once per waiter: a parity wait is only
+// sound when the same thread observes every phase of its barrier in order.
+#pragma once
+
+namespace pq256 {
+
+constexpr int TMQ = 128, KQ = 256, DSQ = 32, GSQ = 4;
+constexpr int NSXQ = 4, NSAQ = 4, NORMQ = 16, NACCQ = 3;
+constexpr int X_STAGEQ = TMQ * DSQ * 4;       // 16 KB
+constexpr int B_SUBQ = 2 * KQ * DSQ * 2;      // 32 KB: [hi 256 rows x 64 B][lo 256 rows x 64 B]
+constexpr int THREADSQ = 512;
+constexpr int CONVQ_WARP0 = 4, CONVQ_WARPS = 4, EPIQ_WARP0 = 8, EPIQ_WARPS = 8;
+constexpr uint32_t AQ_COL0 = 384;
+// rounding of the fp32 direct form sum_e (x_e - c_e)^2 with four chains of 8 FMAs + 2 adds: <= 12 * 2^-24 of the sum,
+// doubled for margin
+constexpr float GAMMA_DIRECT = 12.f * 1.1920929e-7f;
+
+struct PqParams {
+  const float* X; int64_t n; int d; int M; int metric;
+  const __half* Bimg;      // [M][2*KQ][DSQ] fp16, pre-swizzled
+  const float* negcn2;     // [M][KQ]: -|c_k|^2 ('l2') or 0 ('ip')
+  const float* subc;       // [M][4]: e1max, B, cmax, unused
+  const float* consts;
+  int32_t* codes;          // [n][M]
+  uint32_t* pairs; unsigned long long* pair_count; unsigned long long pair_cap; int* overflow;
+  int* err_flag;
+  int64_t n_tiles;
+  int debug;
+};
+
+struct SmemQ {
+  int x_off, b_off, cn2_off, subc_off, norm_off, xch_off, bar_off, holder_off, total;
+};
+__host__ __device__ inline SmemQ smemq_layout() {
+  SmemQ L;
+  L.x_off = 0;
+  L.b_off = L.x_off + NSXQ * X_STAGEQ;
+  L.cn2_off = L.b_off + GSQ * B_SUBQ;
+  L.subc_off = L.cn2_off + GSQ * KQ * 4;
+  L.norm_off = L.subc_off + GSQ * 16;
+  L.xch_off = L.norm_off + NORMQ * TMQ * 4;
+  L.bar_off = L.xch_off + 2 * 3 * TMQ * 4;  // [2 slots][best, others, index][row]
+  L.holder_off = L.bar_off + 80 * 8;
+  L.total = L.holder_off + 16;
+  return L;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+__global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemQ L = smemq_layout();
+  uint8_t* sX = smem + L.x_off;
+  uint8_t* sB = smem + L.b_off;
+  float* sCn2 = reinterpret_cast<float*>(smem + L.cn2_off);
+  float* sSubc = reinterpret_cast<float*>(smem + L.subc_off);
+  float* sNorm = reinterpret_cast<float*>(smem + L.norm_off);
+  float* sXch = reinterpret_cast<float*>(smem + L.xch_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = x_full + NSXQ;
+  uint64_t* a_full = x_empty + NSXQ;
+  uint64_t* a_empty = a_full + NSAQ;
+  uint64_t* st_full = a_empty + NSAQ;
+  uint64_t* acc_full = st_full + NORMQ;
+  uint64_t* acc_empty = acc_full + NACCQ;  // acc_full[buffer] (every epilogue warp waits every phase), acc_empty[2 * buffer + MMA warp]
+  uint64_t* b_full = acc_empty + 2 * NACCQ;
+  uint64_t* b_free = b_full + 1;
+  uint64_t* xch_full = b_free + 1;  // [lane quarter * 2 + slot]: w = 1 warp -> its w = 0 partner
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L.holder_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = p.M;
+  const int ngroups = (M + GSQ - 1) / GSQ;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSXQ; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], CONVQ_WARPS); }
+    for (int s = 0; s < NSAQ; ++s) { ptx::mbar_init(&a_full[s], CONVQ_WARPS); ptx::mbar_init(&a_empty[s], 2); }
+    for (int s = 0; s < NORMQ; ++s) ptx::mbar_init(&st_full[s], CONVQ_WARPS);
+    for (int b = 0; b < NACCQ; ++b) ptx::mbar_init(&acc_full[b], 1);
+    for (int b = 0; b < 2 * NACCQ; ++b) ptx::mbar_init(&acc_empty[b], EPIQ_WARPS);
+    ptx::mbar_init(b_full, 1);
+    ptx::mbar_init(b_free, 2 + EPIQ_WARPS);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&xch_full[i], 1);
+    ptx::mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) ptx::tma_prefetch_desc(&tmap);
+  if (warp == 2) ptx::tmem_alloc(tmem_holder, TMEM_COLS);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer: one [128 x 32] fp32 box per (group, tile, sub-vector) =====
+    uint32_t s = 0, ph = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int sv = 0; sv < gs; ++sv) {
+          if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(&x_empty[s], ph ^ 1, 32))) {
+            if (lane == 0) atomicExch(p.err_flag, 1);
+            return;
+          }
+          if (ptx::elect_one()) {
+            if (p.debug & 16) {  // experiment: no HBM traffic (the stage keeps whatever it holds)
+              ptx::mbar_arrive(&x_full[s]);
+            } else {
+              ptx::mbar_arrive_expect_tx(&x_full[s], X_STAGEQ);
+              ptx::tma_load_2d(sX + (size_t)s * X_STAGEQ, &tmap, (g * GSQ + sv) * DSQ, (int)(tile * TMQ), &x_full[s]);
+            }
+          }
+          __syncwarp();
+          if (++s == NSXQ) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== codebook-group loader: images, -|c|^2 and bound constants of the group's sub-vectors =====
+    for (int g = 0; g < ngroups; ++g) {
+      const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
+      if (g > 0 && !__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(b_free, (g - 1) & 1, 64))) {
+        if (lane == 0) atomicExch(p.err_flag, 7);
+        return;
+      }
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(b_full, (uint32_t)gs * (B_SUBQ + KQ * 4 + 16));
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.Bimg) + (size_t)g * GSQ * B_SUBQ;
+        for (int i = 0; i < gs * (B_SUBQ / 16384); ++i) ptx::bulk_g2s(sB + (size_t)i * 16384, src + (size_t)i * 16384, 16384, b_full);
+        ptx::bulk_g2s(sCn2, p.negcn2 + (size_t)g * GSQ * KQ, (uint32_t)gs * KQ * 4, b_full);
+        ptx::bulk_g2s(sSubc, p.subc + (size_t)g * GSQ * 4, (uint32_t)gs * 16, b_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===== MMA: warp h issues the units (sub-vector, half h) into accumulator buffer h =====
+    const int h = warp - 1;
+    const uint32_t idesc = ptx::umma_idesc_f16_m128(128u);
+    uint32_t as = 0, aph = 0, q = 0, buf = (uint32_t)h, ebits = 0;
+    for (int g = 0; g < ngroups; ++g) {
+      const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
+      if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(b_full, g & 1, 32))) {
+        if (lane == 0) atomicExch(p.err_flag, 3);
+        return;
+      }
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const bool last_tile = tile + gridDim.x >= p.n_tiles;
+        for (int sv = 0; sv < gs; ++sv, ++q) {
+          // unit u = 2q + h lives in buffer u % 3; its previous tenant (unit u - 3, the other half) must be drained
+          if (2 * q + h >= NACCQ) {
+            if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&acc_empty[2 * buf + h], (ebits >> buf) & 1u))) {
+              if (lane == 0) atomicExch(p.err_flag, 2);
+              return;
+            }
+            ebits ^= 1u << buf;
+          }
+          const uint32_t d_tmem = tmem_base + buf * 128u;
+          if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&a_full[as], aph))) {
+            if (lane == 0) atomicExch(p.err_flag, 3);
+            return;
+          }
+          ptx::tc_fence_after_sync();
+          const uint32_t b_hi = ptx::smem_u32(sB + (size_t)sv * B_SUBQ) + (uint32_t)h * 128u * 64u;
+          const uint32_t b_lo = b_hi + (uint32_t)KQ * 64u;
+          if (ptx::elect_one()) {
+            if (!(p.debug & 2)) {
+              const uint32_t a_hi = tmem_base + AQ_COL0 + as * 32, a_lo = a_hi + 16;
+#pragma unroll
+              for (int ks = 0; ks < DSQ / 16; ++ks) {
+                ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, ks != 0 ? 1u : 0u);
+                ptx::umma_f16_ts(d_tmem, a_hi + ks * 8, ptx::umma_desc_sw64(b_lo + ks * 32), idesc, 1u);
+                ptx::umma_f16_ts(d_tmem, a_lo + ks * 8, ptx::umma_desc_sw64(b_hi + ks * 32), idesc, 1u);
+              }
+            }
+            ptx::umma_commit(&a_empty[as]);
+            ptx::umma_commit(&acc_full[buf]);
+            if (last_tile && sv == gs - 1) ptx::umma_commit(b_free);
+          }
+          __syncwarp();
+          if (++as == NSAQ) { as = 0; aph ^= 1; }
+          buf = buf >= 1 ? buf - 1 : buf + 2;  // (u + 2) % 3
+        }
+      }
+    }
+  } else if (warp >= CONVQ_WARP0 && warp < EPIQ_WARP0) {
+    // ===== converters: thread = row; fp32 -> (hi | lo) fp16 into a TMEM operand stage, |x_j|^2 into the norm ring =====
+    const int cw = warp - CONVQ_WARP0;
+    const int row = cw * 32 + lane;
+    const float sx = p.consts[C_SX], inv_sx2 = p.consts[C_INV_SX2];
+    const float2 sx2 = make_float2(sx, sx);
+    const uint32_t src_row = ptx::smem_u32(sX) + (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(cw * 32) << 16) + AQ_COL0;
+    uint32_t xs = 0, xph = 0, as = 0, aph = 0, q = 0, pend_stage = 0, pend_q = 0;
+    bool pending = false;
+    for (int g = 0; g < ngroups; ++g) {
+      const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int sv = 0; sv < gs; ++sv, ++q) {
+          if (!ptx::mbar_wait(&x_full[xs], xph)) { atomicExch(p.err_flag, 4); return; }
+          if (!ptx::mbar_wait_backoff(&a_empty[as], aph ^ 1, 32)) { atomicExch(p.err_flag, 4); return; }
+          ptx::tc_fence_after_sync();
+          uint32_t hi[16], lo[16];
+          float2 norm2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float2 p01, p23;
+            if (p.debug & 8) {  // experiment: no conversion work (one load, constant operands)
+              if (j > 0) { hi[2 * j] = hi[0]; hi[2 * j + 1] = hi[1]; lo[2 * j] = lo[0]; lo[2 * j + 1] = lo[1]; continue; }
+            }
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(p01.x), "=f"(p01.y), "=f"(p23.x), "=f"(p23.y)
+                         : "r"(src_row + xs * X_STAGEQ + (((uint32_t)j ^ sw) << 4)));
+            p01 = ptx::f2_mul(p01, sx2);
+            p23 = ptx::f2_mul(p23, sx2);
+            norm2 = ptx::f2_fma(p01, p01, norm2);
+            norm2 = ptx::f2_fma(p23, p23, norm2);
+            const __half2 h01 = __float22half2_rn(p01), h23 = __float22half2_rn(p23);
+            const __half2 l01 = __float22half2_rn(ptx::f2_sub(p01, __half22float2(h01)));
+            const __half2 l23 = __float22half2_rn(ptx::f2_sub(p23, __half22float2(h23)));
+            hi[2 * j] = *reinterpret_cast<const uint32_t*>(&h01);
+            hi[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+            lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l01);
+            lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+          }
+          // publish the PREVIOUS unit's operand stage: its tcgen05.st had this unit's conversion time to land
+          if (pending) {
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) { ptx::mbar_arrive(&a_full[pend_stage]); ptx::mbar_arrive(&st_full[pend_q & (NORMQ - 1)]); }
+          }
+          ptx::tmem_st16(t_lane + as * 32, hi);
+          ptx::tmem_st16(t_lane + as * 32 + 16, lo);
+          sNorm[(q & (NORMQ - 1)) * TMQ + row] = (norm2.x + norm2.y) * inv_sx2;
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&x_empty[xs]);
+          pending = true;
+          pend_stage = as;
+          pend_q = q;
+          if (++xs == NSXQ) { xs = 0; xph ^= 1; }
+          if (++as == NSAQ) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+    if (pending) {
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) { ptx::mbar_arrive(&a_full[pend_stage]); ptx::mbar_arrive(&st_full[pend_q & (NORMQ - 1)]); }
+    }
+  } else {
+    // ===== epilogue: 8 warps = (column half w of every unit) x (TMEM lane quarter).  A warp reduces the 128 candidates
+    // {k : (k % 128) / 64 == w} of every sub-vector - the w-half of both units, one 64-column tcgen05.ld each - as a
+    // 16 x 8 matrix; the w = 1 warp hands (best, bound on the others, index) to its w = 0 partner through shared memory.
+    // All 8 warps drain the same unit, so a buffer is back with the MMA warps after half a drain.  The drain itself is
+    // bound by the tensor-memory read path (~100 B/clk per SM measured): 24.6 KB of accumulators per row. =====
+    const int ew = warp - EPIQ_WARP0;
+    const int qd = ew & 3, w = ew >> 2;
+    const int rl = qd * 32 + lane;
+    const bool l2 = p.metric == MEVI_METRIC_L2;
+    const float scale = (l2 ? 2.f : 1.f) * p.consts[C_INV];
+    // |x_j|^2 below this guarantees that no scaled element overflowed the fp16 range
+    const float xn2_limit = 65000.f * 65000.f * p.consts[C_INV_SX2];
+    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)w * 64u;
+    uint64_t* pair_bar = xch_full + qd * 2;  // hand-over barriers of the (w = 1 -> w = 0) warp pair, one per slot
+    uint32_t q = 0, fbits = 0, xslot = 0, xbits = 0, buf = 0;
+    bool ok = true;
+    for (int g = 0; g < ngroups && ok; ++g) {
+      const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
+      if (!ptx::mbar_wait_backoff(b_full, g & 1, 64)) { atomicExch(p.err_flag, 6); ok = false; break; }
+      for (int64_t tile = blockIdx.x; tile < p.n_tiles && ok; tile += gridDim.x) {
+        const int64_t row = tile * TMQ + rl;
+        for (int sv = 0; sv < gs; ++sv, ++q) {
+          // this warp's candidates as a 16 x 8 matrix (local index 8 gl + j): row maxima R[gl], column maxima C[j]
+          float R[16], C[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) C[i] = -CUDART_INF_F;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (!ptx::mbar_wait_backoff(&acc_full[buf], (fbits >> buf) & 1u, 20)) { atomicExch(p.err_flag, 6); ok = false; break; }
+            fbits ^= 1u << buf;
+            ptx::tc_fence_after_sync();
+            uint32_t ra[64];
+            ptx::tmem_ld64(taddr + buf * 128u, ra);
+            ptx::tmem_ld_wait();
+            // the registers hold this warp's share of the unit: hand the buffer to its next tenant (unit u + 3, issued by
+            // the other half's MMA warp) before the arithmetic
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc_empty[2 * buf + (h ^ 1)]);
+            buf = buf == NACCQ - 1 ? 0 : buf + 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4* cn = reinterpret_cast<const float4*>(sCn2 + sv * KQ + h * 128 + w * 64 + c * 16);
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 c4 = cn[i];
+                v[4 * i] = fmaf(__uint_as_float(ra[16 * c + 4 * i]), scale, c4.x);
+                v[4 * i + 1] = fmaf(__uint_as_float(ra[16 * c + 4 * i + 1]), scale, c4.y);
+                v[4 * i + 2] = fmaf(__uint_as_float(ra[16 * c + 4 * i + 2]), scale, c4.z);
+                v[4 * i + 3] = fmaf(__uint_as_float(ra[16 * c + 4 * i + 3]), scale, c4.w);
+              }
+              if (p.debug & 4) {
+                R[2 * (4 * h + c)] = v[0];
+                R[2 * (4 * h + c) + 1] = v[8];
+                continue;
+              }
+#pragma unroll
+              for (int r2 = 0; r2 < 2; ++r2) {
+                float m = fmax3(v[8 * r2], v[8 * r2 + 1], v[8 * r2 + 2]);
+                m = fmax3(m, v[8 * r2 + 3], v[8 * r2 + 4]);
+                m = fmax3(m, v[8 * r2 + 5], v[8 * r2 + 6]);
+                R[2 * (4 * h + c) + r2] = fmaxf(m, v[8 * r2 + 7]);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) C[j] = fmax3(C[j], v[j], v[8 + j]);
+            }
+          }
+          // largest and second largest (equal values count twice) of the row maxima and of the column maxima
+          float r1 = -CUDART_INF_F, r2 = -CUDART_INF_F, c1 = -CUDART_INF_F, c2 = -CUDART_INF_F;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            r2 = fmaxf(r2, fminf(r1, R[i]));
+            r1 = fmaxf(r1, R[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            c2 = fmaxf(c2, fminf(c1, C[i]));
+            c1 = fmaxf(c1, C[i]);
+          }
+          int gi = 0, ji = 0;
+#pragma unroll
+          for (int i = 15; i >= 0; --i)
+            if (R[i] == r1) gi = i;
+#pragma unroll
+          for (int i = 7; i >= 0; --i)
+            if (C[i] == r1) ji = i;
+          float best = r1, others = fmaxf(r2, c2);
+          int kbest = (gi >> 3) * 128 + w * 64 + (gi & 7) * 8 + ji;
+          if (c1 != r1) others = CUDART_INF_F;  // cannot happen with finite scores; never decide on it
+          float* xch = sXch + (xslot * 3) * TMQ + rl;
+          // (two slots suffice: the w = 1 warp reaches this slot again two sub-vectors later, whose accumulators exist only
+          // after the partner arrived on acc_empty for the sub-vector in between, i.e. after it read this slot)
+          if (w == 1) {
+            xch[0] = best;
+            xch[TMQ] = others;
+            xch[2 * TMQ] = __int_as_float(kbest);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&pair_bar[xslot]);
+            xslot ^= 1;
+            if (!ok) break;
+            continue;
+          }
+          if (!ok) break;
+          if (!ptx::mbar_wait_backoff(&pair_bar[xslot], (xbits >> xslot) & 1u, 20)) { atomicExch(p.err_flag, 6); ok = false; break; }
+          xbits ^= 1u << xslot;
+          xslot ^= 1;
+          {
+            const float b1 = xch[0], o1 = xch[TMQ];
+            const int k1 = __float_as_int(xch[2 * TMQ]);
+            others = fmaxf(fmaxf(others, o1), fminf(best, b1));
+            if (b1 > best) { best = b1; kbest = k1; }
+          }
+          if (!ptx::mbar_wait_backoff(&st_full[q & (NORMQ - 1)], (q >> 4) & 1, 32)) { atomicExch(p.err_flag, 6); ok = false; break; }
+          const float xn2 = sNorm[(q & (NORMQ - 1)) * TMQ + rl];
+          const float xn = sqrtf(xn2);
+          const float e1max = sSubc[sv * 4], bj = sSubc[sv * 4 + 1], cmax = sSubc[sv * 4 + 2];
+          const float thr = fmaf(2.f * xn, e1max, bj) + 2.f * GAMMA_DIRECT * (xn + cmax) * (xn + cmax);
+          const bool decided = (best - others > thr) && (xn2 < xn2_limit);
+          const bool valid = row < p.n;
+          const int m = g * GSQ + sv;
+          if (valid) p.codes[row * M + m] = kbest;
+          const bool flag = valid && !decided && !(p.debug & 4);
+          const unsigned fm = __ballot_sync(MEVI_FULL_MASK, flag);
+          if (fm != 0u) {
+            const int leader = __ffs(fm) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(p.pair_count, (unsigned long long)__popc(fm));
+            base = __shfl_sync(MEVI_FULL_MASK, base, leader);
+            if (flag) {
+              const unsigned long long slot = base + __popc(fm & ((1u << lane) - 1u));
+              if (slot < p.pair_cap) p.pairs[slot] = (uint32_t)(row * M + m);
+              else atomicExch(p.overflow, 1);
+            }
+          }
+        }
+      }
+      // the group's images and constants may be overwritten once every epilogue warp (and both MMA warps) are done
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(b_free);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Bimg[j][row][32 halfs]: rows 0..255 = hi(c*sc), 256..511 = lo; 16-byte units XOR-swizzled by (row>>1)&3 (UMMA 64B swizzle)
+__global__ void pq_bimg_kernel(const float* __restrict__ cb, int M, const float* __restrict__ consts, __half* __restrict__ Bimg) {
+  const int total = M * KQ * (DSQ / 8);
+  const float sc = consts[C_SC];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int u = i & 3, r = (i >> 2) & (KQ - 1), j = i >> 10;
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float t = cb[((size_t)j * KQ + r) * DSQ + u * 8 + e] * sc;
+      hi[e] = __float2half_rn(t);
+      lo[e] = __float2half_rn(t - __half2float(hi[e]));
+    }
+    const int up = u ^ ((r >> 1) & 3);
+    __half* base = Bimg + (size_t)j * (2 * KQ * DSQ);
+    *reinterpret_cast<uint4*>(base + (size_t)r * DSQ + up * 8) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + (size_t)(KQ + r) * DSQ + up * 8) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+// per sub-vector (one block of 256 threads, thread = centroid): -|c_k|^2 / 0 and the constants of the error bound
+//   |score_k - exact| <= |x_j| * E1_k + B_j/2   (rq_tensor.cu, level_consts_kernel, with no Gram terms)
+__global__ void pq_consts_kernel(const float* __restrict__ cb, int metric, const float* __restrict__ consts,
+                                 float* __restrict__ negcn2, float* __restrict__ subc) {
+  const int j = blockIdx.x, k = threadIdx.x;
+  const float f = metric == MEVI_METRIC_L2 ? 2.f : 1.f;
+  const float EPS_A = 4.8e-7f;
+  double s = 0.0;
+  for (int e = 0; e < DSQ; ++e) {
+    const double v = cb[((size_t)j * KQ + k) * DSQ + e];
+    s += v * v;
+  }
+  const float c2 = (float)s, cn = (float)sqrt(s) * (1.f + 1e-6f);
+  negcn2[j * KQ + k] = metric == MEVI_METRIC_L2 ? -c2 : 0.f;
+  __shared__ float red[2][KQ / 32];
+  float cmax = cn, c2max = c2;
+  for (int o = 16; o > 0; o >>= 1) {
+    cmax = fmaxf(cmax, __shfl_xor_sync(MEVI_FULL_MASK, cmax, o));
+    c2max = fmaxf(c2max, __shfl_xor_sync(MEVI_FULL_MASK, c2max, o));
+  }
+  if ((k & 31) == 0) { red[0][k >> 5] = cmax; red[1][k >> 5] = c2max; }
+  __syncthreads();
+  if (k == 0) {
+    for (int w = 1; w < KQ / 32; ++w) { cmax = fmaxf(cmax, red[0][w]); c2max = fmaxf(c2max, red[1][w]); }
+    subc[j * 4 + 0] = f * (U_REL + EPS_A) * cmax + f * consts[C_FC];
+    subc[j * 4 + 1] = 2.f * (f * consts[C_FX] * cmax + EPS_A * c2max);
+    subc[j * 4 + 2] = cmax;
+    subc[j * 4 + 3] = 0.f;
+  }
+}
+
+}  // namespace pq256

@@ -37,6 +37,9 @@ int mevi_rq_exact_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const 
                          cudaStream_t st);
 int mevi_pq_fix_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* pq_codebook, int M, int K, int metric,
                        int32_t* codes, const int32_t* work_rows, const int64_t* n_work_dev, cudaStream_t st);
+int mevi_pq_fix_pairs_launch(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* pq_codebook, int M, int K, int metric,
+                             int32_t* codes, const uint32_t* pairs, const unsigned long long* n_pairs_dev, unsigned long long cap,
+                             const int* overflow, cudaStream_t st);
 
 namespace {
 
@@ -323,6 +326,7 @@ inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int
 
 #include "rq_tensor4.cuh"
 #include "rq_tensor6.cuh"
+#include "pq_tensor.cuh"
 
 bool shape_ok(mevi_ctx* ctx, int d, int M, int K, int metric) {
   if (!ctx || ctx->cc_major != 10) return false;
@@ -535,6 +539,79 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   }
   if (residual) {
     residual_from_codes_kernel<<<ctx->sm_count * 16, 256, 0, st>>>(X, n, d / 4, cb, M, K, codes, codes_stride, residual);
+    MEVI_COUNT_LAUNCH(ctx, 1);
+  }
+  MEVI_CUDA(ctx, cudaGetLastError());
+  return MEVI_OK;
+}
+
+// ---- wide-codebook PQ encode (pq_tensor.cuh) ---------------------------------------------------------------------
+bool mevi_pq_tensor_supported(mevi_ctx* ctx, int64_t n, int d, int M, int K, int metric) {
+  if (!ctx || ctx->cc_major != 10) return false;
+  if (K != pq256::KQ || M < 1 || d != M * pq256::DSQ) return false;
+  if (n * (int64_t)M >= (int64_t)1 << 32) return false;  // pair ids are 32-bit
+  return metric == MEVI_METRIC_L2 || metric == MEVI_METRIC_IP;
+}
+
+int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const float* cb, int M, int K, int metric,
+                          int32_t* codes, int64_t* stats, cudaStream_t st) {
+  if (!mevi_pq_tensor_supported(ctx, n, d, M, K, metric))
+    return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "tensor PQ path unsupported for d=%d M=%d K=%d", d, M, K);
+  if (n <= 0) return MEVI_OK;
+  if (int rc = mevi_deferred_error(ctx)) return rc;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t o_consts = take(C_NUM * 4), o_abs = take(8), o_cnt = take(8), o_ovf = take(8), o_cn2 = take((size_t)M * K * 4),
+               o_subc = take((size_t)M * 16), o_bimg = take((size_t)M * pq256::B_SUBQ);
+  char* ws = (char*)mevi_ws(ctx, WS_RQ_PREP, off);
+  if (!ws) return MEVI_ERR_NOMEM;
+  const unsigned long long cap = (unsigned long long)(n * (int64_t)M / 8 + 65536);
+  uint32_t* pairs = (uint32_t*)mevi_ws(ctx, WS_RQ_WORK, (size_t)cap * 4);
+  if (!pairs) return MEVI_ERR_NOMEM;
+  float* consts = (float*)(ws + o_consts);
+  unsigned* absmax2 = (unsigned*)(ws + o_abs);
+  unsigned long long* pair_count = (unsigned long long*)(ws + o_cnt);
+  int* overflow = (int*)(ws + o_ovf);
+  float* negcn2 = (float*)(ws + o_cn2);
+  float* subc = (float*)(ws + o_subc);
+  __half* Bimg = (__half*)(ws + o_bimg);
+  int* err_flag = ctx->dev_err + MEVI_ERRSLOT_RQ;
+
+  MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, o_cn2 - o_abs, st));  // absmax2, pair count, overflow flag
+  absmax_kernel<<<32, 256, 0, st>>>(cb, (int64_t)M * K, pq256::DSQ, 1, absmax2);
+  const int64_t sample_rows = 2048;
+  const int64_t row_step = n > sample_rows ? n / sample_rows : 1;
+  absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(X, n, d, row_step, absmax2 + 1);
+  consts_kernel<<<1, 32, 0, st>>>(absmax2, pq256::DSQ, consts);
+  pq256::pq_bimg_kernel<<<(M * K * 4 + 255) / 256, 256, 0, st>>>(cb, M, consts, Bimg);
+  pq256::pq_consts_kernel<<<M, pq256::KQ, 0, st>>>(cb, metric, consts, negcn2, subc);
+  MEVI_CUDA(ctx, cudaGetLastError());
+
+  pq256::PqParams p;
+  p.X = X; p.n = n; p.d = d; p.M = M; p.metric = metric;
+  p.Bimg = Bimg; p.negcn2 = negcn2; p.subc = subc; p.consts = consts;
+  p.codes = codes; p.pairs = pairs; p.pair_count = pair_count; p.pair_cap = cap; p.overflow = overflow;
+  p.err_flag = err_flag;
+  p.n_tiles = (n + pq256::TMQ - 1) / pq256::TMQ;
+  {
+    const char* dbg = getenv("MEVI_RQ_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  CUtensorMap tmap;
+  int trc = make_x_tensormap(ctx, X, n, d, pq256::TMQ, &tmap);
+  if (trc != MEVI_OK) return trc;
+  const size_t smem = (size_t)pq256::smemq_layout().total + 1024;
+  const int grid = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(pq256::pq_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pq256::pq_tensor_kernel<<<grid, pq256::THREADSQ, smem, st>>>(p, tmap);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  poison_codes_kernel<<<ctx->sm_count, 256, 0, st>>>(err_flag, codes, n, M, M);
+  MEVI_COUNT_LAUNCH(ctx, 7);
+  if (int rc = mevi_publish_errors(ctx, st)) return rc;
+  int rc = mevi_pq_fix_pairs_launch(ctx, X, n, d, cb, M, K, metric, codes, pairs, pair_count, cap, overflow, st);
+  if (rc != MEVI_OK) return rc;
+  if (stats) {  // stats[0] += undecided (row, sub-vector) pairs, stats[1] += rows
+    finish_stats_kernel<<<1, 32, 0, st>>>(pair_count, pair_count, n, stats);
     MEVI_COUNT_LAUNCH(ctx, 1);
   }
   MEVI_CUDA(ctx, cudaGetLastError());
