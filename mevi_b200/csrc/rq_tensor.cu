@@ -301,7 +301,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D tensor map over X[n][d] fp32 with a [box_rows x 32 floats] box, 128B-swizzled (one box row = one 128-byte line)
-inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int box_rows, CUtensorMap* out) {
+inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int box_rows, CUtensorMap* out,
+                            CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   if (!ctx->tmap_encode_fn) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -318,7 +319,7 @@ inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = ((EncodeTiledFn)ctx->tmap_encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estr,
                                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return mevi_set_error(ctx, MEVI_ERR_CUDA, "cuTensorMapEncodeTiled (128B swizzle, %d-row box) failed with %d", box_rows, (int)r);
   return MEVI_OK;
@@ -561,8 +562,8 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   if (int rc = mevi_deferred_error(ctx)) return rc;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
-  const size_t o_consts = take(C_NUM * 4), o_abs = take(8), o_cnt = take(8), o_ovf = take(8), o_cn2 = take((size_t)M * K * 4),
-               o_subc = take((size_t)M * 16), o_bimg = take((size_t)M * pq256::B_SUBQ);
+  const size_t o_consts = take(C_NUM * 4), o_abs = take(8), o_cnt = take(8), o_ovf = take(8), o_subc = take((size_t)M * 16 + 64),
+               o_bimg = take((size_t)M * pq256::B_SUBQ);
   char* ws = (char*)mevi_ws(ctx, WS_RQ_PREP, off);
   if (!ws) return MEVI_ERR_NOMEM;
   const unsigned long long cap = (unsigned long long)(n * (int64_t)M / 8 + 65536);
@@ -572,24 +573,23 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   unsigned* absmax2 = (unsigned*)(ws + o_abs);
   unsigned long long* pair_count = (unsigned long long*)(ws + o_cnt);
   int* overflow = (int*)(ws + o_ovf);
-  float* negcn2 = (float*)(ws + o_cn2);
   float* subc = (float*)(ws + o_subc);
   __half* Bimg = (__half*)(ws + o_bimg);
   int* err_flag = ctx->dev_err + MEVI_ERRSLOT_RQ;
 
-  MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, o_cn2 - o_abs, st));  // absmax2, pair count, overflow flag
+  MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, o_subc - o_abs, st));  // absmax2, pair count, overflow flag
   absmax_kernel<<<32, 256, 0, st>>>(cb, (int64_t)M * K, pq256::DSQ, 1, absmax2);
   const int64_t sample_rows = 2048;
   const int64_t row_step = n > sample_rows ? n / sample_rows : 1;
   absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(X, n, d, row_step, absmax2 + 1);
-  consts_kernel<<<1, 32, 0, st>>>(absmax2, pq256::DSQ, consts);
-  pq256::pq_bimg_kernel<<<(M * K * 4 + 255) / 256, 256, 0, st>>>(cb, M, consts, Bimg);
-  pq256::pq_consts_kernel<<<M, pq256::KQ, 0, st>>>(cb, metric, consts, negcn2, subc);
+  pq256::pq_scale_kernel<<<1, 32, 0, st>>>(absmax2, consts);
+  pq256::pq_bimg_kernel<<<(M * K * 4 + 255) / 256, 256, 0, st>>>(cb, M, metric, consts, Bimg);
+  pq256::pq_consts_kernel<<<M, pq256::KQ, 0, st>>>(cb, metric, consts, subc);
   MEVI_CUDA(ctx, cudaGetLastError());
 
   pq256::PqParams p;
   p.X = X; p.n = n; p.d = d; p.M = M; p.metric = metric;
-  p.Bimg = Bimg; p.negcn2 = negcn2; p.subc = subc; p.consts = consts;
+  p.Bimg = Bimg; p.subc = subc; p.consts = consts;
   p.codes = codes; p.pairs = pairs; p.pair_count = pair_count; p.pair_cap = cap; p.overflow = overflow;
   p.err_flag = err_flag;
   p.n_tiles = (n + pq256::TMQ - 1) / pq256::TMQ;
@@ -598,7 +598,8 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     p.debug = dbg ? atoi(dbg) : 0;
   }
   CUtensorMap tmap;
-  int trc = make_x_tensormap(ctx, X, n, d, pq256::TMQ, &tmap);
+  // 128-byte L2 promotion: a pass reads 384-byte row pieces, 256-byte promotion would fetch 512
+  int trc = make_x_tensormap(ctx, X, n, d, pq256::TMQ, &tmap, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (trc != MEVI_OK) return trc;
   const size_t smem = (size_t)pq256::smemq_layout().total + 1024;
   const int grid = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
