@@ -1,5 +1,5 @@
 // pq_tensor.cuh — product-quantiser encode on the tensor cores for the wide codebooks (K = 256 centroids per
-// sub-vector, sub-vector width 32: 24 x 256 at d = 768, 32 x 256 at d = 1024).  Replaces MEVI/pq.py:249-279 for
+// sub-vector, sub-vector width 32 or 24: 24 x 256 and the reference default 32 x 256 at d = 768).  Replaces MEVI/pq.py:249-279 for
 // those shapes; the M*K <= 128 shapes ride on K1 (pq_encode.cu), everything else on the fp32 sub-vector kernel.
 //
 // Per sub-vector j the scores  s_k = 2 x_j.c_k - |c_k|^2  ('l2': the reference's -|x_j - c_k|^2 up to the row constant)
@@ -35,9 +35,9 @@
 
 namespace pq256 {
 
-constexpr int TMQ = 128, KQ = 256, DSQ = 32, GSQ = 3;
+constexpr int TMQ = 128, KQ = 256, DSQ = 32, GSQ = 3;  // DSQ: K extent of a sub-vector's contraction (widths 24 and 32 both use 32)
 constexpr int NSXQ = 4, NSAQ = 3, NORMQ = 16, NACCQ = 3;
-constexpr int X_STAGEQ = TMQ * DSQ * 4;       // 16 KB
+constexpr int X_STAGEQ = TMQ * DSQ * 4;       // 16 KB (12 KB used at sub-vector width 24)
 constexpr int B_BLOCKQ = KQ * DSQ * 2;        // 16 KB: 256 rows x 64 B
 constexpr int B_SUBQ = 3 * B_BLOCKQ;          // 48 KB: [hi][lo][bias: -|c|^2 / 2^8 in three fp16 terms, K slots 0-2]
 constexpr int THREADSQ = 512;
@@ -100,6 +100,8 @@ __device__ __forceinline__ void reduce64(const uint32_t (&ra)[64], const int i0,
   }
 }
 
+// DS = sub-vector width: 32 (128-byte box rows, 128B swizzle) or 24 (96-byte box rows, no swizzle; K elements 24-31 are zero)
+template <int DS>
 __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const SmemQ L = smemq_layout();
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
             if (p.debug & 16) {  // experiment: no HBM traffic (the stage keeps whatever it holds)
               ptx::mbar_arrive(&x_full[s]);
             } else {
-              ptx::mbar_arrive_expect_tx(&x_full[s], X_STAGEQ);
-              ptx::tma_load_2d(sX + (size_t)s * X_STAGEQ, &tmap, (g * GSQ + sv) * DSQ, (int)(tile * TMQ), &x_full[s]);
+              ptx::mbar_arrive_expect_tx(&x_full[s], TMQ * DS * 4);
+              ptx::tma_load_2d(sX + (size_t)s * X_STAGEQ, &tmap, (g * GSQ + sv) * DS, (int)(tile * TMQ), &x_full[s]);
             }
           }
           __syncwarp();
@@ -237,8 +239,8 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
     const int row = cw * 32 + lane;
     const float sx = p.consts[C_SX], inv_sx2 = p.consts[C_INV_SX2];
     const float2 sx2 = make_float2(sx, sx);
-    const uint32_t src_row = ptx::smem_u32(sX) + (uint32_t)row * 128u;
-    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t src_row = ptx::smem_u32(sX) + (uint32_t)row * (uint32_t)(DS * 4);
+    const uint32_t sw = DS == 32 ? (uint32_t)(row & 7) : 0u;
     const uint32_t t_lane = tmem_base + ((uint32_t)(cw * 32) << 16);
     {  // the constant operand tile of the bias MMA: K slots 0-2 = 2^8, the rest 0 (the first publish below waits for it)
       uint32_t ct[16];
@@ -263,6 +265,10 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float2 p01, p23;
+            if (4 * j >= DS) {  // K padding of the narrow sub-vector
+              hi[2 * j] = hi[2 * j + 1] = lo[2 * j] = lo[2 * j + 1] = 0u;
+              continue;
+            }
             if (p.debug & 8) {  // experiment: no conversion work (one load, constant operands)
               if (j > 0) { hi[2 * j] = hi[0]; hi[2 * j + 1] = hi[1]; lo[2 * j] = lo[0]; lo[2 * j + 1] = lo[1]; continue; }
             }
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
 }
 
 // scales for this kernel: 2^s with amax * 2^s in [2^7, 2^8) (the bias -|c|^2 sx sc / f / 2^8 must fit fp16)
-__global__ void pq_scale_kernel(const unsigned* absmax2, float* consts) {
+__global__ void pq_scale_kernel(const unsigned* absmax2, int ds, float* consts) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const float ac = __uint_as_float(absmax2[0]), ax = __uint_as_float(absmax2[1]);
     const float sc = ac > 0.f ? ldexpf(1.f, SCALE_EXPQ - ilogbf(ac)) : 1.f;
@@ -412,7 +418,7 @@ __global__ void pq_scale_kernel(const unsigned* absmax2, float* consts) {
     consts[C_SX] = sx;
     consts[C_INV] = 1.f / (sc * sx);
     consts[C_INV_SX2] = (1.f / sx) * (1.f / sx);
-    const float floor_abs = sqrtf((float)DSQ) * 5.9604645e-8f;  // sqrt(d) * 2^-24: fp16 subnormal spacing of hi+lo
+    const float floor_abs = sqrtf((float)ds) * 5.9604645e-8f;  // sqrt(d) * 2^-24: fp16 subnormal spacing of hi+lo
     consts[C_FX] = floor_abs / sx;
     consts[C_FC] = floor_abs / sc;
   }
@@ -420,24 +426,24 @@ __global__ void pq_scale_kernel(const unsigned* absmax2, float* consts) {
 
 // Bimg[j][block][row][32 halfs], blocks hi(c*sc) | lo | bias; 16-byte units XOR-swizzled by (row>>1)&3 (UMMA 64B swizzle).
 // bias row k: K slots 0-2 = three fp16 terms of  t_k / 2^8,  t_k = -|c_k|^2 sx sc / f  ('l2'; 0 for 'ip'), the rest 0.
-__global__ void pq_bimg_kernel(const float* __restrict__ cb, int M, int metric, const float* __restrict__ consts,
+__global__ void pq_bimg_kernel(const float* __restrict__ cb, int M, int ds, int metric, const float* __restrict__ consts,
                                __half* __restrict__ Bimg) {
   const int total = M * KQ * (DSQ / 8);
   const float sc = consts[C_SC], sx = consts[C_SX];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int u = i & 3, r = (i >> 2) & (KQ - 1), j = i >> 10;
-    const float* crow = cb + ((size_t)j * KQ + r) * DSQ;
+    const float* crow = cb + ((size_t)j * KQ + r) * ds;
     __half hi[8], lo[8], bias[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float t = crow[u * 8 + e] * sc;
+      const float t = u * 8 + e < ds ? crow[u * 8 + e] * sc : 0.f;
       hi[e] = __float2half_rn(t);
       lo[e] = __float2half_rn(t - __half2float(hi[e]));
       bias[e] = __float2half_rn(0.f);
     }
     if (u == 0 && metric == MEVI_METRIC_L2) {
       double s = 0.0;
-      for (int e = 0; e < DSQ; ++e) s += (double)crow[e] * (double)crow[e];
+      for (int e = 0; e < ds; ++e) s += (double)crow[e] * (double)crow[e];
       // the fp32 value the bound constants assume, moved to accumulator units by exact power-of-two factors
       const float t = -(float)s * sx * sc * 0.5f * (1.f / BIAS_A);
       bias[0] = __float2half_rn(t);
@@ -455,14 +461,14 @@ __global__ void pq_bimg_kernel(const float* __restrict__ cb, int M, int metric, 
 
 // per sub-vector (one block of 256 threads, thread = centroid): the constants of the error bound
 //   |score_k - exact| <= |x_j| * E1_k + B_j/2   (rq_tensor.cu, level_consts_kernel, with no Gram terms)
-__global__ void pq_consts_kernel(const float* __restrict__ cb, int metric, const float* __restrict__ consts,
+__global__ void pq_consts_kernel(const float* __restrict__ cb, int ds, int metric, const float* __restrict__ consts,
                                  float* __restrict__ subc) {
   const int j = blockIdx.x, k = threadIdx.x;
   const float f = metric == MEVI_METRIC_L2 ? 2.f : 1.f;
   const float EPS_A = 4.8e-7f;
   double s = 0.0;
-  for (int e = 0; e < DSQ; ++e) {
-    const double v = cb[((size_t)j * KQ + k) * DSQ + e];
+  for (int e = 0; e < ds; ++e) {
+    const double v = cb[((size_t)j * KQ + k) * ds + e];
     s += v * v;
   }
   const float c2 = (float)s, cn = (float)sqrt(s) * (1.f + 1e-6f);

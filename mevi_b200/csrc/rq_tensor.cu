@@ -302,7 +302,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D tensor map over X[n][d] fp32 with a [box_rows x 32 floats] box, 128B-swizzled (one box row = one 128-byte line)
 inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int box_rows, CUtensorMap* out,
-                            CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
+                            CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B, int box_cols = KC32) {
   if (!ctx->tmap_encode_fn) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -315,11 +315,11 @@ inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)n};
   const cuuint64_t gstride[1] = {(cuuint64_t)d * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)KC32, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};  // rows narrower than 128 B: no swizzle
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = ((EncodeTiledFn)ctx->tmap_encode_fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)X, gdim, gstride, box, estr,
-                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    box_cols == KC32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return mevi_set_error(ctx, MEVI_ERR_CUDA, "cuTensorMapEncodeTiled (128B swizzle, %d-row box) failed with %d", box_rows, (int)r);
   return MEVI_OK;
@@ -549,7 +549,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
 // ---- wide-codebook PQ encode (pq_tensor.cuh) ---------------------------------------------------------------------
 bool mevi_pq_tensor_supported(mevi_ctx* ctx, int64_t n, int d, int M, int K, int metric) {
   if (!ctx || ctx->cc_major != 10) return false;
-  if (K != pq256::KQ || M < 1 || d != M * pq256::DSQ) return false;
+  if (K != pq256::KQ || M < 1 || (d != M * 32 && d != M * 24)) return false;
   if (n * (int64_t)M >= (int64_t)1 << 32) return false;  // pair ids are 32-bit
   return metric == MEVI_METRIC_L2 || metric == MEVI_METRIC_IP;
 }
@@ -578,13 +578,14 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   int* err_flag = ctx->dev_err + MEVI_ERRSLOT_RQ;
 
   MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, o_subc - o_abs, st));  // absmax2, pair count, overflow flag
-  absmax_kernel<<<32, 256, 0, st>>>(cb, (int64_t)M * K, pq256::DSQ, 1, absmax2);
+  const int ds = d / M;
+  absmax_kernel<<<32, 256, 0, st>>>(cb, (int64_t)M * K, ds, 1, absmax2);
   const int64_t sample_rows = 2048;
   const int64_t row_step = n > sample_rows ? n / sample_rows : 1;
   absmax_kernel<<<ctx->sm_count, 256, 0, st>>>(X, n, d, row_step, absmax2 + 1);
-  pq256::pq_scale_kernel<<<1, 32, 0, st>>>(absmax2, consts);
-  pq256::pq_bimg_kernel<<<(M * K * 4 + 255) / 256, 256, 0, st>>>(cb, M, metric, consts, Bimg);
-  pq256::pq_consts_kernel<<<M, pq256::KQ, 0, st>>>(cb, metric, consts, subc);
+  pq256::pq_scale_kernel<<<1, 32, 0, st>>>(absmax2, ds, consts);
+  pq256::pq_bimg_kernel<<<(M * K * 4 + 255) / 256, 256, 0, st>>>(cb, M, ds, metric, consts, Bimg);
+  pq256::pq_consts_kernel<<<M, pq256::KQ, 0, st>>>(cb, ds, metric, consts, subc);
   MEVI_CUDA(ctx, cudaGetLastError());
 
   pq256::PqParams p;
@@ -599,12 +600,17 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   }
   CUtensorMap tmap;
   // 128-byte L2 promotion: a pass reads 384-byte row pieces, 256-byte promotion would fetch 512
-  int trc = make_x_tensormap(ctx, X, n, d, pq256::TMQ, &tmap, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  int trc = make_x_tensormap(ctx, X, n, d, pq256::TMQ, &tmap, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, ds);
   if (trc != MEVI_OK) return trc;
   const size_t smem = (size_t)pq256::smemq_layout().total + 1024;
   const int grid = (int)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
-  MEVI_CUDA(ctx, cudaFuncSetAttribute(pq256::pq_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pq256::pq_tensor_kernel<<<grid, pq256::THREADSQ, smem, st>>>(p, tmap);
+  if (ds == 32) {
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(pq256::pq_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq256::pq_tensor_kernel<32><<<grid, pq256::THREADSQ, smem, st>>>(p, tmap);
+  } else {
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(pq256::pq_tensor_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pq256::pq_tensor_kernel<24><<<grid, pq256::THREADSQ, smem, st>>>(p, tmap);
+  }
   MEVI_CUDA(ctx, cudaGetLastError());
   poison_codes_kernel<<<ctx->sm_count, 256, 0, st>>>(err_flag, codes, n, M, M);
   MEVI_COUNT_LAUNCH(ctx, 7);

@@ -76,25 +76,27 @@ def test_pq_encode_tensor_route_equals_subvector_kernel(monkeypatch, n, d, M, bi
     assert (codes_t != codes_s).any(1).mean() < 1e-3
 
 
-@pytest.mark.parametrize("n,M,metric,kind", [(30011, 24, "l2", "gauss"), (30011, 24, "ip", "gauss"), (4096, 32, "l2", "gauss"),
-                                             (50000, 24, "l2", "rows"), (20000, 24, "l2", "scaled"), (9000, 3, "l2", "gauss")])
-def test_pq_encode_wide_codebook_tensor_kernel(monkeypatch, n, M, metric, kind):
-    """K = 256 centroids per sub-vector of width 32 (24 x 256 at d = 768 - BASELINE's PQ shape - and 32 x 256 at d = 1024):
+@pytest.mark.parametrize("n,M,ds,metric,kind", [(30011, 24, 32, "l2", "gauss"), (30011, 24, 32, "ip", "gauss"), (4096, 32, 32, "l2", "gauss"),
+                                                (50000, 24, 32, "l2", "rows"), (20000, 24, 32, "l2", "scaled"), (9000, 3, 32, "l2", "gauss"),
+                                                (30011, 32, 24, "l2", "gauss"), (20000, 32, 24, "ip", "gauss"), (40000, 32, 24, "l2", "rows"),
+                                                (8000, 5, 24, "l2", "scaled")])
+def test_pq_encode_wide_codebook_tensor_kernel(monkeypatch, n, M, ds, metric, kind):
+    """K = 256 centroids per sub-vector of width 32 or 24 (24 x 256 and the reference default 32 x 256 at d = 768):
     mevi_pq_encode runs pq_tensor_kernel (split-fp16 tcgen05 contraction per sub-vector, (row, sub-vector) pairs inside the
     error bound re-decided by the fp32 pair arbiter).  Codes must be IDENTICAL to the sub-vector kernel's (the arbiter
     repeats its arithmetic) and equal the oracle's up to fp32 ties.  `rows`: centroids are data rows (zero distances,
     duplicates of a row among the centroids); `scaled`: 1e-3-scale data with an offset."""
     rs = np.random.RandomState(n + M)
-    d = 32 * M
+    d = ds * M
     X = rs.standard_normal((n, d)).astype(np.float32)
     if kind == "scaled":
         X = (X * 1e-3 + 0.25).astype(np.float32)
     if kind == "rows":
         pick = rs.randint(0, n, size=(M, 256))
         pick[:, 7] = pick[:, 3]  # a duplicated centroid: exact ties, lowest index must win
-        cb = np.stack([X[pick[j], 32 * j:32 * j + 32] for j in range(M)]).astype(np.float32)
+        cb = np.stack([X[pick[j], ds * j:ds * j + ds] for j in range(M)]).astype(np.float32)
     else:
-        cb = (rs.standard_normal((M, 256, 32)) * (1e-3 if kind == "scaled" else 0.8) + (0.25 if kind == "scaled" else 0.0)).astype(np.float32)
+        cb = (rs.standard_normal((M, 256, ds)) * (1e-3 if kind == "scaled" else 0.8) + (0.25 if kind == "scaled" else 0.0)).astype(np.float32)
     c = ctx()
     l0 = c.launches
     codes_t = c.pq_encode(dev(X), dev(cb), metric=metric).cpu().numpy()

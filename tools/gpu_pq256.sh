@@ -21,6 +21,10 @@ for (n, M, metric_scale, shift) in ((200003, 24, 1.0, 0.0), (65536, 24, 1e-3, 0.
         cb = (torch.randn((M, 256, 32), device="cuda") * metric_scale + shift).contiguous()
     a, e = both(X, cb)
     print(f"n {n} M {M} scale {metric_scale} shift {shift}: mismatching codes {int((a != e).sum())} of {a.numel()}", flush=True)
+for (n, M) in ((100003, 32), (4100, 8)):
+    X = torch.randn((n, 24 * M), device="cuda"); cb = torch.randn((M, 256, 24), device="cuda")
+    a, e = both(X, cb)
+    print(f"width 24: n {n} M {M}: mismatching codes {int((a != e).sum())} of {a.numel()}", flush=True)
 n = 8841823
 X = torch.randn((n, 768), device="cuda")
 cb = torch.randn((24, 256, 32), device="cuda")
@@ -33,9 +37,10 @@ def run(tag, reps=5):
     t.record(); torch.cuda.synchronize(); ms = s.elapsed_time(t) / reps
     print(f"{tag:40s} {ms:8.3f} ms  {n*3072/ms/1e6:7.0f} GB/s  frac {n*3072/ms/1e6/6541.8:.3f}", flush=True)
 run("pq 24x256 tensor")
-for dbg, name in ((2, "no MMA"), (4, "no epilogue reduction"), (8, "no conversion"), (16, "no TMA"), (6, "no MMA, no epilogue"), (14, "no MMA/epilogue/conversion"), (30, "handshakes only")):
+for dbg, name in ((2, "no MMA"), (4, "no epilogue reduction"), (6, "no MMA, no epilogue"), (30, "handshakes only")):
     os.environ["MEVI_RQ_DEBUG"] = str(dbg); run(f"debug={dbg} ({name})", reps=3)
 os.environ["MEVI_RQ_DEBUG"] = "0"
+cb24 = torch.randn((32, 256, 24), device="cuda"); cb32 = cb; cb = cb24; run("pq 32x256 (width 24) tensor"); cb = cb32
 a = ctx.pq_encode(X[:200000], cb); os.environ["MEVI_PQ_TENSOR"] = "0"; e = ctx.pq_encode(X[:200000], cb)
 print("mismatch on 200k of the timed matrix:", int((a != e).sum()))
 ctx.check()
