@@ -765,7 +765,7 @@ def run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, 
         wid = {}
         gq = torch.Generator(device=dev)
         gq.manual_seed(77)
-        for Mp, Kp in ((4, 32), (24, 256)):
+        for Mp, Kp in ((4, 32), (24, 256), (32, 256)):  # K1 route | wide-codebook tensor kernel, widths 32 and 24
             cbp = torch.empty((Mp, Kp, D // Mp), device=dev).normal_(generator=gq)
             cp = torch.empty((ns, Mp), dtype=torch.int32, device=dev)
             ms_pq = timed(lambda: ctx.pq_encode(Xs, cbp, metric="l2", codes=cp), 2)

@@ -14,12 +14,14 @@
 // direct-form kernel of rq_exact.cu, the literal restatement of the reference arithmetic.  Rows outside the bounds
 // provably have the same argmin in exact arithmetic, so codes agree with the reference except at fp32-epsilon ties.
 // Two kernels share this protocol (DESIGN.md section 4 has the measurements that led here):
-//   * generation 6 (rq_tensor6.cuh; M >= 2, K == 32 — the shipped RQ shape): ONE fp16 MMA per K step (hi.hi) with a
-//     per-row bound built from the measured norm of the row's fp16 remainder; the 1-5 % of (row, level) decisions the
-//     bound leaves open are refined inside the epilogue by exact fp32 dot products of the two or three open candidates
-//     (row re-read through L2).  A third of the tensor work of the split form: the kernel is no longer power-bound.
-//   * generation 4 (rq_tensor4.cuh; every other supported shape, e.g. the M = 1 k-means assignment, which it runs at
-//     the HBM roofline): split-fp16 contraction hi.hi + hi.lo + lo.hi (22 significant bits, ~2^-22 |x||c| error).
+//   * generation 4 (rq_tensor4.cuh; the default for every supported shape): split-fp16 contraction hi.hi + hi.lo + lo.hi
+//     (22 significant bits, ~2^-22 |x||c| error) with the document operand in tensor memory; runs the M = 1 k-means
+//     assignment at the HBM roofline and the M = 4 encode at 0.62-0.69 of it (tensor work under the power cap).
+//   * generation 6 (rq_tensor6.cuh; M >= 2, K == 32; opt-in with MEVI_RQ_KERNEL=6): ONE fp16 MMA per K step (hi.hi) with a
+//     per-row bound built from the measured norm of the row's fp16 remainder; rows with a level the bound leaves open
+//     (11.9 % on N(0,1) data) are dumped with their tensor-core accumulators and finished by rq_refine6_kernel (exact fp32
+//     dot products of the open candidates), or refined inside the epilogue (MEVI_RQ_REFINE=inline).  Bit-identical codes,
+//     a third of the tensor work, but not faster end to end (7.3 ms vs 6.5 ms): kept as a measured alternative.
 // Roofline: HBM (4*d B/row).
 #include <cuda.h>
 #include <cuda_fp16.h>

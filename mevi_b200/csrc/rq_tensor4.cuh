@@ -1,6 +1,5 @@
 // rq_tensor4.cuh — K1, split-fp16 kernel (generation 4): the document operand goes through TENSOR MEMORY.
-// Serves the shapes generation 6 (rq_tensor6.cuh) does not take: M = 1 (the k-means assignment, which runs at the HBM
-// roofline here), K > 32, d % 128 != 0.
+// The shipped K1 kernel for every supported shape (M = 1 - the k-means assignment - runs at the HBM roofline here).
 //
 // Same algorithm / error model / work-list protocol as the earlier generations (rq_tensor.cu).  v3 is bound
 // by shared-memory bandwidth (70 % of the LSU data pipe: TMA writes + converter loads + converter stores +

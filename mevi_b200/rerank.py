@@ -230,6 +230,8 @@ class ClusterReranker:
     BOOTSTRAP_ROWS = 3072           # rows of the threshold-free first round per query (all appended: must fit the buffers)
     BOOTSTRAP_MIN = 2048            # fewer bootstrap rows than this: first threshold from the streaming kernel instead
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
+    PLAN = "tiles"                  # "tiles": plan_grouped_tile_rounds (default); "prefix": plan_grouped_rounds
+    BOOT_LEAVES = 63                # tiles plan: first tile of this many leading leaves = the bootstrap (<= 8,064 rows)
 
     def __init__(self, all_embeddings, index: ClusterIndex, device_index: Optional[int] = None,
                  leaf_ordered: bool = True, mode: Optional[str] = None, D_leaf: Optional[torch.Tensor] = None):
@@ -374,6 +376,64 @@ def hn_lines_all(texts: Sequence[str], offsets, ids, scores, save_hard_neg: Opti
 ClusterReranker.rerank_all = _rerank_all
 
 
+def _group_items(leaf, q, first_tile, n_tiles):
+    """Work items of one item set: (leaf, query) pairs (1-D, any order) meet the tiles [first_tile[leaf], first_tile[leaf] +
+    n_tiles[leaf]) of their leaf.  Pairs are sorted by leaf, each leaf's queries cut into groups of GROUP_COLS columns,
+    one item per (tile, group), per leaf TILE-major: a document tile (196 KB) comes from HBM once and meets all the query
+    groups of its leaf back to back.  -> (item_tile int32 [I], item_group int32 [I], group_qid int32 [G*GROUP_COLS])."""
+    dev = leaf.device
+    keep = n_tiles[leaf] > 0
+    leaf, q = leaf[keep], q[keep]
+    if leaf.numel() == 0:
+        z = torch.zeros(0, dtype=torch.int32, device=dev)
+        return z, z, z
+    order = torch.argsort(leaf, stable=True)
+    leaf, q = leaf[order], q[order]
+    uleaf, cnt = torch.unique_consecutive(leaf, return_counts=True)
+    run0 = torch.cumsum(cnt, 0) - cnt                                   # first pair of every leaf run
+    gpl = (cnt + GROUP_COLS - 1) // GROUP_COLS                          # groups per leaf
+    grp0 = torch.cumsum(gpl, 0) - gpl
+    G = int(gpl.sum().item())
+    run_of_pair = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), cnt)
+    pos = torch.arange(leaf.numel(), device=dev) - run0[run_of_pair]
+    grp_of_pair = grp0[run_of_pair] + pos // GROUP_COLS
+    group_qid = torch.full((G, GROUP_COLS), -1, dtype=torch.int32, device=dev)
+    group_qid[grp_of_pair, pos % GROUP_COLS] = q.to(torch.int32)
+    ipl = n_tiles[uleaf] * gpl                                          # items per leaf
+    item0 = torch.cumsum(ipl, 0) - ipl
+    leaf_of_item = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), ipl)
+    local = torch.arange(leaf_of_item.numel(), device=dev) - item0[leaf_of_item]
+    g_of = gpl[leaf_of_item]
+    item_tile = first_tile[uleaf[leaf_of_item]] + local // g_of
+    item_group = grp0[leaf_of_item] + local % g_of
+    return item_tile.to(torch.int32).contiguous(), item_group.to(torch.int32).contiguous(), group_qid.reshape(-1).contiguous()
+
+
+def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_leaves: int):
+    """Two rounds that cut the work by TILES instead of by leaf prefixes, so that a leaf's queries stay together:
+      round 0 (threshold-free bootstrap): the FIRST tile of the first `boot_leaves` leaves of every query - at most
+              boot_leaves * TILE_ROWS appended scores per query, a sample spread over the query's leaves;
+      round 1: the first tile for the pairs the bootstrap left out, and every further tile of every leaf against ALL the
+              queries that chose the leaf (full groups: a tile meets ceil(queries / GROUP_COLS) groups once, in one round).
+    The prefix plan (`plan_grouped_rounds`) splits a leaf's queries over its rounds, so every tile is fetched, and its
+    query groups rebuilt, once per round.  -> [(item_tile, item_group, group_qid)] * 2."""
+    dev = ql.device
+    nq, L = ql.shape
+    valid = ql >= 0
+    qidx = torch.arange(nq, device=dev)[:, None].expand(nq, L)
+    rank = torch.arange(L, device=dev)[None, :].expand(nq, L)
+    tpl = leaf_tile0[1:] - leaf_tile0[:-1]
+    first = leaf_tile0[:-1]
+    one = torch.clamp(tpl, max=1)
+    m0 = valid & (rank < boot_leaves)
+    m1 = valid & (rank >= boot_leaves)
+    r0 = _group_items(ql[m0].long(), qidx[m0], first, one)
+    a_t, a_g, a_q = _group_items(ql[m1].long(), qidx[m1], first, one)
+    b_t, b_g, b_q = _group_items(ql[valid].long(), qidx[valid], first + 1, tpl - one)
+    r1 = (torch.cat([a_t, b_t]), torch.cat([a_g, b_g + a_q.numel() // GROUP_COLS]), torch.cat([a_q, b_q]))
+    return [r0, r1]
+
+
 def _rerank_grouped(self, Q, ql, topk):
     """Leaf-grouped tensor-core path; None when it does not apply or could not establish its guarantee for the call.
     Queries whose own guarantee fails (candidate buffer or margin-window overflow: near-duplicate documents, one huge
@@ -391,8 +451,11 @@ def _rerank_grouped(self, Q, ql, topk):
     # one) would enter the next round with no useful threshold: those few queries get the exact k-th score of their
     # first BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
     qsz = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device))
-    after = torch.cumsum(qsz, 1)
-    boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)
+    if self.PLAN == "tiles":  # bootstrap = first tile of the leading BOOT_LEAVES leaves
+        boot_rows = qsz[:, : self.BOOT_LEAVES].clamp(max=TILE_ROWS).sum(1)
+    else:
+        after = torch.cumsum(qsz, 1)
+        boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)
     weak = torch.nonzero((boot_rows < self.BOOTSTRAP_MIN) & (ncand > boot_rows)).squeeze(1)
     tau0 = None
     if weak.numel():
@@ -402,7 +465,9 @@ def _rerank_grouped(self, Q, ql, topk):
         tau0[weak] = s0[:, topk - 1]
     self.last_weak_queries = int(weak.numel())
     ctx.rerank_grouped_begin(Q, g["absmax"], g["maxnorm"], tau0)
-    for item_tile, item_group, group_qid in plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS, self.BOOTSTRAP_ROWS):
+    plan = (plan_grouped_tile_rounds(g["leaf_tile0"], ql, self.BOOT_LEAVES) if self.PLAN == "tiles"
+            else plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS, self.BOOTSTRAP_ROWS))
+    for item_tile, item_group, group_qid in plan:
         if item_tile.numel():
             ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk)
     scores, rows, failed, n_failed = ctx.rerank_grouped_finish(Q, self.D, topk)

@@ -193,3 +193,47 @@ def test_rerank_auto_mode_takes_the_grouped_path_and_equals_the_streaming_kernel
     assert rr.last_path == "stream"
     del rr
     torch.cuda.empty_cache()
+
+
+def test_streaming_rerank_equals_float64_numpy_on_sampled_queries(corpus):
+    """Independent check of the streaming re-rank kernel at the full corpus size (the grouped-vs-streaming test above
+    compares two of this repo's own paths): for a few queries the candidate rows of the decoded leaves are pulled to the
+    host and scored in float64 numpy, sorted by (score desc, id asc) as main_models.py:3915-4014 does.  Ids must agree
+    except where the float64 scores tie within fp32 resolution; scores within 1e-5 relative (north star: 1e-3)."""
+    import numpy as np
+
+    from mevi_b200.pq import ProductQuantization
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker
+
+    X, cb, codes = corpus
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(97)
+    nq, L, k = 6, 100, 100
+    Q = torch.empty((nq, D), device="cuda:0").normal_(generator=g)
+    pq = ProductQuantization("rq", M, 5, "l2", D, "kmeans", "grad")
+    with torch.no_grad():
+        pq.codebook.copy_(cb.cpu())
+    dec = pq.beam_search(Q, L)
+    index = ClusterIndex.from_codes(codes, K)
+    rr = ClusterReranker(X, index, mode="stream")
+    s, i, ncand = rr.rerank(Q, dec, topk=k)
+    assert rr.last_path == "stream"
+    ql = index.lookup(dec).cpu().numpy()
+    off = index.leaf_offsets.cpu().numpy()
+    for q in range(nq):
+        leaves = [int(l) for l in ql[q] if l >= 0]
+        ids = torch.cat([index.leaf_docids[off[l] : off[l + 1]] for l in leaves]).long()
+        assert int(ncand[q]) == ids.numel() and ids.numel() > 50_000
+        rows = X[ids].cpu().numpy().astype(np.float64)
+        sc = rows @ Q[q].cpu().numpy().astype(np.float64)
+        ids_np = ids.cpu().numpy()
+        order = np.lexsort((ids_np, -sc))[:k]
+        got_i, got_s = i[q].cpu().numpy(), s[q].cpu().numpy().astype(np.float64)
+        assert np.allclose(got_s, sc[order], rtol=1e-5, atol=1e-5)
+        bad = np.nonzero(got_i != ids_np[order])[0]
+        for p in bad:  # a different document at this rank: the two must tie at fp32 resolution
+            mine = sc[np.nonzero(ids_np == got_i[p])[0][0]]
+            assert abs(mine - sc[order][p]) <= 4e-6 * max(1.0, abs(mine)), (q, p)
+        assert bad.size <= 2
+    del rr
+    torch.cuda.empty_cache()

@@ -53,8 +53,9 @@ def test_rerank_matches_oracle(case, nb, k, leaf_ordered):
     assert (np.diff(np.where(np.isfinite(scores), scores, -1e30), axis=1) <= 0).all()
 
 
+@pytest.mark.parametrize("plan", ["tiles", "prefix"])
 @pytest.mark.parametrize("nb,k,boot_min", [(10, 100, 128), (100, 100, 128), (100, 7, 128), (100, 100, 100000)])
-def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min):
+def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min, plan):
     """K3g: every leaf read once and scored against all the queries that chose it (tcgen05 prefilter + exact fp32
     re-score) must return what the per-query loop of main_models.py:3915-4014 returns."""
     from mevi_b200.rerank import ClusterIndex, ClusterReranker
@@ -67,9 +68,11 @@ def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min):
     # small corpus: still exercise the threshold-free bootstrap round + three more rounds; boot_min = 100000 makes every
     # query "weak" (first thresholds from the streaming kernel's exact prefix top-k instead)
     rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS, rr.BOOTSTRAP_MIN = (256 if boot_min < 1000 else 32), (600, 3000), boot_min
+    # "tiles" (the default plan): bootstrap = first tile of the 3 leading leaves, everything else in the second round
+    rr.PLAN, rr.BOOT_LEAVES = plan, 3
     scores, ids, ncand = rr.rerank(case.Q, dec, topk=k)
     assert rr.last_path == "grouped" and rr.last_failed_queries == 0
-    if case.name == "gauss768":  # (the other cases' leaves are so small that 32 rows already hold all candidates)
+    if case.name == "gauss768" and plan == "prefix":  # (the other cases' leaves are so small that 32 rows already hold all candidates)
         assert (rr.last_weak_queries > 0) == (boot_min > 1000)
     scores, ids, ncand = scores.cpu().numpy(), ids.cpu().numpy(), ncand.cpu().numpy()
     ref = oracle.cluster_rerank(case.Q, case.X, clus, dec, topk=k)
@@ -106,7 +109,8 @@ def test_grouped_rerank_falls_back_when_the_margin_window_overflows(gauss):
         np.testing.assert_allclose(scores[q].cpu().numpy(), s_, rtol=1e-5, atol=1e-4)
 
 
-def test_grouped_rerank_reruns_only_the_queries_whose_guarantee_failed(gauss):
+@pytest.mark.parametrize("plan", ["tiles", "prefix"])
+def test_grouped_rerank_reruns_only_the_queries_whose_guarantee_failed(gauss, plan):
     """A few queries hit a leaf of near-duplicate documents (margin window overflow), the others do not: only those few
     go through the streaming kernel, and every query's answer is the exact one."""
     from mevi_b200.rerank import ClusterIndex, ClusterReranker
@@ -123,6 +127,7 @@ def test_grouped_rerank_reruns_only_the_queries_whose_guarantee_failed(gauss):
     Q[:3] = X[0]
     rr = ClusterReranker(dev(X), ClusterIndex.from_codes(codes, gauss.K), mode="grouped")
     rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS, rr.BOOTSTRAP_MIN = 256, (600,), 128
+    rr.PLAN, rr.BOOT_LEAVES = plan, 2
     scores, ids, ncand = rr.rerank(Q, dec, topk=100)
     assert rr.last_path == "grouped+stream" and 1 <= rr.last_failed_queries <= 3
     ref = oracle.cluster_rerank(Q, X, clus, dec, topk=100)

@@ -150,6 +150,47 @@ def test_grouped_rerank_plan_covers_every_pair_tile_exactly_once():
     assert len(seen) == len(set(seen)) and set(seen) == exp
 
 
+def test_grouped_rerank_tile_plan_covers_every_pair_tile_exactly_once():
+    """The default plan (plan_grouped_tile_rounds): round 0 = first tile of the leading `boot_leaves` leaves of a query,
+    round 1 = everything else; every (query, leaf) pair meets every tile of its leaf exactly once, and in round 1 the
+    further tiles of a leaf meet ALL its queries in full groups."""
+    import torch
+
+    from mevi_b200.rerank import GROUP_COLS, build_leaf_tiles, plan_grouped_tile_rounds
+
+    rs = np.random.RandomState(1)
+    sizes = rs.randint(1, 700, size=40)
+    sizes[2], sizes[5], sizes[6] = 1, 128, 129
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64))
+    _, _, lt0, _ = build_leaf_tiles(off)
+    nq, L, BL = 200, 12, 5
+    ql = torch.from_numpy(np.stack([rs.choice(40, size=L, replace=False) for _ in range(nq)]).astype(np.int32))
+    ql[4, 2] = -1
+    ql[9, :] = -1
+    plan = plan_grouped_tile_rounds(lt0, ql, BL)
+    assert len(plan) == 2
+    seen = []
+    for r, (it, ig, gq) in enumerate(plan):
+        gq = gq.view(-1, GROUP_COLS)
+        assert it.dtype == torch.int32 and ig.dtype == torch.int32 and (it.numel() == 0 or int(ig.max()) < gq.shape[0])
+        for i in range(it.numel()):
+            t, g = int(it[i]), int(ig[i])
+            leaf = int(np.searchsorted(lt0.numpy(), t, side="right")) - 1
+            seen += [(r, q, leaf, t) for q in gq[g][gq[g] >= 0].tolist()]
+    exp = set()
+    for q in range(nq):
+        for j in range(L):
+            leaf = int(ql[q, j])
+            if leaf < 0:
+                continue
+            t0, t1 = int(lt0[leaf]), int(lt0[leaf + 1])
+            exp.add((0 if j < BL else 1, q, leaf, t0))
+            exp |= {(1, q, leaf, t) for t in range(t0 + 1, t1)}
+    assert len(seen) == len(set(seen)) and set(seen) == exp
+    # per-query rows of the bootstrap fit the candidate buffers by construction
+    assert BL * 128 <= 8192
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the reference's CPU arithmetic, oracle port) must print ONE JSON line with the
     keys the driver reads, without touching CUDA."""

@@ -5,7 +5,7 @@ import os, sys, time, torch
 sys.path.insert(0, os.getcwd())
 import mevi_b200
 from mevi_b200.pq import ProductQuantization
-from mevi_b200.rerank import ClusterIndex, ClusterReranker, plan_grouped_rounds
+from mevi_b200.rerank import ClusterIndex, ClusterReranker, plan_grouped_rounds, plan_grouped_tile_rounds
 ctx = mevi_b200.get_context(0)
 dev = torch.device("cuda", 0)
 cb = torch.load("tests/golden/gauss768/codebook.pt", map_location="cpu", weights_only=False).detach().cuda()
@@ -25,7 +25,23 @@ del X
 rr = ClusterReranker(None, index, mode="grouped", D_leaf=D_leaf)
 ql = index.lookup(dec)
 s_ref, i_ref, _ = ctx.cluster_rerank(Q, D_leaf, index.leaf_offsets, index.leaf_docids, ql, 100, leaf_ordered=True)
+def run_tiles(bl):
+    rr.PLAN, rr.BOOT_LEAVES = "tiles", bl
+    for _ in range(2): out = rr.rerank(Q, dec, topk=100)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(5): out = rr.rerank(Q, dec, topk=100)
+    torch.cuda.synchronize(); ms = (time.perf_counter() - t0) / 5 * 1e3
+    eq = float((out[1] == i_ref).float().mean().item())
+    plan = plan_grouped_tile_rounds(rr._grouped["leaf_tile0"], ql, bl)
+    print(f"tiles plan, boot leaves {bl:3d}           {ms:7.2f} ms  path {rr.last_path:15s} failed {rr.last_failed_queries:5d} weak {rr.last_weak_queries:5d}  ids_eq {eq:.5f}  items/round {[int(p[0].numel()) for p in plan]} groups/round {[int(p[2].numel())//64 for p in plan]}", flush=True)
+    gg = rr._grouped
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(5): plan = plan_grouped_tile_rounds(gg["leaf_tile0"], ql, bl)
+    torch.cuda.synchronize(); print("   planning ms", round((time.perf_counter() - t0) / 5 * 1e3, 2), flush=True)
+for bl in (63, 32, 48):
+    run_tiles(bl)
 def run(tag, boot, rounds):
+    rr.PLAN = "prefix"
     rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS = boot, rounds
     for _ in range(2): out = rr.rerank(Q, dec, topk=100)
     torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -34,7 +50,7 @@ def run(tag, boot, rounds):
     eq = float((out[1] == i_ref).float().mean().item())
     plan = plan_grouped_rounds(index.leaf_offsets, rr._grouped["leaf_tile0"], ql, rounds, boot)
     print(f"{tag:34s} {ms:7.2f} ms  path {rr.last_path:15s} failed {rr.last_failed_queries:5d} weak {rr.last_weak_queries:5d}  ids_eq {eq:.5f}  items/round {[int(p[0].numel()) for p in plan]} groups/round {[int(p[2].numel())//64 for p in plan]}", flush=True)
-for boot, rounds in ((3072, (32768,)), (3072, ()), (3072, (49152,)), (3072, (16384,)), (6144, ()), (4096, ())):
+for boot, rounds in ((3072, (32768,)),):
     run(f"boot {boot} rounds {rounds}", boot, rounds)
 # phase timing of the default plan
 rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS = 3072, (32768,)

@@ -30,7 +30,7 @@ def launches(path, out):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
             fw.write(f"{v[1]:12.3f} ms {v[0]:6d}x {100 * v[1] / tot:6.2f}%  {k}\n")
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+KEYS = ["gpu__time_duration.sum", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -44,7 +44,7 @@ def kernels(rep, fw, seen, all_launches=False):
     nth = collections.Counter()
     for r in rows[2:]:
         name = r[H.index("Kernel Name")]
-        short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "")
+        short = name.split("(")[0].replace("void ", "").replace("<unnamed>::", "").replace("(int)", "").replace("(bool)", "")
         nth[short] += 1
         if short in seen and not (all_launches and nth[short] <= 3): continue
         seen.add(short)
@@ -58,19 +58,20 @@ launches(os.path.join(G, "launches_bench_r02.csv"), os.path.join(OUT, "r02_launc
 seen = set()
 with open(os.path.join(OUT, "r02_ncu_kernels.md"), "w") as fw:
     fw.write("# ncu --set full --clock-control none  (one launch per kernel; B200, round 2; tools/gpu_profiles_r02.sh)\n")
-    fw.write("rq_tensor4_kernel<4, false> (the default K1 kernel) and rq_tensor6_kernel<4> (generation 6, opt-in) captured inside `bench.py` "
-             "at the bench size (8,841,823 x 768); the others on a 3,000,000 x 768 corpus: grouped_gemm_kernel = the rounds of one leaf-grouped "
-             "re-rank call (6,980 queries x 100 leaves), rq_tensor4_kernel<1, true> = the one-pass k-means kernel, flat_gemm_kernel = chunks "
-             "of a 6,980-query search of a persistent index.\n")
+    fw.write("rq_tensor4_kernel<4, false> (the default K1 kernel) captured inside `bench.py` at the bench size (8,841,823 x 768); the others on "
+             "a 3,000,000 x 768 corpus: grouped_gemm_kernel = the three rounds of one leaf-grouped re-rank call (6,980 queries x 100 leaves), "
+             "rq_tensor4_kernel<1, true> = the one-pass k-means kernel, flat_gemm_kernel = two chunks of a 6,980-query search of a persistent "
+             "index, pq_tensor_kernel<32> = the wide-codebook PQ encode (24 x 256).\n")
     rows = kernels(os.path.join(G, "prof_r02_k1.ncu-rep"), fw, seen)
     H = rows[0]; r = rows[2]
     rd = float(r[H.index("dram__bytes_read.sum")]); wr = float(r[H.index("dram__bytes_write.sum")])
     ur, uw = rows[1][H.index("dram__bytes_read.sum")], rows[1][H.index("dram__bytes_write.sum")]
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     traffic = rd * mult[ur] + wr * mult[uw]
-    for rep in ("prof_r02_k1v6.ncu-rep", "prof_r02_others.ncu-rep"):
+    for rep in ("prof_r02_kmfused.ncu-rep", "prof_r02_grouped.ncu-rep", "prof_r02_flat.ncu-rep", "prof_r02_pq256.ncu-rep"):
         if os.path.isfile(os.path.join(G, rep)):
-            kernels(os.path.join(G, rep), fw, seen, all_launches=(rep == "prof_r02_others.ncu-rep"))
+            seen.discard("rq_tensor4_kernel")
+            kernels(os.path.join(G, rep), fw, seen, all_launches=rep in ("prof_r02_grouped.ncu-rep", "prof_r02_flat.ncu-rep"))
 json.dump({"rq_encode_dram_bytes_per_launch": traffic, "source": "profiles/r02_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum of rq_tensor4_kernel<4, false>, one launch at the bench size)"},
           open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
 print("traffic", traffic)
