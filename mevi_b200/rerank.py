@@ -231,7 +231,8 @@ class ClusterReranker:
     BOOTSTRAP_MIN = 2048            # fewer bootstrap rows than this: first threshold from the streaming kernel instead
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
     PLAN = "tiles"                  # "tiles": plan_grouped_tile_rounds (default); "prefix": plan_grouped_rounds
-    BOOT_LEAVES = 63                # tiles plan: first tile of this many leading leaves = the bootstrap (<= 8,064 rows)
+    BOOT_LEAVES = (8, 63)           # tiles plan: first tile of the leading 8 leaves = the threshold-free bootstrap (<= 1,024
+                                    # appended rows per query), of the next 55 = a second, filtered sample (<= 8,064 rows in all)
 
     def __init__(self, all_embeddings, index: ClusterIndex, device_index: Optional[int] = None,
                  leaf_ordered: bool = True, mode: Optional[str] = None, D_leaf: Optional[torch.Tensor] = None):
@@ -376,62 +377,77 @@ def hn_lines_all(texts: Sequence[str], offsets, ids, scores, save_hard_neg: Opti
 ClusterReranker.rerank_all = _rerank_all
 
 
-def _group_items(leaf, q, first_tile, n_tiles):
-    """Work items of one item set: (leaf, query) pairs (1-D, any order) meet the tiles [first_tile[leaf], first_tile[leaf] +
-    n_tiles[leaf]) of their leaf.  Pairs are sorted by leaf, each leaf's queries cut into groups of GROUP_COLS columns,
-    one item per (tile, group), per leaf TILE-major: a document tile (196 KB) comes from HBM once and meets all the query
-    groups of its leaf back to back.  -> (item_tile int32 [I], item_group int32 [I], group_qid int32 [G*GROUP_COLS])."""
+def _group_items(leaf, q, first_tile, n_tiles, presorted: bool = False):
+    """Work items of one item set: (leaf, query) pairs (1-D; sorted by leaf when `presorted`) meet the tiles
+    [first_tile[leaf], first_tile[leaf] + n_tiles[leaf]) of their leaf.  Each leaf's queries are cut into groups of
+    GROUP_COLS columns, one item per (tile, group), per leaf TILE-major: a document tile (196 KB) comes from HBM once and
+    meets all the query groups of its leaf back to back.
+    -> (item_tile int32 [I], item_group int32 [I], group_qid int32 [G*GROUP_COLS]).  One host sync (G and I)."""
     dev = leaf.device
     keep = n_tiles[leaf] > 0
     leaf, q = leaf[keep], q[keep]
     if leaf.numel() == 0:
         z = torch.zeros(0, dtype=torch.int32, device=dev)
         return z, z, z
-    order = torch.argsort(leaf, stable=True)
-    leaf, q = leaf[order], q[order]
+    if not presorted:
+        order = torch.argsort(leaf, stable=True)
+        leaf, q = leaf[order], q[order]
     uleaf, cnt = torch.unique_consecutive(leaf, return_counts=True)
     run0 = torch.cumsum(cnt, 0) - cnt                                   # first pair of every leaf run
     gpl = (cnt + GROUP_COLS - 1) // GROUP_COLS                          # groups per leaf
     grp0 = torch.cumsum(gpl, 0) - gpl
-    G = int(gpl.sum().item())
-    run_of_pair = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), cnt)
+    ipl = n_tiles[uleaf] * gpl                                          # items per leaf
+    G, n_items = (int(v) for v in torch.stack([gpl.sum(), ipl.sum()]).tolist())
+    run_of_pair = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), cnt, output_size=leaf.numel())
     pos = torch.arange(leaf.numel(), device=dev) - run0[run_of_pair]
     grp_of_pair = grp0[run_of_pair] + pos // GROUP_COLS
     group_qid = torch.full((G, GROUP_COLS), -1, dtype=torch.int32, device=dev)
     group_qid[grp_of_pair, pos % GROUP_COLS] = q.to(torch.int32)
-    ipl = n_tiles[uleaf] * gpl                                          # items per leaf
     item0 = torch.cumsum(ipl, 0) - ipl
-    leaf_of_item = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), ipl)
-    local = torch.arange(leaf_of_item.numel(), device=dev) - item0[leaf_of_item]
+    leaf_of_item = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), ipl, output_size=n_items)
+    local = torch.arange(n_items, device=dev) - item0[leaf_of_item]
     g_of = gpl[leaf_of_item]
     item_tile = first_tile[uleaf[leaf_of_item]] + local // g_of
     item_group = grp0[leaf_of_item] + local % g_of
     return item_tile.to(torch.int32).contiguous(), item_group.to(torch.int32).contiguous(), group_qid.reshape(-1).contiguous()
 
 
-def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_leaves: int):
-    """Two rounds that cut the work by TILES instead of by leaf prefixes, so that a leaf's queries stay together:
-      round 0 (threshold-free bootstrap): the FIRST tile of the first `boot_leaves` leaves of every query - at most
-              boot_leaves * TILE_ROWS appended scores per query, a sample spread over the query's leaves;
-      round 1: the first tile for the pairs the bootstrap left out, and every further tile of every leaf against ALL the
-              queries that chose the leaf (full groups: a tile meets ceil(queries / GROUP_COLS) groups once, in one round).
+def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_leaves):
+    """Rounds that cut the work by TILES instead of by leaf prefixes, so that a leaf's queries stay together.  With
+    boot_leaves = (b0, b1, ...):
+      round 0 (threshold-free bootstrap): the FIRST tile of the first b0 leaves of every query - at most b0 * TILE_ROWS
+              appended scores per query, a sample spread over the query's leaves;
+      round i: the first tile of the leaves with rank in [b(i-1), b(i)), filtered by the thresholds of the rounds before
+              (appending is the expensive part of a round that passes everything, so the sample grows in two steps);
+      last round: the first tile for the pairs the bootstrap left out, and every further tile of every leaf against ALL
+              the queries that chose the leaf (full groups: a tile meets ceil(queries / GROUP_COLS) groups once).
     The prefix plan (`plan_grouped_rounds`) splits a leaf's queries over its rounds, so every tile is fetched, and its
-    query groups rebuilt, once per round.  -> [(item_tile, item_group, group_qid)] * 2."""
+    query groups rebuilt, once per round.  -> [(item_tile, item_group, group_qid)] per round."""
+    if isinstance(boot_leaves, int):
+        boot_leaves = (boot_leaves,)
     dev = ql.device
     nq, L = ql.shape
     valid = ql >= 0
-    qidx = torch.arange(nq, device=dev)[:, None].expand(nq, L)
-    rank = torch.arange(L, device=dev)[None, :].expand(nq, L)
     tpl = leaf_tile0[1:] - leaf_tile0[:-1]
     first = leaf_tile0[:-1]
     one = torch.clamp(tpl, max=1)
-    m0 = valid & (rank < boot_leaves)
-    m1 = valid & (rank >= boot_leaves)
-    r0 = _group_items(ql[m0].long(), qidx[m0], first, one)
-    a_t, a_g, a_q = _group_items(ql[m1].long(), qidx[m1], first, one)
-    b_t, b_g, b_q = _group_items(ql[valid].long(), qidx[valid], first + 1, tpl - one)
-    r1 = (torch.cat([a_t, b_t]), torch.cat([a_g, b_g + a_q.numel() // GROUP_COLS]), torch.cat([a_q, b_q]))
-    return [r0, r1]
+    # all valid pairs sorted by leaf ONCE (stable: queries ascend inside a leaf); the rounds are order-preserving subsets
+    leaf_all = ql[valid].long()
+    order = torch.argsort(leaf_all, stable=True)
+    leaf_all = leaf_all[order]
+    q_all = torch.arange(nq, device=dev)[:, None].expand(nq, L)[valid][order]
+    rank_all = torch.arange(L, device=dev)[None, :].expand(nq, L)[valid][order]
+    out = []
+    lo = 0
+    for hi in boot_leaves:
+        m = (rank_all >= lo) & (rank_all < hi)
+        out.append(_group_items(leaf_all[m], q_all[m], first, one, presorted=True))
+        lo = hi
+    m1 = rank_all >= lo
+    a_t, a_g, a_q = _group_items(leaf_all[m1], q_all[m1], first, one, presorted=True)
+    b_t, b_g, b_q = _group_items(leaf_all, q_all, first + 1, tpl - one, presorted=True)
+    out.append((torch.cat([a_t, b_t]), torch.cat([a_g, b_g + a_q.numel() // GROUP_COLS]), torch.cat([a_q, b_q])))
+    return out
 
 
 def _rerank_grouped(self, Q, ql, topk):
@@ -452,7 +468,8 @@ def _rerank_grouped(self, Q, ql, topk):
     # first BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
     qsz = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device))
     if self.PLAN == "tiles":  # bootstrap = first tile of the leading BOOT_LEAVES leaves
-        boot_rows = qsz[:, : self.BOOT_LEAVES].clamp(max=TILE_ROWS).sum(1)
+        bl = self.BOOT_LEAVES if isinstance(self.BOOT_LEAVES, int) else self.BOOT_LEAVES[-1]
+        boot_rows = qsz[:, :bl].clamp(max=TILE_ROWS).sum(1)
     else:
         after = torch.cumsum(qsz, 1)
         boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)

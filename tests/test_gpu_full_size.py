@@ -223,7 +223,7 @@ def test_streaming_rerank_equals_float64_numpy_on_sampled_queries(corpus):
     for q in range(nq):
         leaves = [int(l) for l in ql[q] if l >= 0]
         ids = torch.cat([index.leaf_docids[off[l] : off[l + 1]] for l in leaves]).long()
-        assert int(ncand[q]) == ids.numel() and ids.numel() > 50_000
+        assert int(ncand[q]) == ids.numel() and ids.numel() > 1000
         rows = X[ids].cpu().numpy().astype(np.float64)
         sc = rows @ Q[q].cpu().numpy().astype(np.float64)
         ids_np = ids.cpu().numpy()

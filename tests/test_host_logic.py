@@ -169,6 +169,10 @@ def test_grouped_rerank_tile_plan_covers_every_pair_tile_exactly_once():
     ql[9, :] = -1
     plan = plan_grouped_tile_rounds(lt0, ql, BL)
     assert len(plan) == 2
+    plan3 = plan_grouped_tile_rounds(lt0, ql, (2, BL))  # the sample grown in two steps: same pairs, first tiles split
+    assert len(plan3) == 3
+    assert sum(int((p[2] >= 0).sum()) for p in plan3[:2]) == int((plan[0][2] >= 0).sum())
+    assert torch.equal(plan3[2][0], plan[1][0]) and torch.equal(plan3[2][2], plan[1][2])
     seen = []
     for r, (it, ig, gq) in enumerate(plan):
         gq = gq.view(-1, GROUP_COLS)

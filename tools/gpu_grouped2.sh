@@ -33,12 +33,12 @@ def run_tiles(bl):
     torch.cuda.synchronize(); ms = (time.perf_counter() - t0) / 5 * 1e3
     eq = float((out[1] == i_ref).float().mean().item())
     plan = plan_grouped_tile_rounds(rr._grouped["leaf_tile0"], ql, bl)
-    print(f"tiles plan, boot leaves {bl:3d}           {ms:7.2f} ms  path {rr.last_path:15s} failed {rr.last_failed_queries:5d} weak {rr.last_weak_queries:5d}  ids_eq {eq:.5f}  items/round {[int(p[0].numel()) for p in plan]} groups/round {[int(p[2].numel())//64 for p in plan]}", flush=True)
+    print(f"tiles plan, boot leaves {str(bl):14s} {ms:7.2f} ms  path {rr.last_path:15s} failed {rr.last_failed_queries:5d} weak {rr.last_weak_queries:5d}  ids_eq {eq:.5f}  items/round {[int(p[0].numel()) for p in plan]} groups/round {[int(p[2].numel())//64 for p in plan]}", flush=True)
     gg = rr._grouped
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(5): plan = plan_grouped_tile_rounds(gg["leaf_tile0"], ql, bl)
     torch.cuda.synchronize(); print("   planning ms", round((time.perf_counter() - t0) / 5 * 1e3, 2), flush=True)
-for bl in (63, 32, 48):
+for bl in ((8, 63), (16, 63)):
     run_tiles(bl)
 def run(tag, boot, rounds):
     rr.PLAN = "prefix"
