@@ -59,7 +59,17 @@ struct PqParams {
   int* err_flag;
   int64_t n_tiles;
   int debug;
+  unsigned long long* trace;  // MEVI_PQ_TRACE=<file>: per-warp event clocks of CTA 0 for sub-vector steps [TRQ0, TRQ1)
 };
+
+// pipeline trace (debug aid): lane 0 of every warp of CTA 0 appends (clock << 16 | event << 12 | step) for a window of steps
+constexpr int TRQ_SLOTS = 128, TRQ_WARPS = 16, TRQ0 = 40, TRQ1 = 52;
+__device__ __forceinline__ void trq(const PqParams& p, int warp, int lane, uint32_t& idx, uint32_t q, uint32_t ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && q >= TRQ0 && q < TRQ1 && idx < TRQ_SLOTS) {
+    p.trace[warp * TRQ_SLOTS + idx] = ((unsigned long long)clock64() << 16) | (ev << 12) | (q & 4095u);
+    ++idx;
+  }
+}
 
 struct SmemQ {
   int x_off, b_off, subc_off, norm_off, bar_off, holder_off, total;
@@ -143,15 +153,16 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
 
   if (warp == 0) {
     // ===== TMA producer: one [128 x 32] fp32 box per (group, tile, sub-vector) =====
-    uint32_t s = 0, ph = 0;
+    uint32_t s = 0, ph = 0, tq = 0, tix = 0;
     for (int g = 0; g < ngroups; ++g) {
       const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int sv = 0; sv < gs; ++sv) {
+        for (int sv = 0; sv < gs; ++sv, ++tq) {
           if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(&x_empty[s], ph ^ 1, 32))) {
             if (lane == 0) atomicExch(p.err_flag, 1);
             return;
           }
+          trq(p, warp, lane, tix, tq, 0);
           if (ptx::elect_one()) {
             if (p.debug & 16) {  // experiment: no HBM traffic (the stage keeps whatever it holds)
               ptx::mbar_arrive(&x_full[s]);
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
     // ===== MMA: warp h issues the units (sub-vector, half h); unit u = 2q + h lives in accumulator buffer u % 3 =====
     const int h = warp - 1;
     const uint32_t idesc = ptx::umma_idesc_f16_m128(128u);
-    uint32_t as = 0, aph = 0, q = 0, buf = (uint32_t)h, ebits = 0;
+    uint32_t as = 0, aph = 0, q = 0, buf = (uint32_t)h, ebits = 0, tix = 0;
     for (int g = 0; g < ngroups; ++g) {
       const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
       if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait_backoff(b_full, g & 1, 32))) {
@@ -204,10 +215,12 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
             ebits ^= 1u << buf;
           }
           const uint32_t d_tmem = tmem_base + buf * 128u;
+          trq(p, warp, lane, tix, q, 0);
           if (!__all_sync(MEVI_FULL_MASK, ptx::mbar_wait(&a_full[as], aph))) {
             if (lane == 0) atomicExch(p.err_flag, 3);
             return;
           }
+          trq(p, warp, lane, tix, q, 1);
           ptx::tc_fence_after_sync();
           const uint32_t b_hi = ptx::smem_u32(sB + (size_t)sv * B_SUBQ) + (uint32_t)h * 128u * 64u;
           const uint32_t b_lo = b_hi + (uint32_t)B_BLOCKQ, b_bias = b_lo + (uint32_t)B_BLOCKQ;
@@ -228,6 +241,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
             if (last_tile && sv == gs - 1) ptx::umma_commit(b_free);
           }
           __syncwarp();
+          trq(p, warp, lane, tix, q, 2);
           if (++as == NSAQ) { as = 0; aph ^= 1; }
           buf = buf >= 1 ? buf - 1 : buf + 2;  // (u + 2) % 3
         }
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
     const uint32_t src_row = ptx::smem_u32(sX) + (uint32_t)row * (uint32_t)(DS * 4);
     const uint32_t sw = DS == 32 ? (uint32_t)(row & 7) : 0u;
     const uint32_t t_lane = tmem_base + ((uint32_t)(cw * 32) << 16);
-    {  // the constant operand tile of the bias MMA: K slots 0-2 = 2^8, the rest 0 (the first publish below waits for it)
+    {  // the constant operand tile of the bias MMA: K slots 0-2 = 2^8, the rest 0 (the first publish below waits for it too)
       uint32_t ct[16];
       const __half2 aa = __floats2half2_rn(BIAS_A, BIAS_A), a0 = __floats2half2_rn(BIAS_A, 0.f);
       ct[0] = *reinterpret_cast<const uint32_t*>(&aa);
@@ -251,14 +265,15 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
       for (int i = 2; i < 16; ++i) ct[i] = 0u;
       ptx::tmem_st16(t_lane + AQ_CONST, ct);  // columns 480-495 (only 480-487 are read)
     }
-    uint32_t xs = 0, xph = 0, as = 0, aph = 0, q = 0, pend_stage = 0, pend_q = 0;
-    bool pending = false;
+    uint32_t xs = 0, xph = 0, as = 0, aph = 0, q = 0, tix = 0;
     for (int g = 0; g < ngroups; ++g) {
       const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
       for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int sv = 0; sv < gs; ++sv, ++q) {
           if (!ptx::mbar_wait(&x_full[xs], xph)) { atomicExch(p.err_flag, 4); return; }
+          trq(p, warp, lane, tix, q, 0);
           if (!ptx::mbar_wait_backoff(&a_empty[as], aph ^ 1, 32)) { atomicExch(p.err_flag, 4); return; }
+          trq(p, warp, lane, tix, q, 1);
           ptx::tc_fence_after_sync();
           uint32_t hi[16], lo[16];
           float2 norm2 = make_float2(0.f, 0.f);
@@ -286,31 +301,22 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
             lo[2 * j] = *reinterpret_cast<const uint32_t*>(&l01);
             lo[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&l23);
           }
-          // publish the PREVIOUS unit's operand stage: its tcgen05.st had this unit's conversion time to land
-          if (pending) {
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) { ptx::mbar_arrive(&a_full[pend_stage]); ptx::mbar_arrive(&st_full[pend_q & (NORMQ - 1)]); }
-          }
           ptx::tmem_st16(t_lane + AQ_COL0 + as * 32, hi);
           ptx::tmem_st16(t_lane + AQ_COL0 + as * 32 + 16, lo);
           sNorm[(q & (NORMQ - 1)) * TMQ + row] = (norm2.x + norm2.y) * inv_sx2;
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&x_empty[xs]);
-          pending = true;
-          pend_stage = as;
-          pend_q = q;
+          // publish at once: with three operand stages a publish delayed by one conversion (K1 hides the tcgen05.st
+          // latency that way) would leave only two stages of overlap between conversion and MMA
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) { ptx::mbar_arrive(&a_full[as]); ptx::mbar_arrive(&st_full[q & (NORMQ - 1)]); }
+          trq(p, warp, lane, tix, q, 2);
           if (++xs == NSXQ) { xs = 0; xph ^= 1; }
           if (++as == NSAQ) { as = 0; aph ^= 1; }
         }
       }
-    }
-    if (pending) {
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(&a_full[pend_stage]); ptx::mbar_arrive(&st_full[pend_q & (NORMQ - 1)]); }
     }
   } else {
     // ===== epilogue: group e takes the sub-vectors with (q & 1) == e; thread = (row, sub-vector), all 256 scores =====
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
     const float xn2_limit = 65000.f * 65000.f * p.consts[C_INV_SX2];
     const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
     const bool math = !(p.debug & 4);
-    uint32_t q = 0, fbits = 0;
+    uint32_t q = 0, fbits = 0, tix = 0;
     bool ok = true;
     for (int g = 0; g < ngroups && ok; ++g) {
       const int gs = M - g * GSQ < GSQ ? M - g * GSQ : GSQ;
@@ -341,6 +347,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
             const uint32_t buf = (2 * q + h) % NACCQ;
             if (!ptx::mbar_wait_backoff(&acc_full[2 * buf + e], (fbits >> buf) & 1u, 20)) { atomicExch(p.err_flag, 6); ok = false; break; }
             fbits ^= 1u << buf;
+            trq(p, warp, lane, tix, q, 2 * h);
             ptx::tc_fence_after_sync();
             uint32_t ra[64];
             ptx::tmem_ld64(taddr + buf * 128u, ra);
@@ -352,12 +359,14 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
             ptx::tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&acc_empty[2 * buf + (h ^ 1)]);
+            trq(p, warp, lane, tix, q, 2 * h + 1);
             if (math) reduce64(ra, 2 * h + 1, R, C);
           }
           if (!ok) break;
           if (!ptx::mbar_wait_backoff(&st_full[q & (NORMQ - 1)], (q >> 4) & 1, 32)) { atomicExch(p.err_flag, 6); ok = false; break; }
           const float xn2 = sNorm[(q & (NORMQ - 1)) * TMQ + rl];
           // largest and second largest (equal values count twice) of the row maxima and of the column maxima
+          // (measured: running scans beat shallow compare / select trees here - fewer instructions on the ALU pipe)
           float r1 = -CUDART_INF_F, r2 = -CUDART_INF_F, c1 = -CUDART_INF_F, c2 = -CUDART_INF_F;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -392,6 +401,7 @@ __global__ void __launch_bounds__(THREADSQ, 1) pq_tensor_kernel(PqParams p, cons
               else atomicExch(p.overflow, 1);
             }
           }
+          trq(p, warp, lane, tix, q, 4);
         }
       }
       // the group's images and constants may be overwritten once every epilogue warp (and both MMA warps) are done

@@ -600,6 +600,12 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     const char* dbg = getenv("MEVI_RQ_DEBUG");
     p.debug = dbg ? atoi(dbg) : 0;
   }
+  p.trace = nullptr;
+  const char* pq_trace = getenv("MEVI_PQ_TRACE");
+  if (pq_trace && *pq_trace) {
+    MEVI_CUDA(ctx, cudaMalloc(&p.trace, sizeof(unsigned long long) * pq256::TRQ_SLOTS * pq256::TRQ_WARPS));
+    MEVI_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(unsigned long long) * pq256::TRQ_SLOTS * pq256::TRQ_WARPS, st));
+  }
   CUtensorMap tmap;
   // 128-byte L2 promotion: a pass reads 384-byte row pieces, 256-byte promotion would fetch 512
   int trc = make_x_tensormap(ctx, X, n, d, pq256::TMQ, &tmap, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, ds);
@@ -614,6 +620,16 @@ int mevi_pq_tensor_encode(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     pq256::pq_tensor_kernel<24><<<grid, pq256::THREADSQ, smem, st>>>(p, tmap);
   }
   MEVI_CUDA(ctx, cudaGetLastError());
+  if (p.trace) {
+    std::vector<unsigned long long> host((size_t)pq256::TRQ_SLOTS * pq256::TRQ_WARPS);
+    MEVI_CUDA(ctx, cudaStreamSynchronize(st));
+    MEVI_CUDA(ctx, cudaMemcpy(host.data(), p.trace, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(pq_trace, "wb")) {
+      fwrite(host.data(), sizeof(unsigned long long), host.size(), f);
+      fclose(f);
+    }
+  }
   poison_codes_kernel<<<ctx->sm_count, 256, 0, st>>>(err_flag, codes, n, M, M);
   MEVI_COUNT_LAUNCH(ctx, 7);
   if (int rc = mevi_publish_errors(ctx, st)) return rc;
