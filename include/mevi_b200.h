@@ -268,6 +268,35 @@ int mevi_topk_merge(mevi_ctx* ctx, const float* scores_in, const int64_t* ids_in
 int mevi_dense_scores(mevi_ctx* ctx, const float* Q, int nq, const float* P, int64_t n, int d, float* out,
                       void* stream);
 
+/* ---- ensemble fusion ---------------------------------------- *
+ * replaces: MEVI/ensemble_marco.py:181-191, 221-240 and MEVI/ensemble_nqdpr.py:192-202, 232-251 (python dictionaries
+ * per query) and the list look-ups of their evaluators (ensemble_marco.py:20-31, ensemble_nqdpr.py:23-33).
+ * Candidate lists are dense [nq,P] (P <= 4096) with an optional per-query length cand_count[nq] (NULL = P).
+ *
+ * mevi_ensemble_cluster_ranks: cranks[q,c] = index of document cand_ids[q,c]'s RQ leaf (codes[doc, 0..M), the
+ *   rqmapping) in the query's ordered leaf list query_leaves[q, 0..L, 0..M) (a repeated leaf keeps its last index),
+ *   num_leaves[q] (= number of distinct leaves) when it is not there or the id is the -1 padding, -2 when the id is
+ *   outside [0, n_docs) (the reference raises KeyError).
+ * mevi_ensemble_fuse: score' = score + alpha / (beta * crank + 1), times (1 - gamma * alpha) when crank == num_leaves;
+ *   float64, every operation rounded on its own (bit-identical to the python floats); a document listed several times
+ *   keeps its first position and its last value; out_ids / out_scores [nq,P] = the documents by descending fused score,
+ *   ties in first-position order, padded with -1 / -inf; out_count[nq] = number of distinct documents.
+ * mevi_ensemble_positions: positions[q,g] = index of targets[q,g] in ranked[q, 0..ranked_count[q]) or -1.
+ * mevi_ensemble_first_hit: first j with query_index[q] in array[offsets[doc] .. offsets[doc+1]), doc = ranked[q,j]; -1
+ *   if none (NQ-DPR inverse-answer lists, test_inverse_offsets.bin / test_inverse_array.bin).                        */
+int mevi_ensemble_cluster_ranks(mevi_ctx* ctx, const int64_t* cand_ids, const int32_t* cand_count, int nq, int P,
+                                const int32_t* codes, int64_t n_docs, int M, const int32_t* query_leaves, int L,
+                                int32_t* cranks, int32_t* num_leaves, void* stream);
+int mevi_ensemble_fuse(mevi_ctx* ctx, const int64_t* cand_ids, const double* cand_scores, const int32_t* cranks,
+                       const int32_t* cand_count, int nq, int P, double alpha, double beta, double gamma,
+                       int num_leaves, int64_t* out_ids, double* out_scores, int32_t* out_count, void* stream);
+int mevi_ensemble_positions(mevi_ctx* ctx, const int64_t* ranked, const int32_t* ranked_count, int nq, int P,
+                            const int64_t* targets, const int32_t* target_count, int G, int32_t* positions,
+                            void* stream);
+int mevi_ensemble_first_hit(mevi_ctx* ctx, const int64_t* ranked, const int32_t* ranked_count, int nq, int P,
+                            const int64_t* query_index, const int32_t* offsets, int64_t n_offsets,
+                            const int32_t* array, int32_t* first_hit, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ _MODES = {"auto": MODE_AUTO, "exact": MODE_EXACT, "tensor": MODE_TENSOR}
 _METRICS = {"l2": METRIC_L2, "ip": METRIC_IP}
 
 # every symbol include/mevi_b200.h declares: (restype, argtypes)
-_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vp, _i, _i64, _f, _d = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
 SYMBOLS = {
     "mevi_abi_version": (_i, []),
     "mevi_ctx_create": (_i, [_i, C.POINTER(_vp)]),
@@ -53,6 +53,10 @@ SYMBOLS = {
     "mevi_flat_index_destroy": (None, [_vp, _vp]),
     "mevi_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "mevi_dense_scores": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "mevi_ensemble_cluster_ranks": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp]),
+    "mevi_ensemble_fuse": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp]),
+    "mevi_ensemble_positions": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "mevi_ensemble_first_hit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
 }
 
 
@@ -554,6 +558,87 @@ class Context:
         out = torch.empty((nq, n), dtype=torch.float32, device=Q.device)
         with torch.cuda.device(self.device):
             self._check(self.lib.mevi_dense_scores(self.handle, _ptr(Q), nq, _ptr(P), n, d, _ptr(out), self._stream()))
+        return out
+
+    # ---- ensemble fusion --------------------------------------
+    def ensemble_cluster_ranks(self, cand_ids, cand_count, codes, query_leaves):
+        """cand_ids [nq,P] int64, cand_count [nq] int32 or None, codes [N,M] int32 (the rqmapping), query_leaves
+        [nq,L,M] int32 -> (cranks [nq,P] int32, num_leaves [nq] int32)."""
+        import torch
+
+        cand_ids = self._dev(cand_ids, torch.int64, "cand_ids")
+        codes = self._dev(codes, torch.int32, "codes")
+        leaves = self._dev(query_leaves, torch.int32, "query_leaves")
+        if cand_count is not None:
+            cand_count = self._dev(cand_count, torch.int32, "cand_count")
+        nq, P = cand_ids.shape
+        N, M = codes.shape
+        if leaves.dim() != 3 or leaves.shape[0] != nq or leaves.shape[2] != M:
+            raise MeviError(f"query_leaves must be [nq={nq}, L, M={M}], got {tuple(leaves.shape)}")
+        cranks = torch.empty((nq, P), dtype=torch.int32, device=cand_ids.device)
+        num = torch.empty((nq,), dtype=torch.int32, device=cand_ids.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_ensemble_cluster_ranks(self.handle, _ptr(cand_ids), _ptr(cand_count), nq, P,
+                                                             _ptr(codes), N, M, _ptr(leaves), leaves.shape[1],
+                                                             _ptr(cranks), _ptr(num), self._stream()))
+        return cranks, num
+
+    def ensemble_fuse(self, cand_ids, cand_scores, cranks, cand_count, alpha, beta, gamma, num_leaves):
+        """-> (ranked ids [nq,P] int64, fused scores [nq,P] float64, distinct-document counts [nq] int32)."""
+        import torch
+
+        cand_ids = self._dev(cand_ids, torch.int64, "cand_ids")
+        cand_scores = self._dev(cand_scores, torch.float64, "cand_scores")
+        cranks = self._dev(cranks, torch.int32, "cranks")
+        if cand_count is not None:
+            cand_count = self._dev(cand_count, torch.int32, "cand_count")
+        nq, P = cand_ids.shape
+        if cand_scores.shape != cand_ids.shape or cranks.shape != cand_ids.shape:
+            raise MeviError("cand_ids, cand_scores and cranks must have the same [nq,P] shape")
+        out_ids = torch.empty((nq, P), dtype=torch.int64, device=cand_ids.device)
+        out_scores = torch.empty((nq, P), dtype=torch.float64, device=cand_ids.device)
+        out_count = torch.empty((nq,), dtype=torch.int32, device=cand_ids.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_ensemble_fuse(self.handle, _ptr(cand_ids), _ptr(cand_scores), _ptr(cranks),
+                                                    _ptr(cand_count), nq, P, float(alpha), float(beta), float(gamma),
+                                                    int(num_leaves), _ptr(out_ids), _ptr(out_scores), _ptr(out_count),
+                                                    self._stream()))
+        return out_ids, out_scores, out_count
+
+    def ensemble_positions(self, ranked, ranked_count, targets, target_count):
+        """positions [nq,G] int32 of targets[q,g] in ranked[q] (first occurrence), -1 if absent."""
+        import torch
+
+        ranked = self._dev(ranked, torch.int64, "ranked")
+        targets = self._dev(targets, torch.int64, "targets")
+        if ranked_count is not None:
+            ranked_count = self._dev(ranked_count, torch.int32, "ranked_count")
+        if target_count is not None:
+            target_count = self._dev(target_count, torch.int32, "target_count")
+        nq, P = ranked.shape
+        G = targets.shape[1]
+        out = torch.empty((nq, G), dtype=torch.int32, device=ranked.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_ensemble_positions(self.handle, _ptr(ranked), _ptr(ranked_count), nq, P,
+                                                         _ptr(targets), _ptr(target_count), G, _ptr(out), self._stream()))
+        return out
+
+    def ensemble_first_hit(self, ranked, ranked_count, query_index, offsets, array):
+        """first_hit [nq] int32: first rank whose document lists query_index[q] among its inverse answers, -1 if none."""
+        import torch
+
+        ranked = self._dev(ranked, torch.int64, "ranked")
+        query_index = self._dev(query_index, torch.int64, "query_index")
+        offsets = self._dev(offsets, torch.int32, "offsets")
+        array = self._dev(array, torch.int32, "array")
+        if ranked_count is not None:
+            ranked_count = self._dev(ranked_count, torch.int32, "ranked_count")
+        nq, P = ranked.shape
+        out = torch.empty((nq,), dtype=torch.int32, device=ranked.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_ensemble_first_hit(self.handle, _ptr(ranked), _ptr(ranked_count), nq, P,
+                                                         _ptr(query_index), _ptr(offsets), offsets.numel(), _ptr(array),
+                                                         _ptr(out), self._stream()))
         return out
 
 

@@ -17,6 +17,8 @@ def main(argv=None):
     parser.add_argument("--gammas", type=str, default="0.02")
     parser.add_argument("--recall_num", type=str, default="10,50,1000")
     parser.add_argument("--ofile", type=str, default=None)
+    parser.add_argument("--device", type=str, default="cuda", choices=["cuda", "host"],
+                        help="cuda: fusion / ranking / look-up kernels of libmevi_b200.so; host: the reference's python dictionaries")
     combine_main(parser.parse_args(argv))
 
 

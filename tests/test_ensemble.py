@@ -17,10 +17,12 @@ def _run(kind, tmp_path):
     work = str(tmp_path / "in")
     g.ensemble_inputs(work)
     ofile = str(tmp_path / "report.txt")
+    args = g.marco_args(work, ofile) if kind == "marco" else g.nq_args(work, ofile)
+    args.device = "host"  # the reference's python dictionaries; the device path is tests/test_gpu_ensemble.py
     if kind == "marco":
-        ensemble.combine_main_marco(g.marco_args(work, ofile))
+        ensemble.combine_main_marco(args)
     else:
-        ensemble.combine_main_nqdpr(g.nq_args(work, ofile))
+        ensemble.combine_main_nqdpr(args)
     return open(ofile).read(), work
 
 
@@ -37,10 +39,12 @@ def test_report_text_equals_reference(kind, tmp_path, capsys):
     from mevi_b200 import ensemble
 
     ofile2 = str(tmp_path / "report2.txt")
+    args = g.marco_args(work, ofile2) if kind == "marco" else g.nq_args(work, ofile2)
+    args.device = "host"
     if kind == "marco":
-        ensemble.combine_main_marco(g.marco_args(work, ofile2))
+        ensemble.combine_main_marco(args)
     else:
-        ensemble.combine_main_nqdpr(g.nq_args(work, ofile2))
+        ensemble.combine_main_nqdpr(args)
     assert open(ofile2).read() == golden
 
 
