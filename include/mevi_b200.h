@@ -215,8 +215,20 @@ int mevi_cluster_rerank_all(mevi_ctx* ctx, const float* Q, int nq, const float* 
  *                                   carry the guarantee (fp16 range), keep mevi_cluster_rerank.
  * Call side: _begin (query scale, margins, thresholds from tau0 [nq] device or NULL), one _round per batch of
  * (leaf, query) pairs, _finish.  A round takes
- *   tile_row0, tile_nrows [n_tiles] int32; item_tile, item_group [n_items] int32 work items (tile, query group);
+ *   tile_row0, tile_nrows [n_tiles] int32; item_tile, item_group [n_items] int32 work items: a document tile meets
+ *   up to max_groups_per_item (1, 2 or 4) CONSECUTIVE query groups - item_group = first group | (number of groups << 24),
+ *   0 in the high bits = 1 - so that the tile is fetched once for up to 256 queries;
  *   group_qid [n_groups*64] int32 query index per column of a group, -1 = padding.
+ * _plan / _plan_fill: the rounds of a call planned on the device (replaces the torch index arithmetic of
+ *   mevi_b200/rerank.py plan_grouped_tile_rounds).  ql [nq,L] int32 = leaf index per (query, leaf rank), -1 = none;
+ *   leaf_offsets / leaf_tile0 [n_leaves+1] int64 = first row / first tile of every leaf; boot_leaves [n_boot] ascending
+ *   leaf-rank boundaries: round i < n_boot = first tile of the leaves with rank in [boot[i-1], boot[i]) (threshold
+ *   samples, items of max_groups_sample groups), round n_boot = the remaining first tiles + every further tile of every
+ *   leaf against all the queries that chose it (items of max_groups_last groups).  Outputs: ncand [nq] int32 (device)
+ *   candidates per query, weak [nq] int32 (device) 1 = the query's sample holds fewer than boot_min_rows rows (the
+ *   caller supplies its tau0 from mevi_cluster_rerank_prefix), sizes_host [2*(n_boot+1)+1] = (items, groups) per round,
+ *   then the number of weak queries.  _plan_fill writes round `round` into caller-allocated item_tile / item_group
+ *   [items] and group_qid [groups*64]; ql, leaf_offsets and leaf_tile0 must stay valid until the last _plan_fill.
  * _finish: scores [nq,k] fp32 descending, rows [nq,k] int64 rows of D_leaf, -1 padded; *n_failed = number of queries
  * whose guarantee could not be established (candidate buffer / margin window overflow; marked in failed_or_null [nq]
  * int32 device) - the caller re-runs just those through mevi_cluster_rerank; *n_failed = nq: the whole call is invalid.
@@ -229,7 +241,14 @@ int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, int d, floa
                               const float* tau0, void* stream);
 int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, int d, const void* Aimg, const int32_t* tile_row0,
                               const int32_t* tile_nrows, const int32_t* item_tile, const int32_t* item_group,
-                              int64_t n_items, const int32_t* group_qid, int64_t n_groups, int k, void* stream);
+                              int64_t n_items, const int32_t* group_qid, int64_t n_groups, int max_groups_per_item,
+                              int k, void* stream);
+int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq, int L, const int64_t* leaf_offsets,
+                             const int64_t* leaf_tile0, int64_t n_leaves, const int32_t* boot_leaves, int n_boot,
+                             int boot_min_rows, int max_groups_sample, int max_groups_last, int32_t* ncand,
+                             int32_t* weak, int64_t* sizes_host, void* stream);
+int mevi_rerank_grouped_plan_fill(mevi_ctx* ctx, int round, int32_t* item_tile, int32_t* item_group, int32_t* group_qid,
+                                  void* stream);
 int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int d, int k, float* scores,
                                int64_t* rows, int32_t* failed_or_null, int* n_failed, void* stream);
 

@@ -44,7 +44,10 @@ SYMBOLS = {
     "mevi_cluster_rerank_all": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mevi_rerank_grouped_image": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, C.POINTER(_f), C.POINTER(_f), _vp]),
     "mevi_rerank_grouped_begin": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
-    "mevi_rerank_grouped_round": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "mevi_rerank_grouped_round": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp]),
+    "mevi_rerank_grouped_plan": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, C.POINTER(C.c_int32), _i, _i, _i, _i, _vp, _vp,
+                                      C.POINTER(_i64), _vp]),
+    "mevi_rerank_grouped_plan_fill": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "mevi_rerank_grouped_finish": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i), _vp]),
     "mevi_gather_rows": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "mevi_flat_ip_topk": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
@@ -465,7 +468,38 @@ class Context:
             self._check(self.lib.mevi_rerank_grouped_begin(self.handle, _ptr(Q), Q.shape[0], Q.shape[1], float(d_absmax),
                                                            float(d_maxnorm), _ptr(tau0), self._stream()))
 
-    def rerank_grouped_round(self, Q, img, tile_row0, tile_nrows, item_tile, item_group, group_qid, k):
+    def rerank_grouped_plan(self, ql, leaf_offsets, leaf_tile0, boot_leaves, boot_min_rows, maxg_sample=1, maxg_last=4):
+        """Device-side round plan -> (ncand int32 [nq], weak int32 [nq], [(items, groups)] per round, n_weak)."""
+        import torch
+
+        ql = self._dev(ql, torch.int32, "ql")
+        off = self._dev(leaf_offsets, torch.int64, "leaf_offsets")
+        t0 = self._dev(leaf_tile0, torch.int64, "leaf_tile0")
+        nq, L = ql.shape
+        boot = (C.c_int32 * max(len(boot_leaves), 1))(*[int(b) for b in boot_leaves])
+        sizes = (C.c_int64 * (2 * (len(boot_leaves) + 1) + 1))()
+        ncand = torch.empty(nq, dtype=torch.int32, device=ql.device)
+        weak = torch.empty(nq, dtype=torch.int32, device=ql.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_plan(self.handle, _ptr(ql), nq, L, _ptr(off), _ptr(t0), off.numel() - 1,
+                                                          boot, len(boot_leaves), int(boot_min_rows), int(maxg_sample),
+                                                          int(maxg_last), _ptr(ncand), _ptr(weak), sizes, self._stream()))
+        rounds = [(int(sizes[2 * r]), int(sizes[2 * r + 1])) for r in range(len(boot_leaves) + 1)]
+        return ncand, weak, rounds, int(sizes[2 * (len(boot_leaves) + 1)])
+
+    def rerank_grouped_plan_fill(self, rnd, items, groups, device):
+        """Round `rnd` of the current plan -> (item_tile, item_group, group_qid) device tensors."""
+        import torch
+
+        item_tile = torch.empty(items, dtype=torch.int32, device=device)
+        item_group = torch.empty(items, dtype=torch.int32, device=device)
+        group_qid = torch.empty(groups * 64, dtype=torch.int32, device=device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_plan_fill(self.handle, int(rnd), _ptr(item_tile), _ptr(item_group),
+                                                               _ptr(group_qid), self._stream()))
+        return item_tile, item_group, group_qid
+
+    def rerank_grouped_round(self, Q, img, tile_row0, tile_nrows, item_tile, item_group, group_qid, k, maxg=1):
         import torch
 
         for name, t in (("tile_row0", tile_row0), ("tile_nrows", tile_nrows), ("item_tile", item_tile),
@@ -475,8 +509,8 @@ class Context:
         with torch.cuda.device(self.device):
             self._check(self.lib.mevi_rerank_grouped_round(self.handle, _ptr(Q), Q.shape[0], Q.shape[1], _ptr(img), _ptr(tile_row0),
                                                            _ptr(tile_nrows), _ptr(item_tile), _ptr(item_group),
-                                                           item_tile.numel(), _ptr(group_qid), group_qid.numel() // 64, int(k),
-                                                           self._stream()))
+                                                           item_tile.numel(), _ptr(group_qid), group_qid.numel() // 64, int(maxg),
+                                                           int(k), self._stream()))
 
     def rerank_grouped_finish(self, Q, D_leaf, k):
         """-> (scores, rows, failed int32 [nq] device mask, n_failed); n_failed == nq: the whole call is invalid."""

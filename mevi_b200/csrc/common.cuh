@@ -28,6 +28,7 @@ enum WsSlot {
   WS_PQ_PAD,        // PQ encode on the tensor path: block-padded codebook
   WS_FLAT_IMAGE,    // one-shot flat search: fp16 image of the documents (+ its metadata)
   WS_RQ_OPEN,       // K1 generation 6: open-row list (rows, state, tensor-core accumulators) for the refine kernel
+  WS_GR_PLAN,       // grouped re-rank: device-side round plan (counts, scans, arrival numbers)
   WS_NUM
 };
 

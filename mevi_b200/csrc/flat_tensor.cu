@@ -46,7 +46,8 @@ __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, 
                                      const float* __restrict__ consts, int scale_slot, __half* __restrict__ img,
                                      float* __restrict__ norms, unsigned* __restrict__ max_norm_bits,
                                      int* __restrict__ clamped, int64_t padded_rows,
-                                     const int32_t* __restrict__ src_index = nullptr) {  // image row -> row of X, -1 = zero row
+                                     const int32_t* __restrict__ src_index = nullptr,    // image row -> row of X, -1 = zero row
+                                     const int32_t* __restrict__ tile_rows_used = nullptr) {  // rows of a tile anyone reads
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -56,6 +57,7 @@ __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, 
   for (int64_t prow = warp_global; prow < padded_rows; prow += n_warps) {
     const int64_t tile = prow / rows_per_tile;
     const int r = (int)(prow - tile * rows_per_tile);
+    if (tile_rows_used && r >= tile_rows_used[tile]) continue;  // thin query group: the GEMM takes N = rows used
     // `row` is the source row; without an index it is the image row itself (rows past the end are zero-filled)
     const int64_t row = src_index ? (src_index[prow] >= 0 ? (int64_t)src_index[prow] : rows) : prow;
     float nrm = 0.f;
@@ -448,44 +450,127 @@ int flat_max_clusters(mevi_ctx* ctx, size_t smem) {
   return n;
 }
 
-// one CTA per query: sort approximate candidates, keep FT_KEEP, tau = k-th approximate score;
-// a dropped candidate inside the margin window breaks the guarantee -> overflow flag
+// one CTA per query: tau = k-th best approximate score of (kept + newly appended) candidates, found by a radix SELECT
+// over the bits in which the scores differ (no sort: the list is consumed as a set); everything inside the margin window
+// [tau - margin, inf) is kept, the rest can never reach the exact top-k (tau only rises) and is dropped.  More than
+// `keep` candidates inside the window breaks the guarantee -> overflow flag
 // (`ov_stride` = 0: one flag for the call - flat search; 1: a flag per query - grouped re-rank, which re-runs only the
-// affected queries through the streaming kernel)
+// affected queries through the streaming kernel).  The kept list is NOT ordered.
+__device__ __forceinline__ unsigned ft_key(float f) {  // monotone: larger float -> larger unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ft_unkey(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, const float* margin, int* count, float* cand_score,
                                                                   int32_t* cand_id, int* overflow, int capg, int k, int keep,
                                                                   int ov_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_score = reinterpret_cast<float*>(smem_raw);
-  int32_t* s_id = reinterpret_cast<int32_t*>(s_score + capg);
-  const int q = blockIdx.x;
+  float* s_score = reinterpret_cast<float*>(smem_raw);                 // [capg]
+  float* s_ks = s_score + capg;                                        // [keep]
+  int32_t* s_ki = reinterpret_cast<int32_t*>(s_ks + keep);             // [keep]
+  unsigned* s_hist = reinterpret_cast<unsigned*>(s_ki + keep);         // [256]
+  __shared__ unsigned s_min, s_max, s_digit;
+  __shared__ int s_rem, s_n;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int cnt = count[q];
   if (cnt > capg) cnt = capg;
   if (cnt == 0) return;
-  int nsort = 64;  // next power of two >= cnt: after the first chunks a query holds `keep` + a few new candidates
-  while (nsort < cnt) nsort <<= 1;
-  for (int i = threadIdx.x; i < nsort; i += blockDim.x) {
-    if (i < cnt) {
-      s_score[i] = cand_score[(int64_t)q * capg + i];
-      s_id[i] = cand_id[(int64_t)q * capg + i];
-    } else {
-      s_score[i] = -CUDART_INF_F;
-      s_id[i] = 0x7fffffff;
+  if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; s_n = 0; }
+  __syncthreads();
+  unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+  for (int i = tid; i < cnt; i += blockDim.x) {
+    const float sc = cand_score[(int64_t)q * capg + i];
+    s_score[i] = sc;
+    const unsigned key = ft_key(sc);
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(MEVI_FULL_MASK, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(MEVI_FULL_MASK, kmax, o));
+  }
+  if (lane == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+  __syncthreads();
+  float t = tau[q];
+  if (cnt >= k) {
+    // the k-th largest key: all keys agree above bit `top`; digits of 8 bits from there down
+    const unsigned lo_key = s_min, hi_key = s_max;
+    unsigned prefix = hi_key;  // bits above `top` are common; the digits below are filled in pass by pass
+    int rem = k;
+    if (lo_key != hi_key) {
+      const int top = 31 - __clz(lo_key ^ hi_key);
+      int hi_bit = top;  // most significant undecided bit
+      prefix = (top == 31) ? 0u : (hi_key >> (top + 1)) << (top + 1);
+      while (hi_bit >= 0) {
+        const int width = hi_bit >= 7 ? 8 : hi_bit + 1;
+        const int shift = hi_bit + 1 - width;
+        const unsigned above = (hi_bit == 31) ? 0u : (0xFFFFFFFFu << (hi_bit + 1));  // decided bits
+        s_hist[tid] = 0;
+        __syncthreads();
+        for (int base = 0; base < cnt; base += blockDim.x) {
+          const int i = base + tid;
+          unsigned digit = 0xFFFFu;  // not a candidate of this pass
+          if (i < cnt) {
+            const unsigned key = ft_key(s_score[i]);
+            if ((key & above) == (prefix & above)) digit = (key >> shift) & ((1u << width) - 1u);
+          }
+          const unsigned peers = __match_any_sync(MEVI_FULL_MASK, digit);
+          if (digit != 0xFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
+        }
+        __syncthreads();
+        if (warp == 0) {  // lane l owns digits 255 - 8 l ... 248 - 8 l (descending); find where the running count reaches rem
+          int local[8], sum = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { local[j] = (int)s_hist[255 - (lane * 8 + j)]; sum += local[j]; }
+          int incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(MEVI_FULL_MASK, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const int excl = incl - sum;
+          if (excl < rem && rem <= incl) {
+            int r = rem - excl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (r > 0 && r <= local[j]) { s_digit = 255u - (unsigned)(lane * 8 + j); s_rem = r; r = 0; }
+              else if (r > 0) r -= local[j];
+            }
+          }
+        }
+        __syncthreads();
+        prefix |= s_digit << shift;
+        rem = s_rem;
+        hi_bit = shift - 1;
+        __syncthreads();
+      }
+    }
+    // never below a bound the caller already had (the grouped re-rank starts from a lower bound of the k-th score)
+    t = fmaxf(t, ft_unkey(prefix));
+  }
+  const float window = t - margin[q];
+  for (int i = tid; i < cnt; i += blockDim.x) {
+    const float sc = s_score[i];
+    if (!(sc < window)) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < keep) { s_ks[pos] = sc; s_ki[pos] = cand_id[(int64_t)q * capg + i]; }
     }
   }
   __syncthreads();
-  block_bitonic_sort<int32_t>(s_score, s_id, nsort);
-  const int kept = cnt < keep ? cnt : keep;
-  for (int i = threadIdx.x; i < kept; i += blockDim.x) {
-    cand_score[(int64_t)q * capg + i] = s_score[i];
-    cand_id[(int64_t)q * capg + i] = s_id[i];
+  const int n_in = s_n;
+  const int kept = n_in < keep ? n_in : keep;
+  for (int i = tid; i < kept; i += blockDim.x) {
+    cand_score[(int64_t)q * capg + i] = s_ks[i];
+    cand_id[(int64_t)q * capg + i] = s_ki[i];
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     count[q] = kept;
-    // never below a bound the caller already had (the grouped re-rank starts from a lower bound of the k-th score)
-    const float t = fmaxf(tau[q], (cnt >= k) ? s_score[k - 1] : -CUDART_INF_F);
     tau[q] = t;
-    if (cnt > keep && !(s_score[keep] < t - margin[q])) overflow[(int64_t)q * ov_stride] = 1;
+    if (n_in > keep) overflow[(int64_t)q * ov_stride] = 1;
   }
 }
 
@@ -508,10 +593,10 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(const float* __restri
   }
   __syncthreads();
   // a member of the exact top-k has an approximate score >= (k-th approximate score) - margin: the rest of the kept
-  // list (sorted by approximate score) cannot matter and is not fetched
+  // list (unordered; kept under an earlier, lower threshold) cannot matter and is not fetched
   const float window = tau[q] - margin[q];
   for (int i = warp; i < cnt; i += 8) {
-    if (cand_score[(int64_t)q * capg + i] < window) break;
+    if (cand_score[(int64_t)q * capg + i] < window) continue;
     const int32_t row = cand_id[(int64_t)q * capg + i];
     float acc = 0.f;
     for (int c4 = lane * 4; c4 < d; c4 += 128) {  // same summation pattern as the dense scorer
@@ -714,44 +799,53 @@ int mevi_flat_tensor_search_image(mevi_ctx* ctx, const float* Q, int nq, const f
 // accumulator buffers in TMEM, 8 epilogue warps (lane group x 32-column half).
 namespace {
 
-constexpr int GR_TN = 64;
-constexpr int GR_STAGES = 8;
+constexpr int GR_TN = 64;   // columns (queries) per group
 constexpr int GR_B_BYTES = GR_TN * 128;
-constexpr int GR_STAGE_BYTES = FT_A_BYTES + GR_B_BYTES;  // 24 KB
 constexpr int GR_EPI_WARPS = 8;
 constexpr int GR_THREADS = 64 + 32 * GR_EPI_WARPS;
 constexpr int GR_CAPG = 8192;  // candidate slots per query between compactions (512 kept + what a round appends)
+// A work item = one document tile x up to MAXG CONSECUTIVE column groups of its leaf (item_group packs the first group in
+// its low 24 bits and the number of groups in the bits above; 0 = 1).  The tile's 196 KB then come through L2 once for
+// MAXG * 64 queries.  The ring is cut for the widest item of the instantiation: MAXG 1 -> 8 stages x 24 KB (the sample
+// rounds, whose items are one thin group), 2 -> 6 x 32 KB, 4 -> 4 x 48 KB (the last round: every tile of a leaf against
+// all the queries that chose it).
+constexpr int gr_stage_bytes(int maxg) { return FT_A_BYTES + maxg * GR_B_BYTES; }
+constexpr int gr_stages(int maxg) { return maxg == 1 ? 8 : (maxg == 2 ? 6 : 4); }
+constexpr uint32_t GR_GROUP_MASK = 0xFFFFFFu;
 
 struct GroupedParams {
   const __half* Aimg; const __half* Bimg;
   const int32_t* item_tile; const int32_t* item_group; int64_t n_items;
   const int32_t* tile_row0; const int32_t* tile_nrows;
   const int32_t* group_qid;  // [n_groups][GR_TN], -1 = padding
+  const int32_t* group_ncols; // [n_groups] columns in use, rounded up to 16: a thin group is a narrower GEMM (N = 16 .. 64)
   int nchunks;
   const float* consts; const float* tau; const float* margin;
   int* count; float* cand_score; int32_t* cand_id; int* overflow; int capg;
   int* err_flag;
 };
 
+template <int MAXG>
 __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedParams p) {
+  constexpr int STAGES = gr_stages(MAXG), STAGE_BYTES = gr_stage_bytes(MAXG), ACC_COLS = MAXG * GR_TN;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* ring = smem;  // [GR_STAGES][A 16 KB | B 8 KB]
-  float* s_thr = reinterpret_cast<float*>(smem + (size_t)GR_STAGES * GR_STAGE_BYTES);  // [2][GR_TN]
-  int* s_qid = reinterpret_cast<int*>(s_thr + 2 * GR_TN);                               // [2][GR_TN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qid + 2 * GR_TN);
+  uint8_t* ring = smem;  // [STAGES][A 16 KB | B MAXG x 8 KB]
+  float* s_thr = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);  // [2][ACC_COLS]
+  int* s_qid = reinterpret_cast<int*>(s_thr + 2 * ACC_COLS);                      // [2][ACC_COLS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qid + 2 * ACC_COLS);
   uint64_t* full = bars;
-  uint64_t* empty = full + GR_STAGES;
-  uint64_t* acc_full = empty + GR_STAGES;
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < GR_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], GR_EPI_WARPS); }
     ptx::mbar_fence_init();
   }
-  if (warp == 0) ptx::tmem_alloc(tmem_holder, 2 * GR_TN);
+  if (warp == 0) ptx::tmem_alloc(tmem_holder, 2 * ACC_COLS);
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -763,33 +857,43 @@ __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedPara
       uint32_t g = 0;
       bool ok = true;
       for (int64_t w = blockIdx.x; w < p.n_items && ok; w += gridDim.x) {
+        const uint32_t ig = (uint32_t)p.item_group[w];
+        const int ng = MAXG == 1 ? 1 : min(max((int)(ig >> 24), 1), MAXG);
+        const int64_t grp = ig & GR_GROUP_MASK;
+        const uint32_t last_bytes = (uint32_t)p.group_ncols[grp + ng - 1] * 128u;  // rows in use of the last group
         const __half* a_src = p.Aimg + (size_t)p.item_tile[w] * nchunks * FT_TM * FT_KC;
-        const __half* b_src = p.Bimg + (size_t)p.item_group[w] * nchunks * GR_TN * FT_KC;
+        const __half* b_src = p.Bimg + (size_t)grp * nchunks * GR_TN * FT_KC;
         for (int c = 0; c < nchunks; ++c, ++g) {
-          const uint32_t s = g % GR_STAGES, ph = (g / GR_STAGES) & 1;
+          const uint32_t s = g % STAGES, ph = (g / STAGES) & 1;
           if (!ptx::mbar_wait_backoff(&empty[s], ph ^ 1, 32)) { atomicExch(p.err_flag, 1); ok = false; break; }
-          ptx::mbar_arrive_expect_tx(&full[s], GR_STAGE_BYTES);
-          uint8_t* st_a = ring + (size_t)s * GR_STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(&full[s], FT_A_BYTES + (ng - 1) * GR_B_BYTES + last_bytes);
+          uint8_t* st_a = ring + (size_t)s * STAGE_BYTES;
           ptx::bulk_g2s(st_a, a_src + (size_t)c * FT_TM * FT_KC, FT_A_BYTES, &full[s]);
-          ptx::bulk_g2s(st_a + FT_A_BYTES, b_src + (size_t)c * GR_TN * FT_KC, GR_B_BYTES, &full[s]);
+#pragma unroll
+          for (int j = 0; j < MAXG; ++j)
+            if (j < ng)
+              ptx::bulk_g2s(st_a + FT_A_BYTES + j * GR_B_BYTES, b_src + ((size_t)j * nchunks + c) * GR_TN * FT_KC,
+                            j == ng - 1 ? last_bytes : (uint32_t)GR_B_BYTES, &full[s]);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_f16_m128(GR_TN);
       uint32_t g = 0, it = 0;
       bool ok = true;
       for (int64_t w = blockIdx.x; w < p.n_items && ok; w += gridDim.x, ++it) {
+        const uint32_t ig = (uint32_t)p.item_group[w];
+        const int ng = MAXG == 1 ? 1 : min(max((int)(ig >> 24), 1), MAXG);
+        const uint32_t idesc = ptx::umma_idesc_f16_m128(GR_TN * (ng - 1) + p.group_ncols[(ig & GR_GROUP_MASK) + ng - 1]);
         const uint32_t buf = it & 1, ph = (it >> 1) & 1;
         if (!ptx::mbar_wait(&acc_empty[buf], ph ^ 1)) { atomicExch(p.err_flag, 2); ok = false; break; }
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * GR_TN;
+        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
         for (int c = 0; c < nchunks; ++c, ++g) {
-          const uint32_t s = g % GR_STAGES, ph2 = (g / GR_STAGES) & 1;
+          const uint32_t s = g % STAGES, ph2 = (g / STAGES) & 1;
           if (!ptx::mbar_wait(&full[s], ph2)) { atomicExch(p.err_flag, 3); ok = false; break; }
           ptx::tc_fence_after_sync();
-          const uint32_t a_ad = ptx::smem_u32(ring + (size_t)s * GR_STAGE_BYTES);
+          const uint32_t a_ad = ptx::smem_u32(ring + (size_t)s * STAGE_BYTES);
           const uint32_t b_ad = a_ad + FT_A_BYTES;
 #pragma unroll
           for (int ks = 0; ks < FT_KC / 16; ++ks)
@@ -801,21 +905,24 @@ __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedPara
       }
     }
   } else {
-    // ===== epilogue: warp -> (TMEM lane group = warp % 4, 32-column half) =====
+    // ===== epilogue: warp -> (TMEM lane group = warp % 4, 32-column half of every 64-column group) =====
     const int lg = warp & 3;
-    const int c0 = ((warp - 2) >> 2) * 32;
+    const int ch = ((warp - 2) >> 2) * 32;
     const int etid = tid - 64;
     const float inv = p.consts[FC_INV];
     const float sdsq = p.consts[FC_SD] * p.consts[FC_SQ];
     uint32_t it = 0;
     bool ok = true;
     for (int64_t w = blockIdx.x; w < p.n_items && ok; w += gridDim.x, ++it) {
-      const int tile = p.item_tile[w], grp = p.item_group[w];
+      const int tile = p.item_tile[w];
+      const uint32_t ig = (uint32_t)p.item_group[w];
+      const int ng = MAXG == 1 ? 1 : min(max((int)(ig >> 24), 1), MAXG);
+      const int64_t grp = ig & GR_GROUP_MASK;
       const uint32_t buf = it & 1, ph = (it >> 1) & 1;
-      float* thr = s_thr + buf * GR_TN;
-      int* qid = s_qid + buf * GR_TN;
-      if (etid < GR_TN) {
-        const int q = p.group_qid[(int64_t)grp * GR_TN + etid];
+      float* thr = s_thr + buf * ACC_COLS;
+      int* qid = s_qid + buf * ACC_COLS;
+      if (etid < GR_TN * ng) {
+        const int q = p.group_qid[grp * GR_TN + etid];
         qid[etid] = q;
         thr[etid] = q >= 0 ? (p.tau[q] - p.margin[q]) * sdsq : CUDART_INF_F;
       }
@@ -825,48 +932,58 @@ __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedPara
       const int r = lg * 32 + lane;
       const bool doc_ok = r < p.tile_nrows[tile];
       const int32_t doc = p.tile_row0[tile] + r;  // row of the leaf-ordered matrix
-      uint32_t acc[32];
-      ptx::tmem_ld32(tmem_base + buf * GR_TN + c0 + ((uint32_t)(lg * 32) << 16), acc);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);  // accumulators are in registers: hand the buffer back first
-      const float4* t4 = reinterpret_cast<const float4*>(thr + c0);
-      bool any = false;
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 t = t4[j4];
-        any |= !(__uint_as_float(acc[4 * j4 + 0]) < t.x);
-        any |= !(__uint_as_float(acc[4 * j4 + 1]) < t.y);
-        any |= !(__uint_as_float(acc[4 * j4 + 2]) < t.z);
-        any |= !(__uint_as_float(acc[4 * j4 + 3]) < t.w);
-      }
-      if (__any_sync(MEVI_FULL_MASK, any && doc_ok)) {
-        unsigned mk = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mk |= (!(__uint_as_float(acc[j]) < thr[c0 + j]) ? 1u : 0u) << j;
-        if (!doc_ok) mk = 0;
-        unsigned mym = 0;  // lane j: documents (lanes) passing column j
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const unsigned m = __ballot_sync(MEVI_FULL_MASK, (mk >> j) & 1u);
-          if (lane == j) mym = m;
+      const int nlast = p.group_ncols[grp + ng - 1];
+      for (int sg = 0; sg < ng; ++sg) {
+        const int c0 = sg * GR_TN + ch;
+        const bool in_use = sg < ng - 1 || ch < nlast;  // this warp's 32 columns of a thin last group may not exist
+        uint32_t acc[32];
+        if (in_use) {
+          ptx::tmem_ld32(tmem_base + buf * ACC_COLS + c0 + ((uint32_t)(lg * 32) << 16), acc);
+          ptx::tmem_ld_wait();
         }
-        const int myq = qid[c0 + lane];
-        int base_l = 0;
-        if (mym && myq >= 0) base_l = atomicAdd(&p.count[myq], __popc(mym));
+        if (sg == ng - 1) {  // the last accumulators are in registers: hand the buffer back first
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        }
+        if (!in_use) continue;
+        const float4* t4 = reinterpret_cast<const float4*>(thr + c0);
+        bool any = false;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int b0 = __shfl_sync(MEVI_FULL_MASK, base_l, j);
-          const unsigned m = __shfl_sync(MEVI_FULL_MASK, mym, j);
-          const int q = __shfl_sync(MEVI_FULL_MASK, myq, j);
-          if (((mk >> j) & 1u) && q >= 0) {
-            const int slot = b0 + __popc(m & ((1u << lane) - 1u));
-            if (slot < p.capg) {
-              p.cand_score[(int64_t)q * p.capg + slot] = __uint_as_float(acc[j]) * inv;
-              p.cand_id[(int64_t)q * p.capg + slot] = doc;
-            } else {
-              p.overflow[q] = 1;  // per query: only this query is re-run through the streaming kernel
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = t4[j4];
+          any |= !(__uint_as_float(acc[4 * j4 + 0]) < t.x);
+          any |= !(__uint_as_float(acc[4 * j4 + 1]) < t.y);
+          any |= !(__uint_as_float(acc[4 * j4 + 2]) < t.z);
+          any |= !(__uint_as_float(acc[4 * j4 + 3]) < t.w);
+        }
+        if (__any_sync(MEVI_FULL_MASK, any && doc_ok)) {
+          unsigned mk = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mk |= (!(__uint_as_float(acc[j]) < thr[c0 + j]) ? 1u : 0u) << j;
+          if (!doc_ok) mk = 0;
+          unsigned mym = 0;  // lane j: documents (lanes) passing column j
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const unsigned m = __ballot_sync(MEVI_FULL_MASK, (mk >> j) & 1u);
+            if (lane == j) mym = m;
+          }
+          const int myq = qid[c0 + lane];
+          int base_l = 0;
+          if (mym && myq >= 0) base_l = atomicAdd(&p.count[myq], __popc(mym));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int b0 = __shfl_sync(MEVI_FULL_MASK, base_l, j);
+            const unsigned m = __shfl_sync(MEVI_FULL_MASK, mym, j);
+            const int q = __shfl_sync(MEVI_FULL_MASK, myq, j);
+            if (((mk >> j) & 1u) && q >= 0) {
+              const int slot = b0 + __popc(m & ((1u << lane) - 1u));
+              if (slot < p.capg) {
+                p.cand_score[(int64_t)q * p.capg + slot] = __uint_as_float(acc[j]) * inv;
+                p.cand_id[(int64_t)q * p.capg + slot] = doc;
+              } else {
+                p.overflow[q] = 1;  // per query: only this query is re-run through the streaming kernel
+              }
             }
           }
         }
@@ -877,7 +994,27 @@ __global__ void __launch_bounds__(GR_THREADS, 1) grouped_gemm_kernel(GroupedPara
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, 2 * GR_TN);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
+// columns in use per group, rounded up to the UMMA N granule (the planners fill a group's columns from 0 upwards)
+__global__ void gr_group_cols_kernel(const int32_t* __restrict__ group_qid, int64_t n_groups, int32_t* __restrict__ ncols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= n_groups) return;
+  const int q0 = group_qid[g * GR_TN + lane], q1 = group_qid[g * GR_TN + 32 + lane];
+  const unsigned m0 = __ballot_sync(MEVI_FULL_MASK, q0 >= 0), m1 = __ballot_sync(MEVI_FULL_MASK, q1 >= 0);
+  const int last = m1 ? 64 - __clz(m1) : (m0 ? 32 - __clz(m0) : 0);  // one past the last column in use
+  if (lane == 0) ncols[g] = max(16, (last + 15) & ~15);
+}
+
+template <int MAXG>
+int gr_launch(mevi_ctx* ctx, const GroupedParams& p, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)gr_stages(MAXG) * gr_stage_bytes(MAXG) + 2 * MAXG * GR_TN * 8 +
+                      (2 * gr_stages(MAXG) + 4) * 8 + 16 + 1024;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(grouped_gemm_kernel<MAXG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  grouped_gemm_kernel<MAXG><<<grid, GR_THREADS, smem, st>>>(p);
+  return MEVI_OK;
 }
 
 __global__ void gr_set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
@@ -1010,7 +1147,7 @@ extern "C" int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, 
 extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, int d, const void* Aimg,
                                          const int32_t* tile_row0, const int32_t* tile_nrows, const int32_t* item_tile,
                                          const int32_t* item_group, int64_t n_items, const int32_t* group_qid,
-                                         int64_t n_groups, int k, void* stream) {
+                                         int64_t n_groups, int max_groups_per_item, int k, void* stream) {
   MEVI_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1018,28 +1155,34 @@ extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, 
   MEVI_REQUIRE(ctx, k >= 1 && k <= FT_KEEP / 2, "k must be in [1, %d]", FT_KEEP / 2);
   if (n_items <= 0 || n_groups <= 0) return MEVI_OK;
   MEVI_REQUIRE(ctx, item_tile && item_group && group_qid, "NULL argument");
+  MEVI_REQUIRE(ctx, max_groups_per_item >= 1 && max_groups_per_item <= 4 && n_groups <= (int64_t)GR_GROUP_MASK,
+               "items take 1..4 groups and a round at most %u groups", GR_GROUP_MASK);
   GrState s;
   if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
   const int nchunks = d / FT_KC;
-  __half* Bimg = (__half*)mevi_ws(ctx, WS_TOPK_PART, (size_t)n_groups * GR_TN * d * 2);
-  if (!Bimg) return MEVI_ERR_NOMEM;
+  const size_t img_bytes = ((size_t)n_groups * GR_TN * d * 2 + 255) & ~size_t(255);
+  char* bws = (char*)mevi_ws(ctx, WS_TOPK_PART, img_bytes + (size_t)n_groups * 4);
+  if (!bws) return MEVI_ERR_NOMEM;
+  __half* Bimg = (__half*)bws;
+  int32_t* group_ncols = (int32_t*)(bws + img_bytes);
+  gr_group_cols_kernel<<<(unsigned)((n_groups + 7) / 8), 256, 0, st>>>(group_qid, n_groups, group_ncols);
   to_fp16_image_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(Q, nq, d, GR_TN, s.consts, FC_SQ, Bimg, nullptr, nullptr, s.flags + 2,
-                                                          n_groups * GR_TN, group_qid);
+                                                          n_groups * GR_TN, group_qid, group_ncols);
   GroupedParams p;
   p.Aimg = (const __half*)Aimg; p.Bimg = Bimg; p.item_tile = item_tile; p.item_group = item_group; p.n_items = n_items;
-  p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.group_qid = group_qid; p.nchunks = nchunks;
+  p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.group_qid = group_qid; p.group_ncols = group_ncols; p.nchunks = nchunks;
   p.consts = s.consts; p.tau = s.tau; p.margin = s.margin; p.count = s.count; p.cand_score = s.cand_score;
   p.cand_id = s.cand_id; p.overflow = s.ovq; p.capg = GR_CAPG; p.err_flag = s.flags + 1;
-  const size_t smem = (size_t)GR_STAGES * GR_STAGE_BYTES + 2 * GR_TN * 8 + (2 * GR_STAGES + 4) * 8 + 16 + 1024;
-  MEVI_CUDA(ctx, cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(n_items < ctx->sm_count ? n_items : ctx->sm_count);
-  grouped_gemm_kernel<<<grid, GR_THREADS, smem, st>>>(p);
+  const int maxg = max_groups_per_item <= 1 ? 1 : (max_groups_per_item == 2 ? 2 : 4);
+  if (int rc = maxg == 1 ? gr_launch<1>(ctx, p, grid, st) : (maxg == 2 ? gr_launch<2>(ctx, p, grid, st) : gr_launch<4>(ctx, p, grid, st)))
+    return rc;
   const size_t smem_compact = (size_t)GR_CAPG * 8;
   MEVI_CUDA(ctx, cudaFuncSetAttribute(flat_tensor_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_compact));
   flat_tensor_compact_kernel<<<nq, 256, smem_compact, st>>>(s.tau, s.margin, s.count, s.cand_score, s.cand_id, s.ovq, GR_CAPG, k,
                                                             FT_KEEP, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
-  MEVI_COUNT_LAUNCH(ctx, 3);
+  MEVI_COUNT_LAUNCH(ctx, 4);
   return MEVI_OK;
 }
 

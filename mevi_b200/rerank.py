@@ -230,7 +230,10 @@ class ClusterReranker:
     BOOTSTRAP_ROWS = 3072           # rows of the threshold-free first round per query (all appended: must fit the buffers)
     BOOTSTRAP_MIN = 2048            # fewer bootstrap rows than this: first threshold from the streaming kernel instead
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
-    PLAN = "tiles"                  # "tiles": plan_grouped_tile_rounds (default); "prefix": plan_grouped_rounds
+    PLAN = "device"                 # "device": the tiles plan made by the library (mevi_rerank_grouped_plan; default);
+                                    # "tiles": its torch restatement plan_grouped_tile_rounds; "prefix": plan_grouped_rounds
+    MAXG_SAMPLE = 1                 # query groups (of 64) an item of a sample round takes
+    MAXG_LAST = 4                   # ... and of the last round: a document tile is fetched once for up to 256 queries
     BOOT_LEAVES = (8, 63)           # tiles plan: first tile of the leading 8 leaves = the threshold-free bootstrap (<= 1,024
                                     # appended rows per query), of the next 55 = a second, filtered sample (<= 8,064 rows in all)
 
@@ -270,6 +273,10 @@ class ClusterReranker:
         self.last_path = None
         if os.environ.get("MEVI_RERANK_BOOTSTRAP"):
             self.BOOTSTRAP_ROWS = int(os.environ["MEVI_RERANK_BOOTSTRAP"])
+        if os.environ.get("MEVI_RERANK_PLAN"):
+            self.PLAN = os.environ["MEVI_RERANK_PLAN"]
+        if os.environ.get("MEVI_RERANK_MAXG"):
+            self.MAXG_LAST = int(os.environ["MEVI_RERANK_MAXG"])
         if os.environ.get("MEVI_RERANK_ROUNDS"):
             self.ROUND_ROWS = tuple(int(v) for v in os.environ["MEVI_RERANK_ROUNDS"].split(","))
         build_image = self.mode == "grouped"
@@ -377,11 +384,12 @@ def hn_lines_all(texts: Sequence[str], offsets, ids, scores, save_hard_neg: Opti
 ClusterReranker.rerank_all = _rerank_all
 
 
-def _group_items(leaf, q, first_tile, n_tiles, presorted: bool = False):
+def _group_items(leaf, q, first_tile, n_tiles, presorted: bool = False, maxg: int = 1):
     """Work items of one item set: (leaf, query) pairs (1-D; sorted by leaf when `presorted`) meet the tiles
     [first_tile[leaf], first_tile[leaf] + n_tiles[leaf]) of their leaf.  Each leaf's queries are cut into groups of
     GROUP_COLS columns, one item per (tile, group), per leaf TILE-major: a document tile (196 KB) comes from HBM once and
     meets all the query groups of its leaf back to back.
+    An item takes up to `maxg` consecutive groups of its leaf (item_group = first group | number of groups << 24).
     -> (item_tile int32 [I], item_group int32 [I], group_qid int32 [G*GROUP_COLS]).  One host sync (G and I)."""
     dev = leaf.device
     keep = n_tiles[leaf] > 0
@@ -396,7 +404,8 @@ def _group_items(leaf, q, first_tile, n_tiles, presorted: bool = False):
     run0 = torch.cumsum(cnt, 0) - cnt                                   # first pair of every leaf run
     gpl = (cnt + GROUP_COLS - 1) // GROUP_COLS                          # groups per leaf
     grp0 = torch.cumsum(gpl, 0) - gpl
-    ipl = n_tiles[uleaf] * gpl                                          # items per leaf
+    wpl = (gpl + maxg - 1) // maxg                                      # wide items per tile of the leaf
+    ipl = n_tiles[uleaf] * wpl                                          # items per leaf
     G, n_items = (int(v) for v in torch.stack([gpl.sum(), ipl.sum()]).tolist())
     run_of_pair = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), cnt, output_size=leaf.numel())
     pos = torch.arange(leaf.numel(), device=dev) - run0[run_of_pair]
@@ -406,13 +415,16 @@ def _group_items(leaf, q, first_tile, n_tiles, presorted: bool = False):
     item0 = torch.cumsum(ipl, 0) - ipl
     leaf_of_item = torch.repeat_interleave(torch.arange(uleaf.numel(), device=dev), ipl, output_size=n_items)
     local = torch.arange(n_items, device=dev) - item0[leaf_of_item]
-    g_of = gpl[leaf_of_item]
-    item_tile = first_tile[uleaf[leaf_of_item]] + local // g_of
-    item_group = grp0[leaf_of_item] + local % g_of
+    w_of = wpl[leaf_of_item]
+    item_tile = first_tile[uleaf[leaf_of_item]] + local // w_of
+    j = (local % w_of) * maxg
+    item_group = grp0[leaf_of_item] + j
+    if maxg > 1:
+        item_group = item_group | (torch.clamp(gpl[leaf_of_item] - j, max=maxg) << 24)
     return item_tile.to(torch.int32).contiguous(), item_group.to(torch.int32).contiguous(), group_qid.reshape(-1).contiguous()
 
 
-def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_leaves):
+def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_leaves, maxg_sample: int = 1, maxg_last: int = 1):
     """Rounds that cut the work by TILES instead of by leaf prefixes, so that a leaf's queries stay together.  With
     boot_leaves = (b0, b1, ...):
       round 0 (threshold-free bootstrap): the FIRST tile of the first b0 leaves of every query - at most b0 * TILE_ROWS
@@ -422,7 +434,9 @@ def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_le
       last round: the first tile for the pairs the bootstrap left out, and every further tile of every leaf against ALL
               the queries that chose the leaf (full groups: a tile meets ceil(queries / GROUP_COLS) groups once).
     The prefix plan (`plan_grouped_rounds`) splits a leaf's queries over its rounds, so every tile is fetched, and its
-    query groups rebuilt, once per round.  -> [(item_tile, item_group, group_qid)] per round."""
+    query groups rebuilt, once per round.  -> [(item_tile, item_group, group_qid)] per round.
+    This is the torch restatement of csrc/rerank_plan.cu (mevi_rerank_grouped_plan), which the re-ranker uses by default;
+    the two agree up to the order of the queries inside a leaf's groups."""
     if isinstance(boot_leaves, int):
         boot_leaves = (boot_leaves,)
     dev = ql.device
@@ -441,11 +455,11 @@ def plan_grouped_tile_rounds(leaf_tile0: torch.Tensor, ql: torch.Tensor, boot_le
     lo = 0
     for hi in boot_leaves:
         m = (rank_all >= lo) & (rank_all < hi)
-        out.append(_group_items(leaf_all[m], q_all[m], first, one, presorted=True))
+        out.append(_group_items(leaf_all[m], q_all[m], first, one, presorted=True, maxg=maxg_sample))
         lo = hi
     m1 = rank_all >= lo
-    a_t, a_g, a_q = _group_items(leaf_all[m1], q_all[m1], first, one, presorted=True)
-    b_t, b_g, b_q = _group_items(leaf_all, q_all, first + 1, tpl - one, presorted=True)
+    a_t, a_g, a_q = _group_items(leaf_all[m1], q_all[m1], first, one, presorted=True, maxg=maxg_last)
+    b_t, b_g, b_q = _group_items(leaf_all, q_all, first + 1, tpl - one, presorted=True, maxg=maxg_last)
     out.append((torch.cat([a_t, b_t]), torch.cat([a_g, b_g + a_q.numel() // GROUP_COLS]), torch.cat([a_q, b_q])))
     return out
 
@@ -459,21 +473,28 @@ def _rerank_grouped(self, Q, ql, topk):
         return None
     ctx, idx = self.ctx, self.index
     off = idx.leaf_offsets
-    sizes = off[1:] - off[:-1]
-    ncand = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device)).sum(1)
+    boot = (self.BOOT_LEAVES,) if isinstance(self.BOOT_LEAVES, int) else tuple(self.BOOT_LEAVES)
     # thresholds bootstrap themselves: the first round (the leading leaves of every query, at most BOOTSTRAP_ROWS rows)
     # runs without thresholds and appends every score; its compaction yields each query's first k-th best score.
     # A query whose leading leaves do not add up to BOOTSTRAP_MIN rows within that limit (its first leaf is a huge
     # one) would enter the next round with no useful threshold: those few queries get the exact k-th score of their
     # first BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
-    qsz = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device))
-    if self.PLAN == "tiles":  # bootstrap = first tile of the leading BOOT_LEAVES leaves
-        bl = self.BOOT_LEAVES if isinstance(self.BOOT_LEAVES, int) else self.BOOT_LEAVES[-1]
-        boot_rows = qsz[:, :bl].clamp(max=TILE_ROWS).sum(1)
+    device_plan = None
+    if self.PLAN == "device":  # counts, scans, candidate totals and the weak-sample flags in five launches, one host sync
+        ncand, weak_flags, device_plan, n_weak = ctx.rerank_grouped_plan(ql.contiguous(), off, g["leaf_tile0"], boot,
+                                                                         self.BOOTSTRAP_MIN, self.MAXG_SAMPLE, self.MAXG_LAST)
+        weak = torch.nonzero(weak_flags).squeeze(1) if n_weak else weak_flags[:0].long()
     else:
-        after = torch.cumsum(qsz, 1)
-        boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)
-    weak = torch.nonzero((boot_rows < self.BOOTSTRAP_MIN) & (ncand > boot_rows)).squeeze(1)
+        sizes = off[1:] - off[:-1]
+        qsz = torch.where(ql >= 0, sizes[ql.clamp(min=0).long()], torch.zeros((), dtype=torch.int64, device=ql.device))
+        ncand = qsz.sum(1)
+        if self.PLAN == "tiles":  # bootstrap = first tile of the leading BOOT_LEAVES leaves
+            boot_rows = qsz[:, :boot[-1]].clamp(max=TILE_ROWS).sum(1)
+        else:
+            after = torch.cumsum(qsz, 1)
+            boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)
+        weak = torch.nonzero((boot_rows < self.BOOTSTRAP_MIN) & (ncand > boot_rows)).squeeze(1)
+        ncand = ncand.clamp(max=0x7FFFFFFF).to(torch.int32)
     tau0 = None
     if weak.numel():
         s0, _, _ = ctx.cluster_rerank_prefix(Q[weak].contiguous(), self.D, off, idx.leaf_docids, ql[weak].contiguous(), topk,
@@ -482,11 +503,19 @@ def _rerank_grouped(self, Q, ql, topk):
         tau0[weak] = s0[:, topk - 1]
     self.last_weak_queries = int(weak.numel())
     ctx.rerank_grouped_begin(Q, g["absmax"], g["maxnorm"], tau0)
-    plan = (plan_grouped_tile_rounds(g["leaf_tile0"], ql, self.BOOT_LEAVES) if self.PLAN == "tiles"
-            else plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS, self.BOOTSTRAP_ROWS))
-    for item_tile, item_group, group_qid in plan:
-        if item_tile.numel():
-            ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk)
+    if device_plan is not None:
+        for r, (n_items, n_groups) in enumerate(device_plan):
+            if n_items and n_groups:
+                maxg = self.MAXG_LAST if r == len(device_plan) - 1 else self.MAXG_SAMPLE
+                item_tile, item_group, group_qid = ctx.rerank_grouped_plan_fill(r, n_items, n_groups, Q.device)
+                ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk, maxg)
+    else:
+        plan = (plan_grouped_tile_rounds(g["leaf_tile0"], ql, boot, self.MAXG_SAMPLE, self.MAXG_LAST) if self.PLAN == "tiles"
+                else plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS, self.BOOTSTRAP_ROWS))
+        for r, (item_tile, item_group, group_qid) in enumerate(plan):
+            if item_tile.numel():
+                maxg = 1 if self.PLAN != "tiles" else (self.MAXG_LAST if r == len(plan) - 1 else self.MAXG_SAMPLE)
+                ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk, maxg)
     scores, rows, failed, n_failed = ctx.rerank_grouped_finish(Q, self.D, topk)
     nq = Q.shape[0]
     self.last_failed_queries = n_failed
@@ -501,7 +530,7 @@ def _rerank_grouped(self, Q, ql, topk):
         scores[bad] = s2
         ids[bad] = i2
         self.last_path = "grouped+stream"
-    return scores, ids, ncand.clamp(max=0x7FFFFFFF).to(torch.int32)
+    return scores, ids, ncand
 
 
 ClusterReranker._rerank_grouped = _rerank_grouped

@@ -53,7 +53,7 @@ def test_rerank_matches_oracle(case, nb, k, leaf_ordered):
     assert (np.diff(np.where(np.isfinite(scores), scores, -1e30), axis=1) <= 0).all()
 
 
-@pytest.mark.parametrize("plan", ["tiles", "prefix"])
+@pytest.mark.parametrize("plan", ["device", "tiles", "prefix"])
 @pytest.mark.parametrize("nb,k,boot_min", [(10, 100, 128), (100, 100, 128), (100, 7, 128), (100, 100, 100000)])
 def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min, plan):
     """K3g: every leaf read once and scored against all the queries that chose it (tcgen05 prefilter + exact fp32
@@ -87,6 +87,62 @@ def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min, plan):
                            pool_scores=lambda q, doc: float(X64[doc] @ Q64[q]))
 
 
+@pytest.mark.parametrize("maxg_sample,maxg_last", [(1, 1), (1, 4), (2, 2), (4, 4)])
+def test_device_plan_covers_every_pair_tile_exactly_once(maxg_sample, maxg_last):
+    """mevi_rerank_grouped_plan (csrc/rerank_plan.cu): every (query, leaf) pair meets every tile of its leaf exactly once,
+    in the round its leaf rank assigns; candidate totals and weak-sample flags equal the torch arithmetic."""
+    from mevi_b200.rerank import GROUP_COLS, build_leaf_tiles
+
+    c = ctx()
+    rs = np.random.RandomState(1)
+    n_leaves = 300
+    sizes = rs.randint(1, 700, size=n_leaves)
+    sizes[2], sizes[5], sizes[6], sizes[7] = 1, 128, 129, 5000
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)).cuda()
+    _, _, lt0, _ = build_leaf_tiles(off)
+    nq, L, boot = 700, 12, (2, 5)
+    ql_h = np.stack([rs.choice(40, size=L, replace=False) for _ in range(nq)]).astype(np.int32)  # 40 hot leaves: full groups
+    ql_h[::3, 7:] = rs.randint(40, n_leaves, size=ql_h[::3, 7:].shape)
+    ql_h[4, 2] = -1
+    ql_h[9, :] = -1
+    ql_h[11, :] = 2  # one tiny leaf asked for twelve times: a weak sample
+    ql = torch.from_numpy(ql_h).cuda()
+    ncand, weak, rounds, n_weak = c.rerank_grouped_plan(ql, off, lt0, boot, 300, maxg_sample, maxg_last)
+    want_ncand = np.where(ql_h >= 0, sizes[np.clip(ql_h, 0, None)], 0).sum(1)
+    assert np.array_equal(ncand.cpu().numpy(), want_ncand)
+    boot_rows = np.where(ql_h[:, :5] >= 0, np.minimum(sizes[np.clip(ql_h[:, :5], 0, None)], 128), 0).sum(1)
+    want_weak = (boot_rows < 300) & (want_ncand > boot_rows)
+    assert np.array_equal(weak.cpu().numpy().astype(bool), want_weak) and n_weak == int(want_weak.sum()) and n_weak >= 1
+    assert len(rounds) == 3
+    lt0_h = lt0.cpu().numpy()
+    seen = []
+    for r, (n_items, n_groups) in enumerate(rounds):
+        assert n_items > 0 and n_groups > 0
+        it, ig, gq = c.rerank_grouped_plan_fill(r, n_items, n_groups, ql.device)
+        it, ig, gq = it.cpu().numpy(), ig.cpu().numpy(), gq.cpu().numpy().reshape(-1, GROUP_COLS)
+        cap = maxg_last if r == 2 else maxg_sample
+        for i in range(n_items):
+            t, g0, ng = int(it[i]), int(ig[i]) & 0xFFFFFF, int(ig[i]) >> 24
+            assert 1 <= ng <= cap and g0 + ng <= n_groups
+            leaf = int(np.searchsorted(lt0_h, t, side="right")) - 1
+            for g in range(g0, g0 + ng):
+                seen += [(r, int(q), leaf, t) for q in gq[g][gq[g] >= 0]]
+    # query 11 lists leaf 2 twelve times: the reference scores it twelve times too (a list, not a set)
+    from collections import Counter
+
+    want = Counter()
+    for q in range(nq):
+        for j in range(L):
+            leaf = int(ql_h[q, j])
+            if leaf < 0:
+                continue
+            t0, t1 = int(lt0_h[leaf]), int(lt0_h[leaf + 1])
+            want[(0 if j < 2 else (1 if j < 5 else 2), q, leaf, t0)] += 1
+            for t in range(t0 + 1, t1):
+                want[(2, q, leaf, t)] += 1
+    assert Counter(seen) == want
+
+
 def test_grouped_rerank_falls_back_when_the_margin_window_overflows(gauss):
     """Near-duplicate documents put more candidates inside the fp16 margin than the buffers keep: the grouped path must
     notice and the call must still return the exact answer (through the streaming kernel)."""
@@ -109,7 +165,7 @@ def test_grouped_rerank_falls_back_when_the_margin_window_overflows(gauss):
         np.testing.assert_allclose(scores[q].cpu().numpy(), s_, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("plan", ["tiles", "prefix"])
+@pytest.mark.parametrize("plan", ["device", "tiles", "prefix"])
 def test_grouped_rerank_reruns_only_the_queries_whose_guarantee_failed(gauss, plan):
     """A few queries hit a leaf of near-duplicate documents (margin window overflow), the others do not: only those few
     go through the streaming kernel, and every query's answer is the exact one."""

@@ -193,6 +193,20 @@ def test_grouped_rerank_tile_plan_covers_every_pair_tile_exactly_once():
     assert len(seen) == len(set(seen)) and set(seen) == exp
     # per-query rows of the bootstrap fit the candidate buffers by construction
     assert BL * 128 <= 8192
+    # wide items (a tile meets up to 4 consecutive groups of its leaf: first group | count << 24) cover the same set
+    wide = plan_grouped_tile_rounds(lt0, ql, BL, maxg_sample=2, maxg_last=4)
+    seen_w = []
+    for r, (it, ig, gq) in enumerate(wide):
+        gq = gq.view(-1, GROUP_COLS)
+        assert torch.equal(gq, plan[r][2].view(-1, GROUP_COLS))  # the groups themselves do not change
+        for i in range(it.numel()):
+            t, g0, ng = int(it[i]), int(ig[i]) & 0xFFFFFF, int(ig[i]) >> 24
+            assert 1 <= ng <= (2 if r == 0 else 4) and g0 + ng <= gq.shape[0]
+            leaf = int(np.searchsorted(lt0.numpy(), t, side="right")) - 1
+            for g in range(g0, g0 + ng):
+                seen_w += [(r, q, leaf, t) for q in gq[g][gq[g] >= 0].tolist()]
+    assert len(seen_w) == len(set(seen_w)) and set(seen_w) == exp
+    assert wide[1][0].numel() < plan[1][0].numel()
 
 
 def test_bench_reference_arm_prints_the_contract_line():
