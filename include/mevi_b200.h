@@ -164,6 +164,12 @@ int mevi_rq_beam_search(mevi_ctx* ctx, const float* X, int64_t bs, int d, const 
  *   sorted_keys   [n] int64 out: the key of each entry of sorted_docids      */
 int mevi_build_inverted_lists(mevi_ctx* ctx, const int32_t* codes, int64_t n, int M, int K, int32_t* sorted_docids,
                               int64_t* sorted_keys, void* stream);
+/* replaces: `doc_cluster.get(tuple(leaf), None)` of MEVI/main_models.py:3926-3936 for all (query, leaf) pairs at once.
+ *   leaves [n_pairs, M] int64 code tuples (the beam search's output); leaf_keys [n_leaves] int64 ascending, the
+ *   distinct keys of mevi_build_inverted_lists; leaf_index [n_pairs] int32 out: position of the tuple's key in
+ *   leaf_keys, -1 when no document carries it or a code is outside [0, K).                                        */
+int mevi_leaf_lookup(mevi_ctx* ctx, const int64_t* leaves, int64_t n_pairs, int M, int K, const int64_t* leaf_keys,
+                     int64_t n_leaves, int32_t* leaf_index, void* stream);
 
 /* ---- cluster-restricted re-rank ----------------------------------------- *
  * replaces: MEVI/main_models.py:3915-4014 (per query: leaves -> candidate rows

@@ -39,6 +39,7 @@ SYMBOLS = {
     "mevi_pq_encode": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _vp, _vp]),
     "mevi_rq_beam_search": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "mevi_build_inverted_lists": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "mevi_leaf_lookup": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp]),
     "mevi_cluster_rerank": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "mevi_cluster_rerank_prefix": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _vp]),
     "mevi_cluster_rerank_all": (_i, [_vp, _vp, _i, _vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -467,6 +468,19 @@ class Context:
         with torch.cuda.device(self.device):
             self._check(self.lib.mevi_rerank_grouped_begin(self.handle, _ptr(Q), Q.shape[0], Q.shape[1], float(d_absmax),
                                                            float(d_maxnorm), _ptr(tau0), self._stream()))
+
+    def leaf_lookup(self, leaves, K, leaf_keys):
+        """leaves [..., M] int64 code tuples -> int32 [...] index into the ascending leaf_keys, -1 = no such leaf."""
+        import torch
+
+        leaves = self._dev(leaves, torch.int64, "leaves")
+        leaf_keys = self._dev(leaf_keys, torch.int64, "leaf_keys")
+        M = leaves.shape[-1]
+        out = torch.empty(leaves.shape[:-1], dtype=torch.int32, device=leaves.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_leaf_lookup(self.handle, _ptr(leaves), out.numel(), M, int(K), _ptr(leaf_keys),
+                                                  leaf_keys.numel(), _ptr(out), self._stream()))
+        return out
 
     def rerank_grouped_plan(self, ql, leaf_offsets, leaf_tile0, boot_leaves, boot_min_rows, maxg_sample=1, maxg_last=4):
         """Device-side round plan -> (ncand int32 [nq], weak int32 [nq], [(items, groups)] per round, n_weak)."""

@@ -46,8 +46,7 @@ __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, 
                                      const float* __restrict__ consts, int scale_slot, __half* __restrict__ img,
                                      float* __restrict__ norms, unsigned* __restrict__ max_norm_bits,
                                      int* __restrict__ clamped, int64_t padded_rows,
-                                     const int32_t* __restrict__ src_index = nullptr,    // image row -> row of X, -1 = zero row
-                                     const int32_t* __restrict__ tile_rows_used = nullptr) {  // rows of a tile anyone reads
+                                     const int32_t* __restrict__ src_index = nullptr) {  // image row -> row of X, -1 = zero row
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -57,7 +56,6 @@ __global__ void to_fp16_image_kernel(const float* __restrict__ X, int64_t rows, 
   for (int64_t prow = warp_global; prow < padded_rows; prow += n_warps) {
     const int64_t tile = prow / rows_per_tile;
     const int r = (int)(prow - tile * rows_per_tile);
-    if (tile_rows_used && r >= tile_rows_used[tile]) continue;  // thin query group: the GEMM takes N = rows used
     // `row` is the source row; without an index it is the image row itself (rows past the end are zero-filled)
     const int64_t row = src_index ? (src_index[prow] >= 0 ? (int64_t)src_index[prow] : rows) : prow;
     float nrm = 0.f;
@@ -1008,6 +1006,69 @@ __global__ void gr_group_cols_kernel(const int32_t* __restrict__ group_qid, int6
   if (lane == 0) ncols[g] = max(16, (last + 15) & ~15);
 }
 
+// the call's queries in fp16 (scaled by consts[FC_SQ], clamped like to_fp16_image_kernel), row-major: one warp per row
+__global__ void gr_q16_kernel(const float* __restrict__ Q, int nq, int d, const float* __restrict__ consts,
+                              __half* __restrict__ q16, int* __restrict__ clamped) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nq) return;
+  const float s = consts[FC_SQ];
+  bool clamp = false;
+  for (int u = lane; u < d / 8; u += 32) {
+    const float4 a = ldg_f4(Q + (int64_t)row * d + u * 8), b = ldg_f4(Q + (int64_t)row * d + u * 8 + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = v[e] * s;
+      if (fabsf(t) > 65000.f) { t = copysignf(65000.f, t); clamp = true; }
+      h[e] = __float2half_rn(t);
+    }
+    *reinterpret_cast<uint4*>(q16 + (int64_t)row * d + u * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+  if (clamp) atomicExch(clamped, 1);
+}
+
+// group images [group][K chunk][64 rows][64] (128B-swizzled as UMMA reads them) copied from the fp16 queries; only
+// the rows in use (group_ncols) are written.  One CTA per group (grid-stride), one warp per row, two rows in flight.
+__global__ void __launch_bounds__(256) gr_group_image_kernel(const __half* __restrict__ q16, int d,
+                                                             const int32_t* __restrict__ group_qid,
+                                                             const int32_t* __restrict__ group_ncols, int64_t n_groups,
+                                                             __half* __restrict__ img) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int units = d / 8, nchunks = d / FT_KC;
+  for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const int ncols = group_ncols[g];
+    for (int r0 = warp; r0 < ncols; r0 += 16) {
+      const int r1 = r0 + 8;
+      const int qa = group_qid[g * GR_TN + r0];
+      const int qb = r1 < ncols ? group_qid[g * GR_TN + r1] : -1;
+      for (int u0 = lane; u0 < units; u0 += 96) {
+        uint4 va[3], vb[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int u = u0 + 32 * i;
+          va[i] = make_uint4(0u, 0u, 0u, 0u);
+          vb[i] = va[i];
+          if (u < units) {
+            if (qa >= 0) va[i] = __ldg(reinterpret_cast<const uint4*>(q16 + (int64_t)qa * d) + u);
+            if (qb >= 0) vb[i] = __ldg(reinterpret_cast<const uint4*>(q16 + (int64_t)qb * d) + u);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int u = u0 + 32 * i;
+          if (u >= units) break;
+          const int chunk = u / 8, uu = u & 7;
+          __half* base = img + ((size_t)g * nchunks + chunk) * GR_TN * FT_KC;
+          *reinterpret_cast<uint4*>(base + (size_t)r0 * FT_KC + ((uu ^ (r0 & 7)) * 8)) = va[i];
+          if (r1 < ncols) *reinterpret_cast<uint4*>(base + (size_t)r1 * FT_KC + ((uu ^ (r1 & 7)) * 8)) = vb[i];
+        }
+      }
+    }
+  }
+}
+
 template <int MAXG>
 int gr_launch(mevi_ctx* ctx, const GroupedParams& p, int grid, cudaStream_t st) {
   const size_t smem = (size_t)gr_stages(MAXG) * gr_stage_bytes(MAXG) + 2 * MAXG * GR_TN * 8 +
@@ -1062,21 +1123,24 @@ struct GrState {
   float* consts; unsigned* absmax; int* flags; float* tau; float* margin; float* qnorm; int* count;
   float* cand_score; int32_t* cand_id;
   int* ovq;  // [nq] 1 = the guarantee could not be established for this query (buffer or margin-window overflow)
+  __half* q16;  // [nq][d] the call's queries, scaled and rounded to fp16 once (_begin); the rounds' group images copy rows
 };
 
 // the per-call state lives in one scratch slot from _begin to _finish (same layout recomputed by each entry point)
-bool gr_state(mevi_ctx* ctx, int nq, GrState* s) {
+bool gr_state(mevi_ctx* ctx, int nq, int d, GrState* s) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
   const size_t o_consts = take(FC_NUM * 4), o_abs = take(16), o_flags = take(16), o_tau = take((size_t)nq * 4),
                o_margin = take((size_t)nq * 4), o_qnorm = take((size_t)nq * 4), o_cnt = take((size_t)nq * 4),
-               o_ovq = take((size_t)nq * 4), o_cs = take((size_t)nq * GR_CAPG * 4), o_ci = take((size_t)nq * GR_CAPG * 4);
+               o_ovq = take((size_t)nq * 4), o_cs = take((size_t)nq * GR_CAPG * 4), o_ci = take((size_t)nq * GR_CAPG * 4),
+               o_q16 = take((size_t)nq * d * 2);
   char* ws = (char*)mevi_ws(ctx, WS_TOPK_AUX, off);
   if (!ws) return false;
   s->consts = (float*)(ws + o_consts); s->absmax = (unsigned*)(ws + o_abs); s->flags = (int*)(ws + o_flags);
   s->tau = (float*)(ws + o_tau); s->margin = (float*)(ws + o_margin); s->qnorm = (float*)(ws + o_qnorm);
   s->count = (int*)(ws + o_cnt); s->cand_score = (float*)(ws + o_cs); s->cand_id = (int32_t*)(ws + o_ci);
   s->ovq = (int*)(ws + o_ovq);
+  s->q16 = (__half*)(ws + o_q16);
   return true;
 }
 
@@ -1129,7 +1193,7 @@ extern "C" int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, 
   cudaStream_t st = (cudaStream_t)stream;
   MEVI_REQUIRE(ctx, Q && nq > 0 && d_absmax >= 0.f, "bad argument");
   GrState s;
-  if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
+  if (!gr_state(ctx, nq, d, &s)) return MEVI_ERR_NOMEM;
   gr_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.tau, tau0, s.count, s.flags, s.ovq, nq);
   gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 0, gr_f32_bits(d_absmax));
   gr_set_u32_kernel<<<1, 1, 0, st>>>(s.absmax + 1, 0u);
@@ -1138,8 +1202,9 @@ extern "C" int mevi_rerank_grouped_begin(mevi_ctx* ctx, const float* Q, int nq, 
   gr_consts_kernel<<<1, 32, 0, st>>>(s.absmax, s.consts);
   gr_row_norm_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, d, s.qnorm);
   flat_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.qnorm, nq, s.absmax + 2, s.margin);
+  gr_q16_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, d, s.consts, s.q16, s.flags + 2);
   MEVI_CUDA(ctx, cudaGetLastError());
-  MEVI_COUNT_LAUNCH(ctx, 8);
+  MEVI_COUNT_LAUNCH(ctx, 9);
   return MEVI_OK;
 }
 
@@ -1158,7 +1223,7 @@ extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, 
   MEVI_REQUIRE(ctx, max_groups_per_item >= 1 && max_groups_per_item <= 4 && n_groups <= (int64_t)GR_GROUP_MASK,
                "items take 1..4 groups and a round at most %u groups", GR_GROUP_MASK);
   GrState s;
-  if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
+  if (!gr_state(ctx, nq, d, &s)) return MEVI_ERR_NOMEM;
   const int nchunks = d / FT_KC;
   const size_t img_bytes = ((size_t)n_groups * GR_TN * d * 2 + 255) & ~size_t(255);
   char* bws = (char*)mevi_ws(ctx, WS_TOPK_PART, img_bytes + (size_t)n_groups * 4);
@@ -1166,8 +1231,8 @@ extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, 
   __half* Bimg = (__half*)bws;
   int32_t* group_ncols = (int32_t*)(bws + img_bytes);
   gr_group_cols_kernel<<<(unsigned)((n_groups + 7) / 8), 256, 0, st>>>(group_qid, n_groups, group_ncols);
-  to_fp16_image_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(Q, nq, d, GR_TN, s.consts, FC_SQ, Bimg, nullptr, nullptr, s.flags + 2,
-                                                          n_groups * GR_TN, group_qid, group_ncols);
+  gr_group_image_kernel<<<(unsigned)(n_groups < (int64_t)ctx->sm_count * 8 ? n_groups : (int64_t)ctx->sm_count * 8), 256, 0, st>>>(
+      s.q16, d, group_qid, group_ncols, n_groups, Bimg);
   GroupedParams p;
   p.Aimg = (const __half*)Aimg; p.Bimg = Bimg; p.item_tile = item_tile; p.item_group = item_group; p.n_items = n_items;
   p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.group_qid = group_qid; p.group_ncols = group_ncols; p.nchunks = nchunks;
@@ -1199,7 +1264,7 @@ extern "C" int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq,
   MEVI_REQUIRE(ctx, Q && D_leaf && scores && rows && n_failed, "NULL argument");
   *n_failed = nq;
   GrState s;
-  if (!gr_state(ctx, nq, &s)) return MEVI_ERR_NOMEM;
+  if (!gr_state(ctx, nq, d, &s)) return MEVI_ERR_NOMEM;
   int h_flags[4] = {0, 0, 0, 0};
   gr_count_failed_kernel<<<1, 256, 0, st>>>(s.ovq, nq, s.flags + 3);
   MEVI_COUNT_LAUNCH(ctx, 1);

@@ -17,7 +17,46 @@ __global__ void leaf_key_kernel(const int32_t* __restrict__ codes, int64_t n, in
     rows[i] = (int32_t)i;
   }
 }
+
+// beam-search leaves (code tuples) -> index of the leaf in the sorted key list, -1 when no document lives there
+// (`doc_cluster.get(tuple, None)`, main_models.py:3928) or a code is outside [0, K)
+__global__ void leaf_lookup_kernel(const int64_t* __restrict__ dec, int64_t n_pairs, int M, int K,
+                                   const int64_t* __restrict__ leaf_keys, int64_t n_leaves, int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  int64_t key = 0;
+  bool valid = true;
+  for (int j = 0; j < M; ++j) {
+    const int64_t c = dec[i * M + j];
+    valid &= (c >= 0) && (c < K);
+    key = key * K + c;
+  }
+  int32_t r = -1;
+  if (valid && n_leaves > 0) {
+    int64_t lo = 0, hi = n_leaves;  // lower bound
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (leaf_keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n_leaves && leaf_keys[lo] == key) r = (int32_t)lo;
+  }
+  out[i] = r;
+}
 }  // namespace
+
+extern "C" int mevi_leaf_lookup(mevi_ctx* ctx, const int64_t* leaves, int64_t n_pairs, int M, int K,
+                                const int64_t* leaf_keys, int64_t n_leaves, int32_t* leaf_index, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  MEVI_REQUIRE(ctx, leaves && leaf_index && (leaf_keys || n_leaves == 0), "NULL argument");
+  MEVI_REQUIRE(ctx, M >= 1 && K >= 1 && n_leaves >= 0 && n_leaves < (int64_t)2147483647, "bad shape");
+  if (n_pairs <= 0) return MEVI_OK;
+  leaf_lookup_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(leaves, n_pairs, M, K, leaf_keys,
+                                                                                           n_leaves, leaf_index);
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 1);
+  return MEVI_OK;
+}
 
 extern "C" int mevi_build_inverted_lists(mevi_ctx* ctx, const int32_t* codes, int64_t n, int M, int K,
                                          int32_t* sorted_docids, int64_t* sorted_keys, void* stream) {

@@ -93,18 +93,10 @@ class ClusterIndex:
         [nq, L], -1 where the leaf holds no document (`doc_cluster.get(d, None)`, 3928)."""
         if not isinstance(dec, torch.Tensor):
             dec = torch.from_numpy(np.asarray(dec))
-        dec = dec.to(self.device, torch.int64)
-        key = torch.zeros(dec.shape[:-1], dtype=torch.int64, device=self.device)
-        valid = torch.ones(dec.shape[:-1], dtype=torch.bool, device=self.device)
-        for j in range(dec.shape[-1]):
-            c = dec[..., j]
-            valid &= (c >= 0) & (c < self.K)
-            key = key * self.K + c.clamp(0, self.K - 1)
-        if self.n_leaves == 0:
-            return torch.full(key.shape, -1, dtype=torch.int32, device=self.device)
-        pos = torch.searchsorted(self.leaf_keys, key).clamp(max=self.n_leaves - 1)
-        hit = (self.leaf_keys[pos] == key) & valid
-        return torch.where(hit, pos, torch.full_like(pos, -1)).to(torch.int32).contiguous()
+        dec = dec.to(self.device, torch.int64).contiguous()
+        if self.n_leaves == 0 or dec.numel() == 0:
+            return torch.full(dec.shape[:-1], -1, dtype=torch.int32, device=self.device)
+        return _lib.get_context(self.device.index).leaf_lookup(dec, self.K, self.leaf_keys)
 
     # -- reference-format dictionaries ---------------------------------------
     def to_dicts(self):
