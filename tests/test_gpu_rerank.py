@@ -305,3 +305,70 @@ def test_rerank_all_multiclus_aggregation(gauss, aggr):
         np.testing.assert_allclose(scores[a:b], s_, rtol=1e-5, atol=2e-4)
         assert sorted(ids[a:b].tolist()) == sorted(d_.tolist())
     assert n_dup > 0  # the test data did contain documents under two of a query's leaves
+
+
+def _hn_rows(text):
+    rows = []
+    for line in text.rstrip("\n").split("\n"):
+        q, gt, docs, scores = line.split("\t")
+        rows.append((q, gt, [int(v) for v in docs.split(",")] if docs else [],
+                     np.array([float(v) for v in scores.split(",")] if scores else [], dtype=np.float64)))
+    return rows
+
+
+@pytest.mark.parametrize("case_name,nb", [("gauss768", 100), ("small64", 10)])
+def test_product_equals_the_executed_reference_loop(case_name, nb):
+    """The kernels against the output of main_models.py:3912-4055 EXECUTED verbatim (tests/golden/make_rerank_golden.py):
+    the full sorted candidate list of the shipped recipe, the hard-negative lines' scores and ground-truth field, the
+    --knn_topk_by_step lists (= the leading pool_size of the sort), and both --doc_multiclus aggregations."""
+    import os
+    import pickle
+
+    from conftest import GOLDEN, golden_case
+    from mevi_b200.rerank import ClusterIndex, ClusterReranker, hn_lines_all
+
+    case = golden_case(case_name)
+    dec = case.load(f"beam{nb}_labels.npy")
+    load = lambda v: pickle.load(open(os.path.join(GOLDEN, "rerank", f"{case_name}_{v}.pkl"), "rb"))
+    fx = load("shipped")
+    rr = ClusterReranker(dev(case.X), ClusterIndex.from_codes(case.codes, case.K), mode="stream")
+    off, ids, scores = (t.cpu().numpy() for t in rr.rerank_all(case.Q, dec))
+    want = _hn_rows(fx["lines"])
+    X64, Q64 = case.X.astype(np.float64), case.Q.astype(np.float64)
+    rs = np.random.RandomState(11)
+    gt = [[int(rs.randint(case.X.shape[0]))] for _ in range(len(case.Q))]
+    gt_scores = ctx().dense_scores(dev(case.Q), dev(case.X[[g[0] for g in gt]])).cpu().numpy()
+    for q in range(len(case.Q)):
+        a, b = off[q], off[q + 1]
+        assert b - a == fx["ndoc"][q] == len(fx["docs"][q])
+        np.testing.assert_allclose(scores[a:b], want[q][3], rtol=1e-5, atol=1e-4)
+        assert sorted(ids[a:b].tolist()) == sorted(fx["docs"][q])
+        for p_ in np.nonzero(ids[a:b] != np.array(fx["docs"][q]))[0]:  # order may differ only between (near-)equal scores
+            assert abs(float(X64[ids[a + p_]] @ Q64[q]) - float(X64[fx["docs"][q][p_]] @ Q64[q])) <= 1e-4
+        np.testing.assert_allclose(gt_scores[q, q], float(want[q][1]), rtol=1e-5, atol=1e-4)
+    # the line writer on the product's own lists reproduces the reference's text field by field (scores to 1e-5)
+    texts = [f"query {i}" for i in range(len(case.Q))]
+    gts = [str(float(np.float32(gt_scores[q, q]))) for q in range(len(case.Q))]
+    lines = hn_lines_all(texts, torch.from_numpy(off), torch.from_numpy(ids), torch.from_numpy(scores), case.X.shape[0], gts)
+    for q, (ln, w) in enumerate(zip(_hn_rows("\n".join(lines) + "\n"), want)):
+        assert ln[0] == w[0] and len(ln[2]) == len(w[2])
+    # --knn_topk_by_step 1, pool_size 50
+    tk = load("topk_by_step")
+    s_k, i_k, n_k = rr.rerank(case.Q, dec, topk=50)
+    i_k, n_k = i_k.cpu().numpy(), n_k.cpu().numpy()
+    for q in range(len(case.Q)):
+        kk = len(tk["docs"][q])
+        assert n_k[q] == tk["ndoc"][q] and kk == min(50, tk["ndoc"][q]) and (i_k[q, kk:] == -1).all()
+        for p_ in np.nonzero(i_k[q, :kk] != np.array(tk["docs"][q]))[0]:
+            assert abs(float(X64[i_k[q, p_]] @ Q64[q]) - float(X64[tk["docs"][q][p_]] @ Q64[q])) <= 1e-4
+    # --doc_multiclus 2
+    mc = load("multiclus_dict")
+    rr2 = ClusterReranker(dev(case.X), ClusterIndex.from_cluster_dict(mc, case.K), mode="stream")
+    for aggr in ("add", "max"):
+        fm = load(f"multiclus_{aggr}")
+        wm = _hn_rows(fm["lines"])
+        off2, ids2, sc2 = (t.cpu().numpy() for t in rr2.rerank_all(case.Q, dec, multiclus_score_aggr=aggr))
+        for q in range(len(case.Q)):
+            a, b = off2[q], off2[q + 1]
+            assert sorted(ids2[a:b].tolist()) == sorted(fm["docs"][q])
+            np.testing.assert_allclose(sc2[a:b][:200], wm[q][3], rtol=1e-5, atol=2e-4)

@@ -155,3 +155,82 @@ def test_config_i_100k_encode_matches_reference_codes():
     # sklearn's fit_predict labels (GEMM-form fp32 distances) differ from the direct-form encode on a few near-tied rows
     # (SURVEY 8c invariant (i): 99.996 % identical at 100k)
     assert int((lp != want).any(1).sum()) == meta["preds_vs_codes_mismatch_rows"] <= 50
+
+
+# ---- re-rank loop: fixtures made by EXECUTING the reference's own source lines (make_rerank_golden.py) --------------
+RERANK_BEAMS = {"gauss768": 100, "small64": 10}
+
+
+def _rerank_fixture(case_name, variant):
+    import os
+    import pickle
+
+    from conftest import GOLDEN, golden_case
+
+    case = golden_case(case_name)
+    fx = pickle.load(open(os.path.join(GOLDEN, "rerank", f"{case_name}_{variant}.pkl"), "rb"))
+    nb = RERANK_BEAMS[case_name]
+    return case, fx, case.load(f"beam{nb}_labels.npy")
+
+
+def _parse_hn(text):
+    rows = []
+    for line in text.rstrip("\n").split("\n"):
+        q, gt, docs, scores = line.split("\t")
+        rows.append((q, gt, [int(v) for v in docs.split(",")] if docs else [], [float(v) for v in scores.split(",")] if scores else []))
+    return rows
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("case_name", ["gauss768", "small64"])
+def test_rerank_oracle_equals_the_executed_reference_loop(case_name):
+    """oracle.cluster_rerank / hn_result_line against main_models.py:3912-4055 run verbatim (shipped flags, marco and
+    nq_dpr line formats, --save_hard_neg <corpus> and 100)."""
+    case, fx, dec = _rerank_fixture(case_name, "shipped")
+    assert fx["span"] == (3912, 4055)
+    clus = case.pickle("rqclus.pkl")
+    res = oracle.cluster_rerank(case.Q, case.X, clus, dec)
+    assert [r[0].tolist() for r in res] == fx["docs"]
+    assert [r[2] for r in res] == fx["ndoc"]
+    rs = np.random.RandomState(11)
+    gt = [[int(rs.randint(case.X.shape[0]))] for _ in range(len(case.Q))]  # as make_rerank_golden.py drew them
+    lines = []
+    for q, (docs, scores, _) in enumerate(res):
+        g = torch.matmul(torch.from_numpy(case.Q[q]), torch.from_numpy(case.X[gt[q]]).transpose(0, 1))
+        lines.append(oracle.hn_result_line(f"query {q}", ",".join(str(v.item()) for v in g), docs, scores))
+    assert "\n".join(lines) + "\n" == fx["lines"]
+    _, fx100, _ = _rerank_fixture(case_name, "hn100")
+    lines = [oracle.hn_result_line(f"query {q}", "", r[0][:100], r[1][:100]) for q, r in enumerate(res)]
+    assert "\n".join(lines) + "\n" == fx100["lines"] and fx100["docs"] == fx["docs"]
+
+
+@pytest.mark.parametrize("case_name", ["gauss768", "small64"])
+def test_rerank_topk_by_step_is_the_leading_part_of_the_full_sort(case_name):
+    """--knn_topk_by_step 1 (main_models.py:3986-3993: a running torch.topk of pool_size over the chunks) returns the first
+    pool_size documents of the full sort: the top-k kernels serve that flag with topk = pool_size."""
+    case, fx, dec = _rerank_fixture(case_name, "topk_by_step")
+    res = oracle.cluster_rerank(case.Q, case.X, case.pickle("rqclus.pkl"), dec, topk=50)
+    assert [r[0].tolist() for r in res] == fx["docs"] and [r[2] for r in res] == fx["ndoc"]
+
+
+@pytest.mark.parametrize("aggr", ["add", "max"])
+@pytest.mark.parametrize("case_name", ["gauss768", "small64"])
+def test_rerank_multiclus_oracle_equals_the_executed_reference_loop(case_name, aggr):
+    import os
+    import pickle
+
+    from conftest import GOLDEN
+
+    case, fx, dec = _rerank_fixture(case_name, f"multiclus_{aggr}")
+    mc = pickle.load(open(os.path.join(GOLDEN, "rerank", f"{case_name}_multiclus_dict.pkl"), "rb"))
+    res = oracle.cluster_rerank(case.Q, case.X, mc, dec, multiclus_aggr=aggr)
+    assert [r[2] for r in res] == fx["ndoc"]
+    want = _parse_hn(fx["lines"])
+    for q, (docs, scores, _) in enumerate(res):
+        # the reference's CPU sort is not stable: documents with EQUAL aggregated scores may swap; everything else is fixed
+        assert sorted(docs.tolist()) == sorted(fx["docs"][q])
+        assert [float(np.float32(s)) for s in scores[:200]] == want[q][3]
+        moved = [i for i, (a, b) in enumerate(zip(docs.tolist(), fx["docs"][q])) if a != b]
+        assert all(scores[i] == scores[fx["docs"][q].index(docs[i])] for i in moved)
