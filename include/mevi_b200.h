@@ -123,6 +123,23 @@ int mevi_kmeans_step(mevi_ctx* ctx, const float* R, int64_t n, int d, const floa
 int mevi_kmeans_step_fused(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K,
                            const int32_t* prev_assign, int64_t prev_stride, int32_t* assign_out, int64_t assign_stride,
                            float* sums_counts_prev, double* inertia_or_null, void* stream);
+/* ONE pass over the shard per Lloyd iteration, incremental form: the rows are assigned to `centroids` (the only read of
+ * the shard), then the running sums | counts are corrected by the rows whose assignment changed since the previous
+ * iteration: sums[new] += x, sums[old] -= x (a few per cent of the rows after the first iterations; cost proportional
+ * to their number, no host synchronisation).
+ *   prev_assign [n] int32 (stride prev_stride)   in:  assignment the master currently describes
+ *   assign_out  [n] int32 (stride assign_stride) out: nearest centroid now (a different buffer than prev_assign)
+ *   master_sums_counts [K*d + K] float64 DEVICE  in/out: per-centroid sums | counts under prev_assign on entry, under
+ *                      assign_out on return (float64 so that repeated corrections do not drift; initialise it from the
+ *                      fp32 buffer of one mevi_kmeans_step / mevi_accumulate_by_code)
+ *   sums_counts        [K*d + K] fp32 out: the master rounded to fp32 - the buffer the all-reduce and mevi_kmeans_update take
+ *   n_changed_or_null  int32 DEVICE out: number of rows that moved
+ * Deterministic (ascending row list, fixed slices, no float atomics).  MEVI_ERR_UNSUPPORTED when K > 256 or K*d*4 > 200 KB.
+ * replaces: the same lines as mevi_kmeans_step.                                                                     */
+int mevi_kmeans_step_delta(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K, int mode,
+                           const int32_t* prev_assign, int64_t prev_stride, int32_t* assign_out, int64_t assign_stride,
+                           double* master_sums_counts, float* sums_counts, int32_t* n_changed_or_null,
+                           double* inertia_or_null, void* stream);
 /* centroids[k] = sums[k]/counts[k] where counts[k] > 0 (others unchanged);
  * n_empty_or_null: int32 DEVICE out = number of empty clusters.              */
 int mevi_kmeans_update(mevi_ctx* ctx, const float* sums_counts, int K, int d, float* centroids,

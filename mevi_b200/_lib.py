@@ -33,6 +33,7 @@ SYMBOLS = {
     "mevi_rq_encode_host": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _vp, _i64, _vp]),
     "mevi_kmeans_step": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "mevi_kmeans_step_fused": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "mevi_kmeans_step_delta": (_i, [_vp, _vp, _i64, _i, _vp, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mevi_kmeans_update": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "mevi_residual_update": (_i, [_vp, _vp, _i64, _i, _vp, _i, _vp, _i64, _vp]),
     "mevi_accumulate_by_code": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _i, _vp, _vp]),
@@ -259,6 +260,31 @@ class Context:
             self._check(self.lib.mevi_kmeans_step_fused(self.handle, _ptr(R), n, d, _ptr(c), K, _ptr(prev_assign), int(prev_stride),
                                                         _ptr(assign), int(assign_stride), _ptr(sums_counts_prev), _ptr(inertia),
                                                         self._stream()))
+
+    def kmeans_step_delta(self, R, centroids, prev_assign, assign, master, sums_counts, prev_stride=1, assign_stride=1,
+                          n_changed=None, inertia=None, mode="auto"):
+        """One pass: `assign` = nearest centroid now; `master` (float64 [K*d+K], sums|counts under `prev_assign` on entry)
+        is corrected by the rows whose assignment changed and describes `assign` on return; `sums_counts` = its fp32
+        rounding (mevi_kmeans_step_delta).  Raises MeviError (MEVI_ERR_UNSUPPORTED) for shapes it does not take."""
+        import torch
+
+        R = self._dev(R, torch.float32, "R")
+        c = self._dev(centroids, torch.float32, "centroids")
+        self._dev(sums_counts, torch.float32, "sums_counts")
+        self._dev(master, torch.float64, "master")
+        n, d = R.shape
+        K = c.shape[0]
+        assert sums_counts.numel() == K * d + K and master.numel() == K * d + K
+        assert prev_assign.dtype == torch.int32 and prev_assign.is_cuda and assign.dtype == torch.int32 and assign.is_cuda
+        assert prev_assign.data_ptr() != assign.data_ptr()
+        if inertia is not None:
+            assert inertia.dtype == torch.float64 and inertia.is_cuda
+        if n_changed is not None:
+            assert n_changed.dtype == torch.int32 and n_changed.is_cuda
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_kmeans_step_delta(self.handle, _ptr(R), n, d, _ptr(c), K, _MODES[mode], _ptr(prev_assign),
+                                                        int(prev_stride), _ptr(assign), int(assign_stride), _ptr(master),
+                                                        _ptr(sums_counts), _ptr(n_changed), _ptr(inertia), self._stream()))
 
     def kmeans_update(self, sums_counts, centroids, n_empty=None):
         import torch

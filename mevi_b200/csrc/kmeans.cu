@@ -17,6 +17,8 @@
 // Roofline: HBM (one more read of the shard: 4*d bytes per row + 4 B assignment).
 #include <stdlib.h>
 
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -248,6 +250,95 @@ int accumulate_by_code(mevi_ctx* ctx, const float* R, int64_t n, int d, const in
   return MEVI_OK;
 }
 
+
+// ---- incremental Lloyd iteration: move only the rows whose assignment changed -------------------------------------
+// sums_t[k] = sums_{t-1}[k] + (rows that moved to k) - (rows that moved away from k).  The running sums | counts live in
+// float64 ("master"), so repeated corrections do not drift; the corrections themselves are fresh fp32 sums per CTA over
+// a contiguous slice of the (ascending) list of changed rows, thread = column, rows in list order - no float atomics,
+// bit-reproducible.  Per-CTA partials are folded into the master in CTA order.
+struct ChangedPred {
+  const int32_t* prev; int64_t pstride; const int32_t* cur; int64_t cstride;
+  __host__ __device__ __forceinline__ bool operator()(const int& i) const {
+    return prev[(int64_t)i * pstride] != cur[(int64_t)i * cstride];
+  }
+};
+
+// (row, old centroid | new centroid << 16) per changed row: one 8-byte record, so the accumulation kernel's loads
+// depend on ONE earlier load instead of three
+__global__ void kmeans_delta_pack_kernel(const int32_t* __restrict__ prev, int64_t pstride, const int32_t* __restrict__ cur,
+                                         int64_t cstride, const int32_t* __restrict__ changed, const int* __restrict__ n_changed,
+                                         int K, int2* __restrict__ packed) {
+  const int64_t m = *n_changed;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = changed[i];
+    const int ko = min(max(prev[row * pstride], 0), K - 1), kn = min(max(cur[row * cstride], 0), K - 1);
+    packed[i] = make_int2((int)row, ko | (kn << 16));
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+kmeans_delta_kernel(const float* __restrict__ R, int d, const int2* __restrict__ packed, const int* __restrict__ n_changed,
+                    int K, float* __restrict__ part_sums, int32_t* __restrict__ part_counts) {
+  extern __shared__ float s_acc[];  // [K][d] signed sums of this CTA's slice
+  __shared__ int s_cnt[256];        // [K] signed counts (K <= 256)
+  const int col = threadIdx.x;      // blockDim.x >= d, one column per thread
+  const bool live = col < d;
+  const int64_t m = *n_changed;
+  const int64_t lo = m * blockIdx.x / gridDim.x, hi = m * (blockIdx.x + 1) / gridDim.x;
+  if (live)
+    for (int k = 0; k < K; ++k) s_acc[k * d + col] = 0.f;
+  if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  constexpr int U = 16;  // rows in flight per thread; the records of the next batch are fetched under this batch's rows
+  int2 rec[U], nxt[U];
+#pragma unroll
+  for (int j = 0; j < U; ++j) nxt[j] = lo + j < hi ? __ldg(&packed[lo + j]) : make_int2(-1, 0);
+  for (int64_t i = lo; i < hi; i += U) {
+    float v[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      rec[j] = nxt[j];
+      v[j] = (rec[j].x >= 0 && live) ? __ldg(&R[(int64_t)rec[j].x * d + col]) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) nxt[j] = i + U + j < hi ? __ldg(&packed[i + U + j]) : make_int2(-1, 0);
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (rec[j].x < 0) continue;
+      const int ko = rec[j].y & 0xFFFF, kn = rec[j].y >> 16;
+      if (live) {
+        s_acc[kn * d + col] += v[j];
+        s_acc[ko * d + col] -= v[j];
+      }
+      if (threadIdx.x == 0) { s_cnt[kn] += 1; s_cnt[ko] -= 1; }
+    }
+  }
+  __syncthreads();
+  if (live)
+    for (int k = 0; k < K; ++k) part_sums[((int64_t)blockIdx.x * K + k) * d + col] = s_acc[k * d + col];
+  if (threadIdx.x < K) part_counts[(int64_t)blockIdx.x * K + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// master (float64) += the partials in CTA order; sums_counts = (float) master
+__global__ void kmeans_delta_fold_kernel(const float* __restrict__ part_sums, const int32_t* __restrict__ part_counts, int G,
+                                         int K, int d, double* __restrict__ master, float* __restrict__ sums_counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t kd = (int64_t)K * d;
+  if (i < kd) {
+    double a = master[i];
+    for (int g = 0; g < G; ++g) a += (double)part_sums[(int64_t)g * kd + i];
+    master[i] = a;
+    sums_counts[i] = (float)a;
+  } else if (i < kd + K) {
+    const int k = (int)(i - kd);
+    long long c = 0;
+    for (int g = 0; g < G; ++g) c += part_counts[(int64_t)g * K + k];
+    const double a = master[i] + (double)c;
+    master[i] = a;
+    sums_counts[i] = (float)a;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -332,6 +423,75 @@ int mevi_kmeans_step_fused(mevi_ctx* ctx, const float* R, int64_t n, int d, cons
                                                                                              G, K, d, sums_counts_prev);
   MEVI_COUNT_LAUNCH(ctx, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
+  return MEVI_OK;
+}
+
+
+int mevi_kmeans_step_delta(mevi_ctx* ctx, const float* R, int64_t n, int d, const float* centroids, int K, int mode,
+                           const int32_t* prev_assign, int64_t prev_stride, int32_t* assign_out, int64_t assign_stride,
+                           double* master_sums_counts, float* sums_counts, int32_t* n_changed_or_null,
+                           double* inertia_or_null, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, R && centroids && prev_assign && assign_out && master_sums_counts && sums_counts, "NULL argument");
+  MEVI_REQUIRE(ctx, prev_assign != assign_out, "prev_assign and assign_out must be different buffers");
+  MEVI_REQUIRE(ctx, prev_stride >= 1 && assign_stride >= 1, "strides must be >= 1");
+  MEVI_REQUIRE(ctx, n > 0 && n < (int64_t)2147483647 && d > 0 && d % 4 == 0 && d <= 1024 && K >= 1,
+               "unsupported shape n=%lld d=%d K=%d", (long long)n, d, K);
+  const int64_t kd = (int64_t)K * d;
+  const size_t smem = (size_t)kd * sizeof(float);
+  if (K > 256 || smem > 200 * 1024)  // (codes are packed 16 + 16 bits)
+    return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "incremental k-means step unsupported for K=%d d=%d (use mevi_kmeans_step)", K, d);
+  if (inertia_or_null) MEVI_CUDA(ctx, cudaMemsetAsync(inertia_or_null, 0, sizeof(double), st));
+  // 1. assignment under the current centroids (the one pass over the shard)
+  bool use_tensor = false;
+  if (mode == MEVI_MODE_TENSOR) {
+    if (!mevi_rq_tensor_supported(ctx, d, 1, K, MEVI_METRIC_L2))
+      return mevi_set_error(ctx, MEVI_ERR_UNSUPPORTED, "tensor k-means assignment unsupported for d=%d K=%d", d, K);
+    use_tensor = true;
+  } else if (mode == MEVI_MODE_AUTO) {
+    use_tensor = mevi_rq_tensor_supported(ctx, d, 1, K, MEVI_METRIC_L2) && n >= 4096;
+  }
+  int rc;
+  if (use_tensor)
+    rc = mevi_rq_tensor_assign(ctx, R, n, d, centroids, 1, K, MEVI_METRIC_L2, assign_out, assign_stride, nullptr, nullptr,
+                               inertia_or_null, st);
+  else
+    rc = mevi_rq_exact_launch(ctx, R, n, d, centroids, 1, K, MEVI_METRIC_L2, assign_out, assign_stride, nullptr, nullptr, nullptr,
+                              nullptr, n, inertia_or_null, st);
+  if (rc != MEVI_OK) return rc;
+  // 2. ascending list of the rows whose assignment changed (count stays on the device)
+  const int G = ctx->sm_count * 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~size_t(255); return o; };
+  const size_t o_cnt = take(16), o_list = take((size_t)n * sizeof(int32_t)), o_pack = take((size_t)n * sizeof(int2)),
+               o_ps = take((size_t)G * kd * sizeof(float)), o_pc = take((size_t)G * K * sizeof(int32_t));
+  char* ws = (char*)mevi_ws(ctx, WS_KM_PARTIAL, off);
+  if (!ws) return MEVI_ERR_NOMEM;
+  int* d_count = (int*)(ws + o_cnt);
+  int32_t* list = (int32_t*)(ws + o_list);
+  int2* packed = (int2*)(ws + o_pack);
+  float* ps = (float*)(ws + o_ps);
+  int32_t* pc = (int32_t*)(ws + o_pc);
+  ChangedPred pred{prev_assign, prev_stride, assign_out, assign_stride};
+  cub::CountingInputIterator<int> ids(0);
+  size_t tmp_bytes = 0;
+  MEVI_CUDA(ctx, cub::DeviceSelect::If(nullptr, tmp_bytes, ids, list, d_count, (int)n, pred, st));
+  void* tmp = mevi_ws(ctx, WS_SORT_TMP, tmp_bytes);
+  if (!tmp) return MEVI_ERR_NOMEM;
+  MEVI_CUDA(ctx, cub::DeviceSelect::If(tmp, tmp_bytes, ids, list, d_count, (int)n, pred, st));
+  // 3. signed sums of the changed rows, folded into the float64 master
+  const int threads = ((d + 31) / 32) * 32;
+  MEVI_CUDA(ctx, cudaFuncSetAttribute(kmeans_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kmeans_delta_pack_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(prev_assign, prev_stride, assign_out, assign_stride, list, d_count, K,
+                                                               packed);
+  kmeans_delta_kernel<<<G, threads, smem, st>>>(R, d, packed, d_count, K, ps, pc);
+  kmeans_delta_fold_kernel<<<(int)((kd + K + 255) / 256), 256, 0, st>>>(ps, pc, G, K, d, master_sums_counts, sums_counts);
+  if (n_changed_or_null)
+    MEVI_CUDA(ctx, cudaMemcpyAsync(n_changed_or_null, d_count, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  MEVI_CUDA(ctx, cudaGetLastError());
+  MEVI_COUNT_LAUNCH(ctx, 4);
   return MEVI_OK;
 }
 

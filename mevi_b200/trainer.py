@@ -26,6 +26,11 @@ from .dist_utils import dist_on, gather_rows_to_rank0, rank_world, shard_bounds
 
 
 FUSED_LLOYD = os.environ.get("MEVI_KMEANS_FUSED", "1") != "0"  # one-pass Lloyd iterations (mevi_kmeans_step_fused)
+# how a Lloyd iteration after the first gets its sums: "delta" (default) = assignment pass + correction of float64 running
+# sums by the rows whose assignment changed (mevi_kmeans_step_delta; no host synchronisation); "fused" = the assignment
+# pass also sums every row under the previous assignment, changed rows moved afterwards (mevi_kmeans_step_fused);
+# "twopass" = assignment pass + accumulation pass (mevi_kmeans_step)
+LLOYD_ITERATION = os.environ.get("MEVI_KMEANS_ITER", "delta" if FUSED_LLOYD else "twopass")
 
 
 def kmeanspp_init(sample, K: int, rs: np.random.RandomState) -> torch.Tensor:
@@ -126,21 +131,36 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
     # current centroids also sums them under the PREVIOUS iteration's assignment; the rows whose assignment changed
     # (few after the first iterations) are then moved between their old and new centroid's sums.  The first iteration
     # has no previous assignment and takes the two-pass step.
-    fused = hasattr(be, "kmeans_step_fused") and n >= 4096 and FUSED_LLOYD
-    a_prev = a_cur = moved_buf = None
-    if fused:
+    delta = LLOYD_ITERATION == "delta" and hasattr(be, "kmeans_step_delta")
+    fused = not delta and LLOYD_ITERATION == "fused" and hasattr(be, "kmeans_step_fused") and n >= 4096
+    a_prev = a_cur = moved_buf = master = n_changed = None
+    if fused or delta:
         # buffers of the one-pass iterations, allocated once per training (not per iteration: the changed-row count differs
         # every time and a fresh multi-GB allocation per iteration costs more than the pass itself)
         scratch = scratch if scratch is not None else {}
-        if scratch.get("n") != (n, w):
+        if scratch.get("n") != (n, w, delta):
             scratch.clear()
-            scratch.update(n=(n, w), a=torch.empty(n, dtype=torch.int32, device=dev), b=torch.empty(n, dtype=torch.int32, device=dev),
-                           moved=torch.empty((n // 4 + 1, w), dtype=torch.float32, device=dev))
-        a_prev, a_cur, moved_buf = scratch["a"], scratch["b"], scratch["moved"]
+            scratch.update(n=(n, w, delta), a=torch.empty(n, dtype=torch.int32, device=dev), b=torch.empty(n, dtype=torch.int32, device=dev))
+            if fused:
+                scratch.update(moved=torch.empty((n // 4 + 1, w), dtype=torch.float32, device=dev))
+        a_prev, a_cur, moved_buf = scratch["a"], scratch["b"], scratch.get("moved")
+    if delta:
+        master = torch.empty(K * w + K, dtype=torch.float64, device=dev)
+        n_changed = torch.zeros(1, dtype=torch.int32, device=dev)
+        changed_total = torch.zeros(1, dtype=torch.int64, device=dev)
     have_prev = False
-    stats = {"fused_iters": 0, "two_pass_iters": 0, "changed_rows": 0}
+    stats = {"delta_iters": 0, "fused_iters": 0, "two_pass_iters": 0, "changed_rows": 0}
     t_loop = time.perf_counter()
     for it in range(iters):
+        if delta and have_prev:
+            try:
+                be.kmeans_step_delta(R, C, a_prev, a_cur, master, buf, n_changed=n_changed, inertia=inertia, mode=mode)
+                changed_total += n_changed
+                stats["delta_iters"] += 1
+            except _lib.MeviError as e:
+                if "unsupported" not in str(e):
+                    raise
+                delta = False
         if fused and have_prev:
             try:
                 be.kmeans_step_fused(R, C, a_prev, a_cur, buf, inertia=inertia)
@@ -148,7 +168,9 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
                 if "unsupported" not in str(e):
                     raise
                 fused = False
-        if fused and have_prev:
+        if delta and have_prev:
+            pass
+        elif fused and have_prev:
             changed = torch.nonzero(a_cur != a_prev).squeeze(1)
             nc = int(changed.numel())
             stats["changed_rows"] += nc
@@ -161,9 +183,12 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
                 buf.add_(plus).sub_(minus)
             stats["fused_iters"] += 1
         else:
-            be.kmeans_step(R, C, buf, assign=(a_cur if fused else col), assign_stride=(1 if fused else stride), inertia=inertia, mode=mode)
+            one_pass = fused or delta
+            be.kmeans_step(R, C, buf, assign=(a_cur if one_pass else col), assign_stride=(1 if one_pass else stride), inertia=inertia, mode=mode)
+            if delta:
+                master.copy_(buf)  # fp32 -> float64: the running sums the later iterations correct
             stats["two_pass_iters"] += 1
-        if fused:
+        if fused or delta:
             a_prev, a_cur = a_cur, a_prev
             have_prev = True
         if dist_on():
@@ -178,6 +203,8 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
             if not reseeded and tol is not None and prev - cur <= tol * max(cur, 1e-30):
                 break
             prev = cur
+    if delta and stats["delta_iters"]:
+        stats["changed_rows"] = int(changed_total.item())
     _lloyd_level.last_stats = stats
     _lloyd_level.last_loop_seconds = time.perf_counter() - t_loop  # ends on the .item() of the last check: device time
     be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)

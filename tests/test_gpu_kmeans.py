@@ -150,15 +150,70 @@ def test_trainer_one_pass_iterations_match_two_pass_training(monkeypatch):
     centers = rs.standard_normal((40, 768)).astype(np.float32)
     X = (centers[rs.randint(0, 40, 30000)] + 0.7 * rs.standard_normal((30000, 768))).astype(np.float32)
     out = {}
-    for fused in (True, False):
-        monkeypatch.setattr(trainer, "FUSED_LLOYD", fused)
+    for how in ("delta", "fused", "twopass"):
+        monkeypatch.setattr(trainer, "LLOYD_ITERATION", how)
         cb, codes = trainer.train_rq_lloyd(X, M=2, K=32, seed=41, iters=8, tol=None, device_index=0)
         info = trainer.train_rq_lloyd.last_info
-        out[fused] = (cb.cpu().numpy(), codes, info)
-    assert out[True][2]["levels"][0]["fused_iters"] == 7 and out[False][2]["levels"][0]["fused_iters"] == 0
-    assert out[True][2]["levels"][0]["changed_rows"] > 0
-    np.testing.assert_allclose(out[True][0], out[False][0], rtol=1e-4, atol=1e-4)
-    assert (out[True][1] != out[False][1]).any(1).mean() < 2e-3
-    m1 = oracle.quantisation_mse(X, out[True][0], out[True][1])
-    m0 = oracle.quantisation_mse(X, out[False][0], out[False][1])
-    assert abs(m1 - m0) <= 1e-4 * m0
+        out[how] = (cb.cpu().numpy(), codes, info)
+    lv = lambda how: out[how][2]["levels"][0]
+    assert lv("delta")["delta_iters"] == 7 and lv("fused")["fused_iters"] == 7 and lv("twopass")["two_pass_iters"] == 8
+    assert lv("delta")["fused_iters"] == 0 and lv("twopass")["delta_iters"] == 0
+    assert lv("delta")["changed_rows"] > 0
+    assert abs(lv("delta")["changed_rows"] - lv("fused")["changed_rows"]) <= 0.01 * lv("fused")["changed_rows"] + 5
+    m0 = oracle.quantisation_mse(X, out["twopass"][0], out["twopass"][1])
+    for how in ("delta", "fused"):
+        np.testing.assert_allclose(out[how][0], out["twopass"][0], rtol=1e-4, atol=1e-4)
+        assert (out[how][1] != out["twopass"][1]).any(1).mean() < 2e-3
+        m1 = oracle.quantisation_mse(X, out[how][0], out[how][1])
+        assert abs(m1 - m0) <= 1e-4 * m0
+
+
+@pytest.mark.parametrize("n,d,K,mode", [(20000, 768, 32, "auto"), (4097, 768, 32, "exact"), (70001, 256, 32, "auto"),
+                                         (9000, 512, 16, "auto"), (3000, 64, 8, "auto")])
+def test_delta_step_corrects_running_sums_by_the_moved_rows(n, d, K, mode):
+    """mevi_kmeans_step_delta: one assignment pass + float64 running sums|counts corrected by the rows whose assignment
+    changed.  Five chained iterations against a float64 oracle of the sums under the NEW assignment, the two-pass step
+    (assignment bit-equal), and itself (bit-reproducible)."""
+    rs = np.random.RandomState(n + 1)
+    X = rs.standard_normal((n, d)).astype(np.float32)
+    X[: n // 3] += 2.0 * rs.standard_normal((1, d)).astype(np.float32)
+    C = X[rs.choice(n, K, replace=False)].copy()
+    c = ctx()
+    Xd = dev(X)
+
+    def run():
+        Cd = dev(C)
+        buf = torch.empty(K * d + K, device="cuda:0")
+        a, b = (torch.empty(n, dtype=torch.int32, device="cuda:0") for _ in range(2))
+        master = torch.empty(K * d + K, dtype=torch.float64, device="cuda:0")
+        nchg = torch.zeros(1, dtype=torch.int32, device="cuda:0")
+        inertia = torch.zeros(1, dtype=torch.float64, device="cuda:0")
+        c.kmeans_step(Xd, Cd, buf, assign=a, mode=mode)
+        master.copy_(buf)
+        c.kmeans_update(buf, Cd)
+        trace = []
+        for it in range(5):
+            c.kmeans_step_delta(Xd, Cd, a, b, master, buf, n_changed=nchg, inertia=inertia, mode=mode)
+            trace.append((b.clone(), buf.clone(), int(nchg.item()), float(inertia.item()), Cd.clone(), a.clone()))
+            c.kmeans_update(buf, Cd)
+            a, b = b, a
+        c.check()
+        return trace
+
+    t1, t2 = run(), run()
+    moved_total = 0
+    for (cur, buf, nchg, inertia, Cd, prev), (cur2, buf2, nchg2, _, _, _) in zip(t1, t2):
+        assert torch.equal(cur, cur2) and torch.equal(buf, buf2) and nchg == nchg2  # bit-reproducible
+        want = torch.empty(n, dtype=torch.int32, device="cuda:0")
+        tmp = torch.empty(K * d + K, device="cuda:0")
+        c.kmeans_step(Xd, Cd, tmp, assign=want, mode=mode)
+        assert torch.equal(cur, want)
+        assert nchg == int((cur != prev).sum().item())
+        moved_total += nchg
+        assert torch.equal(buf[K * d :], tmp[K * d :])  # counts are exact
+        s64 = np.zeros((K, d), np.float64)
+        np.add.at(s64, cur.cpu().numpy(), X.astype(np.float64))
+        np.testing.assert_allclose(buf[: K * d].view(K, d).cpu().numpy(), s64, rtol=2e-5, atol=2e-3)
+        _, _, _, i_ref, _ = oracle.lloyd_step(X, Cd.cpu().numpy())
+        assert abs(inertia - i_ref) <= 5e-5 * i_ref  # a convergence statistic: the tensor path's fp16-split distances
+    assert moved_total > 0
