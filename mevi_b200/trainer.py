@@ -33,6 +33,16 @@ FUSED_LLOYD = os.environ.get("MEVI_KMEANS_FUSED", "1") != "0"  # one-pass Lloyd 
 LLOYD_ITERATION = os.environ.get("MEVI_KMEANS_ITER", "delta" if FUSED_LLOYD else "twopass")
 
 
+TRACE = os.environ.get("MEVI_TRAIN_TRACE", "0") != "0"  # phase times (with device synchronisation) into last_info["trace"]
+_trace = []
+
+
+def _mark(name: str):
+    if TRACE:
+        torch.cuda.synchronize()
+        _trace.append((name, time.perf_counter()))
+
+
 def kmeanspp_init(sample, K: int, rs: np.random.RandomState) -> torch.Tensor:
     """k-means++ seeding (D^2 sampling) on a small sample, float64 arithmetic, on the device the sample lives on
     (32 passes over a 16,384 x 768 sample are seconds of numpy but milliseconds of device time).  The reference
@@ -80,7 +90,17 @@ def _init_sample(R, init_sample: int, rs: np.random.RandomState, dev):
     per = max(1, init_sample // world)
     s = min(per, n)
     rs_r = np.random.RandomState(rs.randint(1 << 30) + 7919 * rank) if world > 1 else rs
-    idx = np.sort(rs_r.choice(n, size=s, replace=False)) if s < n else np.arange(n)
+    if s >= n:
+        idx = np.arange(n)
+    elif 4 * s >= n:
+        idx = np.sort(rs_r.choice(n, size=s, replace=False))
+    else:
+        # numpy's choice(replace=False) permutes all n row numbers (155 ms per level at n = 8.8 M, more than the 25 Lloyd
+        # iterations): for s << n draw with replacement, drop the repeats, and keep s of the distinct rows
+        picked = np.unique(rs_r.randint(0, n, size=s + s // 4 + 16))
+        while picked.size < s:
+            picked = np.unique(np.concatenate([picked, rs_r.randint(0, n, size=s)]))
+        idx = picked[np.sort(rs_r.permutation(picked.size)[:s])]
     mine = R[torch.from_numpy(idx).to(dev)].contiguous()
     if world == 1:
         return mine
@@ -119,12 +139,15 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
     rank, _ = rank_world()
     n, w = R.shape
     C = torch.empty((K, w), dtype=torch.float32, device=dev)
+    _mark("level_start")
     sample = _init_sample(R, init_sample, rs, dev)
+    _mark("init_sample")
     if rank == 0:
         C.copy_(kmeanspp_init(sample, K, rs))
     del sample
     if dist_on():
         dist.broadcast(C, 0)
+    _mark("kmeanspp")
     prev = math.inf
     n_it = 0
     # One pass per iteration where the library offers it (mevi_kmeans_step_fused): the pass that assigns the rows to the
@@ -207,11 +230,13 @@ def _lloyd_level(be, R, K, col, stride, rs, iters, tol, init_sample, mode, inert
         stats["changed_rows"] = int(changed_total.item())
     _lloyd_level.last_stats = stats
     _lloyd_level.last_loop_seconds = time.perf_counter() - t_loop  # ends on the .item() of the last check: device time
+    _mark("iterations")
     be.kmeans_step(R, C, buf, assign=col, assign_stride=stride, inertia=inertia, mode=mode)
     if dist_on():
         dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
     if hasattr(be, "check"):
         be.check()
+    _mark("final_labels")
     return C, n_it
 
 
@@ -237,7 +262,10 @@ def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: Opt
         N, d = doc_emb.shape
         start, end = shard_bounds(N, rank, world)
         n = end - start
+    del _trace[:]
+    _mark("start")
     R = _upload_rows(doc_emb, start, end, dev)
+    _mark("working_copy")
     codes = torch.zeros((n, M), dtype=torch.int32, device=dev)
     codebook = torch.empty((M, K, d), dtype=torch.float32, device=dev)
     buf = torch.empty(K * d + K, dtype=torch.float32, device=dev)
@@ -253,10 +281,13 @@ def train_rq_lloyd(doc_emb, M: int, K: int, seed: int, iters: int = 25, tol: Opt
         codebook[j].copy_(C)
         if j != M - 1:  # pq.py:591-593
             be.residual_update(R, C, col, assign_stride=M)
+        _mark("residual")
         info["levels"].append({"level": j, "iters": n_it, "inertia": float(inertia.item()),
                                "mse": float(inertia.item()) / max(N, 1) / d, "seconds": time.time() - t0,
                                "loop_ms_per_iter": getattr(_lloyd_level, "last_loop_seconds", 0.0) / max(n_it, 1) * 1e3,
                                **getattr(_lloyd_level, "last_stats", {})})
+    if TRACE:
+        info["trace"] = [(b[0], round((b[1] - a[1]) * 1e3, 2)) for a, b in zip(_trace, _trace[1:])]
     train_rq_lloyd.last_info = info
     if presharded:
         return codebook, codes

@@ -34,12 +34,14 @@ print("moved fraction   ", [round(int(m.item()) / n, 4) for m in moved])
 fresh = ctx.accumulate_by_code(X, a, K)
 rel = float((buf[: K * d] - fresh[: K * d]).abs().max() / fresh[: K * d].abs().max())
 print("running sums vs fresh accumulation: max rel diff", rel, "counts equal", bool(torch.equal(buf[K * d:], fresh[K * d:])))
-for how in ("delta", "fused", "twopass"):
+for how in ("delta", "delta", "fused", "twopass"):
     trainer.LLOYD_ITERATION = how
+    trainer.TRACE = how == "delta"
     torch.cuda.synchronize(); t0 = time.perf_counter()
     cb, _ = trainer.train_rq_lloyd(X, M=4, K=32, seed=41, iters=25, tol=None, device_index=0, presharded=True)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     info = trainer.train_rq_lloyd.last_info
     print(how, f"train 4 x 25 iterations {dt:.3f} s, loop ms/iter", [round(l["loop_ms_per_iter"], 2) for l in info["levels"]],
           "mse", round(info["levels"][-1]["mse"], 5), "moved rows", [l["changed_rows"] for l in info["levels"]])
+    if "trace" in info: print("   trace (ms):", info["trace"][:9], "...")
 PY
