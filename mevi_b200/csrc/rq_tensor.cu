@@ -17,7 +17,8 @@
 //   * generation 4 (rq_tensor4.cuh; the default for every supported shape): split-fp16 contraction hi.hi + hi.lo + lo.hi
 //     (22 significant bits, ~2^-22 |x||c| error) with the document operand in tensor memory; runs the M = 1 k-means
 //     assignment at the HBM roofline and the M = 4 encode at 0.62-0.69 of it (tensor work under the power cap).
-//   * generation 6 (rq_tensor6.cuh; M >= 2, K == 32; opt-in with MEVI_RQ_KERNEL=6): ONE fp16 MMA per K step (hi.hi) with a
+//   * generation 6 (experiments/rq_tensor6.cuh; NOT part of the shipped library: build with `make GEN6=1`, then M >= 2,
+//     K == 32 and MEVI_RQ_KERNEL=6 select it): ONE fp16 MMA per K step (hi.hi) with a
 //     per-row bound built from the measured norm of the row's fp16 remainder; rows with a level the bound leaves open
 //     (11.9 % on N(0,1) data) are dumped with their tensor-core accumulators and finished by rq_refine6_kernel (exact fp32
 //     dot products of the open candidates), or refined inside the epilogue (MEVI_RQ_REFINE=inline).  Bit-identical codes,
@@ -328,7 +329,9 @@ inline int make_x_tensormap(mevi_ctx* ctx, const float* X, int64_t n, int d, int
 }
 
 #include "rq_tensor4.cuh"
-#include "rq_tensor6.cuh"
+#ifdef MEVI_WITH_GEN6
+#include "experiments/rq_tensor6.cuh"
+#endif
 #include "pq_tensor.cuh"
 
 bool shape_ok(mevi_ctx* ctx, int d, int M, int K, int metric) {
@@ -400,7 +403,12 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
   const char* ver = getenv("MEVI_RQ_KERNEL");
   // MEVI_RQ_KERNEL=6 selects generation 6 for the shapes it takes (bit-identical codes; see DESIGN.md for why it is
   // not the default yet: its in-epilogue refinement is bound by memory latency under the streaming load)
+#ifdef MEVI_WITH_GEN6
   const bool use_v6 = v6_ok(d, M, K) && ver && atoi(ver) == 6;
+#else
+  const bool use_v6 = false;
+  (void)ver;
+#endif
 
   MEVI_CUDA(ctx, cudaMemsetAsync(ws + o_abs, 0, o_cn2 - o_abs, st));  // absmax2, work count, refine count
   absmax_kernel<<<32, 256, 0, st>>>(cb, (int64_t)M * K, d, 1, absmax2);
@@ -439,6 +447,7 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
     MEVI_CUDA(ctx, cudaMemsetAsync(p.trace, 0, sizeof(unsigned long long) * (TRACE_SLOTS * TRACE_WARPS + 4), st));
   }
   CUtensorMap tmap;
+#ifdef MEVI_WITH_GEN6
   if (use_v6) {
     int trc = make_x_tensormap(ctx, X, n, d, v6::TM6, &tmap);
     if (trc != MEVI_OK) return trc;
@@ -481,7 +490,9 @@ int mevi_rq_tensor_assign(mevi_ctx* ctx, const float* X, int64_t n, int d, const
       default: MEVI_LAUNCH_RQ_TENSOR6(4); break;
     }
 #undef MEVI_LAUNCH_RQ_TENSOR6
-  } else {
+  } else
+#endif
+  {
     int trc = make_x_tensormap(ctx, X, n, d, v4::TM4, &tmap);
     if (trc != MEVI_OK) return trc;
     p.n_tiles = (n + v4::TM4 - 1) / v4::TM4;

@@ -181,7 +181,13 @@ def test_config_i_100k_golden_codes():
 
 
 def test_generation6_kernel_matches_the_exact_kernel(monkeypatch, gauss):
-    """The hi.hi prefilter + in-epilogue refinement kernel (MEVI_RQ_KERNEL=6, opt-in): same codes as the direct kernel."""
+    """The hi.hi prefilter + refinement kernel (csrc/experiments/rq_tensor6.cuh; measured slower than generation 4 and not
+    part of the shipped library - `make -C mevi_b200/csrc GEN6=1` and MEVI_TEST_GEN6=1 to run this): same codes as the
+    direct kernel."""
+    import os
+
+    if os.environ.get("MEVI_TEST_GEN6", "0") == "0":
+        pytest.skip("generation 6 is an experiment outside the shipped library (build with GEN6=1, set MEVI_TEST_GEN6=1)")
     c = ctx()
     rs = np.random.RandomState(3)
     X = rs.standard_normal((50000, 768)).astype(np.float32)
