@@ -473,7 +473,8 @@ def _rerank_grouped(self, Q, ql, topk):
     # first BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
     device_plan = None
     if self.PLAN == "device":  # counts, scans, candidate totals and the weak-sample flags in five launches, one host sync
-        ncand, weak_flags, device_plan, n_weak = ctx.rerank_grouped_plan(ql.contiguous(), off, g["leaf_tile0"], boot,
+        ql = ql.contiguous()  # the library keeps the pointer until the last plan_fill of this call
+        ncand, weak_flags, device_plan, n_weak = ctx.rerank_grouped_plan(ql, off, g["leaf_tile0"], boot,
                                                                          self.BOOTSTRAP_MIN, self.MAXG_SAMPLE, self.MAXG_LAST)
         weak = torch.nonzero(weak_flags).squeeze(1) if n_weak else weak_flags[:0].long()
     else:
