@@ -19,21 +19,24 @@ def _step(c, X, C, mode="exact"):
     return assign.cpu().numpy(), b[: K * d].reshape(K, d), b[K * d :], float(inertia.item())
 
 
-@pytest.mark.parametrize("shape", [(5000, 768, 32), (3000, 64, 16), (4097, 256, 64), (2000, 128, 100)])
-def test_one_lloyd_step_vs_float64_oracle(shape):
+@pytest.mark.parametrize("mode", ["exact", "auto"])
+@pytest.mark.parametrize("shape", [(5000, 768, 32), (3000, 64, 16), (4097, 256, 64), (2000, 128, 100), (30000, 768, 32)])
+def test_one_lloyd_step_vs_float64_oracle(shape, mode):
+    """`auto` = what the trainer runs: the tensor assignment kernel (K1 at M = 1) where the shape allows it (the 768- and
+    256-wide cases with n >= 4096 here), the direct fp32 kernel otherwise."""
     n, d, K = shape
     rs = np.random.RandomState(5)
     X = rs.standard_normal((n, d)).astype(np.float32)
     C = X[rs.choice(n, K, replace=False)].copy() * 0.5
     c = ctx()
-    assign, sums, counts, inertia = _step(c, X, C)
+    assign, sums, counts, inertia = _step(c, X, C, mode=mode)
     a_ref, s_ref, c_ref, i_ref, gaps = oracle.lloyd_step(X, C)
     diff = np.nonzero(assign != a_ref)[0]
     assert (gaps[diff] <= oracle.TIE_EPS_DEFAULT * 4).all(), "assignment differs at a non-tie"
     if len(diff) == 0:
         assert np.array_equal(counts, c_ref)
-        np.testing.assert_allclose(sums, s_ref, rtol=2e-5, atol=2e-4)
-    assert abs(inertia - i_ref) <= 1e-5 * i_ref
+        np.testing.assert_allclose(sums, s_ref, rtol=2e-5, atol=2e-4 if n < 10000 else 2e-3)
+    assert abs(inertia - i_ref) <= (1e-5 if mode == "exact" else 5e-5) * i_ref  # tensor path: fp16-split distances
     assert counts.sum() == n
 
 
