@@ -272,6 +272,10 @@ int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq, int L, co
                              int32_t* weak, int64_t* sizes_host, void* stream);
 int mevi_rerank_grouped_plan_fill(mevi_ctx* ctx, int round, int32_t* item_tile, int32_t* item_group, int32_t* group_qid,
                                   void* stream);
+/* between rounds (and before _finish): raise == 0 copies the call's thresholds [nq] out, raise != 0 lifts them to
+ * max(own, tau).  Sharded documents: all-reduce(MAX) in between - the largest local k-th best score is a lower bound of
+ * the global one - so every rank filters and re-scores against the global bound.                                    */
+int mevi_rerank_grouped_thresholds(mevi_ctx* ctx, int nq, int d, float* tau, int raise, void* stream);
 int mevi_rerank_grouped_finish(mevi_ctx* ctx, const float* Q, int nq, const float* D_leaf, int d, int k, float* scores,
                                int64_t* rows, int32_t* failed_or_null, int* n_failed, void* stream);
 

@@ -50,6 +50,7 @@ SYMBOLS = {
     "mevi_rerank_grouped_plan": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, C.POINTER(C.c_int32), _i, _i, _i, _i, _vp, _vp,
                                       C.POINTER(_i64), _vp]),
     "mevi_rerank_grouped_plan_fill": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "mevi_rerank_grouped_thresholds": (_i, [_vp, _i, _i, _vp, _i, _vp]),
     "mevi_rerank_grouped_finish": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, C.POINTER(_i), _vp]),
     "mevi_gather_rows": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _vp]),
     "mevi_flat_ip_topk": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i64, _i, _vp, _vp, _vp]),
@@ -551,6 +552,18 @@ class Context:
                                                            _ptr(tile_nrows), _ptr(item_tile), _ptr(item_group),
                                                            item_tile.numel(), _ptr(group_qid), group_qid.numel() // 64, int(maxg),
                                                            int(k), self._stream()))
+
+    def rerank_grouped_thresholds(self, Q, tau=None):
+        """tau=None: the call's current thresholds [nq] (a copy); else lift them to max(own, tau)."""
+        import torch
+
+        nq, d = Q.shape
+        out = tau if tau is not None else torch.empty(nq, dtype=torch.float32, device=Q.device)
+        self._dev(out, torch.float32, "tau")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.mevi_rerank_grouped_thresholds(self.handle, nq, d, _ptr(out), 0 if tau is None else 1,
+                                                                self._stream()))
+        return out
 
     def rerank_grouped_finish(self, Q, D_leaf, k):
         """-> (scores, rows, failed int32 [nq] device mask, n_failed); n_failed == nq: the whole call is invalid."""

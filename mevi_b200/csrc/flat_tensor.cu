@@ -614,7 +614,9 @@ __global__ void __launch_bounds__(256) flat_rescore_kernel(const float* __restri
   __syncthreads();
   block_bitonic_sort<int32_t>(s_score, s_id, keep_pow2);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const bool ok = i < cnt;
+    // kept candidates below the window were not re-scored (thresholds can rise after the last compaction when ranks
+    // share them): they sorted behind every scored one and are not results
+    const bool ok = i < cnt && s_id[i] != 0x7fffffff;
     scores[(int64_t)q * k + i] = ok ? s_score[i] : -CUDART_INF_F;
     ids[(int64_t)q * k + i] = ok ? id_base + (int64_t)s_id[i] : -1;
   }
@@ -1248,6 +1250,31 @@ extern "C" int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, 
                                                             FT_KEEP, 1);
   MEVI_CUDA(ctx, cudaGetLastError());
   MEVI_COUNT_LAUNCH(ctx, 4);
+  return MEVI_OK;
+}
+
+// thresholds of the call between rounds: raise == 0 copies them out, raise != 0 lifts them to max(own, given).  With the
+// documents sharded over ranks, max over ranks of the local k-th best scores is a lower bound of the global k-th best:
+// an all-reduce(MAX) between the two calls lets every rank filter (and finally re-score) against the global bound.
+__global__ void gr_raise_tau_kernel(float* __restrict__ tau, const float* __restrict__ given, int nq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) tau[i] = fmaxf(tau[i], given[i]);
+}
+
+extern "C" int mevi_rerank_grouped_thresholds(mevi_ctx* ctx, int nq, int d, float* tau, int raise, void* stream) {
+  MEVI_CHECK_CTX(ctx);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  MEVI_REQUIRE(ctx, tau && nq > 0 && d > 0, "bad argument");
+  GrState s;
+  if (!gr_state(ctx, nq, d, &s)) return MEVI_ERR_NOMEM;
+  if (raise) {
+    gr_raise_tau_kernel<<<(nq + 255) / 256, 256, 0, st>>>(s.tau, tau, nq);
+    MEVI_CUDA(ctx, cudaGetLastError());
+    MEVI_COUNT_LAUNCH(ctx, 1);
+  } else {
+    MEVI_CUDA(ctx, cudaMemcpyAsync(tau, s.tau, (size_t)nq * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return MEVI_OK;
 }
 

@@ -224,6 +224,10 @@ class ClusterReranker:
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
     PLAN = "device"                 # "device": the tiles plan made by the library (mevi_rerank_grouped_plan; default);
                                     # "tiles": its torch restatement plan_grouped_tile_rounds; "prefix": plan_grouped_rounds
+    SHARE_THRESHOLDS = False        # sharded documents: all-reduce(MAX) of the thresholds after every round.  Correct and
+                                    # tested (tests/dist_check.py), but measured slower (5.26 vs 5.13 ms per call at N = 4:
+                                    # the sharded call is bound by launches and per-query kernels, not by the candidates
+                                    # the shared bound removes): opt-in, MEVI_RERANK_SHARE=1
     MAXG_SAMPLE = 1                 # query groups (of 64) an item of a sample round takes
     MAXG_LAST = 4                   # ... and of the last round: a document tile is fetched once for up to 256 queries
     BOOT_LEAVES = (8, 63)           # tiles plan: first tile of the leading 8 leaves = the threshold-free bootstrap (<= 1,024
@@ -265,6 +269,8 @@ class ClusterReranker:
         self.last_path = None
         if os.environ.get("MEVI_RERANK_BOOTSTRAP"):
             self.BOOTSTRAP_ROWS = int(os.environ["MEVI_RERANK_BOOTSTRAP"])
+        if os.environ.get("MEVI_RERANK_SHARE"):
+            self.SHARE_THRESHOLDS = os.environ["MEVI_RERANK_SHARE"] != "0"
         if os.environ.get("MEVI_RERANK_PLAN"):
             self.PLAN = os.environ["MEVI_RERANK_PLAN"]
         if os.environ.get("MEVI_RERANK_MAXG"):
@@ -296,6 +302,14 @@ class ClusterReranker:
         ql = self.index.lookup(dec)
         use_grouped = self._grouped is not None and (
             self.mode == "grouped" or ql.numel() >= self.AUTO_QUERIES_PER_LEAF * max(1, self.index.n_leaves))
+        # threshold sharing is a collective inside the grouped path: it runs only when EVERY rank takes that path for this
+        # call (the ranks decide independently: shard size, image fits, leaves shared), agreed on by one all-reduce(MIN)
+        self._share_now = False
+        if dist_on() and self.SHARE_THRESHOLDS:
+            mine = use_grouped and self._grouped["absmax"] >= 0 and topk <= 256 and Q.shape[0] > 0 and self.PLAN in ("device", "tiles")
+            flag = torch.tensor([1 if mine else 0], dtype=torch.int32, device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            self._share_now = bool(flag.item())
         out = self._rerank_grouped(Q, ql, topk) if use_grouped else None
         if out is None:
             self.last_path = "stream"
@@ -496,12 +510,21 @@ def _rerank_grouped(self, Q, ql, topk):
         tau0[weak] = s0[:, topk - 1]
     self.last_weak_queries = int(weak.numel())
     ctx.rerank_grouped_begin(Q, g["absmax"], g["maxnorm"], tau0)
+    def share_thresholds():
+        # documents sharded over ranks: the largest of the ranks' k-th best scores bounds the global k-th best from below,
+        # so after an all-reduce(MAX) of [nq] floats every rank filters the next round - and re-scores - against it
+        if getattr(self, "_share_now", False):
+            tau = ctx.rerank_grouped_thresholds(Q)
+            torch.distributed.all_reduce(tau, op=torch.distributed.ReduceOp.MAX)
+            ctx.rerank_grouped_thresholds(Q, tau)
+
     if device_plan is not None:
         for r, (n_items, n_groups) in enumerate(device_plan):
             if n_items and n_groups:
                 maxg = self.MAXG_LAST if r == len(device_plan) - 1 else self.MAXG_SAMPLE
                 item_tile, item_group, group_qid = ctx.rerank_grouped_plan_fill(r, n_items, n_groups, Q.device)
                 ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk, maxg)
+            share_thresholds()  # every rank, every round (a rank without work in a round still takes part)
     else:
         plan = (plan_grouped_tile_rounds(g["leaf_tile0"], ql, boot, self.MAXG_SAMPLE, self.MAXG_LAST) if self.PLAN == "tiles"
                 else plan_grouped_rounds(off, g["leaf_tile0"], ql, self.ROUND_ROWS, self.BOOTSTRAP_ROWS))
@@ -509,6 +532,8 @@ def _rerank_grouped(self, Q, ql, topk):
             if item_tile.numel():
                 maxg = 1 if self.PLAN != "tiles" else (self.MAXG_LAST if r == len(plan) - 1 else self.MAXG_SAMPLE)
                 ctx.rerank_grouped_round(Q, g["img"], g["row0"], g["nrows"], item_tile, item_group, group_qid, topk, maxg)
+            if self.PLAN == "tiles":  # (the prefix plan's number of rounds can differ between ranks)
+                share_thresholds()
     scores, rows, failed, n_failed = ctx.rerank_grouped_finish(Q, self.D, topk)
     nq = Q.shape[0]
     self.last_failed_queries = n_failed

@@ -60,6 +60,15 @@ if rank == 0:
     same = (i0 == ids).float().mean().item()
     print(f"[rerank] sharded vs single ids equal {same:.4f}, candidates equal {bool((n0 == nc).all())}", flush=True)
     assert same > 0.995 and bool((n0 == nc).all()) and torch.allclose(s0, sc, rtol=1e-5, atol=2e-4)
+# 4. the same through the leaf-grouped tensor path (thresholds shared between the ranks after every round)
+rrg = ClusterReranker(torch.from_numpy(X[s:e]).to(dev), index, mode="grouped")
+rrg.BOOTSTRAP_MIN, rrg.BOOT_LEAVES, rrg.SHARE_THRESHOLDS = 128, (2, 5), True
+sc_g, ids_g, nc_g = rrg.rerank(Q, dec, topk=100)
+assert rrg.last_path.startswith("grouped") and rrg._share_now, (rrg.last_path, rrg._share_now)
+if rank == 0:
+    same = (i0 == ids_g).float().mean().item()
+    print(f"[rerank grouped] sharded vs single ids equal {same:.4f}, path {rrg.last_path}", flush=True)
+    assert same > 0.995 and bool((n0 == nc_g).all()) and torch.allclose(s0, sc_g, rtol=1e-5, atol=2e-4)
 dist.barrier()
 if rank == 0: print("DIST CHECK OK", flush=True)
 dist.destroy_process_group()
