@@ -20,6 +20,7 @@ measured in the same run (verbose details go to stderr and gpurun_out/bench_deta
   rr_stream / rr_group   cluster-restricted re-rank, 6,980 queries x 100 leaves -> top-100 over the sharded corpus
                 (all-gather + merge inside the timed region at N > 1, timed alone as ag_ms); frac_img = reuse-aware
                 roofline (fp16 tile image bytes / time / HBM peak), frac_nr = no-reuse byte count of SURVEY 8d
+  rr_leaf       N > 1: rr_group on a leaf-partitioned index (every leaf whole on one rank)
   rr_clust      the same on the clustered corpus of SURVEY 8d (4,096-Gaussian mixture, sigma 0.3, seed 99)
   enc_nq / flat_nq       NQ shape (21,015,324 x 768 over the N ranks): encode, exact flat IP top-100 of 3,610 queries
   flat          exact flat IP top-100, 6,980 queries x the sharded MSMARCO-shape corpus
@@ -753,7 +754,29 @@ def run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, 
                                "weak_bootstrap_queries": getattr(rrg, "last_weak_queries", None),
                                "max_abs_score_diff_vs_stream": float((sg - ss)[fin].abs().max().item()) if bool(fin.any()) else 0.0,
                                "tile_image_build_s": t_img, "tile_image_bytes": img_bytes}
-        del rrg, D_leaf, index, ql, dec
+        del rrg, D_leaf, index, ql
+        # ---- the same call on a LEAF-partitioned index (N > 1): every leaf moved whole to one rank by one all-to-all of
+        # the rows at index build; the row blocks above give every rank a slice of every leaf
+        if world > 1:
+            t0 = time.perf_counter()
+            index_l, X_own = ClusterIndex.from_sharded_codes(Xs, codes_s, K_CENTS, s0, device_index=dev.index)
+            D_leaf_l = ctx.gather_rows(X_own, index_l.leaf_docids)
+            del X_own
+            rrl = ClusterReranker(None, index_l, mode="grouped", D_leaf=D_leaf_l)
+            torch.cuda.synchronize()
+            t_build = time.perf_counter() - t0
+            lres = {}
+
+            def rl():
+                lres["out"] = rrl.rerank(Q, dec, topk=TOPK)
+
+            ms_l = timed(rl, 3)
+            summary["rr_leaf"] = {"ms": r3(ms_l), "qps": r3(NQ_MARCO / (ms_l / 1e3)), "path": rrl.last_path,
+                                  "ids_eq": r3(float((lres["out"][1] == is_).float().mean().item()))}
+            details["rr_leaf"] = {"rows_this_rank": int(D_leaf_l.shape[0]), "leaves_this_rank": index_l.n_leaves,
+                                  "partition_and_index_build_s": t_build}
+            del rrl, D_leaf_l, index_l
+        del dec
 
     @leg("flat")
     def _():

@@ -29,9 +29,12 @@ class ClusterIndex:
     leaf_docids  int32 [n]          local row indices, ascending inside a leaf
     """
 
-    def __init__(self, leaf_keys, leaf_offsets, leaf_docids, M: int, K: int, id_base: int = 0):
+    def __init__(self, leaf_keys, leaf_offsets, leaf_docids, M: int, K: int, id_base: int = 0, doc_ids=None):
         self.leaf_keys, self.leaf_offsets, self.leaf_docids = leaf_keys, leaf_offsets, leaf_docids
         self.M, self.K, self.id_base = int(M), int(K), int(id_base)
+        # int64 [n] or None: document id of local row i when the rows are not one contiguous id range (a leaf-partitioned
+        # shard, dist_utils.partition_rows_by_leaf); results are then doc_ids[row] instead of id_base + row
+        self.doc_ids = doc_ids
 
     @property
     def n_leaves(self) -> int:
@@ -43,7 +46,7 @@ class ClusterIndex:
 
     # -- construction -------------------------------------------------------
     @classmethod
-    def from_codes(cls, codes, K: int, id_base: int = 0, device_index: Optional[int] = None) -> "ClusterIndex":
+    def from_codes(cls, codes, K: int, id_base: int = 0, device_index: Optional[int] = None, doc_ids=None) -> "ClusterIndex":
         """Replaces the dict loops of pq.py:236-242 / 200-214 with a device sort by leaf key."""
         ctx = _lib.get_context(device_index)
         dev = torch.device("cuda", ctx.device)
@@ -55,7 +58,20 @@ class ClusterIndex:
         leaf_keys, counts = torch.unique_consecutive(keys, return_counts=True)
         offsets = torch.zeros(leaf_keys.numel() + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts, 0, out=offsets[1:])
-        return cls(leaf_keys, offsets, docids, M, K, id_base)
+        if doc_ids is not None:
+            assert id_base == 0 and doc_ids.numel() == codes.shape[0]
+            doc_ids = doc_ids.to(device=dev, dtype=torch.int64).contiguous()
+        return cls(leaf_keys, offsets, docids, M, K, id_base, doc_ids)
+
+    @classmethod
+    def from_sharded_codes(cls, X_local, codes_local, K: int, id_base: int, device_index: Optional[int] = None):
+        """Leaf-partitioned index of a row-block-sharded corpus (torch.distributed initialised): every leaf is moved,
+        whole, to one rank (`dist_utils.partition_rows_by_leaf`).  -> (index, X_own): this rank's leaves and their rows."""
+        from .dist_utils import partition_rows_by_leaf
+
+        ctx = _lib.get_context(device_index)
+        X_own, codes_own, gids = partition_rows_by_leaf(X_local, codes_local.to(torch.int32), K, id_base, gather_rows=ctx.gather_rows)
+        return cls.from_codes(codes_own, K, device_index=device_index, doc_ids=gids), X_own
 
     @classmethod
     def from_cluster_dict(cls, doc_cluster: Dict[Tuple[int, ...], Sequence[int]], K: int, id_base: int = 0,
@@ -316,6 +332,8 @@ class ClusterReranker:
             out = self.ctx.cluster_rerank(Q, self.D, self.index.leaf_offsets, self.index.leaf_docids, ql, topk,
                                           id_base=self.index.id_base, leaf_ordered=self.leaf_ordered)
         scores, ids, ncand = out
+        if self.index.doc_ids is not None:  # leaf-partitioned shard: local rows -> document ids
+            ids = torch.where(ids >= 0, self.index.doc_ids[(ids - self.index.id_base).clamp(min=0)], ids)
         if dist_on():
             s_all = all_gather_stack(scores)
             i_all = all_gather_stack(ids)
@@ -338,6 +356,8 @@ def _rerank_all(self, query_embedding, dec, multiclus_score_aggr: Optional[str] 
         raise ValueError("rerank_all needs the leaf-ordered layout")
     if dist_on():
         raise NotImplementedError("rerank_all under torch.distributed: run it per shard and merge the sorted lists")
+    if self.index.doc_ids is not None:
+        raise NotImplementedError("rerank_all on a leaf-partitioned shard")
     dev = self.D.device
     if not isinstance(query_embedding, torch.Tensor):
         query_embedding = torch.from_numpy(np.ascontiguousarray(query_embedding, dtype=np.float32))

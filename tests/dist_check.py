@@ -69,6 +69,21 @@ if rank == 0:
     same = (i0 == ids_g).float().mean().item()
     print(f"[rerank grouped] sharded vs single ids equal {same:.4f}, path {rrg.last_path}", flush=True)
     assert same > 0.995 and bool((n0 == nc_g).all()) and torch.allclose(s0, sc_g, rtol=1e-5, atol=2e-4)
+# 5. leaf-partitioned index: every leaf moved whole to one rank (one all-to-all of the rows), same answers
+index_l, X_own = ClusterIndex.from_sharded_codes(torch.from_numpy(X[s:e]).to(dev), codes_all[s:e], 32, s, device_index=dev.index)
+tot = torch.tensor([X_own.shape[0]], device=dev); dist.all_reduce(tot)
+assert int(tot.item()) == n and index_l.doc_ids.numel() == X_own.shape[0]
+sizes_l = torch.tensor([index_l.n_leaves], device=dev); dist.all_reduce(sizes_l)
+for mode in ("stream", "grouped"):
+    rrl = ClusterReranker(X_own, index_l, mode=mode)
+    rrl.BOOTSTRAP_MIN, rrl.BOOT_LEAVES = 128, (2, 5)
+    sc_l, ids_l, nc_l = rrl.rerank(Q, dec, topk=100)
+    if rank == 0:
+        same = (i0 == ids_l).float().mean().item()
+        print(f"[rerank leaf-partitioned {mode}] vs single ids equal {same:.4f}, path {rrl.last_path}, leaves over all ranks "
+              f"{int(sizes_l.item())} (single index {full.n_leaves})", flush=True)
+        assert int(sizes_l.item()) == full.n_leaves, "a leaf lives on more than one rank"
+        assert same > 0.995 and bool((n0 == nc_l).all()) and torch.allclose(s0, sc_l, rtol=1e-5, atol=2e-4)
 dist.barrier()
 if rank == 0: print("DIST CHECK OK", flush=True)
 dist.destroy_process_group()

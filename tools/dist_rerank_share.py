@@ -25,18 +25,24 @@ Q = torch.empty((6980, 768), device=dev).normal_(generator=g)
 pq = ProductQuantization("rq", 4, 5, "l2", 768, "kmeans", "grad")
 with torch.no_grad(): pq.codebook.copy_(cb.cpu())
 dec = torch.cat([pq.beam_search(Q[a:a + 1024], 100) for a in range(0, 6980, 1024)])
-index = ClusterIndex.from_codes(codes, 32, id_base=s, device_index=dev.index)
+LEAF = os.environ.get("LEAF_PARTITION", "0") != "0"
+if LEAF:
+    index, X = ClusterIndex.from_sharded_codes(X, codes, 32, s, device_index=dev.index)
+else:
+    index = ClusterIndex.from_codes(codes, 32, id_base=s, device_index=dev.index)
 D_leaf = ctx.gather_rows(X, index.leaf_docids)
 del X
 rr = ClusterReranker(None, index, mode="grouped", D_leaf=D_leaf)
+if rank == 0: print("leaf-partitioned" if LEAF else "row blocks", "rows", D_leaf.shape[0], "leaves", index.n_leaves, flush=True)
 ref = None
-for share in (False, True, False, True):
+for share, boot in ((False, (8, 63)), (True, (8, 63)), (False, (16, 100)), (True, (16, 100))):
     rr.SHARE_THRESHOLDS = share
+    rr.BOOT_LEAVES = boot
     for _ in range(2): out = rr.rerank(Q, dec, topk=100)
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     for _ in range(8): out = rr.rerank(Q, dec, topk=100)
     torch.cuda.synchronize(); dist.barrier(); ms = (time.perf_counter() - t0) / 8 * 1e3
     if ref is None: ref = out
     same = float((out[1] == ref[1]).float().mean())
-    if rank == 0: print(f"world {world} share {share}: {ms:.2f} ms per call, path {rr.last_path}, ids equal to the first run {same:.6f}", flush=True)
+    if rank == 0: print(f"world {world} share {share} boot {boot}: {ms:.2f} ms per call, path {rr.last_path}, weak {rr.last_weak_queries} failed {rr.last_failed_queries}, ids equal to the first run {same:.6f}", flush=True)
 dist.destroy_process_group()
