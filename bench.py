@@ -20,7 +20,7 @@ measured in the same run (verbose details go to stderr and gpurun_out/bench_deta
   rr_stream / rr_group   cluster-restricted re-rank, 6,980 queries x 100 leaves -> top-100 over the sharded corpus
                 (all-gather + merge inside the timed region at N > 1, timed alone as ag_ms); frac_img = reuse-aware
                 roofline (fp16 tile image bytes / time / HBM peak), frac_nr = no-reuse byte count of SURVEY 8d
-  rr_leaf       N > 1: rr_group on a leaf-partitioned index (every leaf whole on one rank)
+  rr_leaf       N > 1 with --rr-leaf: rr_group on a leaf-partitioned index (every leaf whole on one rank)
   rr_clust      the same on the clustered corpus of SURVEY 8d (4,096-Gaussian mixture, sigma 0.3, seed 99)
   enc_nq / flat_nq       NQ shape (21,015,324 x 768 over the N ranks): encode, exact flat IP top-100 of 3,610 queries
   flat          exact flat IP top-100, 6,980 queries x the sharded MSMARCO-shape corpus
@@ -757,7 +757,7 @@ def run_configs(args, ctx, X, cb, codes, dev, rank, world, hbm_peak, bf16_peak, 
         del rrg, D_leaf, index, ql
         # ---- the same call on a LEAF-partitioned index (N > 1): every leaf moved whole to one rank by one all-to-all of
         # the rows at index build; the row blocks above give every rank a slice of every leaf
-        if world > 1:
+        if world > 1 and args.rr_leaf:
             t0 = time.perf_counter()
             index_l, X_own = ClusterIndex.from_sharded_codes(Xs, codes_s, K_CENTS, s0, device_index=dev.index)
             D_leaf_l = ctx.gather_rows(X_own, index_l.leaf_docids)
@@ -991,6 +991,8 @@ def main():
     ap.add_argument("--docs", type=int, default=N_MARCO, help="rows per GPU (default: MSMARCO 8,841,823)")
     ap.add_argument("--flat-docs", type=int, default=N_MARCO, help="rows per GPU of the MSMARCO-shape flat search")
     ap.add_argument("--ref-sample", type=int, default=1 << 20)
+    ap.add_argument("--rr-leaf", action="store_true", help="N > 1: also time the grouped re-rank on a leaf-partitioned index "
+                    "(measured slower than row blocks at N = 2, profiles/r02_rerank_leaf_partition_n2.txt)")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-nq", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
