@@ -1,6 +1,8 @@
 // api.cu — context lifetime, error strings, scratch arenas.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 int mevi_set_error(mevi_ctx* ctx, int code, const char* fmt, ...) {
@@ -143,6 +145,7 @@ void mevi_ctx_destroy(mevi_ctx* ctx) {
     if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
   for (int i = 0; i < 4; ++i)
     if (ctx->aux_event[i]) cudaEventDestroy(ctx->aux_event[i]);
+  free(ctx->gr_plan);
   delete ctx;
 }
 

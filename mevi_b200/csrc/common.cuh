@@ -61,6 +61,9 @@ struct mevi_ctx {
   int64_t km_prev_stride = 0;
   float* km_part_sums = nullptr;
   int32_t* km_part_counts = nullptr;
+  // host-side state of the grouped re-rank's round plan between mevi_rerank_grouped_plan and its _plan_fill calls
+  // (rerank_plan.cu owns the layout; malloc'ed, freed with the context)
+  void* gr_plan = nullptr;
   int64_t launches = 0;            // kernels launched by this context (reported by mevi_device_info)
 };
 

@@ -241,12 +241,8 @@ extern "C" int mevi_ensemble_fuse(mevi_ctx* ctx, const int64_t* cand_ids, const 
   int P2 = 32;
   while (P2 < P) P2 <<= 1;
   size_t smem = (size_t)P2 * (8 + 8 + 8 + 4 + 4);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MEVI_CUDA(ctx, cudaFuncSetAttribute(ensemble_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        ENS_MAX_P * 32));
-    attr_set = true;
-  }
+  if (smem > 48 * 1024)  // (per device: set on every call that needs it)
+    MEVI_CUDA(ctx, cudaFuncSetAttribute(ensemble_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ensemble_fuse_kernel<<<nq, ENS_THREADS, smem, (cudaStream_t)stream>>>(
       cand_ids, cand_scores, cranks, cand_count, P, P2, alpha, beta, gamma, num_leaves, out_ids, out_scores, out_count);
   MEVI_CUDA(ctx, cudaGetLastError());

@@ -276,11 +276,17 @@ __global__ void kmeans_delta_pack_kernel(const int32_t* __restrict__ prev, int64
   }
 }
 
-__global__ void __launch_bounds__(1024, 1)
+// thread = column; a CTA walks a contiguous slice of the packed list in chunks of DELTA_CHUNK records staged in shared
+// memory; rows go through a two-stage register pipeline (8 rows being added while the next 8 are in flight), and the
+// register budget leaves room for two CTAs per SM
+constexpr int DELTA_CHUNK = 256, DELTA_U = 8;
+
+__global__ void __launch_bounds__(1024, 2)
 kmeans_delta_kernel(const float* __restrict__ R, int d, const int2* __restrict__ packed, const int* __restrict__ n_changed,
                     int K, float* __restrict__ part_sums, int32_t* __restrict__ part_counts) {
   extern __shared__ float s_acc[];  // [K][d] signed sums of this CTA's slice
   __shared__ int s_cnt[256];        // [K] signed counts (K <= 256)
+  __shared__ int2 s_rec[DELTA_CHUNK];
   const int col = threadIdx.x;      // blockDim.x >= d, one column per thread
   const bool live = col < d;
   const int64_t m = *n_changed;
@@ -288,29 +294,38 @@ kmeans_delta_kernel(const float* __restrict__ R, int d, const int2* __restrict__
   if (live)
     for (int k = 0; k < K; ++k) s_acc[k * d + col] = 0.f;
   if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  constexpr int U = 16;  // rows in flight per thread; the records of the next batch are fetched under this batch's rows
-  int2 rec[U], nxt[U];
+  const float* Rc = R + (live ? col : 0);
+
+  auto fetch = [&](float (&v)[DELTA_U], int b0, int nrec) {
 #pragma unroll
-  for (int j = 0; j < U; ++j) nxt[j] = lo + j < hi ? __ldg(&packed[lo + j]) : make_int2(-1, 0);
-  for (int64_t i = lo; i < hi; i += U) {
-    float v[U];
+    for (int j = 0; j < DELTA_U; ++j) v[j] = (b0 + j < nrec && live) ? __ldg(Rc + (int64_t)s_rec[b0 + j].x * d) : 0.f;
+  };
+  auto add = [&](const float (&v)[DELTA_U], int b0, int nrec) {
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      rec[j] = nxt[j];
-      v[j] = (rec[j].x >= 0 && live) ? __ldg(&R[(int64_t)rec[j].x * d + col]) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < U; ++j) nxt[j] = i + U + j < hi ? __ldg(&packed[i + U + j]) : make_int2(-1, 0);
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      if (rec[j].x < 0) continue;
-      const int ko = rec[j].y & 0xFFFF, kn = rec[j].y >> 16;
+    for (int j = 0; j < DELTA_U; ++j) {
+      if (b0 + j >= nrec) break;
+      const int kk = s_rec[b0 + j].y;
+      const int ko = kk & 0xFFFF, kn = kk >> 16;
       if (live) {
         s_acc[kn * d + col] += v[j];
         s_acc[ko * d + col] -= v[j];
       }
       if (threadIdx.x == 0) { s_cnt[kn] += 1; s_cnt[ko] -= 1; }
+    }
+  };
+
+  for (int64_t c0 = lo; c0 < hi; c0 += DELTA_CHUNK) {
+    const int nrec = (int)((hi - c0) < DELTA_CHUNK ? (hi - c0) : DELTA_CHUNK);
+    __syncthreads();  // the previous chunk's records are no longer read (and the zeroing above is complete)
+    for (int t = threadIdx.x; t < nrec; t += blockDim.x) s_rec[t] = __ldg(&packed[c0 + t]);
+    __syncthreads();
+    float va[DELTA_U], vb[DELTA_U];
+    fetch(va, 0, nrec);
+    for (int b0 = 0; b0 < nrec; b0 += 2 * DELTA_U) {
+      fetch(vb, b0 + DELTA_U, nrec);
+      add(va, b0, nrec);
+      fetch(va, b0 + 2 * DELTA_U, nrec);
+      add(vb, b0 + DELTA_U, nrec);
     }
   }
   __syncthreads();

@@ -11,6 +11,8 @@
 // groups, see grouped_gemm_kernel); one exclusive scan over [set][groups | items][leaf] gives every leaf its first group
 // and item.  A pair's column is its arrival number among the leaf's pairs (atomic counter): which queries share a
 // group does not influence any score.  One host synchronisation (the sizes the caller allocates).
+#include <stdlib.h>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -153,12 +155,15 @@ __global__ void plan_fill_items_kernel(PlanParams p, FillParams f) {
   f.item_group[f.item_off[part] + li] = (grp0 + j * maxg) | (ng << 24);
 }
 
-struct PlanHost {
+struct PlanHost {  // plain data: lives in mevi_ctx::gr_plan (one grouped call at a time per context)
   PlanParams p;
   int32_t seg[2 * PL_MAX_SETS + 2];
-  bool valid = false;
+  int valid;
 };
-PlanHost g_plan[16];  // per device (a context is per device; one grouped call at a time per context)
+PlanHost* plan_of(mevi_ctx* ctx) {
+  if (!ctx->gr_plan) ctx->gr_plan = calloc(1, sizeof(PlanHost));
+  return (PlanHost*)ctx->gr_plan;
+}
 
 size_t pl_layout(PlanParams* p, char* ws) {
   const int n_sets = p->n_boot + 2;
@@ -188,9 +193,10 @@ extern "C" int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq
   MEVI_REQUIRE(ctx, (max_groups_sample == 1 || max_groups_sample == 2 || max_groups_sample == 4) &&
                         (max_groups_last == 1 || max_groups_last == 2 || max_groups_last == 4),
                "an item takes 1, 2 or 4 groups");
-  MEVI_REQUIRE(ctx, ctx->device >= 0 && ctx->device < 16, "device index");
-  PlanHost& h = g_plan[ctx->device];
-  h.valid = false;
+  PlanHost* hp = plan_of(ctx);
+  if (!hp) return MEVI_ERR_NOMEM;
+  PlanHost& h = *hp;
+  h.valid = 0;
   PlanParams& p = h.p;
   p.ql = ql; p.nq = nq; p.L = L; p.leaf_offsets = leaf_offsets; p.leaf_tile0 = leaf_tile0; p.n_leaves = n_leaves;
   p.n_boot = n_boot;
@@ -231,7 +237,7 @@ extern "C" int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq
     sizes_host[2 * r + 1] = groups;
   }
   sizes_host[2 * (n_boot + 1)] = h.seg[2 * n_sets + 1];
-  h.valid = true;
+  h.valid = 1;
   return MEVI_OK;
 }
 
@@ -240,10 +246,9 @@ extern "C" int mevi_rerank_grouped_plan_fill(mevi_ctx* ctx, int round, int32_t* 
   MEVI_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
-  MEVI_REQUIRE(ctx, ctx->device >= 0 && ctx->device < 16 && g_plan[ctx->device].valid, "no plan: call mevi_rerank_grouped_plan first");
-  PlanHost& h = g_plan[ctx->device];
+  MEVI_REQUIRE(ctx, ctx->gr_plan && ((PlanHost*)ctx->gr_plan)->valid, "no plan: call mevi_rerank_grouped_plan first");
+  PlanHost& h = *(PlanHost*)ctx->gr_plan;
   const PlanParams& p = h.p;
-  const int n_sets = p.n_boot + 2;
   MEVI_REQUIRE(ctx, round >= 0 && round <= p.n_boot, "round %d of %d", round, p.n_boot + 1);
   FillParams f;
   f.n_parts = round == p.n_boot ? 2 : 1;
@@ -257,7 +262,6 @@ extern "C" int mevi_rerank_grouped_plan_fill(mevi_ctx* ctx, int round, int32_t* 
     groups += h.seg[2 * s + 1] - h.seg[2 * s];
     items += f.n_items[part];
   }
-  (void)n_sets;
   if (items <= 0 || groups <= 0) return MEVI_OK;
   MEVI_REQUIRE(ctx, item_tile && item_group && group_qid, "NULL argument");
   f.item_tile = item_tile; f.item_group = item_group; f.group_qid = group_qid;
