@@ -11,7 +11,9 @@
 // so one pass computes the M*K inner products x.c and every level is table arithmetic over beam x K
 // candidates.  Tables and the recurrences are kept in fp64, so each logit is the correctly rounded fp32
 // value (the reference's own fp32 sum over d carries ~1e-4 absolute error at |x|^2 ~ 1e3).
-// One CTA per query row; top-k by a shared-memory bitonic sort in (score desc, candidate index asc) order.
+// One CTA per query row; top-k in (score desc, candidate index asc) order: a radix select finds the num_beams-th best
+// probability, the candidates at or above it (num_beams plus ties) are compacted and only those are sorted; the full
+// shared-memory bitonic sort of all beam x K candidates remains for the degenerate case of more than BEAM_SEL ties.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -19,6 +21,7 @@
 namespace {
 
 constexpr int BEAM_THREADS = 256;
+constexpr int BEAM_SEL_MAX = 1024;  // selection buffer: power of two >= 2 * num_beams, at most this
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -49,7 +52,7 @@ struct BeamParams {
   const float* cb;
   const double* G;
   int64_t bs;
-  int d, M, K, NT, num_beams, cap, metric, prod;
+  int d, M, K, NT, num_beams, cap, sel, metric, prod;
   int32_t* labels;
   float* scores;
 };
@@ -64,7 +67,11 @@ __global__ void __launch_bounds__(BEAM_THREADS) beam_search_kernel(BeamParams p)
   float* cscore = sscore + 2 * B;                                // [cap]
   int32_t* cidx = reinterpret_cast<int32_t*>(cscore + p.cap);    // [cap]
   int32_t* scodes = cidx + p.cap;                                // [2][B*M]
+  float* sel_score = reinterpret_cast<float*>(scodes + 2 * B * M);  // [p.sel]
+  int32_t* sel_idx = reinterpret_cast<int32_t*>(sel_score + p.sel); // [p.sel]
   __shared__ double s_xn2;
+  __shared__ unsigned s_hist[256], s_scratch[4];
+  __shared__ int s_nsel;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = BEAM_THREADS / 32;
   const bool l2 = p.metric == MEVI_METRIC_L2;
@@ -133,14 +140,43 @@ __global__ void __launch_bounds__(BEAM_THREADS) beam_search_kernel(BeamParams p)
       __syncthreads();
       int nb;
       if (B < ncand) {
-        int n2 = 1;
-        while (n2 < ncand) n2 <<= 1;
-        for (int t = ncand + tid; t < n2; t += BEAM_THREADS) {
-          cscore[t] = -CUDART_INF_F;
-          cidx[t] = 0x7fffffff;
+        // the B-th best probability, then everything at or above it (B candidates plus ties at the boundary)
+        const float kth = block256_select_kth(cscore, ncand, B, s_hist, s_scratch);
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+        for (int t = tid; t < ncand; t += BEAM_THREADS) {
+          const float v = cscore[t];
+          if (!(v < kth)) {
+            const int pos = atomicAdd(&s_nsel, 1);
+            if (pos < p.sel) { sel_score[pos] = v; sel_idx[pos] = cidx[t]; }
+          }
         }
         __syncthreads();
-        block_bitonic_sort<int32_t>(cscore, cidx, n2);
+        const int nsel = s_nsel;
+        if (nsel <= p.sel) {
+          int n2 = 32;
+          while (n2 < nsel) n2 <<= 1;
+          for (int t = nsel + tid; t < n2; t += BEAM_THREADS) {
+            sel_score[t] = -CUDART_INF_F;
+            sel_idx[t] = 0x7fffffff;
+          }
+          __syncthreads();
+          block_bitonic_sort<int32_t>(sel_score, sel_idx, n2);
+          for (int t = tid; t < B; t += BEAM_THREADS) {
+            cscore[t] = sel_score[t];
+            cidx[t] = sel_idx[t];
+          }
+          __syncthreads();
+        } else {  // more ties at the boundary than the buffer holds: sort everything
+          int n2 = 1;
+          while (n2 < ncand) n2 <<= 1;
+          for (int t = ncand + tid; t < n2; t += BEAM_THREADS) {
+            cscore[t] = -CUDART_INF_F;
+            cidx[t] = 0x7fffffff;
+          }
+          __syncthreads();
+          block_bitonic_sort<int32_t>(cscore, cidx, n2);
+        }
         nb = B;
       } else {
         nb = ncand;  // every candidate survives, in (beam, centroid) order (pq.py:701-707)
@@ -204,8 +240,11 @@ extern "C" int mevi_rq_beam_search(mevi_ctx* ctx, const float* X, int64_t bs, in
   BeamParams p;
   p.X = X; p.cb = codebook; p.G = G; p.bs = bs; p.d = d; p.M = M; p.K = K; p.NT = NT; p.num_beams = num_beams;
   p.cap = cap; p.metric = metric; p.prod = prod ? 1 : 0; p.labels = labels; p.scores = scores;
+  int sel = 64;
+  while (sel < 2 * num_beams && sel < BEAM_SEL_MAX) sel <<= 1;
+  p.sel = sel;
   const size_t smem = sizeof(double) * (size_t)(NT + 2 * num_beams) + sizeof(float) * (size_t)(d + 2 * num_beams + cap) +
-                      sizeof(int32_t) * (size_t)(cap + 2 * num_beams * M);
+                      sizeof(int32_t) * (size_t)(cap + 2 * num_beams * M) + 8 * (size_t)sel;
   MEVI_REQUIRE(ctx, smem <= 200 * 1024, "beam search state (%zu bytes) does not fit shared memory", smem);
   MEVI_CUDA(ctx, cudaFuncSetAttribute(beam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t max_grid = (int64_t)ctx->sm_count * 8;

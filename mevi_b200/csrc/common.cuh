@@ -157,6 +157,88 @@ __device__ __forceinline__ void group_bitonic_sort(float* s, IdT* id, int n, int
   }
 }
 
+// ---- radix select over shared-memory floats ------------------------------------------------------------------
+// monotone float <-> unsigned key (larger float = larger key)
+__device__ __forceinline__ unsigned sel_key(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float sel_unkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// The k-th largest (1-based, k <= n) of s[0..n) by a radix select over the bits in which the values differ; every thread
+// of a 256-thread CTA calls it and gets the value.  `hist` = 256 unsigned of shared memory, `scratch` = 4 unsigned of
+// shared memory; both may be reused afterwards.  Histogram updates are aggregated per warp (equal digits are common).
+__device__ __forceinline__ float block256_select_kth(const float* s, int n, int k, unsigned* hist, unsigned* scratch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { scratch[0] = 0xFFFFFFFFu; scratch[1] = 0u; }
+  __syncthreads();
+  unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+  for (int i = tid; i < n; i += 256) {
+    const unsigned key = sel_key(s[i]);
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(MEVI_FULL_MASK, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(MEVI_FULL_MASK, kmax, o));
+  }
+  if (lane == 0) { atomicMin(&scratch[0], kmin); atomicMax(&scratch[1], kmax); }
+  __syncthreads();
+  const unsigned lo_key = scratch[0], hi_key = scratch[1];
+  unsigned prefix = hi_key;
+  int rem = k;
+  if (lo_key != hi_key) {
+    const int top = 31 - __clz(lo_key ^ hi_key);
+    int hi_bit = top;
+    prefix = (top == 31) ? 0u : (hi_key >> (top + 1)) << (top + 1);
+    while (hi_bit >= 0) {
+      const int width = hi_bit >= 7 ? 8 : hi_bit + 1;
+      const int shift = hi_bit + 1 - width;
+      const unsigned above = (hi_bit == 31) ? 0u : (0xFFFFFFFFu << (hi_bit + 1));
+      hist[tid] = 0;
+      __syncthreads();
+      for (int base = 0; base < n; base += 256) {
+        const int i = base + tid;
+        unsigned digit = 0xFFFFu;
+        if (i < n) {
+          const unsigned key = sel_key(s[i]);
+          if ((key & above) == (prefix & above)) digit = (key >> shift) & ((1u << width) - 1u);
+        }
+        const unsigned peers = __match_any_sync(MEVI_FULL_MASK, digit);
+        if (digit != 0xFFFFu && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+      }
+      __syncthreads();
+      if (warp == 0) {
+        int local[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { local[j] = (int)hist[255 - (lane * 8 + j)]; sum += local[j]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(MEVI_FULL_MASK, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int excl = incl - sum;
+        if (excl < rem && rem <= incl) {
+          int r = rem - excl;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (r > 0 && r <= local[j]) { scratch[2] = 255u - (unsigned)(lane * 8 + j); scratch[3] = (unsigned)r; r = 0; }
+            else if (r > 0) r -= local[j];
+          }
+        }
+      }
+      __syncthreads();
+      prefix |= scratch[2] << shift;
+      rem = (int)scratch[3];
+      hi_bit = shift - 1;
+      __syncthreads();
+    }
+  }
+  return sel_unkey(prefix);
+}
+
 // shared-memory bitonic sort of n (power of two) (score,id) pairs into topk_before order
 template <typename IdT>
 __device__ __forceinline__ void block_bitonic_sort(float* s, IdT* id, int n) {

@@ -332,7 +332,10 @@ class ProductQuantization(nn.Module):
         cap = 1
         while cap < num_beams * K:
             cap <<= 1
-        smem = 8 * (M * K + 2 * num_beams) + 4 * (d + 2 * num_beams + cap) + 4 * (cap + 2 * num_beams * M)
+        sel = 64
+        while sel < 2 * num_beams and sel < 1024:
+            sel <<= 1
+        smem = 8 * (M * K + 2 * num_beams) + 4 * (d + 2 * num_beams + cap) + 4 * (cap + 2 * num_beams * M) + 8 * sel
         return M * K <= 2048 and cap <= 16384 and smem <= 200 * 1024 and float(K) ** M >= num_beams
 
     def _beam_search_tensor_ops(self, doc_emb, num_beams, return_proba):
