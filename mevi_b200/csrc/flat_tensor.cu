@@ -449,19 +449,11 @@ int flat_max_clusters(mevi_ctx* ctx, size_t smem) {
 }
 
 // one CTA per query: tau = k-th best approximate score of (kept + newly appended) candidates, found by a radix SELECT
-// over the bits in which the scores differ (no sort: the list is consumed as a set); everything inside the margin window
+// over the bits in which the scores differ (block256_select_kth, common.cuh; no sort: the list is consumed as a set); everything inside the margin window
 // [tau - margin, inf) is kept, the rest can never reach the exact top-k (tau only rises) and is dropped.  More than
 // `keep` candidates inside the window breaks the guarantee -> overflow flag
 // (`ov_stride` = 0: one flag for the call - flat search; 1: a flag per query - grouped re-rank, which re-runs only the
 // affected queries through the streaming kernel).  The kept list is NOT ordered.
-__device__ __forceinline__ unsigned ft_key(float f) {  // monotone: larger float -> larger unsigned
-  const unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ft_unkey(unsigned k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
 __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, const float* margin, int* count, float* cand_score,
                                                                   int32_t* cand_id, int* overflow, int capg, int k, int keep,
                                                                   int ov_stride) {
@@ -470,86 +462,18 @@ __global__ void __launch_bounds__(256) flat_tensor_compact_kernel(float* tau, co
   float* s_ks = s_score + capg;                                        // [keep]
   int32_t* s_ki = reinterpret_cast<int32_t*>(s_ks + keep);             // [keep]
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_ki + keep);         // [256]
-  __shared__ unsigned s_min, s_max, s_digit;
-  __shared__ int s_rem, s_n;
-  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned s_scratch[4];
+  __shared__ int s_n;
+  const int q = blockIdx.x, tid = threadIdx.x;
   int cnt = count[q];
   if (cnt > capg) cnt = capg;
   if (cnt == 0) return;
-  if (tid == 0) { s_min = 0xFFFFFFFFu; s_max = 0u; s_n = 0; }
-  __syncthreads();
-  unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-  for (int i = tid; i < cnt; i += blockDim.x) {
-    const float sc = cand_score[(int64_t)q * capg + i];
-    s_score[i] = sc;
-    const unsigned key = ft_key(sc);
-    kmin = min(kmin, key);
-    kmax = max(kmax, key);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    kmin = min(kmin, __shfl_xor_sync(MEVI_FULL_MASK, kmin, o));
-    kmax = max(kmax, __shfl_xor_sync(MEVI_FULL_MASK, kmax, o));
-  }
-  if (lane == 0) { atomicMin(&s_min, kmin); atomicMax(&s_max, kmax); }
+  if (tid == 0) s_n = 0;
+  for (int i = tid; i < cnt; i += blockDim.x) s_score[i] = cand_score[(int64_t)q * capg + i];
   __syncthreads();
   float t = tau[q];
-  if (cnt >= k) {
-    // the k-th largest key: all keys agree above bit `top`; digits of 8 bits from there down
-    const unsigned lo_key = s_min, hi_key = s_max;
-    unsigned prefix = hi_key;  // bits above `top` are common; the digits below are filled in pass by pass
-    int rem = k;
-    if (lo_key != hi_key) {
-      const int top = 31 - __clz(lo_key ^ hi_key);
-      int hi_bit = top;  // most significant undecided bit
-      prefix = (top == 31) ? 0u : (hi_key >> (top + 1)) << (top + 1);
-      while (hi_bit >= 0) {
-        const int width = hi_bit >= 7 ? 8 : hi_bit + 1;
-        const int shift = hi_bit + 1 - width;
-        const unsigned above = (hi_bit == 31) ? 0u : (0xFFFFFFFFu << (hi_bit + 1));  // decided bits
-        s_hist[tid] = 0;
-        __syncthreads();
-        for (int base = 0; base < cnt; base += blockDim.x) {
-          const int i = base + tid;
-          unsigned digit = 0xFFFFu;  // not a candidate of this pass
-          if (i < cnt) {
-            const unsigned key = ft_key(s_score[i]);
-            if ((key & above) == (prefix & above)) digit = (key >> shift) & ((1u << width) - 1u);
-          }
-          const unsigned peers = __match_any_sync(MEVI_FULL_MASK, digit);
-          if (digit != 0xFFFFu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[digit], __popc(peers));
-        }
-        __syncthreads();
-        if (warp == 0) {  // lane l owns digits 255 - 8 l ... 248 - 8 l (descending); find where the running count reaches rem
-          int local[8], sum = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { local[j] = (int)s_hist[255 - (lane * 8 + j)]; sum += local[j]; }
-          int incl = sum;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(MEVI_FULL_MASK, incl, o);
-            if (lane >= o) incl += v;
-          }
-          const int excl = incl - sum;
-          if (excl < rem && rem <= incl) {
-            int r = rem - excl;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (r > 0 && r <= local[j]) { s_digit = 255u - (unsigned)(lane * 8 + j); s_rem = r; r = 0; }
-              else if (r > 0) r -= local[j];
-            }
-          }
-        }
-        __syncthreads();
-        prefix |= s_digit << shift;
-        rem = s_rem;
-        hi_bit = shift - 1;
-        __syncthreads();
-      }
-    }
-    // never below a bound the caller already had (the grouped re-rank starts from a lower bound of the k-th score)
-    t = fmaxf(t, ft_unkey(prefix));
-  }
+  // never below a bound the caller already had (the grouped re-rank starts from a lower bound of the k-th score)
+  if (cnt >= k) t = fmaxf(t, block256_select_kth(s_score, cnt, k, s_hist, s_scratch));
   const float window = t - margin[q];
   for (int i = tid; i < cnt; i += blockDim.x) {
     const float sc = s_score[i];
