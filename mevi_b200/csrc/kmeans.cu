@@ -293,7 +293,7 @@ kmeans_delta_kernel(const float* __restrict__ R, int d, const int2* __restrict__
   const int64_t lo = m * blockIdx.x / gridDim.x, hi = m * (blockIdx.x + 1) / gridDim.x;
   if (live)
     for (int k = 0; k < K; ++k) s_acc[k * d + col] = 0.f;
-  if (threadIdx.x < K) s_cnt[threadIdx.x] = 0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_cnt[k] = 0;  // (a narrow slice has fewer threads than centroids)
   const float* Rc = R + (live ? col : 0);
 
   auto fetch = [&](float (&v)[DELTA_U], int b0, int nrec) {
@@ -331,7 +331,7 @@ kmeans_delta_kernel(const float* __restrict__ R, int d, const int2* __restrict__
   __syncthreads();
   if (live)
     for (int k = 0; k < K; ++k) part_sums[((int64_t)blockIdx.x * K + k) * d + col] = s_acc[k * d + col];
-  if (threadIdx.x < K) part_counts[(int64_t)blockIdx.x * K + threadIdx.x] = s_cnt[threadIdx.x];
+  for (int k = threadIdx.x; k < K; k += blockDim.x) part_counts[(int64_t)blockIdx.x * K + k] = s_cnt[k];
 }
 
 // master (float64) += the partials in CTA order; sums_counts = (float) master

@@ -172,7 +172,8 @@ def test_trainer_one_pass_iterations_match_two_pass_training(monkeypatch):
 
 
 @pytest.mark.parametrize("n,d,K,mode", [(20000, 768, 32, "auto"), (4097, 768, 32, "exact"), (70001, 256, 32, "auto"),
-                                         (9000, 512, 16, "auto"), (3000, 64, 8, "auto")])
+                                         (9000, 512, 16, "auto"), (3000, 64, 8, "auto"), (6000, 32, 256, "auto"),
+                                         (5000, 24, 64, "auto")])
 def test_delta_step_corrects_running_sums_by_the_moved_rows(n, d, K, mode):
     """mevi_kmeans_step_delta: one assignment pass + float64 running sums|counts corrected by the rows whose assignment
     changed.  Five chained iterations against a float64 oracle of the sums under the NEW assignment, the two-pass step
@@ -206,7 +207,11 @@ def test_delta_step_corrects_running_sums_by_the_moved_rows(n, d, K, mode):
     t1, t2 = run(), run()
     moved_total = 0
     for (cur, buf, nchg, inertia, Cd, prev), (cur2, buf2, nchg2, _, _, _) in zip(t1, t2):
-        assert torch.equal(cur, cur2) and torch.equal(buf, buf2) and nchg == nchg2  # bit-reproducible
+        assert torch.equal(cur, cur2) and nchg == nchg2
+        if K <= 64:  # bit-reproducible (for K > 64 the FIRST, two-pass step accumulates with float atomics: kmeans.cu)
+            assert torch.equal(buf, buf2)
+        else:
+            assert torch.allclose(buf, buf2, rtol=1e-5, atol=1e-3)
         want = torch.empty(n, dtype=torch.int32, device="cuda:0")
         tmp = torch.empty(K * d + K, device="cuda:0")
         c.kmeans_step(Xd, Cd, tmp, assign=want, mode=mode)
