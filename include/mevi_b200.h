@@ -248,8 +248,11 @@ int mevi_cluster_rerank_all(mevi_ctx* ctx, const float* Q, int nq, const float* 
  *   leaf-rank boundaries: round i < n_boot = first tile of the leaves with rank in [boot[i-1], boot[i]) (threshold
  *   samples, items of max_groups_sample groups), round n_boot = the remaining first tiles + every further tile of every
  *   leaf against all the queries that chose it (items of max_groups_last groups).  Outputs: ncand [nq] int32 (device)
- *   candidates per query, weak [nq] int32 (device) 1 = the query's sample holds fewer than boot_min_rows rows (the
- *   caller supplies its tau0 from mevi_cluster_rerank_prefix), sizes_host [2*(n_boot+1)+1] = (items, groups) per round,
+ *   candidates per query, weak [nq] int32 (device) 1 = the query's sample is too small for its candidate count (fewer rows
+ *   than min(boot_min_rows, max(2k, candidates * k / pass_budget)) with more than pass_budget candidates (6,144 of the 8,192
+ *   buffer slots is the caller's default): the k-th best of the sample
+ *   would let more through the last round than the candidate buffer holds; the caller supplies such a query's tau0 from
+ *   mevi_cluster_rerank_prefix), sizes_host [2*(n_boot+1)+1] = (items, groups) per round,
  *   then the number of weak queries.  _plan_fill writes round `round` into caller-allocated item_tile / item_group
  *   [items] and group_qid [groups*64]; ql, leaf_offsets and leaf_tile0 must stay valid until the last _plan_fill.
  * _finish: scores [nq,k] fp32 descending, rows [nq,k] int64 rows of D_leaf, -1 padded; *n_failed = number of queries
@@ -268,7 +271,7 @@ int mevi_rerank_grouped_round(mevi_ctx* ctx, const float* Q, int nq, int d, cons
                               int k, void* stream);
 int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq, int L, const int64_t* leaf_offsets,
                              const int64_t* leaf_tile0, int64_t n_leaves, const int32_t* boot_leaves, int n_boot,
-                             int boot_min_rows, int max_groups_sample, int max_groups_last, int32_t* ncand,
+                             int boot_min_rows, int k, int pass_budget, int max_groups_sample, int max_groups_last, int32_t* ncand,
                              int32_t* weak, int64_t* sizes_host, void* stream);
 int mevi_rerank_grouped_plan_fill(mevi_ctx* ctx, int round, int32_t* item_tile, int32_t* item_group, int32_t* group_qid,
                                   void* stream);

@@ -47,7 +47,7 @@ SYMBOLS = {
     "mevi_rerank_grouped_image": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, C.POINTER(_f), C.POINTER(_f), _vp]),
     "mevi_rerank_grouped_begin": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp]),
     "mevi_rerank_grouped_round": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _vp]),
-    "mevi_rerank_grouped_plan": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, C.POINTER(C.c_int32), _i, _i, _i, _i, _vp, _vp,
+    "mevi_rerank_grouped_plan": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, C.POINTER(C.c_int32), _i, _i, _i, _i, _i, _i, _vp, _vp,
                                       C.POINTER(_i64), _vp]),
     "mevi_rerank_grouped_plan_fill": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     "mevi_rerank_grouped_thresholds": (_i, [_vp, _i, _i, _vp, _i, _vp]),
@@ -509,7 +509,7 @@ class Context:
                                                   leaf_keys.numel(), _ptr(out), self._stream()))
         return out
 
-    def rerank_grouped_plan(self, ql, leaf_offsets, leaf_tile0, boot_leaves, boot_min_rows, maxg_sample=1, maxg_last=4):
+    def rerank_grouped_plan(self, ql, leaf_offsets, leaf_tile0, boot_leaves, boot_min_rows, k, maxg_sample=1, maxg_last=4, pass_budget=6144):
         """Device-side round plan -> (ncand int32 [nq], weak int32 [nq], [(items, groups)] per round, n_weak)."""
         import torch
 
@@ -523,7 +523,7 @@ class Context:
         weak = torch.empty(nq, dtype=torch.int32, device=ql.device)
         with torch.cuda.device(self.device):
             self._check(self.lib.mevi_rerank_grouped_plan(self.handle, _ptr(ql), nq, L, _ptr(off), _ptr(t0), off.numel() - 1,
-                                                          boot, len(boot_leaves), int(boot_min_rows), int(maxg_sample),
+                                                          boot, len(boot_leaves), int(boot_min_rows), int(k), int(pass_budget), int(maxg_sample),
                                                           int(maxg_last), _ptr(ncand), _ptr(weak), sizes, self._stream()))
         rounds = [(int(sizes[2 * r]), int(sizes[2 * r + 1])) for r in range(len(boot_leaves) + 1)]
         return ncand, weak, rounds, int(sizes[2 * (len(boot_leaves) + 1)])

@@ -40,7 +40,7 @@ __device__ __forceinline__ int pl_class(const PlanParams& p, int rank) {
 }
 
 // one CTA per query: counts, arrival numbers, candidate totals, the "weak bootstrap" flag
-__global__ void __launch_bounds__(128) plan_count_kernel(PlanParams p, int boot_min_rows, int32_t* __restrict__ ncand,
+__global__ void __launch_bounds__(128) plan_count_kernel(PlanParams p, int boot_min_rows, int k, int pass_budget, int32_t* __restrict__ ncand,
                                                          int32_t* __restrict__ weak) {
   const int q = blockIdx.x;
   const int n_sets = p.n_boot + 2;
@@ -69,7 +69,12 @@ __global__ void __launch_bounds__(128) plan_count_kernel(PlanParams p, int boot_
     total = s_tot[0] + s_tot[1] + s_tot[2] + s_tot[3];
     boot_rows = s_boot[0] + s_boot[1] + s_boot[2] + s_boot[3];
     ncand[q] = (int32_t)(total > 0x7FFFFFFFll ? 0x7FFFFFFFll : total);
-    const int w = (boot_rows < boot_min_rows && total > boot_rows) ? 1 : 0;
+    // a sample of s rows lets about total * k / s candidates through the last round; they must fit the candidate buffer
+    // (pass_budget of its 8,192 slots).  A query with few candidates needs a small sample or none at all.
+    const long long need = total * k / pass_budget;
+    const long long floor_rows = 2ll * k > need ? 2ll * k : need;
+    const long long limit = boot_min_rows < floor_rows ? boot_min_rows : floor_rows;
+    const int w = (total > pass_budget && boot_rows < limit && total > boot_rows) ? 1 : 0;
     weak[q] = w;
     if (w) atomicAdd(&p.seg[2 * n_sets + 1], 1);
   }
@@ -182,13 +187,13 @@ size_t pl_layout(PlanParams* p, char* ws) {
 
 extern "C" int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq, int L, const int64_t* leaf_offsets,
                                         const int64_t* leaf_tile0, int64_t n_leaves, const int32_t* boot_leaves,
-                                        int n_boot, int boot_min_rows, int max_groups_sample, int max_groups_last,
-                                        int32_t* ncand, int32_t* weak, int64_t* sizes_host, void* stream) {
+                                        int n_boot, int boot_min_rows, int k, int pass_budget, int max_groups_sample,
+                                        int max_groups_last, int32_t* ncand, int32_t* weak, int64_t* sizes_host, void* stream) {
   MEVI_CHECK_CTX(ctx);
   DeviceGuard g(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   MEVI_REQUIRE(ctx, ql && leaf_offsets && leaf_tile0 && ncand && weak && sizes_host, "NULL argument");
-  MEVI_REQUIRE(ctx, nq > 0 && L > 0 && n_leaves > 0 && n_leaves < (int64_t)1 << 27, "bad extents");
+  MEVI_REQUIRE(ctx, nq > 0 && L > 0 && k > 0 && pass_budget > 0 && n_leaves > 0 && n_leaves < (int64_t)1 << 27, "bad extents");
   MEVI_REQUIRE(ctx, n_boot >= 0 && n_boot <= PL_MAX_BOOT && (n_boot == 0 || boot_leaves), "0..%d bootstrap boundaries", PL_MAX_BOOT);
   MEVI_REQUIRE(ctx, (max_groups_sample == 1 || max_groups_sample == 2 || max_groups_sample == 4) &&
                         (max_groups_last == 1 || max_groups_last == 2 || max_groups_last == 4),
@@ -217,7 +222,7 @@ extern "C" int mevi_rerank_grouped_plan(mevi_ctx* ctx, const int32_t* ql, int nq
   if (!tmp) return MEVI_ERR_NOMEM;
   MEVI_CUDA(ctx, cudaMemsetAsync(p.cnt, 0, (size_t)n_sets * n_leaves * 4, st));
   MEVI_CUDA(ctx, cudaMemsetAsync(p.seg, 0, (2 * PL_MAX_SETS + 2) * 4, st));
-  plan_count_kernel<<<nq, 128, 0, st>>>(p, boot_min_rows, ncand, weak);
+  plan_count_kernel<<<nq, 128, 0, st>>>(p, boot_min_rows, k, pass_budget, ncand, weak);
   plan_leaf_kernel<<<(unsigned)((n_leaves + 255) / 256), 256, 0, st>>>(p);
   MEVI_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, p.scan_in, p.scan_out, (int)scan_len, st));
   plan_segments_kernel<<<1, 32, 0, st>>>(p);

@@ -236,7 +236,10 @@ class ClusterReranker:
     AUTO_MIN_DOCS = 1 << 18         # mode='auto': corpora below this stay on the streaming kernel (no tile image)
     AUTO_QUERIES_PER_LEAF = 4       # mode='auto': grouped path when nq*L >= this many (query, leaf) pairs per leaf
     BOOTSTRAP_ROWS = 3072           # rows of the threshold-free first round per query (all appended: must fit the buffers)
-    BOOTSTRAP_MIN = 2048            # fewer bootstrap rows than this: first threshold from the streaming kernel instead
+    BOOTSTRAP_MIN = 2048            # fewer bootstrap rows than this: first threshold from the streaming kernel instead ...
+    PASS_BUDGET = 6144              # ... unless the query has so few candidates that its sample's k-th best lets fewer than
+                                    # this many (of the 8,192 buffer slots) through the last round: a sample of s rows
+                                    # passes ~candidates * k / s
     ROUND_ROWS = (32768,)           # pairs whose preceding candidate rows number less than this go first
     PLAN = "device"                 # "device": the tiles plan made by the library (mevi_rerank_grouped_plan; default);
                                     # "tiles": its torch restatement plan_grouped_tile_rounds; "prefix": plan_grouped_rounds
@@ -508,8 +511,8 @@ def _rerank_grouped(self, Q, ql, topk):
     device_plan = None
     if self.PLAN == "device":  # counts, scans, candidate totals and the weak-sample flags in five launches, one host sync
         ql = ql.contiguous()  # the library keeps the pointer until the last plan_fill of this call
-        ncand, weak_flags, device_plan, n_weak = ctx.rerank_grouped_plan(ql, off, g["leaf_tile0"], boot,
-                                                                         self.BOOTSTRAP_MIN, self.MAXG_SAMPLE, self.MAXG_LAST)
+        ncand, weak_flags, device_plan, n_weak = ctx.rerank_grouped_plan(ql, off, g["leaf_tile0"], boot, self.BOOTSTRAP_MIN,
+                                                                         topk, self.MAXG_SAMPLE, self.MAXG_LAST, self.PASS_BUDGET)
         weak = torch.nonzero(weak_flags).squeeze(1) if n_weak else weak_flags[:0].long()
     else:
         sizes = off[1:] - off[:-1]
@@ -520,7 +523,9 @@ def _rerank_grouped(self, Q, ql, topk):
         else:
             after = torch.cumsum(qsz, 1)
             boot_rows = torch.where(after <= self.BOOTSTRAP_ROWS, qsz, torch.zeros_like(qsz)).sum(1)
-        weak = torch.nonzero((boot_rows < self.BOOTSTRAP_MIN) & (ncand > boot_rows)).squeeze(1)
+        # a sample of s rows lets ~ncand * k / s candidates through the last round: they must fit the candidate buffers
+        need = torch.clamp(ncand * topk // self.PASS_BUDGET, min=2 * topk).clamp(max=self.BOOTSTRAP_MIN)
+        weak = torch.nonzero((ncand > self.PASS_BUDGET) & (boot_rows < need) & (ncand > boot_rows)).squeeze(1)
         ncand = ncand.clamp(max=0x7FFFFFFF).to(torch.int32)
     tau0 = None
     if weak.numel():

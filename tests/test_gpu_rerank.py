@@ -68,6 +68,7 @@ def test_grouped_tensor_rerank_matches_oracle(case, nb, k, boot_min, plan):
     # small corpus: still exercise the threshold-free bootstrap round + three more rounds; boot_min = 100000 makes every
     # query "weak" (first thresholds from the streaming kernel's exact prefix top-k instead)
     rr.BOOTSTRAP_ROWS, rr.ROUND_ROWS, rr.BOOTSTRAP_MIN = (256 if boot_min < 1000 else 32), (600, 3000), boot_min
+    rr.PASS_BUDGET = 16  # (a 3,000-document corpus: without this no query would ever need the streaming bootstrap)
     # "tiles" (the default plan): bootstrap = first tile of the 3 leading leaves, everything else in the second round
     rr.PLAN, rr.BOOT_LEAVES = plan, 3
     scores, ids, ncand = rr.rerank(case.Q, dec, topk=k)
@@ -105,13 +106,14 @@ def test_device_plan_covers_every_pair_tile_exactly_once(maxg_sample, maxg_last)
     ql_h[::3, 7:] = rs.randint(40, n_leaves, size=ql_h[::3, 7:].shape)
     ql_h[4, 2] = -1
     ql_h[9, :] = -1
-    ql_h[11, :] = 2  # one tiny leaf asked for twelve times: a weak sample
+    ql_h[11, :] = 2  # one tiny leaf asked for twelve times (few candidates: needs no sample)
     ql = torch.from_numpy(ql_h).cuda()
-    ncand, weak, rounds, n_weak = c.rerank_grouped_plan(ql, off, lt0, boot, 300, maxg_sample, maxg_last)
+    ncand, weak, rounds, n_weak = c.rerank_grouped_plan(ql, off, lt0, boot, 900, 500, maxg_sample, maxg_last, pass_budget=6144)
     want_ncand = np.where(ql_h >= 0, sizes[np.clip(ql_h, 0, None)], 0).sum(1)
     assert np.array_equal(ncand.cpu().numpy(), want_ncand)
     boot_rows = np.where(ql_h[:, :5] >= 0, np.minimum(sizes[np.clip(ql_h[:, :5], 0, None)], 128), 0).sum(1)
-    want_weak = (boot_rows < 300) & (want_ncand > boot_rows)
+    limit = np.minimum(900, np.maximum(2 * 500, want_ncand * 500 // 6144))  # boot_min_rows 900, k 500
+    want_weak = (want_ncand > 6144) & (boot_rows < limit) & (want_ncand > boot_rows)
     assert np.array_equal(weak.cpu().numpy().astype(bool), want_weak) and n_weak == int(want_weak.sum()) and n_weak >= 1
     assert len(rounds) == 3
     lt0_h = lt0.cpu().numpy()

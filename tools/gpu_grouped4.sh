@@ -35,7 +35,7 @@ ms, ql = T(lambda: index.lookup(dec)); print(f"lookup                {ms:6.2f} m
 ms, plan_t = T(lambda: plan_grouped_tile_rounds(gg["leaf_tile0"], ql, (8, 63))); print(f"torch plan            {ms:6.2f} ms")
 off = index.leaf_offsets
 def dplan(ms_, ml_):
-    ncand, weak, rounds, nweak = ctx.rerank_grouped_plan(ql, off, gg["leaf_tile0"], (8, 63), 2048, ms_, ml_)
+    ncand, weak, rounds, nweak = ctx.rerank_grouped_plan(ql, off, gg["leaf_tile0"], (8, 63), 2048, 100, ms_, ml_)
     return [ctx.rerank_grouped_plan_fill(r, a, b, dev) for r, (a, b) in enumerate(rounds)], nweak
 for ms_, ml_ in ((1, 1), (1, 2), (1, 4), (2, 4), (4, 4)):
     ms, (plan, nweak) = T(lambda: dplan(ms_, ml_))
