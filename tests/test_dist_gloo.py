@@ -83,3 +83,43 @@ def test_two_rank_training_equals_single_rank(tmp_path):
     assert abs(mse1 - mse2) / mse1 < 0.25
     rep = oracle.classify_code_mismatches(X, cb2, oracle.rq_encode(X, cb2), codes2)
     assert rep["n_hard"] == 0
+
+
+def _partition_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mevi_b200.dist_utils import all_gather_varlen, partition_rows_by_leaf, shard_bounds
+
+    rs = np.random.RandomState(3)
+    n, d, M, K = 2003, 8, 2, 5
+    X = rs.standard_normal((n, d)).astype(np.float32)
+    codes = rs.randint(0, K, size=(n, M)).astype(np.int32)
+    codes[:700] = (1, 2)  # one leaf holds a third of the corpus: it still goes, whole, to one rank
+    s, e = shard_bounds(n, rank, world)
+    X_own, codes_own, ids_own = partition_rows_by_leaf(torch.from_numpy(X[s:e]), torch.from_numpy(codes[s:e]), K, s)
+    # the rows that arrived are the documents their ids name, with their codes
+    assert torch.equal(X_own, torch.from_numpy(X)[ids_own]) and torch.equal(codes_own, torch.from_numpy(codes)[ids_own])
+    # ascending document ids inside this rank's rows (rank-ordered all-to-all of ascending blocks)
+    assert bool((ids_own[1:] > ids_own[:-1]).all())
+    keys_own = torch.unique(codes_own[:, 0].long() * K + codes_own[:, 1].long())
+    all_keys = all_gather_varlen(keys_own)
+    all_ids = all_gather_varlen(ids_own)
+    counts = all_gather_varlen(torch.tensor([ids_own.numel()]))
+    if rank == 0:
+        assert all_keys.numel() == torch.unique(all_keys).numel(), "a leaf lives on more than one rank"
+        assert torch.equal(torch.sort(all_ids).values, torch.arange(n)), "every document exactly once"
+        # contiguous key ranges of nearly equal row counts: no rank is further from n / world than the largest leaf
+        assert int((counts - n // world).abs().max()) <= 700
+        np.save(os.path.join(out_dir, "counts.npy"), counts.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_leaf_partition_moves_every_leaf_whole_to_one_rank(tmp_path, world):
+    """dist_utils.partition_rows_by_leaf (the leaf-partitioned re-rank index): all-gather of the leaf histogram,
+    contiguous key ranges of equal row counts, one all-to-all each for rows / codes / document ids."""
+    mp.spawn(_partition_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert int(np.load(tmp_path / "counts.npy").sum()) == 2003
