@@ -505,11 +505,11 @@ def _rerank_grouped(self, Q, ql, topk):
     ctx, idx = self.ctx, self.index
     off = idx.leaf_offsets
     boot = (self.BOOT_LEAVES,) if isinstance(self.BOOT_LEAVES, int) else tuple(self.BOOT_LEAVES)
-    # thresholds bootstrap themselves: the first round (the leading leaves of every query, at most BOOTSTRAP_ROWS rows)
-    # runs without thresholds and appends every score; its compaction yields each query's first k-th best score.
-    # A query whose leading leaves do not add up to BOOTSTRAP_MIN rows within that limit (its first leaf is a huge
-    # one) would enter the next round with no useful threshold: those few queries get the exact k-th score of their
-    # first BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
+    # thresholds bootstrap themselves: the first round (first tiles of the leading leaves of every query) runs without
+    # thresholds and appends every score; its compaction yields each query's first k-th best score, the sample rounds
+    # that follow tighten it.  A query whose sample is too small for its candidate count (its k-th best would let more
+    # than PASS_BUDGET scores through the last round: few, huge leaves) gets the exact k-th score of its first
+    # BOOTSTRAP_MIN candidate ROWS from the streaming kernel instead (cuts through the leaf).
     device_plan = None
     if self.PLAN == "device":  # counts, scans, candidate totals and the weak-sample flags in five launches, one host sync
         ql = ql.contiguous()  # the library keeps the pointer until the last plan_fill of this call
