@@ -58,3 +58,41 @@ def test_fuse_arithmetic():
     assert f[2] == 1.0 + 0.6 / 1.0 and f[1] == 1.0 + 0.6 / 1.03
     assert f[3] == (1.0 + 0.6 / 1.06) * (1 - 0.02 * 0.6)
     assert ranking_of(f)[0] == -1 and ranking_of(f)[1] == 2
+
+
+def test_mapping_to_codes_marks_holes():
+    import numpy as np
+
+    from mevi_b200.ensemble import mapping_to_codes
+
+    codes = mapping_to_codes({0: (1, 2, 3), 3: (0, 0, 1), 1: (2, 2, 2)})
+    assert codes.shape == (4, 3) and codes.dtype == np.int32
+    assert codes[0].tolist() == [1, 2, 3] and codes[1].tolist() == [2, 2, 2] and codes[3].tolist() == [0, 0, 1]
+    assert (codes[2] == np.iinfo(np.int32).min).all()  # document 2 is not a key: the rank kernel reports a KeyError for it
+
+
+def test_device_path_is_the_default_and_fails_loudly_without_a_gpu(tmp_path):
+    """`--device cuda` (the CLI default) never falls back to the python dictionaries: without a CUDA device the drivers
+    raise; the host arithmetic runs only when asked for by name."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import make_ensemble_golden as g
+
+    import mevi_b200
+    from mevi_b200 import ensemble
+
+    work = str(tmp_path / "in")
+    g.ensemble_inputs(work)
+    args = g.marco_args(work, str(tmp_path / "r.txt"))  # no `device` attribute: the default applies
+    with pytest.raises(mevi_b200.MeviError):
+        ensemble.combine_main_marco(args)
+    args = g.nq_args(work, str(tmp_path / "r2.txt"))
+    args.device = "cuda"
+    with pytest.raises(mevi_b200.MeviError):
+        ensemble.combine_main_nqdpr(args)
+    args = g.nq_args(work, str(tmp_path / "r3.txt"))  # (the drivers parse the flag strings in place, like the reference)
+    args.device = "tpu"
+    with pytest.raises(ValueError):
+        ensemble.combine_main_nqdpr(args)
