@@ -259,7 +259,7 @@ int mevi_cluster_rerank_all(mevi_ctx* ctx, const float* Q, int nq, const float* 
  * whose guarantee could not be established (candidate buffer / margin window overflow; marked in failed_or_null [nq]
  * int32 device) - the caller re-runs just those through mevi_cluster_rerank; *n_failed = nq: the whole call is invalid.
  * Thresholds: tau0 (a lower bound of every query's k-th best score) or NULL; with NULL the FIRST round must be small
- * enough that all its scores fit the 4,096-slot candidate buffers (they are all appended), which bootstraps them.
+ * enough that all its scores fit the 8,192-slot candidate buffers (they are all appended), which bootstraps them.
  * The state between _begin and _finish lives in the context: one grouped call at a time per context.            */
 int mevi_rerank_grouped_image(mevi_ctx* ctx, const float* D_leaf, int64_t n, int d, const int32_t* src_index,
                               int64_t n_tiles, void* Aimg, float* absmax_out, float* maxnorm_out, void* stream);

@@ -12,7 +12,7 @@ come back.  Text output keeps the reference's byte format.
 from __future__ import annotations
 
 import pickle
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
